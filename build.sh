@@ -1,0 +1,25 @@
+#!/bin/bash
+# Builds liblmb200.so (CUDA core + C ABI) for sm_100a, in-tree so it travels with gpurun.
+set -euo pipefail
+ROOT="$(cd "$(dirname "$0")" && pwd)"
+SRC="$ROOT/lightmetrica-v2_b200/csrc"
+OUT="$ROOT/lightmetrica-v2_b200/lib"
+mkdir -p "$OUT" "$OUT/obj"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+HOSTCXX=/usr/bin/g++
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+NVFLAGS="-O3 -std=c++17 -lineinfo $ARCH -ccbin $HOSTCXX -Xcompiler -fPIC,-O2,-ffp-contract=off,-Wall -Xptxas -v --fmad=true"
+for f in accel render; do
+  if [ -f "$SRC/$f.cu" ]; then
+    if [ ! -f "$OUT/obj/$f.o" ] || [ -n "$(find "$SRC" "$ROOT/include" -newer "$OUT/obj/$f.o" -type f | head -1)" ]; then
+      $NVCC $NVFLAGS -c "$SRC/$f.cu" -o "$OUT/obj/$f.o" 2> "$OUT/obj/$f.ptxas.log" || { cat "$OUT/obj/$f.ptxas.log"; exit 1; }
+    fi
+  fi
+done
+if [ ! -f "$OUT/obj/bvh_build.o" ] || [ -n "$(find "$SRC" -newer "$OUT/obj/bvh_build.o" -type f | head -1)" ]; then
+  $HOSTCXX -O2 -std=c++17 -fPIC -ffp-contract=off -Wall -pthread -c "$SRC/bvh_build.cpp" -o "$OUT/obj/bvh_build.o"
+fi
+OBJS="$OUT/obj/accel.o $OUT/obj/bvh_build.o"
+[ -f "$OUT/obj/render.o" ] && OBJS="$OBJS $OUT/obj/render.o"
+$NVCC $ARCH -shared -ccbin $HOSTCXX -o "$OUT/liblmb200.so" $OBJS -Xlinker -soname=liblmb200.so -lpthread -ldl
+echo "build: $OUT/liblmb200.so"

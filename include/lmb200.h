@@ -1,0 +1,209 @@
+/*
+ * lmb200 — B200-native ray traversal + unidirectional path tracing behind a thin C ABI.
+ *
+ * This header is the drop-in boundary below Lightmetrica v2's plugin API: the two plugins
+ * (accel::lmb200, renderer::lmb200pt) are host C++ that flatten a
+ * `Scene3` into the POD arrays declared here and call these entry points; nothing in the
+ * signatures is a torch or C++ type. Citations are paths under the reference tree
+ * (hi2p-perim/lightmetrica-v2).
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success and a negative LMB200_E_* code on
+ *     failure; lmb200_last_error() gives the message (thread-local). Nothing throws.
+ *   - *_dev entry points take DEVICE pointers on the accel's device and enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = the legacy default stream) without synchronising.
+ *     The plain entry points take HOST pointers and do the H2D/D2H copies themselves.
+ *   - there is no CPU fallback: a build without a usable CUDA device fails with LMB200_E_CUDA.
+ */
+#ifndef LMB200_H
+#define LMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMB200_OK          0
+#define LMB200_E_INVALID  -1   /* bad argument */
+#define LMB200_E_CUDA     -2   /* CUDA runtime error or no device */
+#define LMB200_E_STATE    -3   /* object not built / wrong state */
+#define LMB200_E_NCCL     -4   /* NCCL not loadable or failed */
+
+#define LMB200_MISS 0xffffffffu
+
+/* Ray: origin, direction (NOT renormalised: t is in units of |d|, as in ray.h:39-43) and the
+ * accepted parametric range [tmin, tmax] (accel3.h:68 minT/maxT; tmax may be FLT_MAX). 32 B. */
+typedef struct lmb200_ray {
+    float ox, oy, oz, tmin;
+    float dx, dy, dz, tmax;
+} lmb200_ray;
+
+/* Closest hit. tri = index of the triangle in the order it was given to lmb200_accel_build
+ * (the reference accels' `triangles_` order: primitive-major, face-minor,
+ * accel_qbvh.cpp:161-194), LMB200_MISS if none. t,u,v are exactly the values
+ * TriAccelTriangle::Intersect produces (triaccel.h:129-150): u weights vertex 2, v vertex 3. 16 B. */
+typedef struct lmb200_hit {
+    float t, u, v;
+    uint32_t tri;
+} lmb200_hit;
+
+typedef struct lmb200_accel lmb200_accel;
+
+typedef struct lmb200_accel_stats {
+    uint64_t num_triangles;       /* triangles given to build */
+    uint64_t num_valid_triangles; /* non-degenerate (TriAccel k != 3, triaccel.h:73-77) */
+    uint64_t num_nodes;           /* 80-byte wide nodes */
+    uint64_t node_bytes, tri_bytes;
+    double   build_seconds;       /* host build */
+    double   upload_seconds;
+    float    sah_cost;
+    int      max_depth;
+} lmb200_accel_stats;
+
+const char* lmb200_last_error(void);
+int  lmb200_device_count(void);
+
+/* Replaces Accel::Initialize (accel.h:67). device = CUDA ordinal. */
+lmb200_accel* lmb200_accel_create(int device);
+void lmb200_accel_destroy(lmb200_accel* a);
+
+/* Replaces Accel::Build (accel.h:79; accel_qbvh.cpp:152-396). verts = 9 floats per triangle:
+ * world-space A,B,C exactly as the reference computes them
+ * (Vec3(prim->transform * Vec4(p,1)), accel_qbvh.cpp:182-184). ntris may be 0. */
+int lmb200_accel_build(lmb200_accel* a, const float* verts, uint64_t ntris);
+int lmb200_accel_get_stats(const lmb200_accel* a, lmb200_accel_stats* out);
+
+/* Replaces Accel3::Intersect (accel3.h:68; accel_qbvh.cpp:398-497) for a batch of n rays.
+ * Closest hit with the reference's acceptance rule (reject t<tmin or t>tmax, triaccel.h:137);
+ * on exact ties in t the triangle with the larger index wins (= accel::naive's scan order,
+ * accel_naive.cpp:92-124). */
+int lmb200_trace_closest(lmb200_accel* a, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n);
+int lmb200_trace_closest_dev(lmb200_accel* a, const void* rays_dev, void* hits_dev, uint64_t n, void* stream);
+
+/* Replaces Scene3::Visible's query (scene3.h:107-116): occluded[i] = 1 iff ANY triangle is hit
+ * within [tmin, tmax] (same boolean as the reference's closest-hit query, early exit). */
+int lmb200_trace_any(lmb200_accel* a, const lmb200_ray* rays, uint8_t* occluded, uint64_t n);
+int lmb200_trace_any_dev(lmb200_accel* a, const void* rays_dev, void* occluded_dev, uint64_t n, void* stream);
+
+/* Traversal work counters for the roofline's algorithmic-byte figure: mean
+ * 80-byte nodes and 48-byte triangle records fetched per ray over the given DEVICE ray batch
+ * (instrumented copy of the closest-hit kernel, not timed). */
+int lmb200_trace_count_dev(lmb200_accel* a, const void* rays_dev, uint64_t n, double* nodes_per_ray, double* tris_per_ray);
+
+/* Number of kernels this library has launched so far in this process (bench.py gpu_launches). */
+uint64_t lmb200_launch_count(void);
+
+/* Host copies of the flattened structure, for tests (host logic is checked without a GPU). */
+int lmb200_accel_host_arrays(const lmb200_accel* a, const void** nodes80, uint64_t* num_nodes,
+                             const void** tris48, const uint32_t** tri_index, uint64_t* num_tris);
+/* Build on the host only (no device needed); such an accel cannot trace. For tests. */
+lmb200_accel* lmb200_accel_create_host_only(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Wavefront path tracer (replaces Renderer::Render of renderer::pt / renderer::ptdirect,
+ * renderer_pt.cpp:64-231, renderer_ptdirect.cpp:72-282, and Scheduler_::Process,
+ * scheduler.cpp:78-295).
+ */
+
+#define LMB200_BSDF_NULL          0   /* bsdf_null.cpp:38-56: Type()==None, path ends */
+#define LMB200_BSDF_DIFFUSE       1   /* bsdf_diffuse.cpp:69-104 */
+#define LMB200_BSDF_COOKTORRANCE  2   /* bsdf_cooktorrance.cpp:73-120,187-225,276-293 (GGX) */
+
+typedef struct lmb200_bsdf {
+    int32_t type;
+    float R[3];
+    float eta[3];
+    float k[3];
+    float roughness;
+} lmb200_bsdf;
+
+/* One entry per scene primitive that owns triangles (primitive.h:57-84). */
+typedef struct lmb200_primitive {
+    int32_t  bsdf;        /* index into bsdfs */
+    int32_t  light;       /* index into lights or -1 */
+    uint32_t first_tri;   /* its triangles are [first_tri, first_tri+num_tris) in build order */
+    uint32_t num_tris;
+    int32_t  has_normals; /* 0: shading normal = geometric normal (intersectionutils.h:96-100) */
+} lmb200_primitive;
+
+/* light::area (light_area.cpp:47-115). The area CDF over the primitive's triangles is built
+ * by the library exactly as TriangleUtils::CreateTriangleAreaDist (triangleutils.h:47-68). */
+typedef struct lmb200_light {
+    float   Le[3];
+    int32_t primitive;
+} lmb200_light;
+
+/* sensor::pinhole (sensor_pinhole.cpp:47-61): position = column 3 of the primitive transform,
+ * vx,vy,vz = columns 0..2, fov in radians (vertical), aspect = W/H. */
+typedef struct lmb200_camera {
+    float position[3];
+    float vx[3], vy[3], vz[3];
+    float fov;
+    int32_t width, height;
+} lmb200_camera;
+
+typedef struct lmb200_scene_desc {
+    uint64_t num_tris;
+    const float* verts;        /* 9 floats / triangle, world space (as lmb200_accel_build) */
+    const float* normals;      /* 9 floats / triangle: normalTransform * n_i (intersectionutils.h:88-90), or NULL */
+    const uint32_t* tri_prim;  /* primitive index (into prims) per triangle */
+    uint32_t num_prims;
+    const lmb200_primitive* prims;
+    uint32_t num_bsdfs;
+    const lmb200_bsdf* bsdfs;
+    uint32_t num_lights;
+    const lmb200_light* lights;
+    lmb200_camera camera;
+} lmb200_scene_desc;
+
+typedef struct lmb200_scene lmb200_scene;
+
+#define LMB200_MODE_PT        0   /* renderer::pt: emission on BSDF-sampled hits, no NEE */
+#define LMB200_MODE_PTDIRECT  1   /* renderer::ptdirect: NEE at every vertex incl. the camera vertex */
+#define LMB200_MODE_NORMAL    2   /* primary rays at pixel centres, |sn| as RGB (renderer_raycast.cpp:72-105 ray gen,
+                                     plugin/renderer_normal/renderer_normal.cpp:62-75 shading) */
+
+typedef struct lmb200_render_params {
+    int32_t  mode;
+    int64_t  num_samples;        /* scheduler.cpp:55 num_samples: total over ALL ranks */
+    int64_t  sample_begin;       /* this call renders global sample indices [sample_begin, sample_end) */
+    int64_t  sample_end;
+    int32_t  max_num_vertices;   /* renderer_pt.cpp:59, -1 = unbounded */
+    int32_t  min_num_vertices;   /* renderer_pt.cpp:60 */
+    uint64_t seed;               /* counter-based RNG key; same seed => same image at any GPU count */
+    int32_t  pool_size;          /* wavefront size in paths, 0 = default */
+} lmb200_render_params;
+
+typedef struct lmb200_render_stats {
+    int64_t  samples;
+    int64_t  extend_rays, shadow_rays;
+    int64_t  iterations;
+    uint64_t launches;
+    double   seconds;            /* device time of the wavefront loop (CUDA events) */
+} lmb200_render_stats;
+
+/* Builds the accel (device) and uploads shading data. */
+lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* desc);
+void lmb200_scene_destroy(lmb200_scene* s);
+lmb200_accel* lmb200_scene_accel(lmb200_scene* s);
+
+/* Accumulates UNSCALED splats of the given sample range into film_dev: W*H float4 (rgb + pad,
+ * the layout of film_hdr.cpp's Vec3 data_), row 0 = raster y in [0,1/H) (film_hdr.cpp:218-223).
+ * The caller zeroes the film, sums films across GPUs (NCCL reduce) and applies
+ * lmb200_film_rescale with W*H/num_samples (scheduler.cpp:280-288). Synchronises `stream` once at the end. */
+int lmb200_render_dev(lmb200_scene* s, const lmb200_render_params* p, void* film_dev, void* stream, lmb200_render_stats* stats);
+int lmb200_film_rescale_dev(void* film_dev, int64_t num_pixels, float scale, void* stream);
+
+/* Host-buffer convenience: zero film, render [sample_begin,sample_end), rescale by
+ * W*H/num_samples, copy W*H*4 floats back. The call the Renderer plugin makes on one GPU. */
+int lmb200_render(lmb200_scene* s, const lmb200_render_params* p, float* film_rgba_host, lmb200_render_stats* stats);
+
+/* Single-process multi-GPU render (one host thread + stream per device; per-GPU films summed to
+ * device 0 with ncclReduce, then rescaled). scenes[g] must hold the same scene on device g. */
+int lmb200_render_multi(lmb200_scene** scenes, int num_gpus, const lmb200_render_params* p, float* film_rgba_host, lmb200_render_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMB200_H */

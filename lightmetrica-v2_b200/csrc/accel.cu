@@ -1,0 +1,319 @@
+// Accel object, persistent trace kernels and the C ABI for the traversal path (include/lmb200.h).
+// Replaces Accel::Build / Accel3::Intersect of the reference's in-tree accels
+// (/root/reference/src/liblightmetrica/accel/accel_qbvh.cpp:152-497) for ray BATCHES.
+#include "internal.h"
+#include "traverse.cuh"
+
+#include <chrono>
+#include <cstring>
+
+namespace lmb200 {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    return set_error(LMB200_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernels. Persistent grid: every warp claims 32 rays at a time from a global counter
+// (one atomicAdd per warp), so long rays do not strand a whole block's worth of work.
+
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(LMB_TRACE_BLOCK)
+trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+             const float4* __restrict__ rays, void* __restrict__ out,
+             const uint64_t n_host, const uint32_t* __restrict__ n_dev,
+             unsigned long long* __restrict__ counter, unsigned long long* __restrict__ work_counters)
+{
+    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
+    const unsigned lane = threadIdx.x & 31u;
+    TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint64_t i = base + lane;
+        if (i < n) {
+            const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+            float tmax = rd.w, hu = 0.f, hv = 0.f;
+            uint32_t hid;
+            const bool hit = lmb_traverse<ANY, COUNT>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, &cnt);
+            if (ANY) {
+                reinterpret_cast<uint8_t*>(out)[i] = hit ? 1 : 0;
+            } else {
+                float4 h;
+                h.x = hit ? tmax : 0.f; h.y = hu; h.z = hv; h.w = __uint_as_float(hit ? hid : LMB200_MISS);
+                reinterpret_cast<float4*>(out)[i] = h;
+            }
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+        unsigned long long a = cnt.nodes, b = cnt.tris;
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+        if (lane == 0) { atomicAdd(work_counters, a); atomicAdd(work_counters + 1, b); }
+    }
+}
+
+template <bool ANY, bool COUNT>
+static int launch_trace(Accel* a, const void* rays, void* out, uint64_t n, const uint32_t* n_dev, cudaStream_t st, unsigned long long* work, int slot)
+{
+    unsigned long long* counter = a->d_counter + slot;
+    if (!a->d_nodes) return set_error(LMB200_E_STATE, "accel not built on a device");
+    if (n == 0 && !n_dev) return LMB200_OK;
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counter)");
+    const uint64_t warps_needed = (n + 31) / 32;
+    uint64_t blocks = (warps_needed + (LMB_TRACE_BLOCK / 32) - 1) / (LMB_TRACE_BLOCK / 32);
+    const uint64_t persistent = (uint64_t)a->num_sms * a->trace_blocks_per_sm;
+    if (n_dev || blocks > persistent) blocks = persistent;
+    if (blocks == 0) blocks = 1;
+    trace_kernel<ANY, COUNT><<<(unsigned)blocks, LMB_TRACE_BLOCK, 0, st>>>(
+        reinterpret_cast<const float4*>(a->d_nodes), reinterpret_cast<const float4*>(a->d_tris),
+        reinterpret_cast<const float4*>(rays), out, n, n_dev, counter, work);
+    g_launch_count++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "trace_kernel launch");
+    return LMB200_OK;
+}
+
+int trace_closest_dev(Accel* a, const void* rays, void* hits, uint64_t n, const uint32_t* n_dev, cudaStream_t st, int slot)
+{
+    return launch_trace<false, false>(a, rays, hits, n, n_dev, st, nullptr, slot);
+}
+
+int trace_any_dev(Accel* a, const void* rays, void* occ, uint64_t n, const uint32_t* n_dev, cudaStream_t st, int slot)
+{
+    return launch_trace<true, false>(a, rays, occ, n, n_dev, st, nullptr, slot);
+}
+
+// ------------------------------------------------------------------------------------------------
+
+void Accel::free_device()
+{
+    if (device >= 0) cudaSetDevice(device);
+    if (d_nodes) cudaFree(d_nodes);
+    if (d_tris) cudaFree(d_tris);
+    if (d_counter) cudaFree(d_counter);
+    for (int i = 0; i < 2; i++) {
+        if (stage_rays[i]) cudaFree(stage_rays[i]);
+        if (stage_out[i]) cudaFree(stage_out[i]);
+        if (streams[i]) cudaStreamDestroy(streams[i]);
+        stage_rays[i] = stage_out[i] = nullptr; streams[i] = nullptr;
+    }
+    d_nodes = d_tris = nullptr; d_counter = nullptr;
+}
+
+Accel::~Accel() { free_device(); }
+
+int Accel::upload()
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (d_nodes) { cudaFree(d_nodes); d_nodes = nullptr; }
+    if (d_tris) { cudaFree(d_tris); d_tris = nullptr; }
+    const size_t nb = bvh.nodes.size() * sizeof(Node80);
+    const size_t tb = std::max<size_t>(bvh.tris.size(), 1) * sizeof(TriRecord);
+    if ((e = cudaMalloc(&d_nodes, nb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(nodes)");
+    if ((e = cudaMalloc(&d_tris, tb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tris)");
+    if (!d_counter && (e = cudaMalloc(&d_counter, 4 * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
+    if ((e = cudaMemcpy(d_nodes, bvh.nodes.data(), nb, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(nodes)");
+    if (!bvh.tris.empty() && (e = cudaMemcpy(d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tris)");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false, false>, LMB_TRACE_BLOCK, 0);
+    trace_blocks_per_sm = occ > 0 ? occ : 4;
+    upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return LMB200_OK;
+}
+
+// Host-buffer trace: chunks ping-pong over two streams so the H2D copy of chunk k+1 and the D2H
+// copy of chunk k-1 overlap the kernel of chunk k (when the host buffers are pinned).
+template <bool ANY>
+static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
+{
+    if (!a || (!rays && n) || (!out && n)) return set_error(LMB200_E_INVALID, "null argument");
+    if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
+    if (!a->d_nodes) return set_error(LMB200_E_STATE, "accel not built");
+    cudaError_t e = cudaSetDevice(a->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t out_elem = ANY ? 1 : sizeof(lmb200_hit);
+    const uint64_t chunk = n < (1ull << 22) ? std::max<uint64_t>(n, 1) : (1ull << 22);
+    for (int i = 0; i < 2; i++) {
+        if (!a->streams[i] && (e = cudaStreamCreateWithFlags(&a->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    }
+    if (a->stage_cap < chunk) {
+        for (int i = 0; i < 2; i++) {
+            if (a->stage_rays[i]) cudaFree(a->stage_rays[i]);
+            if (a->stage_out[i]) cudaFree(a->stage_out[i]);
+            a->stage_rays[i] = a->stage_out[i] = nullptr;
+            if ((e = cudaMalloc(&a->stage_rays[i], chunk * sizeof(lmb200_ray))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage rays)");
+            if ((e = cudaMalloc(&a->stage_out[i], chunk * sizeof(lmb200_hit))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(stage out)");
+        }
+        a->stage_cap = chunk;
+    }
+    // each staging stream has its own work counter (slots 2 and 3)
+    int k = 0;
+    for (uint64_t off = 0; off < n; off += chunk, k ^= 1) {
+        const uint64_t m = std::min(chunk, n - off);
+        cudaStream_t st = a->streams[k];
+        if ((e = cudaMemcpyAsync(a->stage_rays[k], rays + off, m * sizeof(lmb200_ray), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D rays");
+        const int rc = ANY ? trace_any_dev(a, a->stage_rays[k], a->stage_out[k], m, nullptr, st, 2 + k)
+                           : trace_closest_dev(a, a->stage_rays[k], a->stage_out[k], m, nullptr, st, 2 + k);
+        if (rc) return rc;
+        if ((e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + off * out_elem, a->stage_out[k], m * out_elem, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H hits");
+    }
+    for (int i = 0; i < 2; i++) {
+        if ((e = cudaStreamSynchronize(a->streams[i])) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return LMB200_OK;
+}
+
+}  // namespace lmb200
+
+using namespace lmb200;
+
+extern "C" {
+
+const char* lmb200_last_error(void) { return g_last_error.c_str(); }
+
+int lmb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+uint64_t lmb200_launch_count(void) { return g_launch_count.load(); }
+
+lmb200_accel* lmb200_accel_create(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error(LMB200_E_CUDA, "no CUDA device available (lmb200 has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { set_error(LMB200_E_INVALID, "bad device ordinal"); return nullptr; }
+    Accel* a = new Accel;
+    a->device = device;
+    return reinterpret_cast<lmb200_accel*>(a);
+}
+
+lmb200_accel* lmb200_accel_create_host_only(void)
+{
+    Accel* a = new Accel;
+    a->host_only = true;
+    return reinterpret_cast<lmb200_accel*>(a);
+}
+
+void lmb200_accel_destroy(lmb200_accel* a) { delete reinterpret_cast<Accel*>(a); }
+
+int lmb200_accel_build(lmb200_accel* h, const float* verts, uint64_t ntris)
+{
+    Accel* a = reinterpret_cast<Accel*>(h);
+    if (!a || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
+    if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27, as the reference's leaf encoding accel_qbvh.cpp:62-72)");
+    build_bvh(verts, ntris, a->bvh, 0);
+    a->built = true;
+    if (a->host_only) return LMB200_OK;
+    return a->upload();
+}
+
+int lmb200_accel_get_stats(const lmb200_accel* h, lmb200_accel_stats* out)
+{
+    const Accel* a = reinterpret_cast<const Accel*>(h);
+    if (!a || !out) return set_error(LMB200_E_INVALID, "null argument");
+    if (!a->built) return set_error(LMB200_E_STATE, "accel not built");
+    out->num_triangles = a->bvh.stats.num_triangles;
+    out->num_valid_triangles = a->bvh.stats.num_valid;
+    out->num_nodes = a->bvh.nodes.size();
+    out->node_bytes = a->bvh.nodes.size() * sizeof(Node80);
+    out->tri_bytes = a->bvh.tris.size() * sizeof(TriRecord);
+    out->build_seconds = a->bvh.stats.build_seconds;
+    out->upload_seconds = a->upload_seconds;
+    out->sah_cost = a->bvh.stats.sah_cost;
+    out->max_depth = a->bvh.stats.max_depth;
+    return LMB200_OK;
+}
+
+int lmb200_accel_host_arrays(const lmb200_accel* h, const void** nodes80, uint64_t* num_nodes,
+                             const void** tris48, const uint32_t** tri_index, uint64_t* num_tris)
+{
+    const Accel* a = reinterpret_cast<const Accel*>(h);
+    if (!a) return set_error(LMB200_E_INVALID, "null argument");
+    if (!a->built) return set_error(LMB200_E_STATE, "accel not built");
+    if (nodes80) *nodes80 = a->bvh.nodes.data();
+    if (num_nodes) *num_nodes = a->bvh.nodes.size();
+    if (tris48) *tris48 = a->bvh.tris.data();
+    if (tri_index) *tri_index = a->bvh.tri_index.data();
+    if (num_tris) *num_tris = a->bvh.tris.size();
+    return LMB200_OK;
+}
+
+int lmb200_trace_closest(lmb200_accel* h, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n)
+{
+    return trace_host<false>(reinterpret_cast<Accel*>(h), rays, hits, n);
+}
+
+int lmb200_trace_any(lmb200_accel* h, const lmb200_ray* rays, uint8_t* occluded, uint64_t n)
+{
+    return trace_host<true>(reinterpret_cast<Accel*>(h), rays, occluded, n);
+}
+
+int lmb200_trace_closest_dev(lmb200_accel* h, const void* rays_dev, void* hits_dev, uint64_t n, void* stream)
+{
+    Accel* a = reinterpret_cast<Accel*>(h);
+    if (!a || (n && (!rays_dev || !hits_dev))) return set_error(LMB200_E_INVALID, "null argument");
+    if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
+    cudaError_t e = cudaSetDevice(a->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return trace_closest_dev(a, rays_dev, hits_dev, n, nullptr, reinterpret_cast<cudaStream_t>(stream), 0);
+}
+
+int lmb200_trace_any_dev(lmb200_accel* h, const void* rays_dev, void* occ_dev, uint64_t n, void* stream)
+{
+    Accel* a = reinterpret_cast<Accel*>(h);
+    if (!a || (n && (!rays_dev || !occ_dev))) return set_error(LMB200_E_INVALID, "null argument");
+    if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
+    cudaError_t e = cudaSetDevice(a->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return trace_any_dev(a, rays_dev, occ_dev, n, nullptr, reinterpret_cast<cudaStream_t>(stream), 0);
+}
+
+int lmb200_trace_count_dev(lmb200_accel* h, const void* rays_dev, uint64_t n, double* nodes_per_ray, double* tris_per_ray)
+{
+    Accel* a = reinterpret_cast<Accel*>(h);
+    if (!a || !rays_dev || !n) return set_error(LMB200_E_INVALID, "null argument");
+    if (a->host_only || !a->d_nodes) return set_error(LMB200_E_STATE, "accel not built on a device");
+    cudaError_t e = cudaSetDevice(a->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    void* scratch = nullptr;
+    unsigned long long* work = nullptr;
+    if ((e = cudaMalloc(&scratch, n * sizeof(lmb200_hit))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+    if ((e = cudaMalloc(&work, 2 * sizeof(unsigned long long))) != cudaSuccess) { cudaFree(scratch); return cuda_fail(e, "cudaMalloc(work)"); }
+    cudaMemset(work, 0, 2 * sizeof(unsigned long long));
+    int rc = launch_trace<false, true>(a, rays_dev, scratch, n, nullptr, 0, work, 0);
+    unsigned long long hw[2] = {0, 0};
+    if (!rc) {
+        e = cudaMemcpy(hw, work, sizeof(hw), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(work)");
+    }
+    cudaFree(scratch); cudaFree(work);
+    if (rc) return rc;
+    if (nodes_per_ray) *nodes_per_ray = (double)hw[0] / (double)n;
+    if (tris_per_ray) *tris_per_ray = (double)hw[1] / (double)n;
+    return LMB200_OK;
+}
+
+}  // extern "C"

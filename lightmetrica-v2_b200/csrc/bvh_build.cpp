@@ -1,0 +1,388 @@
+// Host BVH builder: binned-SAH binary tree (multi-threaded) -> greedy collapse to 8-wide ->
+// octant-ordered, quantised 80-byte nodes + leaf-ordered 48-byte TriAccel records.
+// Replaces Accel_QBVH::Build (/root/reference/src/liblightmetrica/accel/accel_qbvh.cpp:152-396).
+// What is kept from the reference: triangles are world-space, every triangle's box is padded
+// by Math::Eps() = 1e-4 (accel_qbvh.cpp:189-190) so node culling is never tighter than the
+// reference's, and the triangle records come from the bit-exact TriAccel precompute.
+// What is new: 3-axis binning (the reference bins the longest axis only), <=3-triangle leaves,
+// 8-wide nodes with octant slot assignment, contiguous arrays instead of one heap node each.
+#include "bvh.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+namespace lmb200 {
+
+namespace {
+
+struct Ref {            // 32 bytes, partitioned in place
+    float lo[3];
+    uint32_t id;
+    float hi[3];
+    uint32_t pad;
+};
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; } }
+    void grow(const float* l, const float* h) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); } }
+    void grow(const Box& b) { grow(b.lo, b.hi); }
+    float half_area() const {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct BinNode {
+    Box box;
+    uint32_t left;    // children are left, left+1 (count == 0)
+    uint32_t first;   // leaf: refs[first, first+count)
+    uint32_t count;
+};
+
+constexpr int kBins = 16;
+constexpr int kMaxLeaf = 3;           // triangles per leaf slot (3 unary bits in Node80::meta)
+constexpr float kCostNode = 1.0f;     // SAH: one binary split step
+constexpr float kCostTri = 1.0f;      // SAH: one triangle test
+constexpr uint32_t kParallelGrain = 1u << 14;
+
+struct Builder {
+    std::vector<Ref> refs;
+    std::vector<BinNode> nodes;
+    std::atomic<uint32_t> node_count{0};
+
+    // work queue of subtrees for the thread pool
+    struct Task { uint32_t node, begin, end; };
+    std::vector<Task> tasks;
+    std::mutex mu;
+    std::atomic<int> pending{0};
+
+    uint32_t alloc_pair() { return node_count.fetch_add(2); }
+
+    static Box bounds_of(const Ref* r, uint32_t n) {
+        Box b; b.reset();
+        for (uint32_t i = 0; i < n; i++) b.grow(r[i].lo, r[i].hi);
+        return b;
+    }
+
+    // Finds the best binned SAH split of refs[begin,end). Returns false if no split separates them.
+    bool find_split(uint32_t begin, uint32_t end, const Box& box, int& best_axis, float& best_pos, float& best_cost) const {
+        Box cb; cb.reset();
+        for (uint32_t i = begin; i < end; i++) {
+            const Ref& r = refs[i];
+            float c[3] = {0.5f * (r.lo[0] + r.hi[0]), 0.5f * (r.lo[1] + r.hi[1]), 0.5f * (r.lo[2] + r.hi[2])};
+            cb.grow(c, c);
+        }
+        best_cost = INFINITY; best_axis = -1;
+        const float inv_area = 1.0f / std::max(box.half_area(), 1e-30f);
+        for (int axis = 0; axis < 3; axis++) {
+            const float cmin = cb.lo[axis], cmax = cb.hi[axis];
+            if (!(cmax > cmin)) continue;
+            const float scale = kBins / (cmax - cmin);
+            Box bb[kBins]; uint32_t cnt[kBins];
+            for (int b = 0; b < kBins; b++) { bb[b].reset(); cnt[b] = 0; }
+            for (uint32_t i = begin; i < end; i++) {
+                const Ref& r = refs[i];
+                const float c = 0.5f * (r.lo[axis] + r.hi[axis]);
+                int b = (int)((c - cmin) * scale);
+                b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+                bb[b].grow(r.lo, r.hi); cnt[b]++;
+            }
+            float right_area[kBins]; uint32_t right_cnt[kBins];
+            Box acc; acc.reset(); uint32_t n = 0;
+            for (int b = kBins - 1; b > 0; b--) {
+                if (cnt[b]) acc.grow(bb[b]);
+                n += cnt[b];
+                right_area[b] = n ? acc.half_area() : 0.f; right_cnt[b] = n;
+            }
+            acc.reset(); n = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                if (cnt[b]) acc.grow(bb[b]);
+                n += cnt[b];
+                if (n == 0 || right_cnt[b + 1] == 0) continue;
+                const float cost = kCostNode + kCostTri * (acc.half_area() * n + right_area[b + 1] * right_cnt[b + 1]) * inv_area;
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_pos = cmin + (b + 1) / scale; }
+            }
+        }
+        return best_axis >= 0;
+    }
+
+    // Splits node over refs[begin,end); returns mid, or 0 if it became a leaf.
+    uint32_t split_node(uint32_t ni, uint32_t begin, uint32_t end) {
+        BinNode& node = nodes[ni];
+        const uint32_t n = end - begin;
+        node.box = bounds_of(&refs[begin], n);
+        node.count = 0; node.first = begin; node.left = 0;
+        if (n == 1) { node.count = 1; return 0; }
+        int axis; float pos, cost;
+        uint32_t mid = 0;
+        if (find_split(begin, end, node.box, axis, pos, cost)) {
+            if (n <= (uint32_t)kMaxLeaf && kCostTri * n <= cost) { node.count = n; return 0; }
+            Ref* lo = &refs[begin]; Ref* hi = &refs[end];
+            Ref* m = std::partition(lo, hi, [&](const Ref& r) { return 0.5f * (r.lo[axis] + r.hi[axis]) < pos; });
+            mid = begin + (uint32_t)(m - lo);
+        }
+        if (mid == begin || mid == end || mid == 0) {
+            // coincident centroids (or a degenerate bin edge): the reference recurses forever here
+            // (accel_qbvh.cpp:375-377); we fall back to a leaf or an index-median split.
+            if (n <= (uint32_t)kMaxLeaf) { node.count = n; return 0; }
+            mid = begin + n / 2;
+        }
+        const uint32_t l = alloc_pair();
+        nodes[ni].left = l;
+        return mid;
+    }
+
+    void build_serial(uint32_t ni, uint32_t begin, uint32_t end) {
+        // explicit stack: depth can be large for adversarial inputs
+        std::vector<Task> st;
+        st.push_back({ni, begin, end});
+        while (!st.empty()) {
+            const Task t = st.back(); st.pop_back();
+            const uint32_t mid = split_node(t.node, t.begin, t.end);
+            if (!mid) continue;
+            const uint32_t l = nodes[t.node].left;
+            st.push_back({l + 1, mid, t.end});
+            st.push_back({l, t.begin, mid});
+        }
+    }
+
+    void run(int num_threads) {
+        const uint32_t n = (uint32_t)refs.size();
+        nodes.resize(std::max<size_t>(1, 2 * (size_t)n));
+        node_count = 1;
+        if (n == 0) { nodes[0].box.reset(); nodes[0].count = 0; nodes[0].left = 0; nodes[0].first = 0; return; }
+        // Phase A: split the largest open ranges on this thread until there is enough parallel work.
+        std::vector<Task> open;
+        open.push_back({0, 0, n});
+        const size_t want = (size_t)std::max(1, num_threads) * 8;
+        while (open.size() < want) {
+            size_t bi = 0;
+            for (size_t i = 1; i < open.size(); i++) if (open[i].end - open[i].begin > open[bi].end - open[bi].begin) bi = i;
+            const Task t = open[bi];
+            if (t.end - t.begin <= kParallelGrain || num_threads <= 1) break;
+            open.erase(open.begin() + bi);
+            const uint32_t mid = split_node(t.node, t.begin, t.end);
+            if (!mid) continue;
+            const uint32_t l = nodes[t.node].left;
+            open.push_back({l, t.begin, mid});
+            open.push_back({l + 1, mid, t.end});
+        }
+        // Phase B: finish the subtrees in parallel.
+        std::sort(open.begin(), open.end(), [](const Task& a, const Task& b) { return a.end - a.begin > b.end - b.begin; });
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= open.size()) break;
+                build_serial(open[i].node, open[i].begin, open[i].end);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < num_threads; t++) th.emplace_back(worker);
+        worker();
+        for (auto& x : th) x.join();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Collapse + emit
+
+struct Emitter {
+    const Builder& B;
+    const std::vector<TriRecord>& recs;   // per input triangle
+    HostBVH& out;
+    double sah = 0;
+    int max_depth = 0;
+
+    struct Pending { uint32_t bin; uint32_t wide; int depth; };
+
+    void emit_all() {
+        out.nodes.clear(); out.tris.clear(); out.tri_index.clear();
+        out.nodes.emplace_back();
+        memset(&out.nodes[0], 0, sizeof(Node80));
+        const uint32_t nrefs = (uint32_t)B.refs.size();
+        if (nrefs == 0) { out.nodes[0].e[0] = out.nodes[0].e[1] = out.nodes[0].e[2] = 127; return; }
+        out.tris.reserve(nrefs); out.tri_index.reserve(nrefs);
+        std::vector<Pending> st;
+        st.push_back({0, 0, 1});
+        const float root_area = std::max(B.nodes[0].box.half_area(), 1e-30f);
+        while (!st.empty()) {
+            const Pending p = st.back(); st.pop_back();
+            max_depth = std::max(max_depth, p.depth);
+            emit_node(p, st, root_area);
+        }
+    }
+
+    void emit_node(const Pending& p, std::vector<Pending>& st, float root_area) {
+        // 1. gather up to 8 children by repeatedly opening the internal child of largest area
+        uint32_t ch[8]; int n = 0;
+        const BinNode& root = B.nodes[p.bin];
+        if (root.count > 0) { ch[n++] = p.bin; }           // the whole tree is one leaf
+        else { ch[n++] = root.left; ch[n++] = root.left + 1; }
+        for (;;) {
+            int best = -1; float best_area = -1.f;
+            for (int i = 0; i < n; i++) {
+                const BinNode& c = B.nodes[ch[i]];
+                if (c.count == 0) { const float a = c.box.half_area(); if (a > best_area) { best_area = a; best = i; } }
+            }
+            if (best < 0 || n == 8) break;
+            const uint32_t l = B.nodes[ch[best]].left;
+            ch[best] = l; ch[n++] = l + 1;
+        }
+        // 2. node box + quantisation grid
+        Box nb; nb.reset();
+        for (int i = 0; i < n; i++) nb.grow(B.nodes[ch[i]].box);
+        Node80 node; memset(&node, 0, sizeof(node));
+        double scale[3];
+        for (int a = 0; a < 3; a++) {
+            node.p[a] = nb.lo[a];
+            const double ext = (double)nb.hi[a] - (double)nb.lo[a];
+            int e = ext > 0 ? (int)std::ceil(std::log2(ext / 255.0)) : -126;
+            e = std::max(-126, std::min(126, e));
+            while (e < 126 && std::ceil(ext / std::ldexp(1.0, e)) > 255.0) e++;
+            node.e[a] = (uint8_t)(e + 127);
+            scale[a] = std::ldexp(1.0, e);
+        }
+        // 3. octant slot assignment (greedy on the centroid-offset score)
+        float cen[8][3];
+        for (int i = 0; i < n; i++) for (int a = 0; a < 3; a++) {
+            const Box& b = B.nodes[ch[i]].box;
+            cen[i][a] = 0.5f * (b.lo[a] + b.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
+        }
+        int slot_of[8]; bool slot_used[8] = {false}; bool child_done[8] = {false};
+        for (int round = 0; round < n; round++) {
+            int bc = -1, bs = -1; float bscore = -INFINITY;
+            for (int i = 0; i < n; i++) {
+                if (child_done[i]) continue;
+                for (int s = 0; s < 8; s++) {
+                    if (slot_used[s]) continue;
+                    // slot s is visited first by rays whose direction is negative on the axes of its set bits
+                    const float score = ((s & 1) ? cen[i][0] : -cen[i][0]) + ((s & 2) ? cen[i][1] : -cen[i][1]) + ((s & 4) ? cen[i][2] : -cen[i][2]);
+                    if (score > bscore) { bscore = score; bc = i; bs = s; }
+                }
+            }
+            slot_of[bc] = bs; slot_used[bs] = true; child_done[bc] = true;
+        }
+        int child_in_slot[8];
+        for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
+        for (int i = 0; i < n; i++) child_in_slot[slot_of[i]] = i;
+        // 4. allocate children and triangles in slot order
+        node.child_base = (uint32_t)out.nodes.size();
+        node.tri_base = (uint32_t)out.tris.size();
+        uint32_t n_internal = 0, tri_off = 0;
+        const float inv_root = 1.0f / root_area;
+        for (int s = 0; s < 8; s++) {
+            const int i = child_in_slot[s];
+            if (i < 0) { node.meta[s] = 0; for (int a = 0; a < 3; a++) { node.qlo[a][s] = 255; node.qhi[a][s] = 0; } continue; }
+            const BinNode& c = B.nodes[ch[i]];
+            for (int a = 0; a < 3; a++) {
+                double ql = std::floor(((double)c.box.lo[a] - (double)node.p[a]) / scale[a]);
+                double qh = std::ceil(((double)c.box.hi[a] - (double)node.p[a]) / scale[a]);
+                ql = std::max(0.0, std::min(255.0, ql));
+                qh = std::max(0.0, std::min(255.0, qh));
+                node.qlo[a][s] = (uint8_t)ql; node.qhi[a][s] = (uint8_t)qh;
+            }
+            if (c.count > 0) {
+                node.meta[s] = (uint8_t)((((1u << c.count) - 1u) << 5) | tri_off);
+                for (uint32_t k = 0; k < c.count; k++) {
+                    const uint32_t id = B.refs[c.first + k].id;
+                    out.tris.push_back(recs[id]);
+                    out.tri_index.push_back(id);
+                }
+                tri_off += c.count;
+                sah += kCostTri * c.count * c.box.half_area() * inv_root;
+            } else {
+                node.imask |= (uint8_t)(1u << s);
+                node.meta[s] = (uint8_t)(0x20u | (24u + s));
+                n_internal++;
+            }
+        }
+        sah += kCostNode * nb.half_area() * inv_root;
+        out.nodes[p.wide] = node;
+        // 5. reserve the internal children (contiguous, slot order) and schedule them
+        const uint32_t base = node.child_base;
+        out.nodes.resize(out.nodes.size() + n_internal);
+        uint32_t rel = 0;
+        for (int s = 0; s < 8; s++) {
+            const int i = child_in_slot[s];
+            if (i < 0 || B.nodes[ch[i]].count > 0) continue;
+            st.push_back({ch[i], base + rel, p.depth + 1});
+            rel++;
+        }
+    }
+};
+
+}  // namespace
+
+void build_bvh(const float* verts, uint64_t ntris, HostBVH& out, int num_threads)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    if (num_threads <= 0) num_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    num_threads = std::min(num_threads, 64);
+
+    // TriAccel records + scene bounds
+    std::vector<TriRecord> recs(ntris);
+    std::vector<uint8_t> valid(ntris, 0);
+    {
+        auto work = [&](uint64_t b, uint64_t e) {
+            for (uint64_t i = b; i < e; i++) {
+                const float* v = verts + 9 * i;
+                const int degenerate = triaccel_load(recs[i], v, v + 3, v + 6, (uint32_t)i);
+                bool finite = true;
+                for (int k = 0; k < 9; k++) finite = finite && std::isfinite(v[k]);
+                valid[i] = (!degenerate && finite) ? 1 : 0;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < num_threads; t++) th.emplace_back(work, ntris * t / num_threads, ntris * (t + 1) / num_threads);
+        work(0, ntris / num_threads);
+        for (auto& x : th) x.join();
+    }
+    Box scene; scene.reset();
+    uint64_t nvalid = 0;
+    for (uint64_t i = 0; i < ntris; i++) {
+        if (!valid[i]) continue;
+        nvalid++;
+        const float* v = verts + 9 * i;
+        for (int k = 0; k < 3; k++) scene.grow(v + 3 * k, v + 3 * k);
+    }
+    if (nvalid == 0) { for (int a = 0; a < 3; a++) { scene.lo[a] = scene.hi[a] = 0.f; } }
+    float extent = 0.f;
+    for (int a = 0; a < 3; a++) extent = std::max(extent, std::max(std::fabs(scene.lo[a]), std::fabs(scene.hi[a])));
+    // Reference pad (Math::Eps) plus a slack proportional to the scene size that covers the
+    // rounding of the quantised slab test (about 4e-7 * distance), so culling stays conservative.
+    const float pad = 1e-4f + 4e-6f * extent;
+
+    Builder B;
+    B.refs.reserve(nvalid);
+    for (uint64_t i = 0; i < ntris; i++) {
+        if (!valid[i]) continue;
+        const float* v = verts + 9 * i;
+        Ref r; r.id = (uint32_t)i; r.pad = 0;
+        for (int a = 0; a < 3; a++) {
+            r.lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a])) - pad;
+            r.hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a])) + pad;
+        }
+        B.refs.push_back(r);
+    }
+    B.run(num_threads);
+
+    Emitter E{B, recs, out};
+    E.emit_all();
+
+    for (int a = 0; a < 3; a++) { out.scene_lo[a] = scene.lo[a]; out.scene_hi[a] = scene.hi[a]; }
+    out.stats.num_triangles = ntris;
+    out.stats.num_valid = nvalid;
+    out.stats.num_nodes = out.nodes.size();
+    out.stats.sah_cost = (float)E.sah;
+    out.stats.max_depth = E.max_depth;
+    out.stats.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace lmb200

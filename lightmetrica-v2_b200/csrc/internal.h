@@ -1,0 +1,44 @@
+// Internal declarations shared by the .cu translation units of liblmb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <string>
+#include "../../include/lmb200.h"
+#include "bvh.h"
+
+#define LMB_TRACE_BLOCK 128
+
+namespace lmb200 {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launch_count;
+int set_error(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+struct Accel {
+    int device = -1;
+    bool host_only = false;
+    bool built = false;
+    HostBVH bvh;
+    void* d_nodes = nullptr;
+    void* d_tris = nullptr;
+    unsigned long long* d_counter = nullptr;   // work counters: [0],[1] callers' slots, [2],[3] staging streams
+    int num_sms = 148;
+    int trace_blocks_per_sm = 4;
+    double upload_seconds = 0;
+    // staging for the host-pointer entry points
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    void* stage_rays[2] = {nullptr, nullptr};
+    void* stage_out[2] = {nullptr, nullptr};
+    uint64_t stage_cap = 0;
+
+    ~Accel();
+    int upload();
+    void free_device();
+};
+
+// n_dev != nullptr: the ray count is read from device memory (wavefront queues).
+int trace_closest_dev(Accel* a, const void* rays, void* hits, uint64_t n, const uint32_t* n_dev, cudaStream_t st, int slot);
+int trace_any_dev(Accel* a, const void* rays, void* occ, uint64_t n, const uint32_t* n_dev, cudaStream_t st, int slot);
+
+}  // namespace lmb200

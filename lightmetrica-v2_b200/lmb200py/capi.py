@@ -1,0 +1,175 @@
+"""ctypes bindings for include/lmb200.h. Every call goes to liblmb200.so; there is no fallback."""
+import ctypes as C
+import os
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_ROOT, "lib", "liblmb200.so")
+
+MISS = 0xFFFFFFFF
+MODE_PT, MODE_PTDIRECT, MODE_NORMAL = 0, 1, 2
+BSDF_NULL, BSDF_DIFFUSE, BSDF_COOKTORRANCE = 0, 1, 2
+
+RAY_DTYPE = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"),
+                      ("dx", "f4"), ("dy", "f4"), ("dz", "f4"), ("tmax", "f4")])
+HIT_DTYPE = np.dtype([("t", "f4"), ("u", "f4"), ("v", "f4"), ("tri", "u4")])
+
+
+class AccelStats(C.Structure):
+    _fields_ = [("num_triangles", C.c_uint64), ("num_valid_triangles", C.c_uint64), ("num_nodes", C.c_uint64),
+                ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64), ("build_seconds", C.c_double),
+                ("upload_seconds", C.c_double), ("sah_cost", C.c_float), ("max_depth", C.c_int)]
+
+
+class Bsdf(C.Structure):
+    _fields_ = [("type", C.c_int32), ("R", C.c_float * 3), ("eta", C.c_float * 3), ("k", C.c_float * 3), ("roughness", C.c_float)]
+
+
+class Primitive(C.Structure):
+    _fields_ = [("bsdf", C.c_int32), ("light", C.c_int32), ("first_tri", C.c_uint32), ("num_tris", C.c_uint32), ("has_normals", C.c_int32)]
+
+
+class Light(C.Structure):
+    _fields_ = [("Le", C.c_float * 3), ("primitive", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("vx", C.c_float * 3), ("vy", C.c_float * 3), ("vz", C.c_float * 3),
+                ("fov", C.c_float), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("num_tris", C.c_uint64), ("verts", C.c_void_p), ("normals", C.c_void_p), ("tri_prim", C.c_void_p),
+                ("num_prims", C.c_uint32), ("prims", C.POINTER(Primitive)),
+                ("num_bsdfs", C.c_uint32), ("bsdfs", C.POINTER(Bsdf)),
+                ("num_lights", C.c_uint32), ("lights", C.POINTER(Light)),
+                ("camera", Camera)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("num_samples", C.c_int64), ("sample_begin", C.c_int64), ("sample_end", C.c_int64),
+                ("max_num_vertices", C.c_int32), ("min_num_vertices", C.c_int32), ("seed", C.c_uint64), ("pool_size", C.c_int32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("samples", C.c_int64), ("extend_rays", C.c_int64), ("shadow_rays", C.c_int64), ("iterations", C.c_int64),
+                ("launches", C.c_uint64), ("seconds", C.c_double)]
+
+
+EXPORTS = [
+    "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build",
+    "lmb200_accel_get_stats", "lmb200_trace_closest", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
+    "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_arrays", "lmb200_accel_create_host_only",
+    "lmb200_scene_create", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
+    "lmb200_render", "lmb200_render_multi",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads liblmb200.so; raises (loudly) if it has not been built — there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: run ./build.sh (or __graft_entry__.build()). lmb200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.lmb200_last_error.restype = C.c_char_p
+    L.lmb200_accel_create.restype = C.c_void_p
+    L.lmb200_accel_create.argtypes = [C.c_int]
+    L.lmb200_accel_create_host_only.restype = C.c_void_p
+    L.lmb200_accel_destroy.argtypes = [C.c_void_p]
+    L.lmb200_accel_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.lmb200_accel_get_stats.argtypes = [C.c_void_p, C.POINTER(AccelStats)]
+    L.lmb200_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.lmb200_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.lmb200_trace_closest_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.lmb200_trace_any_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.lmb200_trace_count_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.lmb200_launch_count.restype = C.c_uint64
+    L.lmb200_accel_host_arrays.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    if hasattr(L, "lmb200_scene_create"):
+        L.lmb200_scene_create.restype = C.c_void_p
+        L.lmb200_scene_create.argtypes = [C.c_int, C.POINTER(SceneDesc)]
+        L.lmb200_scene_destroy.argtypes = [C.c_void_p]
+        L.lmb200_scene_accel.restype = C.c_void_p
+        L.lmb200_scene_accel.argtypes = [C.c_void_p]
+        L.lmb200_render_dev.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
+        L.lmb200_film_rescale_dev.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+        L.lmb200_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(RenderStats)]
+        L.lmb200_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RenderParams), C.c_void_p, C.POINTER(RenderStats)]
+    _lib = L
+    return L
+
+
+class LmbError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise LmbError(f"lmb200 error {rc}: {lib().lmb200_last_error().decode()}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Accel:
+    """Mirror of the reference's Accel interface (Initialize/Build/Intersect, accel.h:67-79, accel3.h:68) for batches."""
+
+    def __init__(self, device=0, host_only=False):
+        L = lib()
+        self.h = L.lmb200_accel_create_host_only() if host_only else L.lmb200_accel_create(device)
+        if not self.h:
+            raise LmbError(L.lmb200_last_error().decode())
+        self.host_only = host_only
+
+    def close(self):
+        if self.h:
+            lib().lmb200_accel_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build(self, verts):
+        verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 9)
+        self._verts = verts
+        check(lib().lmb200_accel_build(self.h, _ptr(verts), verts.shape[0]))
+        return self.stats()
+
+    def stats(self):
+        s = AccelStats()
+        check(lib().lmb200_accel_get_stats(self.h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in AccelStats._fields_}
+
+    def host_arrays(self):
+        nodes, tris, idx = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nn, nt = C.c_uint64(), C.c_uint64()
+        check(lib().lmb200_accel_host_arrays(self.h, C.byref(nodes), C.byref(nn), C.byref(tris), C.byref(idx), C.byref(nt)))
+        nodes_a = np.ctypeslib.as_array(C.cast(nodes, C.POINTER(C.c_uint8)), shape=(nn.value * 80,)).copy()
+        if nt.value:
+            tris_a = np.ctypeslib.as_array(C.cast(tris, C.POINTER(C.c_uint8)), shape=(nt.value * 48,)).copy()
+            idx_a = np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_uint32)), shape=(nt.value,)).copy()
+        else:
+            tris_a = np.zeros(0, np.uint8)
+            idx_a = np.zeros(0, np.uint32)
+        return nodes_a, tris_a, idx_a
+
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        check(lib().lmb200_trace_closest(self.h, _ptr(rays), _ptr(hits), rays.shape[0]))
+        return hits
+
+    def trace_any(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        occ = np.zeros(rays.shape[0], dtype=np.uint8)
+        check(lib().lmb200_trace_any(self.h, _ptr(rays), _ptr(occ), rays.shape[0]))
+        return occ

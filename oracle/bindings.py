@@ -1,0 +1,196 @@
+"""TEST INFRASTRUCTURE: ctypes bindings for the oracles. Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs import this module.
+
+  liblmoracle.so            C restatement of the reference hot path (travels to the GPU box)
+  _ref/liblightmetrica.so   the reference itself, compiled here from /root/reference (travels as a binary)
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_PATH = os.path.join(HERE, "liblmoracle.so")
+REF_PATH = os.path.join(HERE, "_ref", "liblightmetrica.so")
+
+_port = None
+_ref = None
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def port():
+    global _port
+    if _port is None:
+        L = C.CDLL(PORT_PATH)
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_tris.restype = C.c_void_p
+        L.orc_scene_tris.argtypes = [C.c_void_p]
+        L.orc_closest.restype = C.c_longlong
+        L.orc_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_any.restype = C.c_longlong
+        L.orc_any.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        L.orc_wide_closest.restype = C.c_longlong
+        L.orc_wide_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+        L.orc_triaccel_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _port = L
+    return _port
+
+
+def have_ref():
+    return os.path.exists(REF_PATH)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_PATH, mode=C.RTLD_GLOBAL)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_session_create.restype = C.c_void_p
+        L.ref_session_create.argtypes = [C.c_char_p, C.c_char_p]
+        L.ref_session_destroy.argtypes = [C.c_void_p]
+        L.ref_load_plugin.argtypes = [C.c_char_p]
+        L.ref_register_mesh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_intersect_batch.restype = C.c_longlong
+        L.ref_intersect_batch.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_triaccel_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_world_triangles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_render.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.ref_film_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ref_num_primitives.argtypes = [C.c_void_p]
+        _ref = L
+    return _ref
+
+
+class PortScene:
+    """C restatement: TriAccel records + closest/any hit over a flat world-space triangle list."""
+
+    def __init__(self, verts):
+        self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
+        self.h = port().orc_scene_create(_p(self.verts), self.verts.shape[0])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            port().orc_scene_destroy(self.h)
+            self.h = None
+
+    def records(self):
+        n = self.verts.shape[0]
+        ptr = port().orc_scene_tris(self.h)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(n, 12)).copy()
+
+    def closest(self, rays, use_bvh=True):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        tuv = np.zeros((n, 3), np.float32)
+        tri = np.zeros(n, np.int32)
+        port().orc_closest(self.h, _p(rays), n, 1 if use_bvh else 0, _p(tuv), _p(tri))
+        return tuv, tri
+
+    def any(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        occ = np.zeros(rays.shape[0], np.uint8)
+        port().orc_any(self.h, _p(rays), rays.shape[0], _p(occ))
+        return occ
+
+
+def wide_closest(nodes80, tris48, rays):
+    """Scalar walk of the product's flattened nodes (host-logic checker, no GPU)."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    n = rays.shape[0]
+    tuv = np.zeros((n, 3), np.float32)
+    tri = np.zeros(n, np.int32)
+    port().orc_wide_closest(_p(nodes80), _p(tris48), _p(rays), n, _p(tuv), _p(tri))
+    return tuv, tri
+
+
+def mesh_scene_yaml(handle, accel="qbvh", w=16, h=16):
+    """A minimal Lightmetrica scene around one in-memory mesh (identity transform), as the
+    reference's Stub_Scene does for accel tests (test_accel3.cpp:226-264)."""
+    return f"""
+lightmetrica:
+  assets:
+    mesh1:
+      interface: trianglemesh
+      type: mem
+      params:
+        handle: {handle}
+    white:
+      interface: bsdf
+      type: diffuse
+      params:
+        R: 0.8 0.8 0.8
+    film1:
+      interface: film
+      type: hdr
+      params:
+        w: {w}
+        h: {h}
+    cam:
+      interface: sensor
+      type: pinhole
+      params:
+        film: film1
+        fov: 45
+  accel:
+    type: {accel}
+  scene:
+    sensor: n_cam
+    nodes:
+      - id: n_cam
+        sensor: cam
+        transform:
+          lookat:
+            eye: 0.5 0.5 3
+            center: 0.5 0.5 0
+            up: 0 1 0
+      - mesh: mesh1
+        bsdf: white
+"""
+
+
+class RefSoup:
+    """The reference itself (oracle/_ref) over a flat triangle list: one primitive (index 1, after
+    the camera node) whose mesh holds the triangles unshared, texcoords (0,0),(1,0),(0,1) so that
+    the interpolated uv of the Intersection returns the barycentrics exactly."""
+
+    def __init__(self, verts, accel="qbvh"):
+        L = ref()
+        verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
+        n = verts.shape[0]
+        ps = verts.reshape(-1, 3)
+        fs = np.arange(3 * n, dtype=np.uint32)
+        ts = np.tile(np.array([0, 0, 1, 0, 0, 1], np.float32), n)
+        h = L.ref_register_mesh(_p(ps), 3 * n, None, _p(ts), _p(fs), n)
+        self.s = L.ref_session_create(mesh_scene_yaml(h, accel).encode(), accel.encode())
+        if not self.s:
+            raise RuntimeError(L.ref_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "s", None):
+            ref().ref_session_destroy(self.s)
+            self.s = None
+
+    def intersect(self, rays, threads=1):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        prim = np.zeros(n, np.int32)
+        face = np.zeros(n, np.int32)
+        tuv = np.zeros((n, 3), np.float32)
+        geom = np.zeros((n, 11), np.float32)
+        sec = C.c_double()
+        ref().ref_intersect_batch(self.s, n, _p(rays), threads, _p(prim), _p(face), _p(tuv), _p(geom), C.byref(sec))
+        return dict(prim=prim, face=face, tuv=tuv, geom=geom, seconds=sec.value)
+
+
+def ref_triaccel_records(verts):
+    verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
+    out = np.zeros((verts.shape[0], 12), np.uint32)
+    L = ref()
+    for i in range(verts.shape[0]):
+        v = verts[i]
+        L.ref_triaccel_load(_p(v[0:3].copy()), _p(v[3:6].copy()), _p(v[6:9].copy()), _p(out[i]))
+    return out
