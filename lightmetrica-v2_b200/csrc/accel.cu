@@ -317,3 +317,29 @@ int lmb200_trace_count_dev(lmb200_accel* h, const void* rays_dev, uint64_t n, do
 }
 
 }  // extern "C"
+
+// ---- debugging aid (not part of the public header) ----
+namespace lmb200 {
+__global__ void debug_kernel(const float4* nodes, const float4* tris, const float4* rays, uint32_t n, uint32_t* out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+    const float idx = lmb_safe_inv(rd.x), idy = lmb_safe_inv(rd.y), idz = lmb_safe_inv(rd.z);
+    const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
+    const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
+    const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
+    const float4 n0 = nodes[0], n1 = nodes[1], n2 = nodes[2], n3 = nodes[3], n4 = nodes[4];
+    out[4 * i] = lmb_intersect_node(n0, n1, n2, n3, n4, ro.x, ro.y, ro.z, idx, idy, idz, negx, negy, negz, oct_inv4, ro.w, rd.w);
+    TravCounters c; c.nodes = 0; c.tris = 0;
+    float tmax = rd.w, hu, hv; uint32_t hid;
+    lmb_traverse<false, true>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, &c);
+    out[4 * i + 1] = c.nodes; out[4 * i + 2] = c.tris; out[4 * i + 3] = hid;
+}
+}
+extern "C" int lmb200_debug_trace(lmb200_accel* h, const void* rays_dev, uint32_t n, void* out_dev)
+{
+    Accel* a = reinterpret_cast<Accel*>(h);
+    lmb200::debug_kernel<<<(n + 63) / 64, 64>>>((const float4*)a->d_nodes, (const float4*)a->d_tris, (const float4*)rays_dev, n, (uint32_t*)out_dev);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}

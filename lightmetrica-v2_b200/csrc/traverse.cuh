@@ -30,6 +30,15 @@ __device__ __forceinline__ float lmb_q2f(uint32_t word, uint32_t sel)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
 }
 
+__device__ __forceinline__ uint32_t lmb_sign_extend_s8x4(uint32_t x)
+{
+    // 0xff for every byte whose top bit is set, else 0x00. PRMT's sign-replicate mode (selector
+    // nibble bit 3) is only reachable through PTX: the __byte_perm intrinsic masks it off.
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
 // Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 31..24 =
 // internal children in traversal priority order, bits 23..0 = triangles of hit leaf slots.
 __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
@@ -62,7 +71,7 @@ __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const fl
         // internal slots carry 24+s in their low 5 bits (both bits 3 and 4 set): flip the slot
         // number by the ray octant so that the highest set bit is the nearest child
         const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = __byte_perm(is_inner4 << 3, 0, 0xba98);   // 0xff per inner byte
+        const uint32_t inner_mask4 = lmb_sign_extend_s8x4(is_inner4 << 3);    // 0xff per inner byte
         const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
         const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll

@@ -1,0 +1,44 @@
+"""Generates the golden vectors under tests/golden/ from the REFERENCE ITSELF (oracle/_ref,
+compiled from /root/reference by oracle/ref/build_ref.sh). Run here, commit the .npz files:
+they pin the C oracle (and through it the CUDA path) on machines without /root/reference.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "lightmetrica-v2_b200"))
+from oracle import bindings as ob  # noqa: E402
+from lmb200py import scenes  # noqa: E402
+
+
+def accel_golden():
+    # (1) random soup, the StubTriangleMesh_Random recipe (test_accel3.cpp:191-224)
+    verts = scenes.soup(3000, seed=11, extent=4.0, edge=0.25)
+    lo, hi = scenes.bounds(verts)
+    rays = scenes.random_rays(20000, lo, hi, seed=5)
+    # range-limited and tmin=0 variants, as the reference tests use (test_accel3.cpp:299)
+    rays[5000:10000, 7] = 1.5
+    rays[10000:12000, 3] = 0.0
+    recs = ob.ref_triaccel_records(verts)
+    out = {}
+    for accel in ("qbvh", "naive", "bvh_sahbin"):
+        R = ob.RefSoup(verts, accel)
+        r = R.intersect(rays, threads=1)
+        out[accel] = r
+    for a in ("naive", "bvh_sahbin"):
+        assert np.array_equal(out["qbvh"]["face"], out[a]["face"]), a
+        assert np.array_equal(out["qbvh"]["tuv"].view(np.uint32), out[a]["tuv"].view(np.uint32)), a
+    q = out["qbvh"]
+    np.savez_compressed(os.path.join(HERE, "accel_soup.npz"), verts=verts, rays=rays, records=recs[:, :10],
+                        face=q["face"], tuv=q["tuv"], geom=q["geom"])
+    print("accel_soup.npz:", int((q["face"] >= 0).sum()), "hits of", len(rays))
+
+
+if __name__ == "__main__":
+    accel_golden()

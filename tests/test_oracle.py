@@ -1,0 +1,135 @@
+"""The C oracle (oracle/lm_oracle.c) against the reference's golden vectors and known-answer
+tests. CPU only. The oracle is the checker for the CUDA path, so it is pinned first."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from lmb200py import scenes
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+# Meshes of Accel3Test (src/lightmetrica-test/test_accel3.cpp:75-171)
+SIMPLE_PS = np.array([0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0, 0, 0, -1, 1, 0, -1, 1, 1, -1, 0, 1, -1], np.float32).reshape(-1, 3)
+SIMPLE_FS = np.array([0, 1, 2, 0, 2, 3, 4, 5, 6, 4, 6, 7]).reshape(-1, 3)
+SIMPLE2_PS = np.array([0, 0, 0, 1, 0, -1, 1, 1, -1, 0, 1, 0], np.float32).reshape(-1, 3)
+SIMPLE2_FS = np.array([0, 1, 2, 0, 2, 3]).reshape(-1, 3)
+TS = np.array([0, 0, 1, 0, 1, 1, 0, 1], np.float32).reshape(-1, 2)
+
+
+def tri_verts(ps, fs):
+    return ps[fs].reshape(-1, 9).astype(np.float32)
+
+
+def simple_rays():
+    """Accel3Test.Simple (test_accel3.cpp:283-308): from (0,0,1) through (x,y,0), range [0, Inf]."""
+    rays, exp = [], []
+    for i in range(1, 10):
+        for j in range(1, 10):
+            x, y = np.float32(i) / 10, np.float32(j) / 10
+            o = np.array([0, 0, 1], np.float32)
+            d = np.array([x, y, 0], np.float32) - o
+            d = d / np.float32(np.linalg.norm(d))
+            rays.append([o[0], o[1], o[2], 0, d[0], d[1], d[2], FLT_MAX])
+            exp.append((x, y))
+    return np.array(rays, np.float32), np.array(exp, np.float32)
+
+
+def simple2_rays():
+    """Accel3Test.Simple2 (test_accel3.cpp:323-343): straight down -z from (x,y,1)."""
+    rays, exp = [], []
+    for i in range(1, 10):
+        for j in range(1, 10):
+            x, y = np.float32(i) / 10, np.float32(j) / 10
+            rays.append([x, y, 1, 0, 0, 0, -1, FLT_MAX])
+            exp.append((x, y))
+    return np.array(rays, np.float32), np.array(exp, np.float32)
+
+
+def interp(ps, fs, attr, tri, u, v):
+    a = attr[fs[tri, 0]] * (1 - u - v)[:, None] + attr[fs[tri, 1]] * u[:, None] + attr[fs[tri, 2]] * v[:, None]
+    return a
+
+
+def test_known_answer_simple():
+    verts = tri_verts(SIMPLE_PS, SIMPLE_FS)
+    rays, exp = simple_rays()
+    for use_bvh in (False, True):
+        tuv, tri = ob.PortScene(verts).closest(rays, use_bvh=use_bvh)
+        assert (tri >= 0).all()
+        p = rays[:, 0:3] + rays[:, 4:7] * tuv[:, 0:1]
+        # EpsLarge = 1e-3 in float mode (math.h:1665), the reference test's tolerance
+        assert np.allclose(p[:, 0], exp[:, 0], atol=1e-3) and np.allclose(p[:, 1], exp[:, 1], atol=1e-3)
+        assert np.allclose(p[:, 2], 0, atol=1e-3)
+        assert (tri < 2).all()          # the z=0 quad is in front of the z=-1 quad
+        uv = interp(SIMPLE_PS, SIMPLE_FS, TS[[0, 1, 2, 3, 0, 1, 2, 3]], tri, tuv[:, 1], tuv[:, 2])
+        assert np.allclose(uv, exp, atol=1e-3)
+
+
+def test_known_answer_simple2():
+    verts = tri_verts(SIMPLE2_PS, SIMPLE2_FS)
+    rays, exp = simple2_rays()
+    tuv, tri = ob.PortScene(verts).closest(rays)
+    assert (tri >= 0).all()
+    p = rays[:, 0:3] + rays[:, 4:7] * tuv[:, 0:1]
+    assert np.allclose(p[:, 0], exp[:, 0], atol=1e-3) and np.allclose(p[:, 1], exp[:, 1], atol=1e-3)
+    assert np.allclose(p[:, 2], -exp[:, 0], atol=1e-3)
+    uv = interp(SIMPLE2_PS, SIMPLE2_FS, TS, tri, tuv[:, 1], tuv[:, 2])
+    assert np.allclose(uv, exp, atol=1e-3)
+
+
+def test_golden_soup_bit_exact():
+    """Vectors produced by the reference itself (tests/golden/make_golden.py): TriAccel records,
+    closest-hit face index and t,u,v must match bit for bit."""
+    g = np.load(os.path.join(GOLD, "accel_soup.npz"))
+    P = ob.PortScene(g["verts"])
+    assert np.array_equal(P.records()[:, :10], g["records"])
+    for use_bvh in (True, False):
+        rays = g["rays"] if use_bvh else g["rays"][:2000]
+        n = len(rays)
+        tuv, tri = P.closest(rays, use_bvh=use_bvh)
+        assert np.array_equal(tri, g["face"][:n])
+        assert np.array_equal(tuv.view(np.uint32), g["tuv"][:n].view(np.uint32))
+    occ = P.any(g["rays"])
+    assert np.array_equal(occ.astype(bool), g["face"] >= 0)
+
+
+def test_degenerate_and_empty():
+    # degenerate triangle (k=3, triaccel.h:73-77) is never hit; empty scene misses
+    verts = np.array([[0, 0, 0, 1, 1, 1, 2, 2, 2], [0, 0, 0, 1, 0, 0, 0, 1, 0]], np.float32)
+    rays = np.array([[0.2, 0.2, 1, 0, 0, 0, -1, FLT_MAX]], np.float32)
+    P = ob.PortScene(verts)
+    assert P.records()[0, 0] == 3
+    tuv, tri = P.closest(rays)
+    assert tri[0] == 1
+    tuv, tri = ob.PortScene(np.zeros((0, 9), np.float32)).closest(rays)
+    assert tri[0] == -1
+
+
+def test_tie_rule_larger_index_wins():
+    # two coincident triangles: accel::naive's scan keeps the later one (triaccel.h:137 rejects only t > maxT)
+    t = [0, 0, 0, 1, 0, 0, 0, 1, 0]
+    verts = np.array([t, t, t], np.float32)
+    rays = np.array([[0.2, 0.2, 1, 0, 0, 0, -1, FLT_MAX]], np.float32)
+    for use_bvh in (False, True):
+        tuv, tri = ob.PortScene(verts).closest(rays, use_bvh=use_bvh)
+        assert tri[0] == 2
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_port_vs_reference_live():
+    """Fresh random scene against the compiled reference (all three TriAccel accels agree)."""
+    verts = scenes.soup(5000, seed=123, extent=6.0, edge=0.3)
+    lo, hi = scenes.bounds(verts)
+    rays = scenes.random_rays(30000, lo, hi, seed=9)
+    tuv, tri = ob.PortScene(verts).closest(rays)
+    assert np.array_equal(ob.PortScene(verts).records()[:500, :10], ob.ref_triaccel_records(verts[:500])[:, :10])
+    for accel in ("qbvh", "bvh_sahbin"):
+        r = ob.RefSoup(verts, accel).intersect(rays, threads=2)
+        assert np.array_equal(tri, r["face"])
+        assert np.array_equal(tuv.view(np.uint32), r["tuv"].view(np.uint32))
+        # barycentrics seen through the real Intersection (uv interpolation trick) are the same bits
+        hit = tri >= 0
+        assert np.array_equal(r["geom"][hit, 9:11].view(np.uint32), tuv[hit, 1:3].view(np.uint32))
