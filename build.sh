@@ -8,7 +8,7 @@ mkdir -p "$OUT" "$OUT/obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 HOSTCXX=/usr/bin/g++
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-NVFLAGS="-O3 -std=c++17 -lineinfo $ARCH -ccbin $HOSTCXX -Xcompiler -fPIC,-O2,-ffp-contract=off,-Wall -Xptxas -v --fmad=true"
+NVFLAGS="-O3 -std=c++17 -lineinfo $ARCH -ccbin $HOSTCXX -Xcompiler -fPIC,-O2,-ffp-contract=off,-Wall -Xptxas -v --fmad=false"
 for f in accel render; do
   if [ -f "$SRC/$f.cu" ]; then
     if [ ! -f "$OUT/obj/$f.o" ] || [ -n "$(find "$SRC" "$ROOT/include" -newer "$OUT/obj/$f.o" -type f | head -1)" ]; then

@@ -81,6 +81,12 @@ int lmb200_accel_get_stats(const lmb200_accel* a, lmb200_accel_stats* out);
 int lmb200_trace_closest(lmb200_accel* a, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n);
 int lmb200_trace_closest_dev(lmb200_accel* a, const void* rays_dev, void* hits_dev, uint64_t n, void* stream);
 
+/* One ray, synchronously, on the GPU — the exact shape of Accel3::Intersect (accel3.h:68). Safe to
+ * call concurrently from many host threads (the reference's renderers do, scheduler.cpp:146-175):
+ * each thread owns a stream and a pinned mailbox. Correct but latency-bound (one launch per ray);
+ * batches should use lmb200_trace_closest*. */
+int lmb200_trace_closest_one(lmb200_accel* a, const lmb200_ray* ray, lmb200_hit* hit);
+
 /* Replaces Scene3::Visible's query (scene3.h:107-116): occluded[i] = 1 iff ANY triangle is hit
  * within [tmin, tmax] (same boolean as the reference's closest-hit query, early exit). */
 int lmb200_trace_any(lmb200_accel* a, const lmb200_ray* rays, uint8_t* occluded, uint64_t n);

@@ -61,6 +61,25 @@ trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
     }
 }
 
+// one ray, one warp: the per-ray Accel3::Intersect path (mailbox in mapped pinned host memory)
+__global__ void trace_one_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* ray, float4* out)
+{
+    if (threadIdx.x != 0) return;
+    const float4 ro = ray[0], rd = ray[1];
+    float tmax = rd.w, hu = 0.f, hv = 0.f;
+    uint32_t hid;
+    const bool hit = lmb_traverse<false, false>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, nullptr);
+    out[0] = make_float4(hit ? tmax : 0.f, hu, hv, __uint_as_float(hit ? hid : LMB200_MISS));
+}
+
+struct Mailbox {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    float4* host = nullptr;   // [0..1] ray, [2] hit
+    float4* dev = nullptr;
+    ~Mailbox() { if (host) { cudaSetDevice(device); cudaFreeHost(host); cudaStreamDestroy(stream); } }
+};
+
 template <bool ANY, bool COUNT>
 static int launch_trace(Accel* a, const void* rays, void* out, uint64_t n, const uint32_t* n_dev, cudaStream_t st, unsigned long long* work, int slot)
 {
@@ -269,6 +288,29 @@ int lmb200_trace_closest(lmb200_accel* h, const lmb200_ray* rays, lmb200_hit* hi
 int lmb200_trace_any(lmb200_accel* h, const lmb200_ray* rays, uint8_t* occluded, uint64_t n)
 {
     return trace_host<true>(reinterpret_cast<Accel*>(h), rays, occluded, n);
+}
+
+int lmb200_trace_closest_one(lmb200_accel* h, const lmb200_ray* ray, lmb200_hit* hit)
+{
+    Accel* a = reinterpret_cast<Accel*>(h);
+    if (!a || !ray || !hit) return set_error(LMB200_E_INVALID, "null argument");
+    if (a->host_only || !a->d_nodes) return set_error(LMB200_E_STATE, "accel not built on a device");
+    static thread_local Mailbox mb;
+    cudaError_t e;
+    if (mb.device != a->device) {
+        if ((e = cudaSetDevice(a->device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        if (mb.host) { cudaFreeHost(mb.host); cudaStreamDestroy(mb.stream); mb.host = nullptr; }
+        if ((e = cudaHostAlloc(reinterpret_cast<void**>(&mb.host), 3 * sizeof(float4), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(mailbox)");
+        if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&mb.dev), mb.host, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+        if ((e = cudaStreamCreateWithFlags(&mb.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        mb.device = a->device;
+    }
+    memcpy(mb.host, ray, sizeof(lmb200_ray));
+    trace_one_kernel<<<1, 32, 0, mb.stream>>>(reinterpret_cast<const float4*>(a->d_nodes), reinterpret_cast<const float4*>(a->d_tris), mb.dev, mb.dev + 2);
+    g_launch_count++;
+    if ((e = cudaStreamSynchronize(mb.stream)) != cudaSuccess) return cuda_fail(e, "trace_one");
+    memcpy(hit, mb.host + 2, sizeof(lmb200_hit));
+    return LMB200_OK;
 }
 
 int lmb200_trace_closest_dev(lmb200_accel* h, const void* rays_dev, void* hits_dev, uint64_t n, void* stream)

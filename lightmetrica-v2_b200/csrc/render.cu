@@ -1,0 +1,986 @@
+// Wavefront path tracer on sm_100a: the unidirectional sample loop of the reference
+// (/root/reference/src/liblightmetrica/renderer/renderer_pt.cpp:68-231 and
+// renderer_ptdirect.cpp:76-282, driven by Scheduler_::Process, scheduler.cpp:78-295)
+// re-organised as a pool of path slots advanced by separate kernels per iteration:
+//
+//   k_logic   hit processing: miss / emission splat (pt) / Russian roulette / advance vertex,
+//             regeneration of finished slots from the global sample counter (camera-ray generation),
+//             compaction of live slots into the vertex queue (warp ballot + prefix sum)
+//   k_nee     next-event estimation against area lights -> compacted shadow-ray queue
+//   k_bsdf    BSDF sample + pdf + evaluate, throughput update -> compacted extend-ray queue
+//   extend    closest-hit traversal over the extend queue   (accel.cu trace kernel)
+//   k_shadow  any-hit traversal over the shadow queue fused with the film splat
+//
+// Random numbers are Philox4x32-10 keyed by (seed) with counter (sample index, block), so any
+// partition of the sample range over GPUs gives the same image up to fp32 summation order.
+#include "internal.h"
+#include "traverse.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <thread>
+#include <vector>
+#include <dlfcn.h>
+
+namespace lmb200 {
+
+#define LMB_PI 3.14159265358979323846f
+#define LMB_INV_PI 0.31830988618379067154f
+#define LMB_EPS 1e-4f
+#define LMB_EPS_ISECT 1e-4f
+#define LMB_FLT_MAX 3.402823466e+38f
+
+struct DevScene {
+    const float* verts;        // 9 floats / tri
+    const float* normals;      // 9 floats / tri or nullptr
+    const uint32_t* tri_prim;
+    const lmb200_primitive* prims;
+    const lmb200_bsdf* bsdfs;
+    const lmb200_light* lights;
+    const float* light_cdf;    // concatenated per-light CDFs
+    const uint32_t* light_cdf_off;
+    const float* light_inv_area;
+    uint32_t num_lights;
+    // camera
+    float pos[3], vx[3], vy[3], vz[3];
+    float tan_fov, aspect;
+    int width, height;
+};
+
+struct Pool {
+    // per-slot path state
+    unsigned long long* sample;   // global sample index
+    int* nverts;                  // numVertices; 0 = idle slot
+    float4* thr;                  // throughput rgb, w = raster pixel (int bits, -1 = unset)
+    float4* ray_o;                // current extend ray of the slot: o.xyz,tmin
+    float4* ray_d;                // d.xyz,tmax
+    float4* hit;                  // result of the extend ray: t,u,v,tri
+    uint8_t* traced;              // 1 if the slot has a pending hit record
+    // current vertex (valid between k_logic and k_bsdf)
+    float4* vtx_p;                // p.xyz, w = tri (uint bits) ; camera vertex: tri = 0xffffffff
+    float4* vtx_wi;               // wi.xyz, w = u
+    float*  vtx_v;                // barycentric v
+    // queues
+    uint32_t* vq;                 // vertex queue (slot indices)
+    uint32_t* eq;                 // extend queue (slot indices)
+    float4* sq_o; float4* sq_d;   // shadow rays (compact)
+    float4* sq_c;                 // contribution rgb, w = pixel (int bits)
+    // counters: [0] vq size, [1] eq size, [2] sq size, [3] unused
+    uint32_t* qcount;
+    unsigned long long* next_sample;   // [0] next sample index to hand out, [1] extend rays, [2] shadow rays, [3] samples started
+};
+
+struct RenderCfg {
+    int mode, max_verts, min_verts;
+    unsigned long long seed;
+    unsigned long long sample_end;
+    uint32_t pool;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 F3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 ld3(const float* p) { return F3(p[0], p[1], p[2]); }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return F3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return F3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator*(f3 a, float s) { return F3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 operator*(f3 a, f3 b) { return F3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ f3 neg(f3 a) { return F3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) { return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ f3 normalize(f3 a) { const float l = sqrtf(dot(a, a)); return F3(a.x / l, a.y / l, a.z / l); }
+__device__ __forceinline__ bool black(f3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+
+// Philox4x32-10, counter (sample_lo, sample_hi, block, 0), key (seed_lo, seed_hi) -> 4 uniforms in [0,1)
+__device__ __forceinline__ float4 rng_block(unsigned long long seed, unsigned long long sample, uint32_t block)
+{
+    uint32_t c0 = (uint32_t)sample, c1 = (uint32_t)(sample >> 32), c2 = block, c3 = 0u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const float s = 1.0f / 16777216.0f;
+    return make_float4((float)(c0 >> 8) * s, (float)(c1 >> 8) * s, (float)(c2 >> 8) * s, (float)(c3 >> 8) * s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// surface geometry: the subset of IntersectionUtils::CreateTriangleIntersection
+// (intersectionutils.h:59-135) the estimators read
+
+struct Geom { f3 p, gn, sn, dpdu, dpdv; bool degenerated; };
+
+__device__ __forceinline__ void basis(f3 a, f3& b, f3& c)   // Math::OrthonormalBasis, math.h:2355-2360
+{
+    c = fabsf(a.x) > fabsf(a.y) ? normalize(F3(a.z, 0.f, -a.x)) : normalize(F3(0.f, a.z, -a.y));
+    b = cross(c, a);
+}
+__device__ __forceinline__ f3 to_local(const Geom& g, f3 w) { return F3(dot(g.dpdu, w), dot(g.dpdv, w), dot(g.sn, w)); }
+__device__ __forceinline__ f3 to_world(const Geom& g, f3 l) { return (g.dpdu * l.x + g.dpdv * l.y) + g.sn * l.z; }
+
+__device__ __forceinline__ void tri_geom(const DevScene& S, uint32_t tri, float b0, float b1, f3 p, Geom& g)
+{
+    const float* v = S.verts + 9 * (size_t)tri;
+    const f3 p1 = ld3(v), p2 = ld3(v + 3), p3 = ld3(v + 6);
+    g.p = p;
+    g.degenerated = false;
+    g.gn = normalize(cross(p2 - p1, p3 - p1));
+    const lmb200_primitive& P = S.prims[S.tri_prim[tri]];
+    if (P.has_normals && S.normals) {
+        const float* n = S.normals + 9 * (size_t)tri;
+        g.sn = normalize((ld3(n) * (1.0f - b0 - b1) + ld3(n + 3) * b0) + ld3(n + 6) * b1);
+        if (isnan(g.sn.x) || isnan(g.sn.y) || isnan(g.sn.z)) g.sn = g.gn;
+    } else g.sn = g.gn;
+    basis(g.sn, g.dpdu, g.dpdv);
+}
+
+// ---- sensor::pinhole (sensor_pinhole.cpp:79-90, 137-154, 165-185) ----
+__device__ __forceinline__ bool raster_position(const DevScene& S, f3 wo, float& rx, float& ry)
+{
+    const f3 e = F3(dot(ld3(S.vx), wo), dot(ld3(S.vy), wo), dot(ld3(S.vz), wo));
+    if (e.z >= 0.f) return false;
+    rx = (-e.x / e.z / S.tan_fov / S.aspect + 1.0f) * 0.5f;
+    ry = (-e.y / e.z / S.tan_fov + 1.0f) * 0.5f;
+    return !(rx < 0.f || rx > 1.f || ry < 0.f || ry > 1.f);
+}
+__device__ __forceinline__ float importance(const DevScene& S, f3 wo)
+{
+    float rx, ry;
+    if (!raster_position(S, wo, rx, ry)) return 0.f;
+    const float cosT = -dot(ld3(S.vz), wo), inv = 1.0f / cosT;
+    const float A = S.tan_fov * S.tan_fov * S.aspect * 4.0f;
+    return inv * inv * inv / A;
+}
+__device__ __forceinline__ f3 camera_dir(const DevScene& S, float u0, float u1)
+{
+    const float x = 2.0f * u0 - 1.0f, y = 2.0f * u1 - 1.0f;
+    const f3 e = normalize(F3(S.aspect * S.tan_fov * x, S.tan_fov * y, -1.0f));
+    return (ld3(S.vx) * e.x + ld3(S.vy) * e.y) + ld3(S.vz) * e.z;
+}
+__device__ __forceinline__ int pixel_index(const DevScene& S, float rx, float ry)   // film_hdr.cpp:218-223
+{
+    int px = (int)(rx * (float)S.width), py = (int)(ry * (float)S.height);
+    px = min(max(px, 0), S.width - 1);
+    py = min(max(py, 0), S.height - 1);
+    return py * S.width + px;
+}
+
+// ---- BSDFs (bsdf_diffuse.cpp:69-104, bsdf_cooktorrance.cpp:73-120,187-225,276-293, bsdfutils.h:55-66) ----
+__device__ __forceinline__ float snc(const Geom& g, f3 wi, f3 wo)
+{
+    const float wiNg = dot(wi, g.gn), woNg = dot(wo, g.gn);
+    const float wiNs = to_local(g, wi).z, woNs = to_local(g, wo).z;
+    return (wiNg * wiNs <= 0.f || woNg * woNs <= 0.f) ? 0.f : 1.f;
+}
+__device__ __forceinline__ void concentric_disk(float u0, float u1, float& sx, float& sy)   // sampler.h:44-60
+{
+    const float vx = 2.0f * u0 - 1.0f, vy = 2.0f * u1 - 1.0f;
+    if (vx == 0.f && vy == 0.f) { sx = sy = 0.f; return; }
+    float r, theta;
+    if (vx > -vy) {
+        if (vx > vy) { r = vx; theta = (LMB_PI * 0.25f) * vy / vx; }
+        else { r = vy; theta = (LMB_PI * 0.25f) * (2.0f - vx / vy); }
+    } else {
+        if (vx < vy) { r = -vx; theta = (LMB_PI * 0.25f) * (4.0f + vy / vx); }
+        else { r = -vy; theta = (LMB_PI * 0.25f) * (6.0f - vx / vy); }
+    }
+    sx = r * cosf(theta); sy = r * sinf(theta);
+}
+__device__ __forceinline__ float ggx_D(float alpha, f3 H)
+{
+    const float cosH = H.z;
+    if (cosH <= 0.f) return 0.f;
+    const float s2 = 1.0f - cosH * cosH;
+    const float tanH = s2 <= 0.f ? 0.f : sqrtf(s2) / cosH;
+    const float t1 = alpha * alpha;
+    const float t = alpha * alpha + tanH * tanH;
+    return t1 / (LMB_PI * cosH * cosH * cosH * cosH * t * t);
+}
+__device__ __forceinline__ bool bsdf_sample(const lmb200_bsdf& B, const Geom& g, f3 wi, float u0, float u1, f3& wo)
+{
+    const f3 lwi = to_local(g, wi);
+    if (lwi.z <= 0.f) return false;
+    if (B.type == LMB200_BSDF_DIFFUSE) {
+        float sx, sy;
+        concentric_disk(u0, u1, sx, sy);
+        wo = to_world(g, F3(sx, sy, sqrtf(fmaxf(0.f, 1.0f - sx * sx - sy * sy))));
+        return true;
+    }
+    if (B.type == LMB200_BSDF_COOKTORRANCE) {
+        const float a = B.roughness;
+        const float v0 = (1.0f - LMB_EPS) * u0 + LMB_EPS;
+        const float v1 = (1.0f - 2.0f * LMB_EPS) * u1 + LMB_EPS;
+        const float den = sqrtf(1.0f - (1.0f - a * a) * v0);
+        const float cosT = sqrtf(1.0f - v0) / den, sinT = a * (sqrtf(v0) / den);
+        const float phi = LMB_PI * (2.0f * v1 - 1.0f);
+        const f3 H = F3(sinT * cosf(phi), sinT * sinf(phi), cosT);
+        const f3 nwi = neg(lwi);
+        const f3 lwo = nwi - H * (2.0f * dot(nwi, H));
+        if (lwo.z <= 0.f) return false;
+        wo = to_world(g, lwo);
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ float bsdf_pdf(const lmb200_bsdf& B, const Geom& g, f3 wi, f3 wo)
+{
+    const f3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (lwi.z <= 0.f || lwo.z <= 0.f) return 0.f;
+    if (B.type == LMB200_BSDF_DIFFUSE) return LMB_INV_PI;
+    if (B.type == LMB200_BSDF_COOKTORRANCE) {
+        const f3 H = normalize(lwi + lwo);
+        const float D = ggx_D(B.roughness, H);
+        return D * H.z / (4.0f * dot(lwo, H)) / lwo.z;
+    }
+    return 0.f;
+}
+__device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 wi, f3 wo)
+{
+    const f3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (lwi.z <= 0.f || lwo.z <= 0.f) return F3(0, 0, 0);
+    if (B.type == LMB200_BSDF_DIFFUSE) return (ld3(B.R) * LMB_INV_PI) * snc(g, wi, wo);
+    if (B.type == LMB200_BSDF_COOKTORRANCE) {
+        const f3 H = normalize(lwi + lwo);
+        const float D = ggx_D(B.roughness, H);
+        const float woH = fabsf(dot(lwo, H));
+        // sic: the reference uses wo.H for both masking terms (bsdf_cooktorrance.cpp:281-283)
+        const float G = fminf(1.0f, fminf(2.0f * H.z * lwo.z / woH, 2.0f * H.z * lwi.z / woH));
+        const float c = dot(lwi, H);
+        float F[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float eta = B.eta[i], k = B.k[i];
+            const float tmp = (eta * eta + k * k) * (c * c);
+            const float rP = (tmp - eta * (2.0f * c) + 1.0f) / (tmp + eta * (2.0f * c) + 1.0f);
+            const float tmpF = eta * eta + k * k;
+            const float rS = (tmpF - eta * (2.0f * c) + c * c) / (tmpF + eta * (2.0f * c) + c * c);
+            F[i] = (rP + rS) * 0.5f;
+        }
+        const float s = D * G / (4.0f * lwi.z) / lwo.z * snc(g, wi, wo);
+        return F3(B.R[0] * F[0] * s, B.R[1] * F[1] * s, B.R[2] * F[2] * s);
+    }
+    return F3(0, 0, 0);
+}
+
+// ---- light::area position sampling (triangleutils.h:71-122, dist.h:70-76, sampler.h:97-101) ----
+__device__ __forceinline__ void light_sample(const DevScene& S, int li, float u0, float u1, Geom& g)
+{
+    const lmb200_primitive& P = S.prims[S.lights[li].primitive];
+    const float* cdf = S.light_cdf + S.light_cdf_off[li];
+    const int n = (int)P.num_tris;
+    int lo = 0, hi = n + 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (u0 < cdf[mid]) hi = mid; else lo = mid + 1; }
+    int i = min(max(lo - 1, 0), n - 1);
+    const float u2x = (u0 - cdf[i]) / (cdf[i + 1] - cdf[i]);
+    const float s = sqrtf(fmaxf(0.f, u2x)), bx = 1.0f - s, by = u1 * s;
+    const float* v = S.verts + 9 * (size_t)(P.first_tri + (uint32_t)i);
+    const f3 p1 = ld3(v), p2 = ld3(v + 3), p3 = ld3(v + 6);
+    g.p = (p1 * (1.0f - bx - by) + p2 * bx) + p3 * by;
+    g.degenerated = false;
+    g.gn = normalize(cross(p2 - p1, p3 - p1));
+    g.sn = g.gn;
+    basis(g.sn, g.dpdu, g.dpdv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// queue append: warp-aggregated (ballot + popc prefix, one atomicAdd per warp)
+__device__ __forceinline__ uint32_t queue_slot(uint32_t* counter, bool want)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void film_add(float4* film, int pixel, f3 c)
+{
+    float* f = reinterpret_cast<float*>(film + pixel);
+    atomicAdd(f, c.x); atomicAdd(f + 1, c.y); atomicAdd(f + 2, c.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_logic: consume the hit of every traced slot, then (re)generate camera paths into finished slots.
+__global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg, float4* film)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (cfg.pool + stride - 1) / stride;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool inb = i < cfg.pool;
+        int nv = inb ? P.nverts[i] : 0;
+        bool alive = false;
+        if (inb && nv > 0 && P.traced[i]) {
+            // --- the slot's extend ray came back ---
+            const float4 h = P.hit[i];
+            const uint32_t tri = __float_as_uint(h.w);
+            P.traced[i] = 0;
+            if (tri != LMB200_MISS) {
+                const float4 ro = P.ray_o[i], rd = P.ray_d[i];
+                const f3 o = F3(ro.x, ro.y, ro.z), d = F3(rd.x, rd.y, rd.z);
+                float4 thr = P.thr[i];
+                const lmb200_primitive& prim = S.prims[S.tri_prim[tri]];
+                bool cont = true;
+                if (cfg.mode == LMB200_MODE_PT && prim.light >= 0 && nv + 1 >= cfg.min_verts) {
+                    // emission on hit (renderer_pt.cpp:183-194; light_area.cpp:105-115)
+                    Geom g;
+                    tri_geom(S, tri, h.y, h.z, o + d * h.x, g);
+                    if (to_local(g, neg(d)).z > 0.f)
+                        film_add(film, __float_as_int(thr.w), F3(thr.x, thr.y, thr.z) * ld3(S.lights[prim.light].Le));
+                }
+                // Russian roulette with the 4th uniform of this iteration's first block (renderer_pt.cpp:207-215)
+                const float4 ua = rng_block(cfg.seed, P.sample[i], (uint32_t)(2 * nv - 1));
+                if (ua.w > 0.5f) cont = false;
+                if (cont) {
+                    thr.x = thr.x / 0.5f; thr.y = thr.y / 0.5f; thr.z = thr.z / 0.5f;
+                    nv++;
+                    // loop-top test of the next iteration (renderer_pt.cpp:120-123) and bsdf::null termination
+                    if (cfg.max_verts != -1 && nv >= cfg.max_verts) cont = false;
+                    if (S.bsdfs[prim.bsdf].type == LMB200_BSDF_NULL) cont = false;
+                }
+                if (cont) {
+                    const f3 p = o + d * h.x;
+                    P.thr[i] = thr;
+                    P.nverts[i] = nv;
+                    P.vtx_p[i] = make_float4(p.x, p.y, p.z, h.w);
+                    P.vtx_wi[i] = make_float4(-d.x, -d.y, -d.z, h.y);
+                    P.vtx_v[i] = h.z;
+                    alive = true;
+                }
+            }
+        }
+        // --- regeneration: camera vertex (sensor_pinhole.cpp:79-90) ---
+        bool need = inb && !alive;
+        unsigned long long sidx = 0;
+        {
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (mask) {
+                const unsigned lane = threadIdx.x & 31u;
+                const int leader = __ffs(mask) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(P.next_sample, (unsigned long long)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                sidx = base + __popc(mask & ((1u << lane) - 1u));
+            }
+        }
+        if (need) {
+            if (sidx < cfg.sample_end) {
+                bool ok = true;
+                int pixel = -1;
+                if (cfg.mode == LMB200_MODE_PT) {
+                    // renderer::pt computes the raster position up front and drops the sample if it fails (renderer_pt.cpp:94-99)
+                    const float4 u = rng_block(cfg.seed, sidx, 0u);
+                    float rx, ry;
+                    ok = raster_position(S, camera_dir(S, u.y, u.z), rx, ry);
+                    if (ok) pixel = pixel_index(S, rx, ry);
+                }
+                if (ok && !(cfg.max_verts != -1 && 1 >= cfg.max_verts)) {
+                    P.sample[i] = sidx;
+                    P.nverts[i] = 1;
+                    P.thr[i] = make_float4(1.f, 1.f, 1.f, __int_as_float(pixel));
+                    P.vtx_p[i] = make_float4(S.pos[0], S.pos[1], S.pos[2], __uint_as_float(LMB200_MISS));
+                    alive = true;
+                } else {
+                    P.nverts[i] = 0;   // sample consumed without a path; the slot is refilled next iteration
+                }
+            } else {
+                P.nverts[i] = 0;
+            }
+        }
+        const uint32_t q = queue_slot(P.qcount + 0, alive);
+        if (alive) P.vq[q] = i;
+    }
+}
+
+// k_nee: direct light sampling at every live vertex, camera vertex included (renderer_ptdirect.cpp:123-177)
+__global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
+{
+    const uint32_t nq = P.qcount[0];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (nq + stride - 1) / stride;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t qi = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool emit = false;
+        f3 C = F3(0, 0, 0), p = F3(0, 0, 0), pl = F3(0, 0, 0);
+        int pixel = 0;
+        if (qi < nq && S.num_lights > 0) {
+            const uint32_t i = P.vq[qi];
+            const int nv = P.nverts[i];
+            const float4 vp = P.vtx_p[i];
+            const uint32_t tri = __float_as_uint(vp.w);
+            const bool is_sensor = tri == LMB200_MISS;
+            const float4 thr = P.thr[i];
+            const float4 ua = rng_block(cfg.seed, P.sample[i], (uint32_t)(2 * nv - 1));
+            const int nL = (int)S.num_lights;
+            const int li = min(max((int)(ua.x * (float)nL), 0), nL - 1);      // scene3.cpp:508-513
+            const float pdfL = 1.0f / (float)nL;                               // scene3.cpp:526-530
+            Geom gL;
+            light_sample(S, li, ua.y, ua.z, gL);
+            const float pdfPL = S.light_inv_area[li];                          // light_area.cpp:100-103
+            p = F3(vp.x, vp.y, vp.z);
+            pl = gL.p;
+            const f3 ppL = normalize(gL.p - p);
+            f3 fsE;
+            Geom g;
+            if (is_sensor) { const float im = importance(S, ppL); fsE = F3(im, im, im); g.degenerated = true; }
+            else {
+                const float4 vw = P.vtx_wi[i];
+                tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
+                fsE = bsdf_eval(S.bsdfs[S.prims[S.tri_prim[tri]].bsdf], g, F3(vw.x, vw.y, vw.z), ppL);
+            }
+            const f3 fsL = to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le);   // light_area.cpp:105-110
+            f3 d = gL.p - p;                                                   // RenderUtils::GeometryTerm, renderutils.h:46-56
+            const float d2 = dot(d, d), dl = sqrtf(d2);
+            d = F3(d.x / dl, d.y / dl, d.z / dl);
+            float G = 1.0f;
+            if (!is_sensor) G *= fabsf(dot(g.sn, d));
+            G *= fabsf(dot(gL.sn, neg(d)));
+            G = G / d2;
+            C = ((F3(thr.x, thr.y, thr.z) * fsE) * fsL) * G;
+            if (!black(C)) {
+                C = C * (1.0f / pdfL / pdfPL);
+                pixel = __float_as_int(thr.w);
+                if (is_sensor) {                                               // renderer_ptdirect.cpp:165-170
+                    float rx = 0.f, ry = 0.f;
+                    raster_position(S, ppL, rx, ry);
+                    pixel = pixel_index(S, rx, ry);
+                }
+                emit = true;
+            }
+        }
+        const uint32_t q = queue_slot(P.qcount + 2, emit);
+        if (emit) {
+            // Scene3::Visible's shadow ray (scene3.h:107-116)
+            const f3 dd = pl - p;
+            const float L = sqrtf(dot(dd, dd));
+            P.sq_o[q] = make_float4(p.x, p.y, p.z, LMB_EPS_ISECT);
+            P.sq_d[q] = make_float4(dd.x / L, dd.y / L, dd.z / L, L * (1.0f - LMB_EPS_ISECT));
+            P.sq_c[q] = make_float4(C.x, C.y, C.z, __int_as_float(pixel));
+        }
+    }
+}
+
+// k_bsdf: sample the next direction, evaluate pdf and fs, update throughput, emit the extend ray
+// (renderer_pt.cpp:128-176 / renderer_ptdirect.cpp:183-246)
+__global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
+{
+    const uint32_t nq = P.qcount[0];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounds = (nq + stride - 1) / stride;
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t qi = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool emit = false;
+        uint32_t i = 0;
+        if (qi < nq) {
+            i = P.vq[qi];
+            const int nv = P.nverts[i];
+            const float4 vp = P.vtx_p[i];
+            const uint32_t tri = __float_as_uint(vp.w);
+            const bool is_sensor = tri == LMB200_MISS;
+            const f3 p = F3(vp.x, vp.y, vp.z);
+            float4 thr = P.thr[i];
+            f3 wo = F3(0, 0, 0), fs;
+            float pdfD;
+            bool ok = true;
+            if (is_sensor) {
+                const float4 u = rng_block(cfg.seed, P.sample[i], 0u);
+                wo = camera_dir(S, u.y, u.z);
+                const float im = importance(S, wo);
+                pdfD = im; fs = F3(im, im, im);
+                if (cfg.mode == LMB200_MODE_PTDIRECT) {
+                    float rx, ry;
+                    ok = raster_position(S, wo, rx, ry);                       // renderer_ptdirect.cpp:200-208
+                    if (ok) thr.w = __int_as_float(pixel_index(S, rx, ry));
+                }
+            } else {
+                const float4 vw = P.vtx_wi[i];
+                const f3 wi = F3(vw.x, vw.y, vw.z);
+                Geom g;
+                tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
+                const lmb200_bsdf& B = S.bsdfs[S.prims[S.tri_prim[tri]].bsdf];
+                const float4 ub = rng_block(cfg.seed, P.sample[i], (uint32_t)(2 * nv));
+                bsdf_sample(B, g, wi, ub.x, ub.y, wo);
+                pdfD = bsdf_pdf(B, g, wi, wo);
+                fs = bsdf_eval(B, g, wi, wo);
+            }
+            if (ok && !black(fs)) {
+                thr.x *= fs.x / pdfD; thr.y *= fs.y / pdfD; thr.z *= fs.z / pdfD;
+                P.thr[i] = thr;
+                P.ray_o[i] = make_float4(p.x, p.y, p.z, LMB_EPS_ISECT);       // scene3.cpp:461
+                P.ray_d[i] = make_float4(wo.x, wo.y, wo.z, LMB_FLT_MAX);
+                P.traced[i] = 1;
+                emit = true;
+            } else {
+                P.nverts[i] = 0;                                               // path ends; slot is refilled by k_logic
+            }
+        }
+        const uint32_t q = queue_slot(P.qcount + 1, emit);
+        if (emit) P.eq[q] = i;
+    }
+}
+
+// extend: closest hit over the extend queue (slot indirection), persistent warps
+__global__ void __launch_bounds__(LMB_TRACE_BLOCK)
+k_extend(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter)
+{
+    const uint32_t n = P.qcount[1];
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t qi = (uint32_t)base + lane;
+        if (qi < n) {
+            const uint32_t i = P.eq[qi];
+            const float4 ro = P.ray_o[i], rd = P.ray_d[i];
+            float tmax = rd.w, hu = 0.f, hv = 0.f;
+            uint32_t hid;
+            const bool hit = lmb_traverse<false, false>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, nullptr);
+            P.hit[i] = make_float4(hit ? tmax : 0.f, hu, hv, __uint_as_float(hit ? hid : LMB200_MISS));
+        }
+        __syncwarp();
+    }
+}
+
+// shadow: any hit over the shadow queue, unoccluded contributions are splatted (film_hdr.cpp:218-223)
+__global__ void __launch_bounds__(LMB_TRACE_BLOCK)
+k_shadow(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter, float4* film)
+{
+    const uint32_t n = P.qcount[2];
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t qi = (uint32_t)base + lane;
+        if (qi < n) {
+            const float4 ro = P.sq_o[qi], rd = P.sq_d[qi];
+            float tmax = rd.w, hu, hv;
+            uint32_t hid;
+            const bool occ = lmb_traverse<true, false>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, nullptr);
+            if (!occ) {
+                const float4 c = P.sq_c[qi];
+                film_add(film, __float_as_int(c.w), F3(c.x, c.y, c.z));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_stats(Pool P)
+{
+    // fold the queue sizes of this iteration into the running ray counters
+    P.next_sample[1] += P.qcount[1];
+    P.next_sample[2] += P.qcount[2];
+}
+
+__global__ void k_rescale(float4* film, long long n, float s)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float4 v = film[i]; v.x *= s; v.y *= s; v.z *= s; film[i] = v; }
+}
+
+// primary-ray normal renderer (config 1): pixel-centre rays (renderer_raycast.cpp:77-83), |sn| shading
+__global__ void k_normal_raygen(DevScene S, float4* rays)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.width * S.height) return;
+    const int x = i % S.width, y = i / S.width;
+    const f3 wo = camera_dir(S, ((float)x + 0.5f) / (float)S.width, ((float)y + 0.5f) / (float)S.height);
+    rays[2 * i] = make_float4(S.pos[0], S.pos[1], S.pos[2], LMB_EPS_ISECT);
+    rays[2 * i + 1] = make_float4(wo.x, wo.y, wo.z, LMB_FLT_MAX);
+}
+__global__ void k_normal_shade(DevScene S, const float4* hits, float4* film)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.width * S.height) return;
+    const float4 h = hits[i];
+    const uint32_t tri = __float_as_uint(h.w);
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tri != LMB200_MISS) {
+        Geom g;
+        tri_geom(S, tri, h.y, h.z, F3(0, 0, 0), g);
+        c = make_float4(fabsf(g.sn.x), fabsf(g.sn.y), fabsf(g.sn.z), 0.f);
+    }
+    film[i] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+struct Scene {
+    int device = 0;
+    Accel accel;
+    DevScene dev{};
+    std::vector<void*> allocs;
+    // pool (lazily sized)
+    Pool pool{};
+    uint32_t pool_size = 0;
+    std::vector<void*> pool_allocs;
+    void* h_pinned = nullptr;   // 8 x u64 readback
+    int num_sms = 148;
+
+    ~Scene()
+    {
+        cudaSetDevice(device);
+        for (void* p : pool_allocs) cudaFree(p);
+        for (void* p : allocs) cudaFree(p);
+        if (h_pinned) cudaFreeHost(h_pinned);
+    }
+};
+
+template <typename T>
+static int dev_upload(Scene* s, const T* src, size_t n, const T** out)
+{
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scene)");
+    s->allocs.push_back(d);
+    if (n && (e = cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(scene)");
+    *out = reinterpret_cast<const T*>(d);
+    return LMB200_OK;
+}
+
+template <typename T>
+static int pool_alloc(Scene* s, T** out, size_t n)
+{
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(pool)");
+    s->pool_allocs.push_back(d);
+    *out = reinterpret_cast<T*>(d);
+    return LMB200_OK;
+}
+
+static int ensure_pool(Scene* s, uint32_t n)
+{
+    if (s->pool_size == n) return LMB200_OK;
+    for (void* p : s->pool_allocs) cudaFree(p);
+    s->pool_allocs.clear();
+    s->pool_size = 0;
+    Pool& P = s->pool;
+    int rc = 0;
+    if ((rc = pool_alloc(s, &P.sample, n))) return rc;
+    if ((rc = pool_alloc(s, &P.nverts, n))) return rc;
+    if ((rc = pool_alloc(s, &P.thr, n))) return rc;
+    if ((rc = pool_alloc(s, &P.ray_o, n))) return rc;
+    if ((rc = pool_alloc(s, &P.ray_d, n))) return rc;
+    if ((rc = pool_alloc(s, &P.hit, n))) return rc;
+    if ((rc = pool_alloc(s, &P.traced, n))) return rc;
+    if ((rc = pool_alloc(s, &P.vtx_p, n))) return rc;
+    if ((rc = pool_alloc(s, &P.vtx_wi, n))) return rc;
+    if ((rc = pool_alloc(s, &P.vtx_v, n))) return rc;
+    if ((rc = pool_alloc(s, &P.vq, n))) return rc;
+    if ((rc = pool_alloc(s, &P.eq, n))) return rc;
+    if ((rc = pool_alloc(s, &P.sq_o, n))) return rc;
+    if ((rc = pool_alloc(s, &P.sq_d, n))) return rc;
+    if ((rc = pool_alloc(s, &P.sq_c, n))) return rc;
+    if ((rc = pool_alloc(s, &P.qcount, 4))) return rc;
+    if ((rc = pool_alloc(s, &P.next_sample, 4))) return rc;
+    s->pool_size = n;
+    return LMB200_OK;
+}
+
+static int render_normal(Scene* s, float4* film, cudaStream_t st)
+{
+    const int npx = s->dev.width * s->dev.height;
+    int rc = ensure_pool(s, (uint32_t)std::max(npx, 1));
+    if (rc) return rc;
+    // rays live in ray_o/ray_d-sized scratch: reuse sq_o (2*npx float4 needed) -> allocate temp
+    float4* rays = nullptr; float4* hits = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&rays, sizeof(float4) * 2 * (size_t)npx)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(rays)");
+    if ((e = cudaMalloc(&hits, sizeof(float4) * (size_t)npx)) != cudaSuccess) { cudaFree(rays); return cuda_fail(e, "cudaMalloc(hits)"); }
+    k_normal_raygen<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, rays); g_launch_count++;
+    rc = trace_closest_dev(&s->accel, rays, hits, (uint64_t)npx, nullptr, st, 0);
+    if (!rc) { k_normal_shade<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, hits, film); g_launch_count++; }
+    e = cudaStreamSynchronize(st);
+    cudaFree(rays); cudaFree(hits);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "render_normal");
+    return LMB200_OK;
+}
+
+static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, cudaStream_t st, lmb200_render_stats* stats)
+{
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    float4* film = reinterpret_cast<float4*>(film_dev);
+    const uint64_t launches0 = g_launch_count.load();
+    if (p->mode == LMB200_MODE_NORMAL) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = render_normal(s, film, st);
+        if (stats) {
+            memset(stats, 0, sizeof(*stats));
+            stats->samples = (int64_t)s->dev.width * s->dev.height;
+            stats->extend_rays = stats->samples;
+            stats->iterations = 1;
+            stats->launches = g_launch_count.load() - launches0;
+            stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+        return rc;
+    }
+    if (p->mode != LMB200_MODE_PT && p->mode != LMB200_MODE_PTDIRECT) return set_error(LMB200_E_INVALID, "unknown render mode");
+    if (p->sample_end < p->sample_begin) return set_error(LMB200_E_INVALID, "sample_end < sample_begin");
+    const int64_t todo = p->sample_end - p->sample_begin;
+    uint32_t pool = p->pool_size > 0 ? (uint32_t)p->pool_size : (1u << 21);
+    if ((int64_t)pool > todo) pool = (uint32_t)std::max<int64_t>(todo, 1);
+    pool = (pool + 31u) & ~31u;
+    int rc = ensure_pool(s, pool);
+    if (rc) return rc;
+    Pool& P = s->pool;
+    if (!s->h_pinned && (e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    volatile unsigned long long* hp = reinterpret_cast<volatile unsigned long long*>(s->h_pinned);
+
+    RenderCfg cfg;
+    cfg.mode = p->mode; cfg.max_verts = p->max_num_vertices; cfg.min_verts = p->min_num_vertices;
+    cfg.seed = p->seed; cfg.sample_end = (unsigned long long)p->sample_end; cfg.pool = pool;
+
+    cudaMemsetAsync(P.nverts, 0, sizeof(int) * pool, st);
+    cudaMemsetAsync(P.traced, 0, pool, st);
+    unsigned long long init[4] = {(unsigned long long)p->sample_begin, 0ull, 0ull, 0ull};
+    cudaMemcpyAsync(P.next_sample, init, sizeof(init), cudaMemcpyHostToDevice, st);
+
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+    const int logic_blocks = s->num_sms * 8;
+    const int trace_blocks = s->accel.num_sms * s->accel.trace_blocks_per_sm;
+    int64_t iters = 0;
+    for (;;) {
+        cudaMemsetAsync(P.qcount, 0, 4 * sizeof(uint32_t), st);
+        cudaMemsetAsync(s->accel.d_counter, 0, 2 * sizeof(unsigned long long), st);
+        k_logic<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg, film);
+        if (cfg.mode == LMB200_MODE_PTDIRECT) k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
+        k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
+        k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel.d_nodes), reinterpret_cast<const float4*>(s->accel.d_tris), P, s->accel.d_counter);
+        if (cfg.mode == LMB200_MODE_PTDIRECT)
+            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel.d_nodes), reinterpret_cast<const float4*>(s->accel.d_tris), P, s->accel.d_counter + 1, film);
+        k_stats<<<1, 1, 0, st>>>(P);
+        g_launch_count += (cfg.mode == LMB200_MODE_PTDIRECT) ? 6 : 4;
+        cudaMemcpyAsync(s->h_pinned, P.qcount, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(s->h_pinned) + 4, P.next_sample, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return cuda_fail(e, "wavefront iteration"); }
+        iters++;
+        const uint32_t live = reinterpret_cast<volatile uint32_t*>(s->h_pinned)[0];
+        if (live == 0 && hp[4] >= cfg.sample_end) break;     // no live vertex and the sample counter is exhausted
+    }
+    cudaEventRecord(ev1, st);
+    cudaMemcpyAsync(s->h_pinned, P.next_sample, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return cuda_fail(e, "wavefront end"); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (stats) {
+        stats->samples = todo;
+        stats->extend_rays = (int64_t)hp[1];
+        stats->shadow_rays = (int64_t)hp[2];
+        stats->iterations = iters;
+        stats->launches = g_launch_count.load() - launches0;
+        stats->seconds = ms * 1e-3;
+    }
+    return LMB200_OK;
+}
+
+}  // namespace lmb200
+
+using namespace lmb200;
+
+extern "C" {
+
+lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d)
+{
+    if (!d || (d->num_tris && (!d->verts || !d->tri_prim)) || !d->prims || !d->bsdfs) { set_error(LMB200_E_INVALID, "null scene field"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error(LMB200_E_CUDA, "no CUDA device available (lmb200 has no CPU fallback)"); return nullptr; }
+    if (device < 0 || device >= ndev) { set_error(LMB200_E_INVALID, "bad device ordinal"); return nullptr; }
+    for (uint64_t t = 0; t < d->num_tris; t++) if (d->tri_prim[t] >= d->num_prims) { set_error(LMB200_E_INVALID, "tri_prim out of range"); return nullptr; }
+    for (uint32_t i = 0; i < d->num_prims; i++) {
+        const lmb200_primitive& P = d->prims[i];
+        if (P.bsdf < 0 || (uint32_t)P.bsdf >= d->num_bsdfs || P.light >= (int32_t)d->num_lights || (uint64_t)P.first_tri + P.num_tris > d->num_tris) { set_error(LMB200_E_INVALID, "primitive out of range"); return nullptr; }
+    }
+    Scene* s = new Scene;
+    s->device = device;
+    s->accel.device = device;
+    cudaSetDevice(device);
+    build_bvh(d->verts, d->num_tris, s->accel.bvh, 0);
+    s->accel.built = true;
+    if (s->accel.upload()) { delete s; return nullptr; }
+    s->num_sms = s->accel.num_sms;
+    DevScene& D = s->dev;
+    int rc = 0;
+    rc |= dev_upload(s, d->verts, 9 * d->num_tris, &D.verts);
+    if (d->normals) rc |= dev_upload(s, d->normals, 9 * d->num_tris, &D.normals); else D.normals = nullptr;
+    rc |= dev_upload(s, d->tri_prim, d->num_tris, &D.tri_prim);
+    rc |= dev_upload(s, d->prims, d->num_prims, &D.prims);
+    rc |= dev_upload(s, d->bsdfs, d->num_bsdfs, &D.bsdfs);
+    rc |= dev_upload(s, d->lights, d->num_lights, &D.lights);
+    // area CDFs exactly as TriangleUtils::CreateTriangleAreaDist + Distribution1D::Normalize
+    // (triangleutils.h:47-68, dist.h:44-60); Length uses the _mm_dp_ps summation order
+    std::vector<float> cdf; std::vector<uint32_t> off; std::vector<float> inv_area;
+    for (uint32_t li = 0; li < d->num_lights; li++) {
+        if (d->lights[li].primitive < 0 || (uint32_t)d->lights[li].primitive >= d->num_prims) { set_error(LMB200_E_INVALID, "light primitive out of range"); delete s; return nullptr; }
+        const lmb200_primitive& P = d->prims[d->lights[li].primitive];
+        off.push_back((uint32_t)cdf.size());
+        const size_t base = cdf.size();
+        cdf.push_back(0.f);
+        float sum = 0.f;
+        for (uint32_t i = 0; i < P.num_tris; i++) {
+            const float* v = d->verts + 9 * (size_t)(P.first_tri + i);
+            const float e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
+            volatile float a0 = e1[1] * e2[2], a1 = e1[2] * e2[1], b0 = e1[2] * e2[0], b1 = e1[0] * e2[2], c0 = e1[0] * e2[1], c1 = e1[1] * e2[0];
+            const float cx = a0 - a1, cy = b0 - b1, cz = c0 - c1;
+            volatile float xx = cx * cx, yy = cy * cy, zz = cz * cz;
+            volatile float s01 = xx + yy, s23 = zz + 0.0f;
+            const float area = std::sqrt(s01 + s23) * 0.5f;
+            cdf.push_back(cdf.back() + area);
+            sum += area;
+        }
+        const float inv = 1.0f / cdf.back();
+        for (size_t k = base; k < cdf.size(); k++) cdf[k] *= inv;
+        inv_area.push_back(1.0f / sum);
+    }
+    rc |= dev_upload(s, cdf.data(), cdf.size(), &D.light_cdf);
+    rc |= dev_upload(s, off.data(), off.size(), &D.light_cdf_off);
+    rc |= dev_upload(s, inv_area.data(), inv_area.size(), &D.light_inv_area);
+    if (rc) { delete s; return nullptr; }
+    D.num_lights = d->num_lights;
+    for (int k = 0; k < 3; k++) { D.pos[k] = d->camera.position[k]; D.vx[k] = d->camera.vx[k]; D.vy[k] = d->camera.vy[k]; D.vz[k] = d->camera.vz[k]; }
+    D.tan_fov = std::tan(d->camera.fov * 0.5f);
+    D.width = d->camera.width; D.height = d->camera.height;
+    D.aspect = (float)d->camera.width / (float)d->camera.height;
+    return reinterpret_cast<lmb200_scene*>(s);
+}
+
+void lmb200_scene_destroy(lmb200_scene* s) { delete reinterpret_cast<Scene*>(s); }
+
+lmb200_accel* lmb200_scene_accel(lmb200_scene* s) { return s ? reinterpret_cast<lmb200_accel*>(&reinterpret_cast<Scene*>(s)->accel) : nullptr; }
+
+int lmb200_render_dev(lmb200_scene* h, const lmb200_render_params* p, void* film_dev, void* stream, lmb200_render_stats* stats)
+{
+    if (!h || !p || !film_dev) return set_error(LMB200_E_INVALID, "null argument");
+    return render_dev(reinterpret_cast<Scene*>(h), p, film_dev, reinterpret_cast<cudaStream_t>(stream), stats);
+}
+
+int lmb200_film_rescale_dev(void* film_dev, int64_t num_pixels, float scale, void* stream)
+{
+    if (!film_dev) return set_error(LMB200_E_INVALID, "null argument");
+    k_rescale<<<(unsigned)((num_pixels + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4*>(film_dev), num_pixels, scale);
+    g_launch_count++;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? LMB200_OK : cuda_fail(e, "k_rescale");
+}
+
+int lmb200_render(lmb200_scene* h, const lmb200_render_params* p, float* film_host, lmb200_render_stats* stats)
+{
+    if (!h || !p || !film_host) return set_error(LMB200_E_INVALID, "null argument");
+    Scene* s = reinterpret_cast<Scene*>(h);
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const int64_t npx = (int64_t)s->dev.width * s->dev.height;
+    void* film = nullptr;
+    if ((e = cudaMalloc(&film, sizeof(float4) * (size_t)npx)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(film)");
+    cudaMemset(film, 0, sizeof(float4) * (size_t)npx);
+    int rc = render_dev(s, p, film, 0, stats);
+    if (!rc && p->mode != LMB200_MODE_NORMAL) rc = lmb200_film_rescale_dev(film, npx, (float)npx / (float)p->num_samples, 0);
+    if (!rc && (e = cudaMemcpy(film_host, film, sizeof(float4) * (size_t)npx, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(film)");
+    cudaFree(film);
+    return rc;
+}
+
+// Single-process multi-GPU: one host thread per device renders a contiguous slice of the sample
+// range into its own film; the films are summed to device 0 with one ncclReduce over NVLink
+// (replaces contexts.combine_each(film->Accumulate), scheduler.cpp:280-285), then rescaled.
+int lmb200_render_multi(lmb200_scene** scenes, int num_gpus, const lmb200_render_params* p, float* film_host, lmb200_render_stats* stats)
+{
+    if (!scenes || num_gpus < 1 || !p || !film_host) return set_error(LMB200_E_INVALID, "null argument");
+    if (num_gpus == 1) return lmb200_render(scenes[0], p, film_host, stats);
+    typedef int (*fn_init_all)(void**, int, const int*);
+    typedef int (*fn_void)(void);
+    typedef int (*fn_reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+    typedef int (*fn_destroy)(void*);
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return set_error(LMB200_E_NCCL, std::string("cannot load libnccl: ") + dlerror());
+    fn_init_all nccl_init = (fn_init_all)dlsym(lib, "ncclCommInitAll");
+    fn_void nccl_gs = (fn_void)dlsym(lib, "ncclGroupStart"), nccl_ge = (fn_void)dlsym(lib, "ncclGroupEnd");
+    fn_reduce nccl_reduce = (fn_reduce)dlsym(lib, "ncclReduce");
+    fn_destroy nccl_destroy = (fn_destroy)dlsym(lib, "ncclCommDestroy");
+    if (!nccl_init || !nccl_gs || !nccl_ge || !nccl_reduce || !nccl_destroy) return set_error(LMB200_E_NCCL, "libnccl lacks required symbols");
+
+    std::vector<Scene*> sc(num_gpus);
+    std::vector<int> devs(num_gpus);
+    for (int g = 0; g < num_gpus; g++) { sc[g] = reinterpret_cast<Scene*>(scenes[g]); if (!sc[g]) return set_error(LMB200_E_INVALID, "null scene"); devs[g] = sc[g]->device; }
+    const int64_t npx = (int64_t)sc[0]->dev.width * sc[0]->dev.height;
+    std::vector<void*> films(num_gpus, nullptr);
+    std::vector<cudaStream_t> streams(num_gpus, nullptr);
+    std::vector<int> rcs(num_gpus, 0);
+    std::vector<std::string> errs(num_gpus);
+    std::vector<lmb200_render_stats> st(num_gpus);
+    const int64_t b = p->sample_begin, todo = p->sample_end - p->sample_begin;
+    auto work = [&](int g) {
+        cudaSetDevice(devs[g]);
+        cudaError_t e = cudaMalloc(&films[g], sizeof(float4) * (size_t)npx);
+        if (e != cudaSuccess) { rcs[g] = LMB200_E_CUDA; errs[g] = cudaGetErrorString(e); return; }
+        cudaStreamCreateWithFlags(&streams[g], cudaStreamNonBlocking);
+        cudaMemsetAsync(films[g], 0, sizeof(float4) * (size_t)npx, streams[g]);
+        lmb200_render_params q = *p;
+        q.sample_begin = b + todo * g / num_gpus;
+        q.sample_end = b + todo * (g + 1) / num_gpus;
+        rcs[g] = render_dev(sc[g], &q, films[g], streams[g], &st[g]);
+        if (rcs[g]) errs[g] = g_last_error;
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < num_gpus; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto& t : th) t.join();
+    int rc = 0;
+    for (int g = 0; g < num_gpus; g++) if (rcs[g]) rc = set_error(rcs[g], errs[g]);
+    std::vector<void*> comms(num_gpus, nullptr);
+    if (!rc && nccl_init(comms.data(), num_gpus, devs.data()) != 0) rc = set_error(LMB200_E_NCCL, "ncclCommInitAll failed");
+    if (!rc) {
+        nccl_gs();
+        for (int g = 0; g < num_gpus; g++) {
+            cudaSetDevice(devs[g]);
+            if (nccl_reduce(films[g], films[g], (size_t)npx * 4, 7 /*ncclFloat32*/, 0 /*ncclSum*/, 0, comms[g], streams[g]) != 0) rc = set_error(LMB200_E_NCCL, "ncclReduce failed");
+        }
+        nccl_ge();
+        for (int g = 0; g < num_gpus; g++) { cudaSetDevice(devs[g]); cudaStreamSynchronize(streams[g]); }
+    }
+    if (!rc) {
+        cudaSetDevice(devs[0]);
+        if (p->mode != LMB200_MODE_NORMAL) rc = lmb200_film_rescale_dev(films[0], npx, (float)npx / (float)p->num_samples, streams[0]);
+        cudaError_t e = cudaMemcpyAsync(film_host, films[0], sizeof(float4) * (size_t)npx, cudaMemcpyDeviceToHost, streams[0]);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(streams[0]);
+        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "film readback");
+    }
+    for (int g = 0; g < num_gpus; g++) {
+        cudaSetDevice(devs[g]);
+        if (comms[g]) nccl_destroy(comms[g]);
+        if (films[g]) cudaFree(films[g]);
+        if (streams[g]) cudaStreamDestroy(streams[g]);
+    }
+    if (stats && !rc) {
+        memset(stats, 0, sizeof(*stats));
+        for (int g = 0; g < num_gpus; g++) {
+            stats->samples += st[g].samples; stats->extend_rays += st[g].extend_rays; stats->shadow_rays += st[g].shadow_rays;
+            stats->iterations = std::max(stats->iterations, st[g].iterations); stats->launches += st[g].launches;
+            stats->seconds = std::max(stats->seconds, st[g].seconds);
+        }
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -58,7 +58,7 @@ class RenderStats(C.Structure):
 
 EXPORTS = [
     "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build",
-    "lmb200_accel_get_stats", "lmb200_trace_closest", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
+    "lmb200_accel_get_stats", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
     "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_arrays", "lmb200_accel_create_host_only",
     "lmb200_scene_create", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
     "lmb200_render", "lmb200_render_multi",
@@ -83,6 +83,7 @@ def lib():
     L.lmb200_accel_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.lmb200_accel_get_stats.argtypes = [C.c_void_p, C.POINTER(AccelStats)]
     L.lmb200_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.lmb200_trace_closest_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.lmb200_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.lmb200_trace_closest_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.lmb200_trace_any_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -173,3 +174,40 @@ class Accel:
         occ = np.zeros(rays.shape[0], dtype=np.uint8)
         check(lib().lmb200_trace_any(self.h, _ptr(rays), _ptr(occ), rays.shape[0]))
         return occ
+
+
+class Scene:
+    """Mirror of the reference's Renderer interface (Initialize/Render, renderer.h:68-81) over a flattened scene."""
+
+    def __init__(self, scene, device=0):
+        self.desc, self.keep = scene.flatten()
+        self.w, self.h = scene.camera["w"], scene.camera["h"]
+        self.h_ = lib().lmb200_scene_create(device, C.byref(self.desc))
+        if not self.h_:
+            raise LmbError(lib().lmb200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h_", None):
+            lib().lmb200_scene_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def params(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None, pool=0):
+        p = RenderParams()
+        p.mode, p.num_samples, p.sample_begin = mode, num_samples, begin
+        p.sample_end = num_samples if end is None else end
+        p.max_num_vertices, p.min_num_vertices, p.seed, p.pool_size = max_verts, min_verts, seed, pool
+        return p
+
+    def render(self, mode, num_samples, **kw):
+        """Host-buffer render through lmb200_render: returns (film (H,W,3) float32, stats dict)."""
+        p = self.params(mode, num_samples, **kw)
+        film = np.zeros((self.h, self.w, 4), np.float32)
+        st = RenderStats()
+        check(lib().lmb200_render(self.h_, C.byref(p), _ptr(film), C.byref(st)))
+        return film[..., :3], {f: getattr(st, f) for f, _ in RenderStats._fields_}

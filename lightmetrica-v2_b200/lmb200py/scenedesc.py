@@ -1,0 +1,182 @@
+"""Scene model shared by the tests and the bench: one description, two consumers.
+
+  to_yaml()  -> the Lightmetrica YAML the reference consumes, meshes passed
+                through the harness's in-memory `trianglemesh::mem` asset
+  flatten()  -> the POD arrays of include/lmb200.h (lmb200_scene_desc), in the reference's
+                primitive order (scene3.cpp:136-389: nodes in document order, camera node included)
+All meshes are given in world space (identity node transforms).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi, scenes
+
+
+class Scene:
+    def __init__(self):
+        self.meshes = []      # dict(verts (nv,3) f32, faces (nf,3) u32, normals (nv,3) f32 or None)
+        self.nodes = []       # dict(mesh=int, bsdf=str or None, light=str or None)
+        self.bsdfs = {}       # name -> dict(type='diffuse'|'cook_torrance', R, eta, k, roughness)
+        self.lights = {}      # name -> Le (3,)
+        self.camera = None    # dict(eye, center, up, fov, w, h)
+
+    # ---- construction helpers ----
+    def add_bsdf(self, name, type="diffuse", R=(0.8, 0.8, 0.8), roughness=0.1,
+                 eta=(0.14, 0.129, 0.1585), k=(4.58625, 3.348125, 2.329375)):
+        self.bsdfs[name] = dict(type=type, R=tuple(R), roughness=float(roughness), eta=tuple(eta), k=tuple(k))
+
+    def add_light(self, name, Le):
+        self.lights[name] = tuple(Le)
+
+    def add_mesh_tris(self, tris9, bsdf=None, light=None, normals=None):
+        """tris9: (n,9) world-space triangles, stored unshared (3 vertices per face)."""
+        tris9 = np.ascontiguousarray(tris9, np.float32).reshape(-1, 9)
+        n = tris9.shape[0]
+        m = dict(verts=tris9.reshape(-1, 3).copy(), faces=np.arange(3 * n, dtype=np.uint32).reshape(-1, 3),
+                 normals=None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3))
+        self.meshes.append(m)
+        self.nodes.append(dict(mesh=len(self.meshes) - 1, bsdf=bsdf, light=light))
+
+    def add_quad(self, a, b, c, d, bsdf=None, light=None):
+        a, b, c, d = (np.asarray(x, np.float32) for x in (a, b, c, d))
+        self.add_mesh_tris(np.stack([np.concatenate([a, b, c]), np.concatenate([a, c, d])]), bsdf, light)
+
+    def set_camera(self, eye, center, up, fov, w, h):
+        self.camera = dict(eye=tuple(eye), center=tuple(center), up=tuple(up), fov=float(fov), w=int(w), h=int(h))
+
+    # ---- consumers ----
+    def to_yaml(self, mesh_handles, accel="qbvh", renderer="ptdirect", renderer_params=None):
+        def v3(x):
+            return " ".join(repr(float(t)) for t in x)
+        out = ["lightmetrica:", "  version: 1.1.0", "  assets:"]
+        for i, h in enumerate(mesh_handles):
+            out += [f"    mesh{i}:", "      interface: trianglemesh", "      type: mem", "      params:", f"        handle: {h}"]
+        for name, b in self.bsdfs.items():
+            out += [f"    {name}:", "      interface: bsdf", f"      type: {b['type']}", "      params:", f"        R: {v3(b['R'])}"]
+            if b["type"] == "cook_torrance":
+                out += [f"        eta: {v3(b['eta'])}", f"        k: {v3(b['k'])}", f"        roughness: {b['roughness']!r}"]
+        for name, le in self.lights.items():
+            out += [f"    {name}:", "      interface: light", "      type: area", "      params:", f"        Le: {v3(le)}"]
+        c = self.camera
+        out += ["    film1:", "      interface: film", "      type: hdr", "      params:", f"        w: {c['w']}", f"        h: {c['h']}"]
+        out += ["    cam:", "      interface: sensor", "      type: pinhole", "      params:", "        film: film1", f"        fov: {c['fov']!r}"]
+        out += ["  accel:", f"    type: {accel}"]
+        out += ["  scene:", "    type: scene3", "    params:", "      sensor: n_cam", "      nodes:"]
+        out += ["        - id: n_cam", "          sensor: cam", "          transform:", "            lookat:",
+                f"              eye: {v3(c['eye'])}", f"              center: {v3(c['center'])}", f"              up: {v3(c['up'])}"]
+        for nd in self.nodes:
+            out += [f"        - mesh: mesh{nd['mesh']}"]
+            if nd["bsdf"]:
+                out += [f"          bsdf: {nd['bsdf']}"]
+            if nd["light"]:
+                out += [f"          light: {nd['light']}"]
+        out += ["  renderer:", f"    type: {renderer}"]
+        if renderer_params:
+            out += ["    params:"] + [f"      {k}: {v}" for k, v in renderer_params.items()]
+        return "\n".join(out) + "\n"
+
+    def flatten(self):
+        """Returns (SceneDesc, keepalive) in the reference's primitive order: primitive 0 is the camera node."""
+        bs_names = list(self.bsdfs.keys())
+        bs = (capi.Bsdf * (len(bs_names) + 1))()
+        for i, n in enumerate(bs_names):
+            b = self.bsdfs[n]
+            bs[i].type = capi.BSDF_DIFFUSE if b["type"] == "diffuse" else capi.BSDF_COOKTORRANCE
+            bs[i].R = (C.c_float * 3)(*b["R"])
+            bs[i].eta = (C.c_float * 3)(*b["eta"])
+            bs[i].k = (C.c_float * 3)(*b["k"])
+            bs[i].roughness = b["roughness"]
+        null_idx = len(bs_names)          # nodes without a bsdf get bsdf::null (scene3.cpp:315-319)
+        bs[null_idx].type = capi.BSDF_NULL
+        prims = (capi.Primitive * (len(self.nodes) + 1))()
+        prims[0].bsdf = null_idx
+        prims[0].light = -1
+        lights, verts, norms, tri_prim = [], [], [], []
+        any_normals = any(self.meshes[nd["mesh"]]["normals"] is not None for nd in self.nodes)
+        first = 0
+        for pi, nd in enumerate(self.nodes, start=1):
+            m = self.meshes[nd["mesh"]]
+            t = m["verts"][m["faces"].reshape(-1)].reshape(-1, 9)
+            verts.append(t)
+            if any_normals:
+                norms.append(m["normals"][m["faces"].reshape(-1)].reshape(-1, 9) if m["normals"] is not None else np.zeros_like(t))
+            tri_prim.append(np.full(t.shape[0], pi, np.uint32))
+            prims[pi].bsdf = bs_names.index(nd["bsdf"]) if nd["bsdf"] else null_idx
+            prims[pi].light = -1
+            prims[pi].first_tri = first
+            prims[pi].num_tris = t.shape[0]
+            prims[pi].has_normals = 1 if m["normals"] is not None else 0
+            if nd["light"]:
+                prims[pi].light = len(lights)
+                lights.append((self.lights[nd["light"]], pi))
+            first += t.shape[0]
+        verts = np.ascontiguousarray(np.concatenate(verts), np.float32) if verts else np.zeros((0, 9), np.float32)
+        tri_prim = np.ascontiguousarray(np.concatenate(tri_prim), np.uint32) if tri_prim else np.zeros(0, np.uint32)
+        norms = np.ascontiguousarray(np.concatenate(norms), np.float32) if any_normals else None
+        ls = (capi.Light * max(1, len(lights)))()
+        for i, (le, pi) in enumerate(lights):
+            ls[i].Le = (C.c_float * 3)(*le)
+            ls[i].primitive = pi
+        c = self.camera
+        vx, vy, vz = scenes.lookat(c["eye"], c["center"], c["up"])
+        cam = capi.Camera()
+        cam.position = (C.c_float * 3)(*c["eye"])
+        cam.vx = (C.c_float * 3)(*vx)
+        cam.vy = (C.c_float * 3)(*vy)
+        cam.vz = (C.c_float * 3)(*vz)
+        cam.fov = float(np.radians(np.float32(c["fov"])))
+        cam.width, cam.height = c["w"], c["h"]
+        d = capi.SceneDesc()
+        d.num_tris = verts.shape[0]
+        d.verts = verts.ctypes.data_as(C.c_void_p)
+        d.normals = norms.ctypes.data_as(C.c_void_p) if norms is not None else None
+        d.tri_prim = tri_prim.ctypes.data_as(C.c_void_p)
+        d.num_prims = len(self.nodes) + 1
+        d.prims = C.cast(prims, C.POINTER(capi.Primitive))
+        d.num_bsdfs = len(bs_names) + 1
+        d.bsdfs = C.cast(bs, C.POINTER(capi.Bsdf))
+        d.num_lights = len(lights)
+        d.lights = C.cast(ls, C.POINTER(capi.Light))
+        d.camera = cam
+        keep = dict(verts=verts, norms=norms, tri_prim=tri_prim, prims=prims, bs=bs, ls=ls)
+        return d, keep
+
+
+def _box(scene, center, half, angle_deg, bsdf):
+    """Axis-aligned cuboid rotated about +y, 12 triangles, outward normals."""
+    cx, cy, cz = center
+    hx, hy, hz = half
+    a = np.radians(angle_deg)
+    ca, sa = np.cos(a), np.sin(a)
+
+    def P(x, y, z):
+        return (cx + ca * x + sa * z, cy + y, cz - sa * x + ca * z)
+    v = [P(sx * hx, sy * hy, sz * hz) for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]
+    # vertex index = 4*ix + 2*iy + iz
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    tris = []
+    for q in quads:
+        a_, b_, c_, d_ = (np.asarray(v[i], np.float32) for i in q)
+        tris += [np.concatenate([a_, b_, c_]), np.concatenate([a_, c_, d_])]
+    scene.add_mesh_tris(np.stack(tris), bsdf)
+
+
+def cornell_box(w=512, h=512, glossy_block=False):
+    """Cornell-style box, 36 triangles: 5 walls, 2 blocks, 1 ceiling light (config 0 of BASELINE.json)."""
+    s = Scene()
+    s.add_bsdf("white", "diffuse", (0.75, 0.75, 0.75))
+    s.add_bsdf("red", "diffuse", (0.75, 0.25, 0.25))
+    s.add_bsdf("green", "diffuse", (0.25, 0.75, 0.25))
+    s.add_bsdf("metal", "cook_torrance", (1.0, 1.0, 1.0), roughness=0.2)
+    s.add_light("lamp", (17.0, 12.0, 4.0))
+    s.add_quad((-1, 0, -1), (-1, 0, 1), (1, 0, 1), (1, 0, -1), "white")          # floor (normal +y)
+    s.add_quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1), "white")          # ceiling (normal -y)
+    s.add_quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1), "white")        # back wall (normal +z)
+    s.add_quad((-1, 0, -1), (-1, 2, -1), (-1, 2, 1), (-1, 0, 1), "red")          # left wall (normal +x)
+    s.add_quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1), "green")            # right wall (normal -x)
+    _box(s, (-0.35, 0.6, -0.3), (0.3, 0.6, 0.3), 18.0, "white")                  # tall block
+    _box(s, (0.4, 0.3, 0.3), (0.3, 0.3, 0.3), -17.0, "metal" if glossy_block else "white")   # short block
+    s.add_quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), "white", "lamp")  # light, faces down
+    s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h)
+    return s

@@ -194,3 +194,97 @@ def ref_triaccel_records(verts):
         v = verts[i]
         L.ref_triaccel_load(_p(v[0:3].copy()), _p(v[3:6].copy()), _p(v[6:9].copy()), _p(out[i]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Path tracing oracles
+
+
+def _port_pt():
+    L = port()
+    if not hasattr(L, "_pt_ready"):
+        L.orc_pt_scene_create.restype = C.c_void_p
+        L.orc_pt_scene_create.argtypes = [C.c_void_p]
+        L.orc_pt_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_pt_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_render_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L._pt_ready = True
+    return L
+
+
+class PortPT:
+    """C restatement of renderer::pt / renderer::ptdirect over a flattened scene (same POD layout as lmb200_scene_desc)."""
+
+    def __init__(self, scene):
+        self.desc, self.keep = scene.flatten()
+        self.w, self.h = scene.camera["w"], scene.camera["h"]
+        self.s = _port_pt().orc_pt_scene_create(C.byref(self.desc))
+
+    def __del__(self):
+        if getattr(self, "s", None):
+            _port_pt().orc_pt_scene_destroy(self.s)
+            self.s = None
+
+    def render(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None):
+        """Returns (film (H,W,3) scaled by W*H/num_samples, counts [extend, shadow])."""
+        end = num_samples if end is None else end
+        film = np.zeros((self.h, self.w, 4), np.float32)
+        counts = np.zeros(2, np.int64)
+        _port_pt().orc_pt_render(self.s, mode, max_verts, min_verts, seed, begin, end, _p(film), _p(counts))
+        return film[..., :3] * np.float32(self.w * self.h / num_samples), counts
+
+    def render_normal(self):
+        film = np.zeros((self.h, self.w, 4), np.float32)
+        tri = np.zeros((self.h, self.w), np.int32)
+        _port_pt().orc_render_normal(self.s, _p(film), _p(tri))
+        return film[..., :3], tri
+
+
+class RefScene:
+    """The reference itself (oracle/_ref) on a scenedesc.Scene: real scene3 + assets + renderers."""
+
+    def __init__(self, scene, accel="qbvh", plugins=()):
+        L = ref()
+        for p in plugins:
+            if not L.ref_load_plugin(p.encode()):
+                raise RuntimeError(f"failed to load plugin {p}")
+        handles = []
+        self._keep = []
+        for m in scene.meshes:
+            ps = np.ascontiguousarray(m["verts"], np.float32)
+            fs = np.ascontiguousarray(m["faces"], np.uint32)
+            ns = None if m["normals"] is None else np.ascontiguousarray(m["normals"], np.float32)
+            handles.append(L.ref_register_mesh(_p(ps), ps.shape[0], _p(ns) if ns is not None else None, None, _p(fs), fs.shape[0]))
+        self.scene = scene
+        self.yaml = scene.to_yaml(handles, accel=accel)
+        self.s = L.ref_session_create(self.yaml.encode(), accel.encode())
+        if not self.s:
+            raise RuntimeError(L.ref_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "s", None):
+            ref().ref_session_destroy(self.s)
+            self.s = None
+
+    def render(self, renderer, num_samples, seed=1, threads=1, max_verts=-1, extra=None):
+        w, h = self.scene.camera["w"], self.scene.camera["h"]
+        out = np.zeros((h, w, 3), np.float32)
+        params = f"num_samples: {int(num_samples)}\nmax_num_vertices: {int(max_verts)}\nmin_num_vertices: 0\n"
+        for k, v in (extra or {}).items():
+            params += f"{k}: {v}\n"
+        ow, oh, sec = C.c_int(), C.c_int(), C.c_double()
+        ok = ref().ref_render(self.s, renderer.encode(), params.encode(), seed, threads, _p(out), C.byref(ow), C.byref(oh), C.byref(sec))
+        if not ok:
+            raise RuntimeError(ref().ref_last_error().decode())
+        return out, sec.value
+
+    def intersect(self, rays, threads=1):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        prim = np.zeros(n, np.int32)
+        face = np.zeros(n, np.int32)
+        tuv = np.zeros((n, 3), np.float32)
+        geom = np.zeros((n, 11), np.float32)
+        sec = C.c_double()
+        ref().ref_intersect_batch(self.s, n, _p(rays), threads, _p(prim), _p(face), _p(tuv), _p(geom), C.byref(sec))
+        return dict(prim=prim, face=face, tuv=tuv, geom=geom, seconds=sec.value)

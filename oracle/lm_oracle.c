@@ -198,77 +198,82 @@ static int orc_bound_intersect(const orc_node* b, const float* o, const float* d
     return tmin < tMax && tmax > tMin;
 }
 
-/* rays: 8 floats (ox,oy,oz,tmin,dx,dy,dz,tmax); hits: t,u,v as floats + triangle index (-1 = miss).
- * use_bvh = 0: accel::naive's linear scan (accel_naive.cpp:92-124). Returns the hit count. */
+/* One ray: 8 floats (ox,oy,oz,tmin,dx,dy,dz,tmax) -> t,u,v and the triangle index (-1 = miss).
+ * use_bvh = 0: accel::naive's linear scan (accel_naive.cpp:92-124). */
+int orc_closest_one(const orc_scene* s, const float* r, int use_bvh, float* tuv, int32_t* tri)
+{
+    const float* o = r; const float* d = r + 4;
+    const float mint = r[3];
+    float maxt = r[7], bu = 0, bv = 0;
+    int32_t best = -1;
+    if (!use_bvh) {
+        uint64_t j;
+        for (j = 0; j < s->n; j++) {
+            float t, u, v;
+            if (orc_triaccel_intersect(&s->tris[j], o, d, mint, maxt, &u, &v, &t)) { maxt = t; bu = u; bv = v; best = (int32_t)j; }
+        }
+    } else if (s->n) {
+        int32_t stack[128]; int sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const orc_node* nd = &s->nodes[stack[--sp]];
+            /* Bound::Intersect compares strictly against [tMin,tMax]; the boxes are padded by 1e-4,
+             * so a triangle hit at exactly maxt still lies strictly inside its box's range. */
+            if (!orc_bound_intersect(nd, o, d, mint, maxt)) continue;
+            if (nd->count) {
+                int32_t k;
+                for (k = nd->first; k < nd->first + nd->count; k++) {
+                    const uint32_t id = s->order[k];
+                    float t, u, v;
+                    if (orc_triaccel_intersect(&s->tris[id], o, d, mint, maxt, &u, &v, &t)) {
+                        if (t < maxt || best < 0 || (int32_t)id > best) { maxt = t; bu = u; bv = v; best = (int32_t)id; }
+                    }
+                }
+            } else { stack[sp++] = nd->left; stack[sp++] = nd->right; }
+        }
+    }
+    if (best >= 0) { tuv[0] = maxt; tuv[1] = bu; tuv[2] = bv; }
+    else { tuv[0] = tuv[1] = tuv[2] = 0.0f; }
+    *tri = best;
+    return best >= 0;
+}
+
+/* Batch form; returns the hit count. */
 long long orc_closest(const orc_scene* s, const float* rays, long long n, int use_bvh, float* tuv, int32_t* tri)
 {
     long long hits = 0, i;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : hits)
-    for (i = 0; i < n; i++) {
-        const float* r = rays + 8 * i;
-        const float* o = r; const float* d = r + 4;
-        const float mint = r[3];
-        float maxt = r[7], bu = 0, bv = 0;
-        int32_t best = -1;
-        if (!use_bvh) {
-            uint64_t j;
-            for (j = 0; j < s->n; j++) {
-                float t, u, v;
-                if (orc_triaccel_intersect(&s->tris[j], o, d, mint, maxt, &u, &v, &t)) { maxt = t; bu = u; bv = v; best = (int32_t)j; }
-            }
-        } else if (s->n) {
-            int32_t stack[128]; int sp = 0;
-            stack[sp++] = 0;
-            while (sp) {
-                const orc_node* nd = &s->nodes[stack[--sp]];
-                /* Bound::Intersect compares strictly against [tMin,tMax]; the boxes are padded by 1e-4,
-                 * so a triangle hit at exactly maxt still lies strictly inside its box's range. */
-                if (!orc_bound_intersect(nd, o, d, mint, maxt)) continue;
-                if (nd->count) {
-                    int32_t k;
-                    for (k = nd->first; k < nd->first + nd->count; k++) {
-                        const uint32_t id = s->order[k];
-                        float t, u, v;
-                        if (orc_triaccel_intersect(&s->tris[id], o, d, mint, maxt, &u, &v, &t)) {
-                            if (t < maxt || best < 0 || (int32_t)id > best) { maxt = t; bu = u; bv = v; best = (int32_t)id; }
-                        }
-                    }
-                } else { stack[sp++] = nd->left; stack[sp++] = nd->right; }
-            }
-        }
-        if (best >= 0) { hits++; tuv[3 * i] = maxt; tuv[3 * i + 1] = bu; tuv[3 * i + 2] = bv; }
-        else { tuv[3 * i] = tuv[3 * i + 1] = tuv[3 * i + 2] = 0.0f; }
-        tri[i] = best;
-    }
+    for (i = 0; i < n; i++) hits += orc_closest_one(s, rays + 8 * i, use_bvh, tuv + 3 * i, tri + i);
     return hits;
 }
 
 /* Scene3::Visible's query (include/lightmetrica/scene3.h:107-116): any triangle within [tmin,tmax]. */
+int orc_any_one(const orc_scene* s, const float* r)
+{
+    int found = 0;
+    if (s->n) {
+        int32_t stack[128]; int sp = 0;
+        stack[sp++] = 0;
+        while (sp && !found) {
+            const orc_node* nd = &s->nodes[stack[--sp]];
+            if (!orc_bound_intersect(nd, r, r + 4, r[3], r[7])) continue;
+            if (nd->count) {
+                int32_t k;
+                for (k = nd->first; k < nd->first + nd->count && !found; k++) {
+                    float t, u, v;
+                    if (orc_triaccel_intersect(&s->tris[s->order[k]], r, r + 4, r[3], r[7], &u, &v, &t)) found = 1;
+                }
+            } else { stack[sp++] = nd->left; stack[sp++] = nd->right; }
+        }
+    }
+    return found;
+}
+
 long long orc_any(const orc_scene* s, const float* rays, long long n, uint8_t* occluded)
 {
     long long hits = 0, i;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : hits)
-    for (i = 0; i < n; i++) {
-        const float* r = rays + 8 * i;
-        int found = 0;
-        if (s->n) {
-            int32_t stack[128]; int sp = 0;
-            stack[sp++] = 0;
-            while (sp && !found) {
-                const orc_node* nd = &s->nodes[stack[--sp]];
-                if (!orc_bound_intersect(nd, r, r + 4, r[3], r[7])) continue;
-                if (nd->count) {
-                    int32_t k;
-                    for (k = nd->first; k < nd->first + nd->count && !found; k++) {
-                        float t, u, v;
-                        if (orc_triaccel_intersect(&s->tris[s->order[k]], r, r + 4, r[3], r[7], &u, &v, &t)) found = 1;
-                    }
-                } else { stack[sp++] = nd->left; stack[sp++] = nd->right; }
-            }
-        }
-        occluded[i] = (uint8_t)found;
-        hits += found;
-    }
+    for (i = 0; i < n; i++) { const int f = orc_any_one(s, rays + 8 * i); occluded[i] = (uint8_t)f; hits += f; }
     return hits;
 }
 

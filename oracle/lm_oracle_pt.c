@@ -1,0 +1,484 @@
+/*
+ * TEST INFRASTRUCTURE — CPU restatement ("oracle") of the reference's unidirectional path tracers
+ * renderer::pt and renderer::ptdirect and of the primary-ray normal renderer. Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this.
+ *
+ * It follows the reference's per-sample loop line by line (one sample = one call of the lambda
+ * handed to Scheduler::Process) but draws its random numbers from the counter-based generator
+ * the CUDA renderer uses (Philox4x32-10 keyed by seed, counter = (sample, block)), so the same
+ * sample index produces the same path on both sides up to libm-vs-CUDA ulp differences.
+ *
+ * Parity status: the estimator has no golden vectors in the reference (no renderer test exists,
+ * SURVEY.md §4). It is pinned STATISTICALLY against the reference itself (oracle/_ref running
+ * renderer::pt / renderer::ptdirect with dSFMT): tests/test_oracle_pt.py compares mean radiance
+ * and per-pixel images within the Monte-Carlo noise floor measured between two reference seeds,
+ * and tests/golden/pt_*.npz holds reference images rendered here for machines without
+ * /root/reference. Differences by design: exact sqrt-normalisation instead of the reference's
+ * 12-bit SSE rsqrt (math.h:1872-1875).
+ *
+ * Citations are paths under /root/reference.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+/* from lm_oracle.c */
+typedef struct orc_scene orc_scene;
+typedef struct { uint32_t k; float n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv; uint32_t faceIndex, primIndex; } orc_tri;
+orc_scene* orc_scene_create(const float* verts9, uint64_t ntris);
+void orc_scene_destroy(orc_scene* s);
+int orc_closest_one(const orc_scene* s, const float* ray, int use_bvh, float* tuv, int32_t* tri);
+int orc_any_one(const orc_scene* s, const float* ray);
+
+/* Same field layout as include/lmb200.h (restated here; the oracle does not include product headers). */
+typedef struct { int32_t type; float R[3], eta[3], k[3], roughness; } orc_bsdf;
+typedef struct { int32_t bsdf, light; uint32_t first_tri, num_tris; int32_t has_normals; } orc_prim;
+typedef struct { float Le[3]; int32_t primitive; } orc_light;
+typedef struct { float position[3], vx[3], vy[3], vz[3], fov; int32_t width, height; } orc_camera;
+typedef struct {
+    uint64_t num_tris; const float* verts; const float* normals; const uint32_t* tri_prim;
+    uint32_t num_prims; const orc_prim* prims;
+    uint32_t num_bsdfs; const orc_bsdf* bsdfs;
+    uint32_t num_lights; const orc_light* lights;
+    orc_camera camera;
+} orc_scene_desc;
+
+typedef struct {
+    orc_scene_desc d;
+    orc_scene* accel;
+    float** cdf;       /* per light: num_tris+1 entries (dist.h:37-60) */
+    float* inv_area;   /* per light */
+    float tan_fov, aspect;
+} orc_pt_scene;
+
+#define ORC_PI 3.14159265358979323846f
+#define ORC_INV_PI 0.31830988618379067154f
+#define ORC_EPS 1e-4f      /* Math::Eps(), math.h:1664 */
+#define ORC_EPS_ISECT 1e-4f
+
+typedef struct { float x, y, z; } v3;
+static v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 vmul(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
+static v3 vmulv(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
+static float vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static v3 vnorm(v3 a) { const float l = sqrtf(vdot(a, a)); return V(a.x / l, a.y / l, a.z / l); }
+static v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static int vblack(v3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }   /* SPD::Black, spectrum.h */
+static v3 ld3(const float* p) { return V(p[0], p[1], p[2]); }
+
+/* ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011) ---- */
+static void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    int r;
+    for (r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static void rng_block(uint64_t seed, uint64_t sample, uint32_t block, float u[4])
+{
+    uint32_t o[4]; int i;
+    philox4x32((uint32_t)sample, (uint32_t)(sample >> 32), block, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    for (i = 0; i < 4; i++) u[i] = (float)(o[i] >> 8) * (1.0f / 16777216.0f);
+}
+
+/* ---- surface geometry (include/lightmetrica/intersectionutils.h:59-135, subset used by the estimators) ---- */
+typedef struct { v3 p, gn, sn, dpdu, dpdv; int degenerated; } geom_t;
+
+static void basis(v3 a, v3* b, v3* c)   /* Math::OrthonormalBasis, math.h:2355-2360 */
+{
+    *c = fabsf(a.x) > fabsf(a.y) ? vnorm(V(a.z, 0.0f, -a.x)) : vnorm(V(0.0f, a.z, -a.y));
+    *b = vcross(*c, a);
+}
+static v3 to_local(const geom_t* g, v3 w) { return V(vdot(g->dpdu, w), vdot(g->dpdv, w), vdot(g->sn, w)); }
+static v3 to_world(const geom_t* g, v3 l) { return vadd(vadd(vmul(g->dpdu, l.x), vmul(g->dpdv, l.y)), vmul(g->sn, l.z)); }
+
+static void tri_geom(const orc_pt_scene* S, uint32_t tri, float b0, float b1, v3 p, geom_t* g)
+{
+    const float* v = S->d.verts + 9 * (size_t)tri;
+    const v3 p1 = ld3(v), p2 = ld3(v + 3), p3 = ld3(v + 6);
+    const orc_prim* P = &S->d.prims[S->d.tri_prim[tri]];
+    g->p = p;
+    g->degenerated = 0;
+    g->gn = vnorm(vcross(vsub(p2, p1), vsub(p3, p1)));
+    if (P->has_normals && S->d.normals) {
+        const float* n = S->d.normals + 9 * (size_t)tri;
+        g->sn = vnorm(vadd(vadd(vmul(ld3(n), 1.0f - b0 - b1), vmul(ld3(n + 3), b0)), vmul(ld3(n + 6), b1)));
+        if (isnan(g->sn.x) || isnan(g->sn.y) || isnan(g->sn.z)) g->sn = g->gn;
+    } else g->sn = g->gn;
+    basis(g->sn, &g->dpdu, &g->dpdv);
+}
+
+/* ---- sensor::pinhole (src/liblightmetrica/asset/sensor/sensor_pinhole.cpp) ---- */
+static int raster_position(const orc_pt_scene* S, v3 wo, float* rx, float* ry)   /* :165-185 */
+{
+    const orc_camera* c = &S->d.camera;
+    const v3 e = V(vdot(ld3(c->vx), wo), vdot(ld3(c->vy), wo), vdot(ld3(c->vz), wo));
+    if (e.z >= 0.0f) return 0;
+    *rx = (-e.x / e.z / S->tan_fov / S->aspect + 1.0f) * 0.5f;
+    *ry = (-e.y / e.z / S->tan_fov + 1.0f) * 0.5f;
+    if (*rx < 0.0f || *rx > 1.0f || *ry < 0.0f || *ry > 1.0f) return 0;
+    return 1;
+}
+static float importance(const orc_pt_scene* S, v3 wo)   /* :137-154 */
+{
+    const orc_camera* c = &S->d.camera;
+    float rx, ry;
+    if (!raster_position(S, wo, &rx, &ry)) return 0.0f;
+    {
+        const float cosT = -vdot(ld3(c->vz), wo), inv = 1.0f / cosT;
+        const float A = S->tan_fov * S->tan_fov * S->aspect * 4.0f;
+        return inv * inv * inv / A;
+    }
+}
+static v3 camera_dir(const orc_pt_scene* S, float u0, float u1)   /* :79-90 */
+{
+    const orc_camera* c = &S->d.camera;
+    const float x = 2.0f * u0 - 1.0f, y = 2.0f * u1 - 1.0f;
+    const v3 e = vnorm(V(S->aspect * S->tan_fov * x, S->tan_fov * y, -1.0f));
+    return vadd(vadd(vmul(ld3(c->vx), e.x), vmul(ld3(c->vy), e.y)), vmul(ld3(c->vz), e.z));
+}
+
+/* ---- BSDFs ---- */
+static float snc(const geom_t* g, v3 wi, v3 wo)   /* BSDFUtils::ShadingNormalCorrection, bsdfutils.h:55-66 (EL) */
+{
+    const float wiNg = vdot(wi, g->gn), woNg = vdot(wo, g->gn);
+    const float wiNs = to_local(g, wi).z, woNs = to_local(g, wo).z;
+    if (wiNg * wiNs <= 0.0f || woNg * woNs <= 0.0f) return 0.0f;
+    return 1.0f;
+}
+static void concentric_disk(float u0, float u1, float* sx, float* sy)   /* sampler.h:44-60 */
+{
+    const float vx = 2.0f * u0 - 1.0f, vy = 2.0f * u1 - 1.0f;
+    float r, theta;
+    if (vx == 0.0f && vy == 0.0f) { *sx = *sy = 0.0f; return; }
+    if (vx > -vy) {
+        if (vx > vy) { r = vx; theta = (ORC_PI * 0.25f) * vy / vx; }
+        else { r = vy; theta = (ORC_PI * 0.25f) * (2.0f - vx / vy); }
+    } else {
+        if (vx < vy) { r = -vx; theta = (ORC_PI * 0.25f) * (4.0f + vy / vx); }
+        else { r = -vy; theta = (ORC_PI * 0.25f) * (6.0f - vx / vy); }
+    }
+    *sx = r * cosf(theta); *sy = r * sinf(theta);
+}
+static float ggx_D(float alpha, v3 H)   /* bsdf_cooktorrance.cpp:187-198 */
+{
+    const float cosH = H.z;
+    float tanH, t1, t;
+    if (cosH <= 0.0f) return 0.0f;
+    {   /* Math::LocalTan (math.h): sqrt(1 - cos^2) / cos, with the sin^2 clamped at 0 */
+        const float c2 = cosH * cosH, s2 = 1.0f - c2;
+        tanH = s2 <= 0.0f ? 0.0f : sqrtf(s2) / cosH;
+    }
+    t1 = alpha * alpha;
+    t = alpha * alpha + tanH * tanH;
+    return t1 / (ORC_PI * cosH * cosH * cosH * cosH * t * t);
+}
+/* Sample wo (returns 0 if no direction is produced, in which case the reference leaves wo
+ * untouched (zero) and the pdf / fs evaluate to 0). */
+static int bsdf_sample(const orc_bsdf* B, const geom_t* g, v3 wi, float u0, float u1, v3* wo)
+{
+    const v3 lwi = to_local(g, wi);
+    if (lwi.z <= 0.0f) return 0;
+    if (B->type == 1) {            /* bsdf_diffuse.cpp:69-79 */
+        float sx, sy;
+        concentric_disk(u0, u1, &sx, &sy);
+        *wo = to_world(g, V(sx, sy, sqrtf(fmaxf(0.0f, 1.0f - sx * sx - sy * sy))));
+        return 1;
+    }
+    if (B->type == 2) {            /* bsdf_cooktorrance.cpp:73-89, 200-225 */
+        const float a = B->roughness;
+        const float v0 = (1.0f - ORC_EPS) * u0 + ORC_EPS;
+        const float v1 = (1.0f - 2.0f * ORC_EPS) * u1 + ORC_EPS;
+        const float den = sqrtf(1.0f - (1.0f - a * a) * v0);
+        const float cosT = sqrtf(1.0f - v0) / den, sinT = a * (sqrtf(v0) / den);
+        const float phi = ORC_PI * (2.0f * v1 - 1.0f);
+        const v3 H = V(sinT * cosf(phi), sinT * sinf(phi), cosT);
+        const v3 nwi = vneg(lwi);
+        const v3 lwo = vsub(nwi, vmul(H, 2.0f * vdot(nwi, H)));
+        if (lwo.z <= 0.0f) return 0;
+        *wo = to_world(g, lwo);
+        return 1;
+    }
+    return 0;
+}
+static float bsdf_pdf(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo)   /* projected solid angle */
+{
+    const v3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (lwi.z <= 0.0f || lwo.z <= 0.0f) return 0.0f;
+    if (B->type == 1) return ORC_INV_PI;   /* bsdf_diffuse.cpp:81-91 */
+    if (B->type == 2) {                    /* bsdf_cooktorrance.cpp:91-103 */
+        const v3 H = vnorm(vadd(lwi, lwo));
+        const float D = ggx_D(B->roughness, H);
+        return D * H.z / (4.0f * vdot(lwo, H)) / lwo.z;
+    }
+    return 0.0f;
+}
+static v3 bsdf_eval(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo)
+{
+    const v3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (lwi.z <= 0.0f || lwo.z <= 0.0f) return V(0, 0, 0);
+    if (B->type == 1) {                    /* bsdf_diffuse.cpp:93-104 */
+        return vmul(vmul(ld3(B->R), ORC_INV_PI), snc(g, wi, wo));
+    }
+    if (B->type == 2) {                    /* bsdf_cooktorrance.cpp:105-120, 276-293 */
+        const v3 H = vnorm(vadd(lwi, lwo));
+        const float D = ggx_D(B->roughness, H);
+        const float woH = fabsf(vdot(lwo, H));
+        /* sic: the reference uses wo.H for both terms (bsdf_cooktorrance.cpp:281-283) */
+        const float G = fminf(1.0f, fminf(2.0f * H.z * lwo.z / woH, 2.0f * H.z * lwi.z / woH));
+        const float c = vdot(lwi, H);
+        float F[3]; int i;
+        for (i = 0; i < 3; i++) {
+            const float eta = B->eta[i], k = B->k[i];
+            const float tmp = (eta * eta + k * k) * (c * c);
+            const float rP = (tmp - eta * (2.0f * c) + 1.0f) / (tmp + eta * (2.0f * c) + 1.0f);
+            const float tmpF = eta * eta + k * k;
+            const float rS = (tmpF - eta * (2.0f * c) + c * c) / (tmpF + eta * (2.0f * c) + c * c);
+            F[i] = (rP + rS) * 0.5f;
+        }
+        {
+            const float s = D * G / (4.0f * lwi.z) / lwo.z * snc(g, wi, wo);
+            return V(B->R[0] * F[0] * s, B->R[1] * F[1] * s, B->R[2] * F[2] * s);
+        }
+    }
+    return V(0, 0, 0);
+}
+
+/* ---- light::area (src/liblightmetrica/asset/light/light_area.cpp, include/lightmetrica/triangleutils.h) ---- */
+static void light_sample(const orc_pt_scene* S, int li, float u0, float u1, geom_t* g)   /* triangleutils.h:71-122 */
+{
+    const orc_light* L = &S->d.lights[li];
+    const orc_prim* P = &S->d.prims[L->primitive];
+    const float* cdf = S->cdf[li];
+    const int n = (int)P->num_tris;
+    int lo = 0, hi = n + 1, i;
+    float u2x, s, bx, by;
+    /* upper_bound(cdf, cdf+n+1, u0) - 1, clamped to [0, n-1] (dist.h:70-76) */
+    while (lo < hi) { const int mid = (lo + hi) / 2; if (u0 < cdf[mid]) hi = mid; else lo = mid + 1; }
+    i = lo - 1; if (i < 0) i = 0; if (i > n - 1) i = n - 1;
+    u2x = (u0 - cdf[i]) / (cdf[i + 1] - cdf[i]);
+    s = sqrtf(fmaxf(0.0f, u2x)); bx = 1.0f - s; by = u1 * s;    /* sampler.h:97-101 */
+    {
+        const float* v = S->d.verts + 9 * (size_t)(P->first_tri + (uint32_t)i);
+        const v3 p1 = ld3(v), p2 = ld3(v + 3), p3 = ld3(v + 6);
+        g->p = vadd(vadd(vmul(p1, 1.0f - bx - by), vmul(p2, bx)), vmul(p3, by));
+        g->degenerated = 0;
+        g->gn = vnorm(vcross(vsub(p2, p1), vsub(p3, p1)));
+        g->sn = g->gn;
+        basis(g->sn, &g->dpdu, &g->dpdv);
+    }
+}
+
+static int visible(const orc_pt_scene* S, v3 p1, v3 p2)   /* Scene3::Visible, scene3.h:107-116 */
+{
+    const v3 d = vsub(p2, p1);
+    const float L = sqrtf(vdot(d, d));
+    float ray[8];
+    ray[0] = p1.x; ray[1] = p1.y; ray[2] = p1.z; ray[3] = ORC_EPS_ISECT;
+    ray[4] = d.x / L; ray[5] = d.y / L; ray[6] = d.z / L; ray[7] = L * (1.0f - ORC_EPS_ISECT);
+    return !orc_any_one(S->accel, ray);
+}
+
+static void splat(const orc_pt_scene* S, float* film, float rx, float ry, v3 c)   /* film_hdr.cpp:218-223 */
+{
+    const int W = S->d.camera.width, H = S->d.camera.height;
+    int px = (int)(rx * (float)W), py = (int)(ry * (float)H);
+    float* f;
+    if (px < 0) px = 0; if (px > W - 1) px = W - 1;
+    if (py < 0) py = 0; if (py > H - 1) py = H - 1;
+    f = film + 4 * ((size_t)py * W + px);
+    f[0] += c.x; f[1] += c.y; f[2] += c.z;
+}
+
+/* One sample of renderer::pt (mode 0, renderer_pt.cpp:68-231) or renderer::ptdirect (mode 1,
+ * renderer_ptdirect.cpp:76-282). RNG blocks: 0 = camera (x1,x2 = raster sample); iteration `it`
+ * (= numVertices at loop top) uses block 2it-1 = (light pick, light u0, light u1, RR) and block
+ * 2it = (bsdf u0, bsdf u1, component, -). */
+static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed, uint64_t sample,
+                        float* film, int64_t* n_extend, int64_t* n_shadow)
+{
+    float u[4], rx = 0.0f, ry = 0.0f;
+    v3 init_wo, thr = V(1, 1, 1), wi = V(0, 0, 0);
+    geom_t geom;
+    int is_sensor = 1, num_verts = 1;
+    const orc_bsdf* bsdf = NULL;
+    rng_block(seed, sample, 0u, u);
+    init_wo = camera_dir(S, u[1], u[2]);
+    memset(&geom, 0, sizeof(geom));
+    geom.degenerated = 1; geom.p = ld3(S->d.camera.position);
+    if (mode == 0 && !raster_position(S, init_wo, &rx, &ry)) return;      /* renderer_pt.cpp:94-99 */
+
+    for (;;) {
+        float ua[4], ub[4];
+        v3 wo, fs;
+        float pdfD;
+        if (max_verts != -1 && num_verts >= max_verts) break;
+        rng_block(seed, sample, (uint32_t)(2 * num_verts - 1), ua);
+        rng_block(seed, sample, (uint32_t)(2 * num_verts), ub);
+
+        if (mode == 1 && S->d.num_lights > 0) {   /* direct light sampling, renderer_ptdirect.cpp:123-177 */
+            const int nL = (int)S->d.num_lights;
+            int li = (int)(ua[0] * (float)nL);
+            geom_t gL;
+            v3 ppL, fsE, fsL, C, d;
+            float pdfL, pdfPL, G, d2, dl;
+            if (li < 0) li = 0; if (li > nL - 1) li = nL - 1;                       /* scene3.cpp:508-513 */
+            pdfL = 1.0f / (float)nL;                                                 /* scene3.cpp:526-530 */
+            light_sample(S, li, ua[1], ua[2], &gL);
+            pdfPL = S->inv_area[li];                                                 /* light_area.cpp:100-103 */
+            ppL = vnorm(vsub(gL.p, geom.p));
+            if (is_sensor) { const float im = importance(S, ppL); fsE = V(im, im, im); }
+            else fsE = bsdf_eval(bsdf, &geom, wi, ppL);
+            fsL = to_local(&gL, vneg(ppL)).z <= 0.0f ? V(0, 0, 0) : ld3(S->d.lights[li].Le);   /* light_area.cpp:105-110 */
+            d = vsub(gL.p, geom.p); d2 = vdot(d, d); dl = sqrtf(d2); d = V(d.x / dl, d.y / dl, d.z / dl);   /* renderutils.h:46-56 */
+            G = 1.0f;
+            if (!geom.degenerated) G *= fabsf(vdot(geom.sn, d));
+            G *= fabsf(vdot(gL.sn, vneg(d)));
+            G = G / d2;
+            C = vmul(vmulv(vmulv(thr, fsE), fsL), G);
+            if (!vblack(C)) {
+                /* V is evaluated unconditionally by the reference; skipping it for black C does not change the film */
+                (*n_shadow)++;
+                if (visible(S, geom.p, gL.p)) {
+                    float prx = rx, pry = ry;
+                    C = vmul(C, 1.0f / pdfL / pdfPL);
+                    C = V(C.x, C.y, C.z);
+                    if (is_sensor) raster_position(S, ppL, &prx, &pry);              /* renderer_ptdirect.cpp:165-170 */
+                    splat(S, film, prx, pry, C);
+                }
+            }
+        }
+
+        if (is_sensor) wo = init_wo;
+        else { wo = V(0, 0, 0); bsdf_sample(bsdf, &geom, wi, ub[0], ub[1], &wo); }
+        pdfD = is_sensor ? importance(S, wo) : bsdf_pdf(bsdf, &geom, wi, wo);
+        if (mode == 1 && is_sensor) { if (!raster_position(S, wo, &rx, &ry)) break; }   /* renderer_ptdirect.cpp:200-208 */
+        if (is_sensor) { const float im = importance(S, wo); fs = V(im, im, im); }
+        else fs = bsdf_eval(bsdf, &geom, wi, wo);
+        if (vblack(fs)) break;
+        thr = vmulv(thr, V(fs.x / pdfD, fs.y / pdfD, fs.z / pdfD));
+
+        {   /* intersection, scene3.cpp:458-478 */
+            float ray[8], tuv[3]; int32_t tri;
+            const orc_prim* P;
+            v3 hp;
+            ray[0] = geom.p.x; ray[1] = geom.p.y; ray[2] = geom.p.z; ray[3] = ORC_EPS_ISECT;
+            ray[4] = wo.x; ray[5] = wo.y; ray[6] = wo.z; ray[7] = FLT_MAX;
+            (*n_extend)++;
+            orc_closest_one(S->accel, ray, 1, tuv, &tri);
+            if (tri < 0) break;
+            hp = vadd(geom.p, vmul(wo, tuv[0]));
+            P = &S->d.prims[S->d.tri_prim[tri]];
+            tri_geom(S, (uint32_t)tri, tuv[1], tuv[2], hp, &geom);
+            if (mode == 0 && P->light >= 0 && num_verts + 1 >= min_verts) {          /* renderer_pt.cpp:183-194 */
+                if (to_local(&geom, vneg(wo)).z > 0.0f) splat(S, film, rx, ry, vmulv(thr, ld3(S->d.lights[P->light].Le)));
+            }
+            if (ua[3] > 0.5f) break;                                                 /* renderer_pt.cpp:207-215 */
+            thr = V(thr.x / 0.5f, thr.y / 0.5f, thr.z / 0.5f);
+            bsdf = &S->d.bsdfs[P->bsdf];
+            is_sensor = 0;
+            wi = vneg(wo);
+            num_verts++;
+        }
+    }
+}
+
+orc_pt_scene* orc_pt_scene_create(const orc_scene_desc* d)
+{
+    orc_pt_scene* S = (orc_pt_scene*)calloc(1, sizeof(orc_pt_scene));
+    uint32_t li;
+    S->d = *d;
+    S->accel = orc_scene_create(d->verts, d->num_tris);
+    S->tan_fov = tanf(d->camera.fov * 0.5f);
+    S->aspect = (float)d->camera.width / (float)d->camera.height;
+    S->cdf = (float**)calloc(d->num_lights ? d->num_lights : 1, sizeof(float*));
+    S->inv_area = (float*)calloc(d->num_lights ? d->num_lights : 1, sizeof(float));
+    for (li = 0; li < d->num_lights; li++) {     /* TriangleUtils::CreateTriangleAreaDist, triangleutils.h:47-68 */
+        const orc_prim* P = &d->prims[d->lights[li].primitive];
+        float* cdf = (float*)malloc(sizeof(float) * (P->num_tris + 1));
+        float sum = 0.0f, inv;
+        uint32_t i;
+        cdf[0] = 0.0f;
+        for (i = 0; i < P->num_tris; i++) {
+            const float* v = d->verts + 9 * (size_t)(P->first_tri + i);
+            const v3 c = vcross(vsub(ld3(v + 3), ld3(v)), vsub(ld3(v + 6), ld3(v)));
+            const float area = sqrtf((c.x * c.x + c.y * c.y) + (c.z * c.z + 0.0f)) * 0.5f;   /* _mm_dp_ps order */
+            cdf[i + 1] = cdf[i] + area;
+            sum += area;
+        }
+        inv = 1.0f / cdf[P->num_tris];
+        for (i = 0; i <= P->num_tris; i++) cdf[i] *= inv;
+        S->cdf[li] = cdf;
+        S->inv_area[li] = 1.0f / sum;
+    }
+    return S;
+}
+
+void orc_pt_scene_destroy(orc_pt_scene* S)
+{
+    uint32_t li;
+    if (!S) return;
+    for (li = 0; li < S->d.num_lights; li++) free(S->cdf[li]);
+    free(S->cdf); free(S->inv_area);
+    orc_scene_destroy(S->accel);
+    free(S);
+}
+
+/* Renders global sample indices [begin,end) of a num_samples job into film (W*H*4 floats, zeroed by
+ * the caller), UNSCALED; threads accumulate into private films that are summed at the end, as
+ * Scheduler_::Process does (scheduler.cpp:157-164, 280-285). counts[0]=extend rays, [1]=shadow rays. */
+void orc_pt_render(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
+                   int64_t begin, int64_t end, float* film, int64_t* counts)
+{
+    const size_t npx = (size_t)S->d.camera.width * S->d.camera.height;
+    int64_t ne = 0, ns = 0;
+#pragma omp parallel reduction(+ : ne, ns)
+    {
+        float* local = (float*)calloc(npx * 4, sizeof(float));
+        int64_t i;
+        size_t k;
+#pragma omp for schedule(dynamic, 4096)
+        for (i = begin; i < end; i++) sample_path(S, mode, max_verts, min_verts, seed, (uint64_t)i, local, &ne, &ns);
+#pragma omp critical
+        for (k = 0; k < npx * 4; k++) film[k] += local[k];
+        free(local);
+    }
+    if (counts) { counts[0] = ne; counts[1] = ns; }
+}
+
+/* Primary-ray normal renderer: pixel-centre rays as renderer_raycast.cpp:72-105 generates them,
+ * shaded abs(sn) as plugin/renderer_normal/renderer_normal.cpp:62-75 intends. film: W*H*4. */
+void orc_render_normal(const orc_pt_scene* S, float* film, int32_t* tri_out)
+{
+    const int W = S->d.camera.width, H = S->d.camera.height;
+    int y;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (y = 0; y < H; y++) {
+        int x;
+        for (x = 0; x < W; x++) {
+            const v3 wo = camera_dir(S, ((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+            float ray[8], tuv[3]; int32_t tri;
+            float* f = film + 4 * ((size_t)y * W + x);
+            ray[0] = S->d.camera.position[0]; ray[1] = S->d.camera.position[1]; ray[2] = S->d.camera.position[2]; ray[3] = ORC_EPS_ISECT;
+            ray[4] = wo.x; ray[5] = wo.y; ray[6] = wo.z; ray[7] = FLT_MAX;
+            orc_closest_one(S->accel, ray, 1, tuv, &tri);
+            if (tri_out) tri_out[(size_t)y * W + x] = tri;
+            if (tri < 0) { f[0] = f[1] = f[2] = 0.0f; continue; }
+            {
+                geom_t g;
+                tri_geom(S, (uint32_t)tri, tuv[1], tuv[2], V(0, 0, 0), &g);
+                f[0] = fabsf(g.sn.x); f[1] = fabsf(g.sn.y); f[2] = fabsf(g.sn.z);
+            }
+        }
+    }
+}
