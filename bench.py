@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the lmb200 hot path (see DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[3]): incoherent closest-hit ray casting, 64 Mi random rays against a
+4 M-triangle synthetic soup BVH, per GPU (weak scaling: every rank traces its own batch, BVH replicated,
+no data-path collective). One "step" = one pass of lmb200_trace_closest over the whole batch.
+
+  value     Mrays/s, device-resident rays/hits, CUDA events on the launching stream, max over ranks
+  e2e       Mrays/s through the host-buffer C-ABI call (pinned host rays in, hits out, copies inside)
+  roofline  algorithmic bytes per ray (48 + nodes/ray*80 + tris/ray*48, counted by the instrumented
+            kernel) * rays / kernel time, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the CPU oracle on a bounded ray sample of the same scene (rank 0, N=1 only)
+  path_tracing  secondary figure: wavefront ptdirect Msamples/s on the 1 M-triangle scene of
+                configs[2] at reduced spp, films summed over ranks with one NCCL reduce
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: accel::qbvh through the
+real Accel3::Intersect, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "lightmetrica-v2_b200"))
+
+METRIC = "Mrays/s incoherent closest-hit (64Mi random rays vs 4M-tri synthetic BVH, per-GPU batch)"
+UNIT = "Mrays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lmb200", choices=["lmb200", "reference"])
+    ap.add_argument("--tris", type=int, default=4_000_000)
+    ap.add_argument("--rays", type=int, default=64 * 1024 * 1024)
+    ap.add_argument("--cpu-rays", type=int, default=1_000_000, help="bounded CPU sample")
+    ap.add_argument("--no-pt", action="store_true", help="skip the secondary path-tracing figure")
+    ap.add_argument("--pt-tris", type=int, default=1_000_000)
+    ap.add_argument("--pt-spp", type=int, default=16)
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {"workload": "configs[3] incoherent ray-cast microbench", "triangles": a.tris, "rays_per_gpu": a.rays,
+            "scene": "soup: centres U[0,100]^3, edge 0.2, seed 42", "ray_seed": 7,
+            "l2": "inputs (rays 32 B + hits 16 B per ray = %.1f GB) exceed the 126 MB L2; no explicit flush" % (a.rays * 48 / 1e9)}
+
+
+def gen_rays_device(torch, n, lo, hi, seed, device):
+    """Same recipe as scenes.random_rays (origins uniform in the AABB, directions uniform on the sphere), on the GPU."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rays = torch.empty((n, 8), dtype=torch.float32, device=device)
+    lo_t = torch.tensor(lo, device=device)
+    hi_t = torch.tensor(hi, device=device)
+    chunk = 1 << 24
+    for b in range(0, n, chunk):
+        m = min(chunk, n - b)
+        u = torch.rand((m, 5), generator=g, device=device, dtype=torch.float32)
+        r = rays[b:b + m]
+        r[:, 0:3] = lo_t + u[:, 0:3] * (hi_t - lo_t)
+        z = 1 - 2 * u[:, 3]
+        rad = torch.sqrt(torch.clamp(1 - z * z, min=0))
+        phi = 2 * np.pi * u[:, 4]
+        r[:, 4] = rad * torch.cos(phi)
+        r[:, 5] = rad * torch.sin(phi)
+        r[:, 6] = z
+        r[:, 3] = 1e-4
+        r[:, 7] = 3.4028234663852886e38
+    return rays
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.strip().split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_baseline(verts, rays_host, n):
+    """The C oracle (kind "port") on a bounded ray sample, all host threads (OpenMP)."""
+    from oracle import bindings as ob
+    P = ob.PortScene(verts)
+    sample = np.ascontiguousarray(rays_host[:n])
+    t0 = time.perf_counter()
+    tuv, tri = P.closest(sample)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt / 1e6, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"first {n} rays of the batch on the same 4M-tri scene, oracle/lm_oracle.c (OpenMP), {dt:.1f} s"}, tuv, tri
+
+
+def run_reference(a):
+    """--impl reference: the reference's own accel::qbvh through Accel3::Intersect on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import bindings as ob
+    from lmb200py import scenes
+    cfg = workload_config(a)
+    cores = os.cpu_count() or 1
+    verts = scenes.soup(a.tris, seed=42, extent=100.0, edge=0.2)
+    lo, hi = scenes.bounds(verts)
+    n = max(50_000, a.cpu_rays // 4)
+    if ob.have_ref():
+        t0 = time.perf_counter()
+        R = ob.RefSoup(verts, "qbvh")
+        build_s = time.perf_counter() - t0
+        kind = "reference"
+
+        def step(k):
+            rays = scenes.random_rays(n, lo, hi, seed=7 + k)
+            r = R.intersect(rays, threads=cores)
+            return r["seconds"]
+        sample = f"{n} rays per step, accel::qbvh via Accel3::Intersect (oracle/_ref), build {build_s:.0f} s not timed"
+    else:
+        P = ob.PortScene(verts)
+        kind = "port"
+
+        def step(k):
+            rays = scenes.random_rays(n, lo, hi, seed=7 + k)
+            t0 = time.perf_counter()
+            P.closest(rays)
+            return time.perf_counter() - t0
+        sample = f"{n} rays per step, oracle/lm_oracle.c (OpenMP); oracle/_ref not present"
+    for k in range(a.warmup):
+        step(k)
+    times = [step(a.warmup + k) for k in range(a.steps)]
+    total = sum(times)
+    value = n * a.steps / total / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    from lmb200py import capi, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: lmb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = capi.lib()
+    launches0 = L.lmb200_launch_count()
+
+    # ---- scene + BVH (replicated per rank) ----
+    verts = scenes.soup(a.tris, seed=42, extent=100.0, edge=0.2)
+    lo, hi = scenes.bounds(verts)
+    accel = capi.Accel(local)
+    bst = accel.build(verts)
+
+    # ---- rays: generated on the device, mirrored once into pinned host memory for the e2e leg ----
+    d_rays = gen_rays_device(torch, a.rays, lo.tolist(), hi.tolist(), 7 + rank, dev)
+    d_hits = torch.empty((a.rays, 4), dtype=torch.float32, device=dev)
+    h_rays = torch.empty((a.rays, 8), dtype=torch.float32, pin_memory=True)
+    h_rays.copy_(d_rays)
+    h_hits = torch.empty((a.rays, 4), dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        capi.check(L.lmb200_trace_closest_dev(accel.h, d_rays.data_ptr(), d_hits.data_ptr(), a.rays, stream))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step_dev()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    ev[0].record()
+    for k in range(a.steps):
+        step_dev()
+        ev[k + 1].record()
+    barrier()
+    clock_info = clocks.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = a.rays * world * a.steps / (max_ms * 1e-3) / 1e6
+
+    # ---- e2e: host-buffer C-ABI call, pinned rays in / hits out, copies inside the timed region ----
+    def step_e2e():
+        capi.check(L.lmb200_trace_closest(accel.h, h_rays.data_ptr(), h_hits.data_ptr(), a.rays))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(a.steps, 3))
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = a.rays * world * e2e_steps / float(t.item()) / 1e6
+
+    # ---- roofline of the traversal kernel ----
+    npr, tpr = C.c_double(), C.c_double()
+    ncount = min(a.rays, 1 << 22)
+    capi.check(L.lmb200_trace_count_dev(accel.h, d_rays.data_ptr(), ncount, C.byref(npr), C.byref(tpr)))
+    b_ray = 48.0 + npr.value * 80.0 + tpr.value * 48.0
+    mean_kernel_s = float(np.mean(kernel_ms)) * 1e-3
+    achieved = b_ray * a.rays / mean_kernel_s / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("trace_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- parity spot check + CPU baseline (rank 0, N=1) ----
+    cpu = None
+    parity = None
+    if rank == 0:
+        n_chk = min(a.cpu_rays, a.rays) if world == 1 else min(100_000, a.rays)
+        step_dev()
+        torch.cuda.synchronize()
+        hits = d_hits[:n_chk].cpu().numpy()
+        base, tuv, tri = cpu_port_baseline(verts, h_rays.numpy(), n_chk)
+        gtri = hits[:, 3].view(np.uint32).astype(np.int64)
+        gtri[gtri == capi.MISS] = -1
+        parity = {"rays_checked": int(n_chk), "index_mismatches": int(np.count_nonzero(gtri != tri)),
+                  "tuv_bit_mismatches": int(np.count_nonzero(hits[:, :3].view(np.uint32) != tuv.view(np.uint32)))}
+        if world == 1:
+            cpu = base
+
+    # ---- secondary: path-traced samples/s on the configs[2] scene (reduced spp), NCCL film reduce ----
+    pt = None
+    if not a.no_pt:
+        pt = bench_pt(a, torch, dist, capi, world, rank, local, dev)
+
+    launches = int(L.lmb200_launch_count() - launches0)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(a),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.rays * 32, "d2h_bytes_per_step": a.rays * 16,
+                        "api": "lmb200_trace_closest(host pinned rays -> host pinned hits)"},
+                "gpu_launches": launches, "clocks": clock_info,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": npr.value, "tris_per_ray": tpr.value,
+                             "kernel": "lmb200::trace_kernel<false,false>", "kernel_ms": mean_kernel_s * 1e3},
+                "cpu_baseline": cpu, "parity": parity,
+                "bvh": {"nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
+                "path_tracing": pt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_pt(a, torch, dist, capi, world, rank, local, dev):
+    """ptdirect on the 1M-triangle mesh scene (BASELINE configs[2] geometry/materials/lights) at pt_spp samples per pixel,
+    sample range sharded contiguously over ranks, films summed with one NCCL reduce, then rescaled."""
+    from lmb200py import scenedesc, scenes
+    sc = scenedesc.config2_scene(a.pt_tris, 1920, 1080)
+    S = capi.Scene(sc, device=local)
+    W, H = 1920, 1080
+    N = W * H * a.pt_spp
+    film = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    L = capi.lib()
+    b, e = N * rank // world, N * (rank + 1) // world
+    st = capi.RenderStats()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def once():
+        film.zero_()
+        p = S.params(capi.MODE_PTDIRECT, N, seed=1, begin=b, end=e)
+        capi.check(L.lmb200_render_dev(S.h_, C.byref(p), film.data_ptr(), stream, C.byref(st)))
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        capi.check(L.lmb200_film_rescale_dev(film.data_ptr(), W * H, float(W * H) / float(N), stream))
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 2
+    for _ in range(reps):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    rays = torch.tensor([st.extend_rays + st.shadow_rays], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    S.close()
+    return {"metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene", "value": N / (float(ms.item()) * 1e-3) / 1e6,
+            "unit": "Msamples/s", "spp": a.pt_spp, "samples": N, "ms": float(ms.item()), "rays_per_sample": float(rays.item()) / N,
+            "mrays_per_s": float(rays.item()) / (float(ms.item()) * 1e-3) / 1e6, "film_reduce": "torch.distributed NCCL reduce" if world > 1 else "none (1 GPU)",
+            "mean_rgb": [float(x) for x in film[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None}
+
+
+if __name__ == "__main__":
+    main()

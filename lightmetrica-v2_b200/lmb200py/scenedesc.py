@@ -95,6 +95,7 @@ class Scene:
         lights, verts, norms, tri_prim = [], [], [], []
         any_normals = any(self.meshes[nd["mesh"]]["normals"] is not None for nd in self.nodes)
         first = 0
+        first_prim_of_light = {}
         for pi, nd in enumerate(self.nodes, start=1):
             m = self.meshes[nd["mesh"]]
             t = m["verts"][m["faces"].reshape(-1)].reshape(-1, 9)
@@ -108,8 +109,12 @@ class Scene:
             prims[pi].num_tris = t.shape[0]
             prims[pi].has_normals = 1 if m["normals"] is not None else 0
             if nd["light"]:
+                # A light asset is loaded once, with the FIRST primitive that references it
+                # (assets.cpp:50-122 caches by id; light_area.cpp:50-55 binds mesh/transform/area
+                # distribution at Load): later primitives sharing the asset sample the first one's mesh.
+                bound = first_prim_of_light.setdefault(nd["light"], pi)
                 prims[pi].light = len(lights)
-                lights.append((self.lights[nd["light"]], pi))
+                lights.append((self.lights[nd["light"]], bound))
             first += t.shape[0]
         verts = np.ascontiguousarray(np.concatenate(verts), np.float32) if verts else np.zeros((0, 9), np.float32)
         tri_prim = np.ascontiguousarray(np.concatenate(tri_prim), np.uint32) if tri_prim else np.zeros(0, np.uint32)
@@ -179,4 +184,38 @@ def cornell_box(w=512, h=512, glossy_block=False):
     _box(s, (0.4, 0.3, 0.3), (0.3, 0.3, 0.3), -17.0, "metal" if glossy_block else "white")   # short block
     s.add_quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), "white", "lamp")  # light, faces down
     s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h)
+    return s
+
+
+def config2_scene(target_tris=1_000_000, w=1920, h=1080, seed=42, half=50.0, n_objects=200, n_lights=6):
+    """BASELINE.json configs[2]: ground + ~200 tessellated objects (about target_tris triangles) in
+    [-half,half]^3, 70 % diffuse (R uniform in [0.2,0.8]^3) / 30 % cook_torrance (roughness in
+    {0.05,0.1,0.3}, default eta/k), n_lights area-light quads facing down."""
+    g = np.random.Generator(np.random.Philox(seed + 1000))
+    verts, oid = scenes.mesh_scene(target_tris, seed=seed, half=half, n_objects=n_objects)
+    s = Scene()
+    n_pal = 24
+    for i in range(n_pal):
+        if i % 10 < 7:
+            s.add_bsdf(f"m{i}", "diffuse", tuple(0.2 + 0.6 * g.random(3)))
+        else:
+            s.add_bsdf(f"m{i}", "cook_torrance", (1.0, 1.0, 1.0), roughness=[0.05, 0.1, 0.3][i % 3])
+    s.add_bsdf("ground", "diffuse", (0.6, 0.6, 0.6))
+    s.add_bsdf("lampb", "diffuse", (0.8, 0.8, 0.8))
+    for k in range(n_lights):
+        s.add_light(f"lamp{k}", (60.0, 55.0, 45.0))   # one asset per light primitive (see Scene.flatten)
+    # objects are contiguous in oid
+    bounds_idx = np.flatnonzero(np.diff(oid)) + 1
+    starts = np.concatenate([[0], bounds_idx])
+    ends = np.concatenate([bounds_idx, [len(oid)]])
+    for k, (b, e) in enumerate(zip(starts, ends)):
+        s.add_mesh_tris(verts[b:e], "ground" if oid[b] == 0 else f"m{int(g.integers(n_pal))}")
+    for k in range(n_lights):
+        cx = (k % 3 - 1) * half * 0.6
+        cz = (k // 3 - 0.5) * half * 0.8
+        y = half * 0.75
+        r = half * 0.08
+        # faces down: (b-a)x(c-a) = -y
+        s.add_quad((cx - r, y, cz - r), (cx + r, y, cz - r), (cx + r, y, cz + r), (cx - r, y, cz + r), "lampb", f"lamp{k}")
+    s.set_camera((0.0, half * 0.45, half * 1.05), (0.0, half * 0.1, 0.0), (0, 1, 0), 45.0, w, h)
     return s

@@ -53,7 +53,8 @@ def torus(center, R, r, nu, nv, tilt=0.0):
     z = (R + r * np.cos(V)) * np.sin(U)
     ct, st = np.cos(tilt), np.sin(tilt)
     P = np.stack([x, ct * y - st * z, st * y + ct * z], axis=-1) + np.asarray(center)
-    return _grid_tris(P.astype(np.float32))
+    t = _grid_tris(P.astype(np.float32))
+    return t[:, [0, 1, 2, 6, 7, 8, 3, 4, 5]]   # wind so that normals point out of the tube
 
 
 def ground(half, n, seed, amp=1.0):

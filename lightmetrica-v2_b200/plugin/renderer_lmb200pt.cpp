@@ -1,0 +1,301 @@
+// renderer::lmb200pt — Lightmetrica v2 plugin that drops in for renderer::pt / renderer::ptdirect
+// (/root/reference/src/liblightmetrica/renderer/renderer_pt.cpp, renderer_ptdirect.cpp) and, with
+// mode "normal", for the primary-ray renderers (renderer_raycast.cpp, plugin/renderer_normal).
+// Selected from the scene YAML with
+//     renderer: {type: lmb200pt, params: {mode: ptdirect, num_samples: ..., max_num_vertices: -1,
+//                                         min_num_vertices: 0, num_gpus: 1, device: 0, pool_size: 0}}
+// It reads the scene through the reference's interfaces (Scene3::PrimitiveAt, TriangleMesh::*,
+// BSDF::Reflectance/Glossiness, Light::Emittance, Sensor::GetFilm/GetProjectionMatrix), flattens
+// it into the POD arrays of include/lmb200.h and calls liblmb200.so; the film comes back through
+// Film::SetPixel and is written with Film::Save, exactly where the reference renderers save
+// (renderer_pt.cpp:236-241). Scenes using assets outside the supported set (delta BSDFs, textures,
+// point/directional/env lights, non-pinhole sensors) are rejected with an error, never mis-rendered.
+#include <lightmetrica/lightmetrica.h>
+#include <vector>
+#include <map>
+#include <cstring>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include "lmb200.h"
+#include "flatten.h"
+
+LM_NAMESPACE_BEGIN
+
+class Renderer_LMB200PT final : public Renderer
+{
+public:
+
+    LM_IMPL_CLASS(Renderer_LMB200PT, Renderer);
+
+public:
+
+    // prop may be nullptr (main.cpp:767)
+    LM_IMPL_F(Initialize) = [this](const PropertyNode* prop) -> bool
+    {
+        prop_ = prop;
+        std::string mode = "ptdirect";
+        if (prop)
+        {
+            if (prop->Child("mode")) mode = prop->ChildAs<std::string>("mode", "ptdirect");
+            // same keys and defaults as Scheduler_::Load (scheduler.cpp:44-58) and renderer_pt.cpp:56-62
+            numSamples_ = prop->ChildAs<long long>("num_samples", 10000000L);
+            maxNumVertices_ = prop->ChildAs<int>("max_num_vertices", -1);
+            minNumVertices_ = prop->ChildAs<int>("min_num_vertices", 0);
+            if (prop->Child("num_gpus")) numGpus_ = prop->ChildAs<int>("num_gpus", 1);
+            if (prop->Child("device")) device_ = prop->ChildAs<int>("device", 0);
+            if (prop->Child("pool_size")) poolSize_ = prop->ChildAs<int>("pool_size", 0);
+        }
+        if (mode == "pt") mode_ = LMB200_MODE_PT;
+        else if (mode == "ptdirect") mode_ = LMB200_MODE_PTDIRECT;
+        else if (mode == "normal") mode_ = LMB200_MODE_NORMAL;
+        else { LM_LOG_ERROR("renderer::lmb200pt: unknown mode '" + mode + "' (pt | ptdirect | normal)"); return false; }
+        if (numGpus_ < 1) numGpus_ = 1;
+        if (lmb200_device_count() < device_ + numGpus_ && !std::getenv("LMB200_DUMP_SCENE"))
+        {
+            LM_LOG_ERROR("renderer::lmb200pt: needs " + std::to_string(numGpus_) + " CUDA device(s) starting at " + std::to_string(device_) +
+                         ", found " + std::to_string(lmb200_device_count()) + " (there is no CPU fallback)");
+            return false;
+        }
+        return true;
+    };
+
+    LM_IMPL_F(Render) = [this](const Scene* scene_, Random* initRng, const std::string& outputPath) -> void
+    {
+        const auto* scene = static_cast<const Scene3*>(scene_);
+        const auto* sensorPrim = scene->GetSensor();
+        auto* film = static_cast<const Sensor*>(sensorPrim->emitter)->GetFilm();   // renderer_pt.cpp:67
+
+        // ---- flatten geometry ----
+        std::vector<float> verts, normals;
+        std::vector<uint32_t> primOfTri, faceOfTri;
+        std::vector<lmb200_primitive> prims;
+        lmb200plugin::FlattenTriangles(scene, verts, &normals, primOfTri, faceOfTri, &prims);
+        bool anyNormals = false;
+        for (const auto& p : prims) anyNormals = anyNormals || p.has_normals;
+
+        // ---- materials and lights through the reference interfaces ----
+        std::vector<lmb200_bsdf> bsdfs;
+        std::vector<lmb200_light> lights;
+        std::map<const BSDF*, int> bsdfIndex;
+        std::map<const Light*, int> lightBound;
+        const int np = scene->NumPrimitives();
+        for (int i = 0; i < np; i++)
+        {
+            const auto* prim = scene->PrimitiveAt(i);
+            int bi = -1;
+            if (prim->bsdf)
+            {
+                auto it = bsdfIndex.find(prim->bsdf);
+                if (it != bsdfIndex.end()) bi = it->second;
+                else
+                {
+                    lmb200_bsdf b;
+                    if (!ConvertBSDF(prim->bsdf, b)) return;
+                    bi = (int)bsdfs.size();
+                    bsdfs.push_back(b);
+                    bsdfIndex[prim->bsdf] = bi;
+                }
+            }
+            if (bi < 0)
+            {
+                lmb200_bsdf b; memset(&b, 0, sizeof(b)); b.type = LMB200_BSDF_NULL;
+                bi = (int)bsdfs.size(); bsdfs.push_back(b);
+            }
+            prims[i].bsdf = bi;
+            prims[i].light = -1;
+            if (prim->light)
+            {
+                if (std::string(prim->light->implName) != "Light_Area")
+                {
+                    LM_LOG_ERROR(std::string("renderer::lmb200pt: unsupported light '") + prim->light->implName + "' (only light::area)");
+                    return;
+                }
+                const auto Le = prim->light->Emittance().ToRGB();
+                // A light asset is loaded once, with the first primitive that references it
+                // (assets.cpp:50-122; light_area.cpp:50-55 binds mesh, transform and area
+                // distribution at Load): primitives sharing the asset all sample that first mesh.
+                auto bound = lightBound.find(prim->light);
+                if (bound == lightBound.end()) bound = lightBound.emplace(prim->light, i).first;
+                lmb200_light L; L.Le[0] = Le.x; L.Le[1] = Le.y; L.Le[2] = Le.z; L.primitive = bound->second;
+                prims[i].light = (int)lights.size();
+                lights.push_back(L);
+            }
+        }
+
+        // ---- sensor::pinhole (sensor_pinhole.cpp:47-61) ----
+        if (std::string(sensorPrim->sensor->implName) != "Sensor_Pinhole")
+        {
+            LM_LOG_ERROR(std::string("renderer::lmb200pt: unsupported sensor '") + sensorPrim->sensor->implName + "' (only sensor::pinhole)");
+            return;
+        }
+        lmb200_scene_desc d;
+        memset(&d, 0, sizeof(d));
+        {
+            const Vec3 pos(sensorPrim->transform * Vec4(0_f, 0_f, 0_f, 1_f));
+            const Vec3 vx(sensorPrim->transform[0]), vy(sensorPrim->transform[1]), vz(sensorPrim->transform[2]);
+            d.camera.position[0] = pos.x; d.camera.position[1] = pos.y; d.camera.position[2] = pos.z;
+            d.camera.vx[0] = vx.x; d.camera.vx[1] = vx.y; d.camera.vx[2] = vx.z;
+            d.camera.vy[0] = vy.x; d.camera.vy[1] = vy.y; d.camera.vy[2] = vy.z;
+            d.camera.vz[0] = vz.x; d.camera.vz[1] = vz.y; d.camera.vz[2] = vz.z;
+            // fov is not exposed by the interface: the YAML value if reachable, else recovered from
+            // GetProjectionMatrix()[1][1] = 1/tan(fov/2) (sensor_pinhole.cpp:192-202)
+            Float fovDeg = -1_f;
+            if (const auto* ap = AssetParams(sensorPrim->sensor)) fovDeg = ap->ChildAs<Float>("fov", 45_f);
+            if (fovDeg > 0_f) d.camera.fov = Math::Radians(fovDeg);
+            else d.camera.fov = 2_f * std::atan(1_f / sensorPrim->sensor->GetProjectionMatrix(1_f, 2_f)[1][1]);
+            d.camera.width = film->Width();
+            d.camera.height = film->Height();
+        }
+        d.num_tris = verts.size() / 9;
+        d.verts = verts.data();
+        d.normals = anyNormals ? normals.data() : nullptr;
+        d.tri_prim = primOfTri.data();
+        d.num_prims = (uint32_t)prims.size();
+        d.prims = prims.data();
+        d.num_bsdfs = (uint32_t)bsdfs.size();
+        d.bsdfs = bsdfs.data();
+        d.num_lights = (uint32_t)lights.size();
+        d.lights = lights.data();
+
+        if (const char* dump = std::getenv("LMB200_DUMP_SCENE"))
+        {
+            // debugging aid: the flattened scene exactly as handed to lmb200_scene_create
+            if (FILE* f = fopen(dump, "wb"))
+            {
+                const uint64_t hdr[5] = { d.num_tris, d.num_prims, d.num_bsdfs, d.num_lights, d.normals ? 1u : 0u };
+                fwrite(hdr, sizeof(hdr), 1, f);
+                fwrite(&d.camera, sizeof(d.camera), 1, f);
+                fwrite(d.verts, sizeof(float), 9 * d.num_tris, f);
+                fwrite(d.tri_prim, sizeof(uint32_t), d.num_tris, f);
+                fwrite(d.prims, sizeof(lmb200_primitive), d.num_prims, f);
+                fwrite(d.bsdfs, sizeof(lmb200_bsdf), d.num_bsdfs, f);
+                fwrite(d.lights, sizeof(lmb200_light), d.num_lights, f);
+                fclose(f);
+            }
+        }
+
+        // ---- render ----
+        std::vector<lmb200_scene*> scenes;
+        for (int g = 0; g < numGpus_; g++)
+        {
+            auto* s = lmb200_scene_create(device_ + g, &d);
+            if (!s)
+            {
+                LM_LOG_ERROR(std::string("renderer::lmb200pt: ") + lmb200_last_error());
+                for (auto* t : scenes) lmb200_scene_destroy(t);
+                return;
+            }
+            scenes.push_back(s);
+        }
+        lmb200_render_params p;
+        memset(&p, 0, sizeof(p));
+        p.mode = mode_;
+        p.num_samples = numSamples_;
+        p.sample_begin = 0;
+        p.sample_end = numSamples_;
+        p.max_num_vertices = maxNumVertices_;
+        p.min_num_vertices = minNumVertices_;
+        // one seed from the host RNG replaces the per-thread seeds of scheduler.cpp:157-164
+        p.seed = (uint64_t)initRng->NextUInt();
+        p.pool_size = poolSize_;
+        const int W = film->Width(), H = film->Height();
+        std::vector<float> rgba((size_t)W * H * 4, 0.f);
+        lmb200_render_stats st;
+        memset(&st, 0, sizeof(st));
+        const int rc = numGpus_ > 1 ? lmb200_render_multi(scenes.data(), numGpus_, &p, rgba.data(), &st)
+                                    : lmb200_render(scenes[0], &p, rgba.data(), &st);
+        for (auto* s : scenes) lmb200_scene_destroy(s);
+        if (rc != LMB200_OK)
+        {
+            LM_LOG_ERROR(std::string("renderer::lmb200pt: ") + lmb200_last_error());
+            return;
+        }
+        LM_LOG_INFO("renderer::lmb200pt: " + std::to_string(st.samples) + " samples, " + std::to_string(st.extend_rays) + " extend rays, " +
+                    std::to_string(st.shadow_rays) + " shadow rays in " + std::to_string(st.seconds) + " s on " + std::to_string(numGpus_) + " GPU(s)");
+
+        // ---- hand the image back through the Film interface (film.h) ----
+        film->Clear();
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++)
+            {
+                const float* c = &rgba[4 * ((size_t)y * W + x)];
+                film->SetPixel(x, y, SPD::FromRGB(Vec3(c[0], c[1], c[2])));
+            }
+        {
+            LM_LOG_INFO("Saving image");
+            LM_LOG_INDENTER();
+            film->Save(outputPath);
+        }
+    };
+
+private:
+
+    // "lightmetrica/assets[/params]/<asset id>/params" of the loaded YAML, or nullptr
+    auto AssetParams(const Asset* asset) const -> const PropertyNode*
+    {
+        if (!prop_ || !prop_->Tree() || !prop_->Tree()->Root()) return nullptr;
+        const auto* lm = prop_->Tree()->Root()->Child("lightmetrica");
+        if (!lm) return nullptr;
+        const auto* assets = lm->Child("assets");
+        if (!assets) return nullptr;
+        if (assets->Child("type") && assets->Child("params")) assets = assets->Child("params");
+        const auto* a = assets->Child(asset->ID());
+        return a ? a->Child("params") : nullptr;
+    }
+
+    auto ConvertBSDF(const BSDF* bsdf, lmb200_bsdf& b) const -> bool
+    {
+        memset(&b, 0, sizeof(b));
+        const std::string impl = bsdf->implName;
+        if (impl == "BSDF_Null") { b.type = LMB200_BSDF_NULL; return true; }
+        if (impl != "BSDF_Diffuse" && impl != "BSDF_CookTorrance")
+        {
+            LM_LOG_ERROR("renderer::lmb200pt: unsupported BSDF '" + impl + "' (diffuse | cook_torrance | null)");
+            return false;
+        }
+        const auto* ap = AssetParams(bsdf);
+        if (ap && ap->Child("TexR"))
+        {
+            LM_LOG_ERROR("renderer::lmb200pt: textured reflectance (TexR) is not supported");
+            return false;
+        }
+        const auto R = bsdf->Reflectance().ToRGB();
+        b.R[0] = R.x; b.R[1] = R.y; b.R[2] = R.z;
+        if (impl == "BSDF_Diffuse") { b.type = LMB200_BSDF_DIFFUSE; return true; }
+        b.type = LMB200_BSDF_COOKTORRANCE;
+        b.roughness = bsdf->Glossiness();                           // bsdf_cooktorrance.cpp:157-162
+        // eta/k are not exposed by the interface (bsdf_cooktorrance.cpp:297-301): YAML values or the defaults of :61-62
+        const Vec3 etaDef(0.140000_f, 0.129000_f, 0.158500_f), kDef(4.586250_f, 3.348125_f, 2.329375_f);
+        Vec3 eta = etaDef, k = kDef;
+        if (ap)
+        {
+            // const defaults select ChildAs(name, const T& def) -> T, not the bool-returning overload
+            eta = ap->ChildAs<Vec3>("eta", etaDef);
+            k = ap->ChildAs<Vec3>("k", kDef);
+        }
+        else
+        {
+            LM_LOG_WARN("renderer::lmb200pt: scene tree not reachable, using default eta/k for cook_torrance '" + bsdf->ID() + "'");
+        }
+        b.eta[0] = eta.x; b.eta[1] = eta.y; b.eta[2] = eta.z;
+        b.k[0] = k.x; b.k[1] = k.y; b.k[2] = k.z;
+        return true;
+    }
+
+private:
+
+    const PropertyNode* prop_ = nullptr;
+    int mode_ = LMB200_MODE_PTDIRECT;
+    long long numSamples_ = 10000000L;
+    int maxNumVertices_ = -1;
+    int minNumVertices_ = 0;
+    int numGpus_ = 1;
+    int device_ = 0;
+    int poolSize_ = 0;
+
+};
+
+LM_COMPONENT_REGISTER_IMPL(Renderer_LMB200PT, "renderer::lmb200pt");
+
+LM_NAMESPACE_END

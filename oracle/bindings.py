@@ -36,6 +36,8 @@ def port():
         L.orc_wide_closest.restype = C.c_longlong
         L.orc_wide_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         L.orc_triaccel_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_triaccel_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                             C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         _port = L
     return _port
 
@@ -256,6 +258,8 @@ class RefScene:
             ns = None if m["normals"] is None else np.ascontiguousarray(m["normals"], np.float32)
             handles.append(L.ref_register_mesh(_p(ps), ps.shape[0], _p(ns) if ns is not None else None, None, _p(fs), fs.shape[0]))
         self.scene = scene
+        self.handles = handles
+        self.accel = accel
         self.yaml = scene.to_yaml(handles, accel=accel)
         self.s = L.ref_session_create(self.yaml.encode(), accel.encode())
         if not self.s:
@@ -266,14 +270,26 @@ class RefScene:
             ref().ref_session_destroy(self.s)
             self.s = None
 
-    def render(self, renderer, num_samples, seed=1, threads=1, max_verts=-1, extra=None):
+    def render(self, renderer, num_samples, seed=1, threads=1, max_verts=-1, extra=None, in_tree=False):
+        """in_tree=True: the renderer params live in the scene YAML itself (as with the real CLI), so a
+        plugin can walk prop->Tree() to the assets; costs a fresh session."""
         w, h = self.scene.camera["w"], self.scene.camera["h"]
         out = np.zeros((h, w, 3), np.float32)
-        params = f"num_samples: {int(num_samples)}\nmax_num_vertices: {int(max_verts)}\nmin_num_vertices: 0\n"
-        for k, v in (extra or {}).items():
-            params += f"{k}: {v}\n"
+        pd = {"num_samples": int(num_samples), "max_num_vertices": int(max_verts), "min_num_vertices": 0}
+        pd.update(extra or {})
         ow, oh, sec = C.c_int(), C.c_int(), C.c_double()
-        ok = ref().ref_render(self.s, renderer.encode(), params.encode(), seed, threads, _p(out), C.byref(ow), C.byref(oh), C.byref(sec))
+        if in_tree:
+            y = self.scene.to_yaml(self.handles, accel=self.accel, renderer=renderer, renderer_params=pd)
+            s = ref().ref_session_create(y.encode(), self.accel.encode())
+            if not s:
+                raise RuntimeError(ref().ref_last_error().decode())
+            try:
+                ok = ref().ref_render(s, None, None, seed, threads, _p(out), C.byref(ow), C.byref(oh), C.byref(sec))
+            finally:
+                ref().ref_session_destroy(s)
+        else:
+            params = "".join(f"{k}: {v}\n" for k, v in pd.items())
+            ok = ref().ref_render(self.s, renderer.encode(), params.encode(), seed, threads, _p(out), C.byref(ow), C.byref(oh), C.byref(sec))
         if not ok:
             raise RuntimeError(ref().ref_last_error().decode())
         return out, sec.value

@@ -40,5 +40,31 @@ def accel_golden():
     print("accel_soup.npz:", int((q["face"] >= 0).sum()), "hits of", len(rays))
 
 
+
+
+def pt_golden():
+    """Reference images of the Cornell-style box (configs[0] geometry at 48x48) rendered by the
+    reference's own renderer::pt / renderer::ptdirect with accel::qbvh and dSFMT, two seeds each
+    (the second seed measures the Monte-Carlo noise floor)."""
+    from lmb200py import scenedesc
+    sc = scenedesc.cornell_box(48, 48, glossy_block=True)
+    R = ob.RefScene(sc, "qbvh")
+    spp = 16384
+    N = 48 * 48 * spp
+    out = {}
+    for name in ("ptdirect", "pt"):
+        a, _ = R.render(name, N, seed=1, threads=8)
+        b, _ = R.render(name, N, seed=2, threads=8)
+        out[name + "_a"] = a
+        out[name + "_b"] = b
+        rel = float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(a))
+        print(name, "mean", a.mean(axis=(0, 1)), "two-seed relRMSE", rel)
+    np.savez_compressed(os.path.join(HERE, "pt_cornell.npz"), spp=spp, **out)
+
+
 if __name__ == "__main__":
-    accel_golden()
+    which = sys.argv[1:] or ["accel", "pt"]
+    if "accel" in which:
+        accel_golden()
+    if "pt" in which:
+        pt_golden()

@@ -1,0 +1,132 @@
+"""The drop-in boundary on the GPU: accel::lmb200 and renderer::lmb200pt loaded by the reference's own
+ComponentFactory (oracle/_ref host) and driven through Accel3::Intersect / Renderer::Render."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from lmb200py import scenedesc, scenes
+
+from test_oracle import simple_rays, simple2_rays
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUG = os.path.join(ROOT, "lightmetrica-v2_b200", "plugin")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (ob.have_ref() and os.path.exists(os.path.join(PLUG, "accel_lmb200.so"))),
+                                 reason="needs the prebuilt oracle/_ref and plugins (built where /root/reference exists)")]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def plugins():
+    L = ob.ref()
+    assert L.ref_load_plugin(os.path.join(PLUG, "accel_lmb200").encode()) == 1
+    assert L.ref_load_plugin(os.path.join(PLUG, "renderer_lmb200pt").encode()) == 1
+
+
+def rel_rmse(a, b):
+    return float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
+
+
+SIMPLE_YAML_MESH = """
+    mesh1:
+      interface: trianglemesh
+      type: raw
+      params:
+        positions: {ps}
+        normals: {ns}
+        texcoords: {ts}
+        faces: {fs}
+"""
+
+
+def simple_scene_yaml(which, accel):
+    # the meshes of Accel3Test (test_accel3.cpp:75-171), through the reference's own trianglemesh::raw
+    if which == 1:
+        ps = "0 0 0 1 0 0 1 1 0 0 1 0 0 0 -1 1 0 -1 1 1 -1 0 1 -1"
+        ns = " ".join(["0 0 1"] * 8)
+        ts = "0 0 1 0 1 1 0 1 0 0 1 0 1 1 0 1"
+        fs = "0 1 2 0 2 3 4 5 6 4 6 7"
+    else:
+        ps = "0 0 0 1 0 -1 1 1 -1 0 1 0"
+        ns = " ".join(["0.707106781186547 0 0.707106781186547"] * 4)
+        ts = "0 0 1 0 1 1 0 1"
+        fs = "0 1 2 0 2 3"
+    y = ob.mesh_scene_yaml(0, accel)
+    head, tail = y.split("    mesh1:\n")
+    tail = tail.split("    white:\n", 1)[1]
+    return head + SIMPLE_YAML_MESH.format(ps=ps, ns=ns, ts=ts, fs=fs).lstrip("\n") + "    white:\n" + tail
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_accel3test_through_the_real_interface(which):
+    """Accel3Test.Simple / Simple2 (test_accel3.cpp:272-345) with accel::lmb200 in the parameter list."""
+    L = ob.ref()
+    s = L.ref_session_create(simple_scene_yaml(which, "lmb200").encode(), b"lmb200")
+    assert s, L.ref_last_error()
+    R = ob.RefSoup.__new__(ob.RefSoup)
+    R.s = s
+    rays, exp = simple_rays() if which == 1 else simple2_rays()
+    r = R.intersect(rays)
+    assert (r["prim"] >= 0).all()
+    g = r["geom"]
+    z = 0 * exp[:, 0] if which == 1 else -exp[:, 0]
+    n = np.array([0, 0, 1], np.float32) if which == 1 else np.array([1, 0, 1], np.float32) / np.sqrt(2)
+    assert np.allclose(g[:, 0:2], exp, atol=1e-3) and np.allclose(g[:, 2], z, atol=1e-3)      # p
+    assert np.allclose(g[:, 3:6], n, atol=1e-3) and np.allclose(g[:, 6:9], n, atol=1e-3)        # gn, sn
+    assert np.allclose(g[:, 9:11], exp, atol=1e-3)                                              # uv
+
+
+def test_intersect_equals_reference_accel():
+    verts = scenes.soup(3000, seed=21, extent=4.0, edge=0.3)
+    lo, hi = scenes.bounds(verts)
+    rays = scenes.random_rays(3000, lo, hi, seed=4)
+    a = ob.RefSoup(verts, "lmb200").intersect(rays)
+    b = ob.RefSoup(verts, "qbvh").intersect(rays)
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["face"], b["face"])
+    assert np.array_equal(a["tuv"].view(np.uint32), b["tuv"].view(np.uint32))
+    assert np.array_equal(a["geom"].view(np.uint32), b["geom"].view(np.uint32))     # full Intersection fields
+
+
+def test_reference_renderer_on_our_accel_is_bit_identical():
+    """renderer::ptdirect of the reference, single thread, same dSFMT seed: swapping accel::qbvh for
+    accel::lmb200 must not change a single bit of the image."""
+    sc = scenedesc.cornell_box(24, 24, glossy_block=True)
+    N = 24 * 24 * 4
+    a, _ = ob.RefScene(sc, accel="lmb200").render("ptdirect", N, seed=9, threads=1)
+    b, _ = ob.RefScene(sc, accel="qbvh").render("ptdirect", N, seed=9, threads=1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["ptdirect", "pt"])
+def test_renderer_plugin_vs_reference_renderer(mode):
+    """renderer::lmb200pt selected like any renderer; compared with the reference's renderer of the same
+    name at equal spp against the reference's own two-seed noise floor (bar: 1.25x)."""
+    sc = scenedesc.cornell_box(32, 32, glossy_block=True)
+    spp = 2048
+    N = 32 * 32 * spp
+    R = ob.RefScene(sc, accel="lmb200")
+    ours, _ = R.render("lmb200pt", N, seed=1, extra={"mode": mode}, in_tree=True)
+    ra, _ = R2(sc).render(mode, N, seed=1, threads=os.cpu_count() or 1)
+    rb, _ = R2(sc).render(mode, N, seed=2, threads=os.cpu_count() or 1)
+    floor = rel_rmse(ra, rb)
+    assert rel_rmse(ours, ra) < 1.25 * floor, (rel_rmse(ours, ra), floor)
+    assert np.allclose(ours.mean(axis=(0, 1)), ra.mean(axis=(0, 1)), rtol=0.02 if mode == "ptdirect" else 0.06)
+
+
+_cache = {}
+
+
+def R2(sc):
+    if id(sc) not in _cache:
+        _cache[id(sc)] = ob.RefScene(sc, accel="qbvh")
+    return _cache[id(sc)]
+
+
+def test_renderer_plugin_rejects_unsupported_scene():
+    """Unknown mode => Initialize fails loudly (no mis-render)."""
+    sc = scenedesc.cornell_box(16, 16)
+    R = ob.RefScene(sc, accel="qbvh")
+    with pytest.raises(RuntimeError, match="renderer init failed"):
+        R.render("lmb200pt", 100, extra={"mode": "bdpt"})

@@ -1,0 +1,79 @@
+"""The two Lightmetrica plugins against the reference host (oracle/_ref), CPU only: they load through
+the reference's own ComponentFactory, register their keys, and fail loudly without a CUDA device."""
+import os
+
+import pytest
+
+from oracle import bindings as ob
+from lmb200py import capi, scenedesc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUG = os.path.join(ROOT, "lightmetrica-v2_b200", "plugin")
+
+pytestmark = pytest.mark.skipif(
+    not (ob.have_ref() and os.path.exists(os.path.join(PLUG, "accel_lmb200.so"))),
+    reason="needs oracle/_ref and the built plugins (both need /root/reference to build)")
+
+
+def load_plugins():
+    L = ob.ref()
+    assert L.ref_load_plugin(os.path.join(PLUG, "accel_lmb200").encode()) == 1
+    assert L.ref_load_plugin(os.path.join(PLUG, "renderer_lmb200pt").encode()) == 1
+
+
+def test_plugins_load_and_register():
+    load_plugins()
+    # a missing plugin is reported, not fatal (component.cpp:101-125)
+    assert ob.ref().ref_load_plugin(os.path.join(PLUG, "does_not_exist").encode()) == 0
+
+
+def test_no_gpu_fails_loudly():
+    if capi.lib().lmb200_device_count() > 0:
+        pytest.skip("GPU present")
+    load_plugins()
+    sc = scenedesc.cornell_box(16, 16)
+    with pytest.raises(RuntimeError, match="accel init failed"):
+        ob.RefScene(sc, accel="lmb200")
+    R = ob.RefScene(sc, accel="qbvh")
+    with pytest.raises(RuntimeError, match="renderer init failed"):
+        R.render("lmb200pt", 100)
+
+
+def test_renderer_plugin_scene_extraction(tmp_path, monkeypatch):
+    """What renderer::lmb200pt reads through the reference's interfaces (Scene3::PrimitiveAt,
+    TriangleMesh, BSDF::Reflectance/Glossiness, YAML eta/k, Light::Emittance, pinhole transform/fov)
+    equals the scene that was described. Uses the plugin's LMB200_DUMP_SCENE aid, so no GPU is needed."""
+    import ctypes as C
+    import numpy as np
+    dump = str(tmp_path / "scene.bin")
+    monkeypatch.setenv("LMB200_DUMP_SCENE", dump)
+    load_plugins()
+    sc = scenedesc.cornell_box(32, 24, glossy_block=True)
+    R = ob.RefScene(sc, accel="qbvh")
+    # Render returns void (renderer.h:81): without a device it logs the CUDA error and returns after the dump
+    R.render("lmb200pt", 10, extra={"mode": "ptdirect"}, in_tree=True)
+    with open(dump, "rb") as f:
+        nt, npr, nb, nl, has_n = (int(x) for x in np.frombuffer(f.read(40), np.uint64))
+        cam = capi.Camera.from_buffer_copy(f.read(C.sizeof(capi.Camera)))
+        verts = np.frombuffer(f.read(36 * nt), np.float32).reshape(-1, 9)
+        tri_prim = np.frombuffer(f.read(4 * nt), np.uint32)
+        prims = (capi.Primitive * npr).from_buffer_copy(f.read(C.sizeof(capi.Primitive) * npr))
+        bsdfs = (capi.Bsdf * nb).from_buffer_copy(f.read(C.sizeof(capi.Bsdf) * nb))
+        lights = (capi.Light * nl).from_buffer_copy(f.read(C.sizeof(capi.Light) * nl))
+    d, keep = sc.flatten()
+    assert (nt, npr, nl, has_n) == (d.num_tris, d.num_prims, d.num_lights, 0)
+    assert np.array_equal(verts, keep["verts"]) and np.array_equal(tri_prim, keep["tri_prim"])
+    for i in range(npr):
+        a, b = prims[i], keep["prims"][i]
+        assert (a.light, a.first_tri, a.num_tris, a.has_normals) == (b.light, b.first_tri, b.num_tris, b.has_normals)
+        ba, bb = bsdfs[a.bsdf], keep["bs"][b.bsdf]
+        assert ba.type == bb.type
+        if ba.type != capi.BSDF_NULL:
+            assert list(ba.R) == list(bb.R)
+        if ba.type == capi.BSDF_COOKTORRANCE:
+            assert list(ba.eta) == list(bb.eta) and list(ba.k) == list(bb.k) and ba.roughness == bb.roughness
+    assert list(lights[0].Le) == [17.0, 12.0, 4.0] and lights[0].primitive == keep["ls"][0].primitive
+    # the camera basis comes from the reference's lookat (rsqrt-normalised, math.h:1872-1875): equal to 1e-3
+    for k in ("position", "vx", "vy", "vz"):
+        assert np.allclose(list(getattr(cam, k)), list(getattr(d.camera, k)), atol=1e-3)
+    assert abs(cam.fov - d.camera.fov) < 1e-6 and (cam.width, cam.height) == (32, 24)
