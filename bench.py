@@ -282,7 +282,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("trace_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("dram_bytes_per_ray") * a.rays   # per launch, like `achieved`
         except Exception:
             traffic = None
 
