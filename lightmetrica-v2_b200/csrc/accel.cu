@@ -20,8 +20,25 @@ int cuda_fail(cudaError_t e, const char* what)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernels. Persistent grid: every warp claims 32 rays at a time from a global counter
-// (one atomicAdd per warp), so long rays do not strand a whole block's worth of work.
+// Kernels. Persistent grid of warps; lanes are refilled individually from a global work counter
+// (traverse.cuh persistent_trace), so long rays do not strand the rest of their warp.
+
+struct BatchIoClosest {
+    const float4* __restrict__ rays; float4* __restrict__ out; uint64_t n;
+    __device__ __forceinline__ uint64_t count() const { return n; }
+    __device__ __forceinline__ void load(uint64_t i, float4& ro, float4& rd) const { ro = __ldg(rays + 2 * i); rd = __ldg(rays + 2 * i + 1); }
+    __device__ __forceinline__ void store(uint64_t i, const Trav& T) const
+    {
+        const bool hit = T.hid != LMB200_MISS;
+        out[i] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
+    }
+};
+struct BatchIoAny {
+    const float4* __restrict__ rays; uint8_t* __restrict__ out; uint64_t n;
+    __device__ __forceinline__ uint64_t count() const { return n; }
+    __device__ __forceinline__ void load(uint64_t i, float4& ro, float4& rd) const { ro = __ldg(rays + 2 * i); rd = __ldg(rays + 2 * i + 1); }
+    __device__ __forceinline__ void store(uint64_t i, const Trav& T) const { out[i] = T.hid != LMB200_MISS ? 1 : 0; }
+};
 
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK)
@@ -30,31 +47,18 @@ trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
              const uint64_t n_host, const uint32_t* __restrict__ n_dev,
              unsigned long long* __restrict__ counter, unsigned long long* __restrict__ work_counters)
 {
+    __shared__ uint2 smem[LMB_SM_STACK * LMB_TRACE_BLOCK];
     const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
-    const unsigned lane = threadIdx.x & 31u;
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint64_t i = base + lane;
-        if (i < n) {
-            const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
-            float tmax = rd.w, hu = 0.f, hv = 0.f;
-            uint32_t hid;
-            const bool hit = lmb_traverse<ANY, COUNT>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, &cnt);
-            if (ANY) {
-                reinterpret_cast<uint8_t*>(out)[i] = hit ? 1 : 0;
-            } else {
-                float4 h;
-                h.x = hit ? tmax : 0.f; h.y = hu; h.z = hv; h.w = __uint_as_float(hit ? hid : LMB200_MISS);
-                reinterpret_cast<float4*>(out)[i] = h;
-            }
-        }
-        __syncwarp();
+    if (ANY) {
+        BatchIoAny io{rays, reinterpret_cast<uint8_t*>(out), n};
+        persistent_trace<true, COUNT>(nodes, tris, io, counter, smem, cnt);
+    } else {
+        BatchIoClosest io{rays, reinterpret_cast<float4*>(out), n};
+        persistent_trace<false, COUNT>(nodes, tris, io, counter, smem, cnt);
     }
     if (COUNT) {
+        const unsigned lane = threadIdx.x & 31u;
         unsigned long long a = cnt.nodes, b = cnt.tris;
         for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
         if (lane == 0) { atomicAdd(work_counters, a); atomicAdd(work_counters + 1, b); }
@@ -64,12 +68,12 @@ trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
 // one ray, one warp: the per-ray Accel3::Intersect path (mailbox in mapped pinned host memory)
 __global__ void trace_one_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* ray, float4* out)
 {
+    __shared__ uint2 smem[LMB_SM_STACK * 32];
     if (threadIdx.x != 0) return;
-    const float4 ro = ray[0], rd = ray[1];
-    float tmax = rd.w, hu = 0.f, hv = 0.f;
-    uint32_t hid;
-    const bool hit = lmb_traverse<false, false>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, nullptr);
-    out[0] = make_float4(hit ? tmax : 0.f, hu, hv, __uint_as_float(hit ? hid : LMB200_MISS));
+    Trav T;
+    TravCounters cnt;
+    const bool hit = lmb_traverse<false, false>(nodes, tris, ray[0], ray[1], T, smem, cnt);
+    out[0] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
 }
 
 struct Mailbox {
@@ -360,28 +364,3 @@ int lmb200_trace_count_dev(lmb200_accel* h, const void* rays_dev, uint64_t n, do
 
 }  // extern "C"
 
-// ---- debugging aid (not part of the public header) ----
-namespace lmb200 {
-__global__ void debug_kernel(const float4* nodes, const float4* tris, const float4* rays, uint32_t n, uint32_t* out)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
-    const float idx = lmb_safe_inv(rd.x), idy = lmb_safe_inv(rd.y), idz = lmb_safe_inv(rd.z);
-    const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
-    const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
-    const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
-    const float4 n0 = nodes[0], n1 = nodes[1], n2 = nodes[2], n3 = nodes[3], n4 = nodes[4];
-    out[4 * i] = lmb_intersect_node(n0, n1, n2, n3, n4, ro.x, ro.y, ro.z, idx, idy, idz, negx, negy, negz, oct_inv4, ro.w, rd.w);
-    TravCounters c; c.nodes = 0; c.tris = 0;
-    float tmax = rd.w, hu, hv; uint32_t hid;
-    lmb_traverse<false, true>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, &c);
-    out[4 * i + 1] = c.nodes; out[4 * i + 2] = c.tris; out[4 * i + 3] = hid;
-}
-}
-extern "C" int lmb200_debug_trace(lmb200_accel* h, const void* rays_dev, uint32_t n, void* out_dev)
-{
-    Accel* a = reinterpret_cast<Accel*>(h);
-    lmb200::debug_kernel<<<(n + 63) / 64, 64>>>((const float4*)a->d_nodes, (const float4*)a->d_tris, (const float4*)rays_dev, n, (uint32_t*)out_dev);
-    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
-}

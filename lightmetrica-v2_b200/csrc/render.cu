@@ -529,54 +529,46 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
     }
 }
 
-// extend: closest hit over the extend queue (slot indirection), persistent warps
+// extend: closest hit over the extend queue (slot indirection), persistent warps with lane refill
+struct ExtendIo {
+    Pool P; uint32_t n;
+    __device__ __forceinline__ uint64_t count() const { return n; }
+    __device__ __forceinline__ void load(uint64_t qi, float4& ro, float4& rd) const { const uint32_t i = P.eq[qi]; ro = P.ray_o[i]; rd = P.ray_d[i]; }
+    __device__ __forceinline__ void store(uint64_t qi, const Trav& T) const
+    {
+        const bool hit = T.hid != LMB200_MISS;
+        P.hit[P.eq[qi]] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
+    }
+};
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK)
 k_extend(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter)
 {
-    const uint32_t n = P.qcount[1];
-    const unsigned lane = threadIdx.x & 31u;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t qi = (uint32_t)base + lane;
-        if (qi < n) {
-            const uint32_t i = P.eq[qi];
-            const float4 ro = P.ray_o[i], rd = P.ray_d[i];
-            float tmax = rd.w, hu = 0.f, hv = 0.f;
-            uint32_t hid;
-            const bool hit = lmb_traverse<false, false>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, nullptr);
-            P.hit[i] = make_float4(hit ? tmax : 0.f, hu, hv, __uint_as_float(hit ? hid : LMB200_MISS));
-        }
-        __syncwarp();
-    }
+    __shared__ uint2 smem[LMB_SM_STACK * LMB_TRACE_BLOCK];
+    ExtendIo io{P, P.qcount[1]};
+    TravCounters cnt;
+    persistent_trace<false, false>(nodes, tris, io, counter, smem, cnt);
 }
 
 // shadow: any hit over the shadow queue, unoccluded contributions are splatted (film_hdr.cpp:218-223)
+struct ShadowIo {
+    Pool P; uint32_t n; float4* film;
+    __device__ __forceinline__ uint64_t count() const { return n; }
+    __device__ __forceinline__ void load(uint64_t qi, float4& ro, float4& rd) const { ro = P.sq_o[qi]; rd = P.sq_d[qi]; }
+    __device__ __forceinline__ void store(uint64_t qi, const Trav& T) const
+    {
+        if (T.hid == LMB200_MISS) {
+            const float4 c = P.sq_c[qi];
+            film_add(film, __float_as_int(c.w), F3(c.x, c.y, c.z));
+        }
+    }
+};
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK)
 k_shadow(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter, float4* film)
 {
-    const uint32_t n = P.qcount[2];
-    const unsigned lane = threadIdx.x & 31u;
-    for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t qi = (uint32_t)base + lane;
-        if (qi < n) {
-            const float4 ro = P.sq_o[qi], rd = P.sq_d[qi];
-            float tmax = rd.w, hu, hv;
-            uint32_t hid;
-            const bool occ = lmb_traverse<true, false>(nodes, tris, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, tmax, hu, hv, hid, nullptr);
-            if (!occ) {
-                const float4 c = P.sq_c[qi];
-                film_add(film, __float_as_int(c.w), F3(c.x, c.y, c.z));
-            }
-        }
-        __syncwarp();
-    }
+    __shared__ uint2 smem[LMB_SM_STACK * LMB_TRACE_BLOCK];
+    ShadowIo io{P, P.qcount[2], film};
+    TravCounters cnt;
+    persistent_trace<true, false>(nodes, tris, io, counter, smem, cnt);
 }
 
 __global__ void k_stats(Pool P)

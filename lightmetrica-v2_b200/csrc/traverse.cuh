@@ -1,8 +1,15 @@
 // Device traversal of the 80-byte wide BVH (bvh.h) with the bit-exact TriAccel leaf test.
 // Replaces the reference's stack(64) QBVH loop (/root/reference/src/liblightmetrica/accel/
 // accel_qbvh.cpp:398-497: unordered child push, SSE 4-box slab test) with an octant-ordered
-// 8-wide traversal: one thread per ray, a (node-group, triangle-group) pair in registers and a
-// short stack of 8-byte entries.
+// 8-wide traversal written for SIMT efficiency:
+//   * persistent warps; a lane whose ray finishes is refilled from the global work counter
+//     (warp-level fetch: one atomicAdd per refill for all idle lanes) instead of idling until the
+//     slowest ray of its warp is done,
+//   * one thread per ray, (node-group, triangle-group) pairs in registers and a short stack of
+//     8-byte entries in shared memory (overflow to local memory),
+//   * triangle tests are postponed (pushed back as a triangle group) while too few lanes of the
+//     warp have triangle work, so the warp alternates between "all lanes test boxes" and "many
+//     lanes test triangles" phases.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -10,7 +17,10 @@
 
 namespace lmb200 {
 
-#define LMB_STACK_SIZE 32
+#define LMB_SM_STACK 8          // entries per thread in shared memory
+#define LMB_LOCAL_STACK 24      // overflow entries in local memory
+#define LMB_REFILL_BELOW 22     // refill the warp when fewer lanes than this are active
+#define LMB_TRI_POSTPONE_BELOW 8   // postpone triangle tests while fewer lanes than this have some
 
 struct TravCounters { uint32_t nodes, tris; };
 
@@ -95,71 +105,172 @@ __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const fl
     return hitmask;
 }
 
-// Closest hit (ANY=false) or any hit (ANY=true). On return for closest: tmax/hu/hv/hid hold the
-// winner (hid = 0xffffffff if none). Tie rule: equal t -> larger triangle index wins, which is
-// what a linear scan with the reference's "reject t > maxT" rule yields (accel_naive.cpp:92-124).
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ bool lmb_traverse(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                             const float ox, const float oy, const float oz,
-                                             const float dx, const float dy, const float dz,
-                                             const float tmin, float& tmax, float& hu, float& hv, uint32_t& hid,
-                                             TravCounters* cnt)
+// Per-lane traversal state. hid == 0xffffffff <=> no hit yet (triangle ids are < 2^27).
+struct Trav {
+    float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tmax, hu, hv;
+    uint32_t hid, oct_inv4;
+    uint2 ngroup;      // y: bits 31..24 pending internal children (priority order) | imask ; or a postponed triangle group (y < 2^24)
+    int sp;
+};
+
+__device__ __forceinline__ void trav_init(Trav& T, const float4 ro, const float4 rd)
 {
-    const float idx = lmb_safe_inv(dx), idy = lmb_safe_inv(dy), idz = lmb_safe_inv(dz);
+    T.ox = ro.x; T.oy = ro.y; T.oz = ro.z; T.tmin = ro.w;
+    T.dx = rd.x; T.dy = rd.y; T.dz = rd.z; T.tmax = rd.w;
+    T.idx = lmb_safe_inv(rd.x); T.idy = lmb_safe_inv(rd.y); T.idz = lmb_safe_inv(rd.z);
     // signs taken from the clamped reciprocal so that -0.0 picks the same near/far planes it scales
-    const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
-    const uint32_t oct = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
-    const uint32_t oct_inv4 = (7u - oct) * 0x01010101u;
+    const uint32_t oct = (T.idx < 0.f ? 1u : 0u) | (T.idy < 0.f ? 2u : 0u) | (T.idz < 0.f ? 4u : 0u);
+    T.oct_inv4 = (7u - oct) * 0x01010101u;
+    T.hu = 0.f; T.hv = 0.f; T.hid = 0xffffffffu;
+    T.ngroup = make_uint2(0u, 0x80000000u);   // root: node 0 (imask 0 resolves to relative index 0)
+    T.sp = 0;
+}
 
-    uint2 stack[LMB_STACK_SIZE];
-    int sp = 0;
-    uint2 ngroup = make_uint2(0u, 0x80000000u);   // root: node 0, "slot 7 ^ oct_inv" resolved below via imask=0
-    uint2 tgroup = make_uint2(0u, 0u);
-    hid = 0xffffffffu;
-    bool found = false;
+// shared-memory stack: entry e of thread t lives at smem[e * blockDim.x + t] (conflict-free)
+__device__ __forceinline__ void trav_push(Trav& T, uint2* __restrict__ smem, uint2* __restrict__ lstack, const uint2 v)
+{
+    if (T.sp < LMB_SM_STACK) smem[T.sp * blockDim.x + threadIdx.x] = v;
+    else lstack[T.sp - LMB_SM_STACK] = v;
+    T.sp++;
+}
+__device__ __forceinline__ uint2 trav_pop(Trav& T, const uint2* __restrict__ smem, const uint2* __restrict__ lstack)
+{
+    T.sp--;
+    return T.sp < LMB_SM_STACK ? smem[T.sp * blockDim.x + threadIdx.x] : lstack[T.sp - LMB_SM_STACK];
+}
 
-    for (;;) {
-        if (ngroup.y & 0xff000000u) {
-            const uint32_t hits_imask = ngroup.y;
-            const uint32_t bit = 31u - __clz(hits_imask);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y & 0xff000000u) { stack[sp++] = ngroup; }
-            const uint32_t slot = (bit - 24u) ^ (oct_inv4 & 7u);
-            const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot) & 0xffu);
-            const uint32_t ni = ngroup.x + rel;
-            const float4* np = nodes + (size_t)ni * 5u;
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            if (COUNT) cnt->nodes++;
-            const uint32_t hitmask = lmb_intersect_node(n0, n1, n2, n3, n4, ox, oy, oz, idx, idy, idz, negx, negy, negz, oct_inv4, tmin, tmax);
-            ngroup.x = __float_as_uint(n1.x);
-            ngroup.y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
-            tgroup.x = __float_as_uint(n1.y);
-            tgroup.y = hitmask & 0x00ffffffu;
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
-        }
+// One traversal step of an active lane: open one node (or take a postponed triangle group), test
+// the pending triangles unless the warp decides to postpone them, fetch the next group.
+// Returns true when the ray is finished. Closest hit: tie on t -> larger triangle index wins, which
+// is what a linear scan with the reference's "reject t > maxT" rule yields (accel_naive.cpp:92-124).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                          uint2* __restrict__ smem, uint2* __restrict__ lstack, TravCounters& cnt)
+{
+    uint2 tgroup;
+    bool fresh = false;   // tgroup comes from a node opened in this step (may be postponed once)
+    if (T.ngroup.y & 0xff000000u) {
+        const uint32_t hits_imask = T.ngroup.y;
+        const uint32_t bit = 31u - __clz(hits_imask);
+        T.ngroup.y &= ~(1u << bit);
+        if (T.ngroup.y & 0xff000000u) trav_push(T, smem, lstack, T.ngroup);
+        const uint32_t slot = (bit - 24u) ^ (T.oct_inv4 & 7u);
+        const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot) & 0xffu);
+        const float4* np = nodes + (size_t)(T.ngroup.x + rel) * 5u;
+        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        if (COUNT) cnt.nodes++;
+        const uint32_t hitmask = lmb_intersect_node(n0, n1, n2, n3, n4, T.ox, T.oy, T.oz, T.idx, T.idy, T.idz,
+                                                    T.idx < 0.f, T.idy < 0.f, T.idz < 0.f, T.oct_inv4, T.tmin, T.tmax);
+        T.ngroup.x = __float_as_uint(n1.x);
+        T.ngroup.y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
+        tgroup.x = __float_as_uint(n1.y);
+        tgroup.y = hitmask & 0x00ffffffu;
+        fresh = true;
+    } else {
+        tgroup = T.ngroup;                 // a postponed triangle group came off the stack
+        T.ngroup = make_uint2(0u, 0u);
+    }
 
-        while (tgroup.y) {
-            const uint32_t i = __ffs(tgroup.y) - 1;
-            tgroup.y &= tgroup.y - 1;
-            const float4* tp = tris + (size_t)(tgroup.x + i) * 3u;
-            const float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
-            if (COUNT) cnt->tris++;
-            float t, u, v;
-            if (triaccel_intersect(r0, r1, r2, ox, oy, oz, dx, dy, dz, tmin, tmax, t, u, v)) {
-                if (ANY) return true;
-                const uint32_t id = __float_as_uint(r2.z);
-                if (t < tmax || !found || id > hid) { tmax = t; hu = u; hv = v; hid = id; found = true; }
+    // triangle phase
+    {
+        const unsigned lanes = __activemask();
+        const unsigned want = __ballot_sync(lanes, tgroup.y != 0u);
+        if (want) {
+            // Postpone only triangles of a node opened in THIS step (so the same group is never
+            // postponed twice: a group popped from the stack is always tested -> progress), and
+            // only while the lane still has boxes to test next (otherwise it would just pop them back).
+            const bool few = __popc(want) < LMB_TRI_POSTPONE_BELOW;
+            if (few && fresh && tgroup.y && (T.ngroup.y & 0xff000000u)) {
+                trav_push(T, smem, lstack, tgroup);
+            } else {
+                while (tgroup.y) {
+                    const uint32_t i = __ffs(tgroup.y) - 1;
+                    tgroup.y &= tgroup.y - 1;
+                    const float4* tp = tris + (size_t)(tgroup.x + i) * 3u;
+                    const float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
+                    if (COUNT) cnt.tris++;
+                    float t, u, v;
+                    if (triaccel_intersect(r0, r1, r2, T.ox, T.oy, T.oz, T.dx, T.dy, T.dz, T.tmin, T.tmax, t, u, v)) {
+                        if (ANY) { T.hid = 0u; return true; }
+                        const uint32_t id = __float_as_uint(r2.z);
+                        if (t < T.tmax || T.hid == 0xffffffffu || id > T.hid) { T.tmax = t; T.hu = u; T.hv = v; T.hid = id; }
+                    }
+                }
             }
         }
+    }
 
-        if ((ngroup.y & 0xff000000u) == 0u) {
-            if (sp == 0) break;
-            ngroup = stack[--sp];
+    if ((T.ngroup.y & 0xff000000u) == 0u) {
+        if (T.sp == 0) return true;
+        T.ngroup = trav_pop(T, smem, lstack);
+    }
+    return false;
+}
+
+// Persistent-warp driver. `Io` supplies rays and consumes results:
+//   uint64_t count() const;                          number of rays
+//   void load(uint64_t i, float4& ro, float4& rd);   ray i
+//   void store(uint64_t i, const Trav& T);           result of ray i (T.hid == 0xffffffff: miss)
+template <bool ANY, bool COUNT, typename Io>
+__device__ __forceinline__ void persistent_trace(const float4* __restrict__ nodes, const float4* __restrict__ tris, Io& io,
+                                                 unsigned long long* __restrict__ counter, uint2* __restrict__ smem, TravCounters& cnt)
+{
+    const uint64_t n = io.count();
+    const unsigned lane = threadIdx.x & 31u;
+    uint2 lstack[LMB_LOCAL_STACK];
+    Trav T;
+    bool active = false;
+    bool exhausted = false;      // warp-uniform: the work counter has run past n
+    uint64_t ray_index = 0;
+
+    for (;;) {
+        // ---- refill idle lanes (all 32 lanes converge here) ----
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(0xffffffffu, !active);
+            if (idle) {
+                unsigned long long base = 0;
+                const int leader = __ffs(idle) - 1;
+                if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!active) {
+                    const uint64_t i = base + __popc(idle & ((1u << lane) - 1u));
+                    if (i < n) {
+                        float4 ro, rd;
+                        io.load(i, ro, rd);
+                        trav_init(T, ro, rd);
+                        ray_index = i;
+                        active = true;
+                    }
+                }
+                if (base + __popc(idle) >= n) exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+
+        // ---- traverse until enough lanes have finished to make a refill worthwhile ----
+        for (;;) {
+            if (active) {
+                if (trav_step<ANY, COUNT>(T, nodes, tris, smem, lstack, cnt)) {
+                    io.store(ray_index, T);
+                    active = false;
+                }
+            }
+            const unsigned live = __ballot_sync(0xffffffffu, active);
+            if (live == 0u) break;
+            if (!exhausted && __popc(live) < LMB_REFILL_BELOW) break;
         }
     }
-    return found;
+}
+
+// Whole-ray helper for single-ray callers (per-ray Accel3::Intersect path, debug kernels).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool lmb_traverse(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                             const float4 ro, const float4 rd, Trav& T, uint2* __restrict__ smem, TravCounters& cnt)
+{
+    uint2 lstack[LMB_LOCAL_STACK];
+    trav_init(T, ro, rd);
+    while (!trav_step<ANY, COUNT>(T, nodes, tris, smem, lstack, cnt)) {}
+    return T.hid != 0xffffffffu;
 }
 
 }  // namespace lmb200
