@@ -50,6 +50,7 @@ constexpr int kMaxLeaf = 3;           // triangles per leaf slot (3 unary bits i
 constexpr float kCostNode = 1.0f;     // SAH: one binary split step
 constexpr float kCostTri = 1.0f;      // SAH: one triangle test
 constexpr uint32_t kParallelGrain = 1u << 14;
+constexpr double kQSlack = 1.0 / 256.0;   // grid steps added around every quantised child box (see emit_node)
 
 struct Builder {
     std::vector<Ref> refs;
@@ -243,9 +244,11 @@ struct Emitter {
         for (int a = 0; a < 3; a++) {
             node.p[a] = nb.lo[a];
             const double ext = (double)nb.hi[a] - (double)nb.lo[a];
-            int e = ext > 0 ? (int)std::ceil(std::log2(ext / 255.0)) : -126;
-            e = std::max(-126, std::min(126, e));
-            while (e < 126 && std::ceil(ext / std::ldexp(1.0, e)) > 255.0) e++;
+            // the traversal evaluates q*step + base as fma(1 + q*2^-15, step*2^15, base - step*2^15): child
+            // boxes are widened by kQSlack grid steps to cover that rounding, and e+15 must stay a valid exponent
+            int e = ext > 0 ? (int)std::ceil(std::log2(ext / 254.0)) : -126;
+            e = std::max(-126, std::min(110, e));
+            while (e < 110 && std::ceil(ext / std::ldexp(1.0, e) + 2 * kQSlack) > 255.0) e++;
             node.e[a] = (uint8_t)(e + 127);
             scale[a] = std::ldexp(1.0, e);
         }
@@ -282,8 +285,8 @@ struct Emitter {
             if (i < 0) { node.meta[s] = 0; for (int a = 0; a < 3; a++) { node.qlo[a][s] = 255; node.qhi[a][s] = 0; } continue; }
             const BinNode& c = B.nodes[ch[i]];
             for (int a = 0; a < 3; a++) {
-                double ql = std::floor(((double)c.box.lo[a] - (double)node.p[a]) / scale[a]);
-                double qh = std::ceil(((double)c.box.hi[a] - (double)node.p[a]) / scale[a]);
+                double ql = std::floor(((double)c.box.lo[a] - (double)node.p[a]) / scale[a] - kQSlack);
+                double qh = std::ceil(((double)c.box.hi[a] - (double)node.p[a]) / scale[a] + kQSlack);
                 ql = std::max(0.0, std::min(255.0, ql));
                 qh = std::max(0.0, std::min(255.0, qh));
                 node.qlo[a][s] = (uint8_t)ql; node.qhi[a][s] = (uint8_t)qh;

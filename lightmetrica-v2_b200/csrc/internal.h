@@ -6,7 +6,9 @@
 #include "../../include/lmb200.h"
 #include "bvh.h"
 
+#ifndef LMB_TRACE_BLOCK
 #define LMB_TRACE_BLOCK 128
+#endif
 
 namespace lmb200 {
 

@@ -7,9 +7,9 @@
 //     slowest ray of its warp is done,
 //   * one thread per ray, (node-group, triangle-group) pairs in registers and a short stack of
 //     8-byte entries in shared memory (overflow to local memory),
-//   * triangle tests are postponed (pushed back as a triangle group) while too few lanes of the
-//     warp have triangle work, so the warp alternates between "all lanes test boxes" and "many
-//     lanes test triangles" phases.
+//   * triangle tests can be postponed (pushed back as a triangle group) while too few lanes of the
+//     warp have triangle work (LMB_TRI_POSTPONE_BELOW); measured on B200 this does not pay with
+//     <=3-triangle leaves (profiles/r01_sweep.md), so the default threshold is 0 = test at once.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,10 +17,16 @@
 
 namespace lmb200 {
 
+#ifndef LMB_SM_STACK
 #define LMB_SM_STACK 8          // entries per thread in shared memory
+#endif
 #define LMB_LOCAL_STACK 24      // overflow entries in local memory
-#define LMB_REFILL_BELOW 22     // refill the warp when fewer lanes than this are active
-#define LMB_TRI_POSTPONE_BELOW 8   // postpone triangle tests while fewer lanes than this have some
+#ifndef LMB_REFILL_BELOW
+#define LMB_REFILL_BELOW 26     // refill the warp when fewer lanes than this are active
+#endif
+#ifndef LMB_TRI_POSTPONE_BELOW
+#define LMB_TRI_POSTPONE_BELOW 0   // postpone triangle tests while fewer lanes than this have some
+#endif
 
 struct TravCounters { uint32_t nodes, tris; };
 
@@ -34,10 +40,22 @@ __device__ __forceinline__ float lmb_safe_inv(float d)
     return 1.0f / c;
 }
 
-__device__ __forceinline__ float lmb_q2f(uint32_t word, uint32_t sel)
+// 0x3F800000 read from constant memory: ptxas cannot fold it, so PRMT takes it as its register /
+// constant-bank operand and the byte selectors stay immediates (an immediate here forces every
+// selector into a register, one extra move per PRMT).
+static __constant__ uint32_t lmb_c_one = 0x3F800000u;
+__device__ __forceinline__ uint32_t lmb_one_bits() { return lmb_c_one; }
+
+// Byte J of `word` placed into mantissa bits 15..8 of 1.0f: the float 1 + q * 2^-15, exactly.
+// With s' = 2^15 * s and b' = b - s' (per node and axis) the slab distance q*s + b becomes a
+// single fma(m, s', b'): PRMT + FFMA per plane instead of PRMT + FADD + FFMA. The rounding of b'
+// costs at most 2^-9 grid steps, which the builder covers by widening child boxes by 2^-8 step.
+template <int J>
+__device__ __forceinline__ float lmb_q2m(uint32_t word, uint32_t one)
 {
-    // byte `sel&3` of word -> float, via the 2^23 mantissa trick (PRMT + FADD instead of I2F)
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(one), "n"(0x7604 | (J << 4)));
+    return __uint_as_float(r);
 }
 
 __device__ __forceinline__ uint32_t lmb_sign_extend_s8x4(uint32_t x)
@@ -49,21 +67,42 @@ __device__ __forceinline__ uint32_t lmb_sign_extend_s8x4(uint32_t x)
     return r;
 }
 
+template <int J>
+__device__ __forceinline__ void lmb_child(const uint32_t nearx, const uint32_t neary, const uint32_t nearz,
+                                          const uint32_t farx, const uint32_t fary, const uint32_t farz,
+                                          const float sx, const float sy, const float sz, const float bx, const float by, const float bz,
+                                          const float tmin, const float tmax, const uint32_t one,
+                                          const uint32_t child_bits4, const uint32_t bit_index4, uint32_t& hitmask)
+{
+    const float tnx = fmaf(lmb_q2m<J>(nearx, one), sx, bx);
+    const float tny = fmaf(lmb_q2m<J>(neary, one), sy, by);
+    const float tnz = fmaf(lmb_q2m<J>(nearz, one), sz, bz);
+    const float tfx = fmaf(lmb_q2m<J>(farx, one), sx, bx);
+    const float tfy = fmaf(lmb_q2m<J>(fary, one), sy, by);
+    const float tfz = fmaf(lmb_q2m<J>(farz, one), sz, bz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
+    const uint32_t idx5 = (bit_index4 >> (8 * J)) & 0xffu;
+    if (tn <= tf) hitmask |= bits << idx5;
+}
+
 // Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 31..24 =
 // internal children in traversal priority order, bits 23..0 = triangles of hit leaf slots.
 __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
                                                        const float ox, const float oy, const float oz,
                                                        const float idx, const float idy, const float idz,
                                                        const bool negx, const bool negy, const bool negz,
-                                                       const uint32_t oct_inv4, const float tmin, const float tmax)
+                                                       const uint32_t oct_inv4, const float tmin, const float tmax, const uint32_t one)
 {
     const uint32_t ew = __float_as_uint(n0.w);
-    const float sx = __uint_as_float((ew & 0xffu) << 23) * idx;
-    const float sy = __uint_as_float(((ew >> 8) & 0xffu) << 23) * idy;
-    const float sz = __uint_as_float(((ew >> 16) & 0xffu) << 23) * idz;
-    const float bx = (n0.x - ox) * idx;
-    const float by = (n0.y - oy) * idy;
-    const float bz = (n0.z - oz) * idz;
+    // grid step * 2^15 (exponent bytes are biased; the builder keeps e + 15 <= 254)
+    const float sx = __uint_as_float(((ew & 0xffu) + 15u) << 23) * idx;
+    const float sy = __uint_as_float((((ew >> 8) & 0xffu) + 15u) << 23) * idy;
+    const float sz = __uint_as_float((((ew >> 16) & 0xffu) + 15u) << 23) * idz;
+    const float bx = fmaf(n0.x - ox, idx, -sx);
+    const float by = fmaf(n0.y - oy, idy, -sy);
+    const float bz = fmaf(n0.z - oz, idz, -sz);
 
     uint32_t hitmask = 0;
 #pragma unroll
@@ -84,23 +123,10 @@ __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const fl
         const uint32_t inner_mask4 = lmb_sign_extend_s8x4(is_inner4 << 3);    // 0xff per inner byte
         const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
         const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t sel = 0x7650u | (uint32_t)j;
-            const float tnx = fmaf(lmb_q2f(nearx, sel), sx, bx);
-            const float tny = fmaf(lmb_q2f(neary, sel), sy, by);
-            const float tnz = fmaf(lmb_q2f(nearz, sel), sz, bz);
-            const float tfx = fmaf(lmb_q2f(farx, sel), sx, bx);
-            const float tfy = fmaf(lmb_q2f(fary, sel), sy, by);
-            const float tfz = fmaf(lmb_q2f(farz, sel), sz, bz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (tn <= tf) {
-                const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
-                const uint32_t idx5 = (bit_index4 >> (8 * j)) & 0xffu;
-                hitmask |= bits << idx5;
-            }
-        }
+        lmb_child<0>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
+        lmb_child<1>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
+        lmb_child<2>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
+        lmb_child<3>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
     }
     return hitmask;
 }
@@ -109,12 +135,14 @@ __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const fl
 struct Trav {
     float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tmax, hu, hv;
     uint32_t hid, oct_inv4;
+    uint32_t one;      // lmb_one_bits()
     uint2 ngroup;      // y: bits 31..24 pending internal children (priority order) | imask ; or a postponed triangle group (y < 2^24)
     int sp;
 };
 
 __device__ __forceinline__ void trav_init(Trav& T, const float4 ro, const float4 rd)
 {
+    T.one = lmb_one_bits();
     T.ox = ro.x; T.oy = ro.y; T.oz = ro.z; T.tmin = ro.w;
     T.dx = rd.x; T.dy = rd.y; T.dz = rd.z; T.tmax = rd.w;
     T.idx = lmb_safe_inv(rd.x); T.idy = lmb_safe_inv(rd.y); T.idz = lmb_safe_inv(rd.z);
@@ -160,7 +188,7 @@ __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ no
         const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
         if (COUNT) cnt.nodes++;
         const uint32_t hitmask = lmb_intersect_node(n0, n1, n2, n3, n4, T.ox, T.oy, T.oz, T.idx, T.idy, T.idz,
-                                                    T.idx < 0.f, T.idy < 0.f, T.idz < 0.f, T.oct_inv4, T.tmin, T.tmax);
+                                                    T.idx < 0.f, T.idy < 0.f, T.idz < 0.f, T.oct_inv4, T.tmin, T.tmax, T.one);
         T.ngroup.x = __float_as_uint(n1.x);
         T.ngroup.y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
         tgroup.x = __float_as_uint(n1.y);

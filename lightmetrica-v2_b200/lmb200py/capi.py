@@ -4,7 +4,7 @@ import os
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_ROOT, "lib", "liblmb200.so")
+LIB_PATH = os.environ.get("LMB200_LIB", os.path.join(_ROOT, "lib", "liblmb200.so"))   # override: tuning variants only
 
 MISS = 0xFFFFFFFF
 MODE_PT, MODE_PTDIRECT, MODE_NORMAL = 0, 1, 2
