@@ -330,14 +330,14 @@ def main():
 def bench_pt(a, torch, dist, capi, world, rank, local, dev):
     """ptdirect on the 1M-triangle mesh scene (BASELINE configs[2] geometry/materials/lights) at pt_spp samples per pixel,
     sample range sharded contiguously over ranks, films summed with one NCCL reduce, then rescaled."""
-    from lmb200py import scenedesc, scenes
+    from lmb200py import scenedesc, distributed
     sc = scenedesc.config2_scene(a.pt_tris, 1920, 1080)
     S = capi.Scene(sc, device=local)
     W, H = 1920, 1080
     N = W * H * a.pt_spp
     film = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     L = capi.lib()
-    b, e = N * rank // world, N * (rank + 1) // world
+    b, e = distributed.shard_range(N, rank, world)
     st = capi.RenderStats()
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -345,9 +345,8 @@ def bench_pt(a, torch, dist, capi, world, rank, local, dev):
         film.zero_()
         p = S.params(capi.MODE_PTDIRECT, N, seed=1, begin=b, end=e)
         capi.check(L.lmb200_render_dev(S.h_, C.byref(p), film.data_ptr(), stream, C.byref(st)))
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
-        capi.check(L.lmb200_film_rescale_dev(film.data_ptr(), W * H, float(W * H) / float(N), stream))
+        distributed.reduce_film(film, dist if world > 1 else None)
+        capi.check(L.lmb200_film_rescale_dev(film.data_ptr(), W * H, distributed.film_scale(W, H, N), stream))
     once()
     torch.cuda.synchronize()
     if world > 1:

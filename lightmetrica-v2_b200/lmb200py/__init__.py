@@ -4,4 +4,4 @@ Test/bench convenience only: the product is the CUDA library and the two Lightme
 nothing here computes anything. Importing this package never falls back to a CPU path: if the
 shared library is missing, `capi.lib()` raises.
 """
-from . import capi, scenes  # noqa: F401
+from . import capi, scenes, scenedesc, distributed  # noqa: F401

@@ -105,3 +105,22 @@ def test_render_dev_with_caller_owned_film():
     capi.check(L.lmb200_film_rescale_dev(film.data_ptr(), 32 * 32, float(32 * 32) / N, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert np.allclose(film.cpu().numpy()[..., :3], ref, rtol=2e-4, atol=1e-5)
+
+
+def test_render_multi_nccl_reduce():
+    """Single-process multi-GPU entry point (what renderer::lmb200pt calls with num_gpus > 1): per-GPU films are
+    summed with ncclReduce; the image must equal the 1-GPU image of the same seed."""
+    L = capi.lib()
+    if L.lmb200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = scenedesc.cornell_box(48, 48, glossy_block=True)
+    N = 48 * 48 * 64
+    scenes_ = [capi.Scene(sc, device=g) for g in range(2)]
+    one, _ = scenes_[0].render(capi.MODE_PTDIRECT, N, seed=3)
+    arr = (C.c_void_p * 2)(*[s.h_ for s in scenes_])
+    p = scenes_[0].params(capi.MODE_PTDIRECT, N, seed=3)
+    film = np.zeros((48, 48, 4), np.float32)
+    st = capi.RenderStats()
+    capi.check(L.lmb200_render_multi(arr, 2, C.byref(p), film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    assert st.samples == N
+    assert np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
