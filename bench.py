@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-pt", action="store_true", help="skip the secondary path-tracing figure")
     ap.add_argument("--pt-tris", type=int, default=1_000_000)
     ap.add_argument("--pt-spp", type=int, default=16)
+    ap.add_argument("--pt-pool", type=int, default=0, help="wavefront pool size (0 = library default)")
     return ap.parse_args()
 
 
@@ -343,7 +344,7 @@ def bench_pt(a, torch, dist, capi, world, rank, local, dev):
 
     def once():
         film.zero_()
-        p = S.params(capi.MODE_PTDIRECT, N, seed=1, begin=b, end=e)
+        p = S.params(capi.MODE_PTDIRECT, N, seed=1, begin=b, end=e, pool=a.pt_pool)
         capi.check(L.lmb200_render_dev(S.h_, C.byref(p), film.data_ptr(), stream, C.byref(st)))
         distributed.reduce_film(film, dist if world > 1 else None)
         capi.check(L.lmb200_film_rescale_dev(film.data_ptr(), W * H, distributed.film_scale(W, H, N), stream))

@@ -41,13 +41,13 @@ struct BatchIoAny {
 };
 
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(LMB_TRACE_BLOCK)
+__global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
 trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
              const float4* __restrict__ rays, void* __restrict__ out,
              const uint64_t n_host, const uint32_t* __restrict__ n_dev,
              unsigned long long* __restrict__ counter, unsigned long long* __restrict__ work_counters)
 {
-    __shared__ uint2 smem[LMB_SM_STACK * LMB_TRACE_BLOCK];
+    __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     if (ANY) {
@@ -68,7 +68,7 @@ trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
 // one ray, one warp: the per-ray Accel3::Intersect path (mailbox in mapped pinned host memory)
 __global__ void trace_one_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* ray, float4* out)
 {
-    __shared__ uint2 smem[LMB_SM_STACK * 32];
+    __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(32)];
     if (threadIdx.x != 0) return;
     Trav T;
     TravCounters cnt;
@@ -124,12 +124,14 @@ void Accel::free_device()
     if (d_nodes) cudaFree(d_nodes);
     if (d_tris) cudaFree(d_tris);
     if (d_counter) cudaFree(d_counter);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < LMB_NBUF; i++) {
         if (stage_rays[i]) cudaFree(stage_rays[i]);
         if (stage_out[i]) cudaFree(stage_out[i]);
-        if (streams[i]) cudaStreamDestroy(streams[i]);
-        stage_rays[i] = stage_out[i] = nullptr; streams[i] = nullptr;
+        stage_rays[i] = stage_out[i] = nullptr;
     }
+    for (int i = 0; i < 3; i++) { if (streams[i]) cudaStreamDestroy(streams[i]); streams[i] = nullptr; }
+    for (int i = 0; i < 3 * LMB_NBUF; i++) { if (events[i]) cudaEventDestroy(events[i]); events[i] = nullptr; }
+    stage_cap = 0;
     d_nodes = d_tris = nullptr; d_counter = nullptr;
 }
 
@@ -159,23 +161,28 @@ int Accel::upload()
     return LMB200_OK;
 }
 
-// Host-buffer trace: chunks ping-pong over two streams so the H2D copy of chunk k+1 and the D2H
-// copy of chunk k-1 overlap the kernel of chunk k (when the host buffers are pinned).
+// Host-buffer trace: a three-stage pipeline (H2D copy | kernel | D2H copy) over three streams and
+// LMB_NBUF staging buffers, so that with pinned host memory the PCIe traffic of chunk k+1 and k-1
+// overlaps the kernel of chunk k.
 template <bool ANY>
 static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
 {
     if (!a || (!rays && n) || (!out && n)) return set_error(LMB200_E_INVALID, "null argument");
     if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
     if (!a->d_nodes) return set_error(LMB200_E_STATE, "accel not built");
+    if (n == 0) return LMB200_OK;
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     const size_t out_elem = ANY ? 1 : sizeof(lmb200_hit);
-    const uint64_t chunk = n < (1ull << 22) ? std::max<uint64_t>(n, 1) : (1ull << 22);
-    for (int i = 0; i < 2; i++) {
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << 23);
+    for (int i = 0; i < 3; i++) {
         if (!a->streams[i] && (e = cudaStreamCreateWithFlags(&a->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
     }
+    for (int i = 0; i < 3 * LMB_NBUF; i++) {
+        if (!a->events[i] && (e = cudaEventCreateWithFlags(&a->events[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+    }
     if (a->stage_cap < chunk) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < LMB_NBUF; i++) {
             if (a->stage_rays[i]) cudaFree(a->stage_rays[i]);
             if (a->stage_out[i]) cudaFree(a->stage_out[i]);
             a->stage_rays[i] = a->stage_out[i] = nullptr;
@@ -184,18 +191,25 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
         }
         a->stage_cap = chunk;
     }
-    // each staging stream has its own work counter (slots 2 and 3)
-    int k = 0;
-    for (uint64_t off = 0; off < n; off += chunk, k ^= 1) {
+    cudaStream_t s_in = a->streams[0], s_k = a->streams[1], s_out = a->streams[2];
+    uint64_t c = 0;
+    for (uint64_t off = 0; off < n; off += chunk, c++) {
+        const int b = (int)(c % LMB_NBUF);
+        cudaEvent_t ev_in = a->events[3 * b], ev_k = a->events[3 * b + 1], ev_out = a->events[3 * b + 2];
         const uint64_t m = std::min(chunk, n - off);
-        cudaStream_t st = a->streams[k];
-        if ((e = cudaMemcpyAsync(a->stage_rays[k], rays + off, m * sizeof(lmb200_ray), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail(e, "H2D rays");
-        const int rc = ANY ? trace_any_dev(a, a->stage_rays[k], a->stage_out[k], m, nullptr, st, 2 + k)
-                           : trace_closest_dev(a, a->stage_rays[k], a->stage_out[k], m, nullptr, st, 2 + k);
+        if (c >= LMB_NBUF) cudaStreamWaitEvent(s_in, ev_out, 0);        // buffer b is free again
+        if ((e = cudaMemcpyAsync(a->stage_rays[b], rays + off, m * sizeof(lmb200_ray), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D rays");
+        cudaEventRecord(ev_in, s_in);
+        cudaStreamWaitEvent(s_k, ev_in, 0);
+        const int rc = ANY ? trace_any_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, 2)
+                           : trace_closest_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, 2);
         if (rc) return rc;
-        if ((e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + off * out_elem, a->stage_out[k], m * out_elem, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail(e, "D2H hits");
+        cudaEventRecord(ev_k, s_k);
+        cudaStreamWaitEvent(s_out, ev_k, 0);
+        if ((e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + off * out_elem, a->stage_out[b], m * out_elem, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return cuda_fail(e, "D2H hits");
+        cudaEventRecord(ev_out, s_out);
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         if ((e = cudaStreamSynchronize(a->streams[i])) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
     }
     return LMB200_OK;

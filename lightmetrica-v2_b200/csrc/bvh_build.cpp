@@ -41,14 +41,22 @@ struct Box {
 struct BinNode {
     Box box;
     uint32_t left;    // children are left, left+1 (count == 0)
-    uint32_t first;   // leaf: refs[first, first+count)
-    uint32_t count;
+    uint32_t first;   // the subtree covers refs[first, first+total)
+    uint32_t count;   // > 0: binary leaf with `count` triangles
+    uint32_t total;   // triangles in the subtree
 };
 
 constexpr int kBins = 16;
 constexpr int kMaxLeaf = 3;           // triangles per leaf slot (3 unary bits in Node80::meta)
-constexpr float kCostNode = 1.0f;     // SAH: one binary split step
-constexpr float kCostTri = 1.0f;      // SAH: one triangle test
+constexpr float kCostNode = 1.0f;     // binary build SAH: one split step
+constexpr float kCostTri = 1.0f;      // binary build SAH: one triangle test
+// wide-node SAH used by the collapse (Ylitie et al. 2017, sec. 4.1): one 8-wide node visit vs one triangle test
+#ifndef LMB_WIDE_COST_NODE
+#define LMB_WIDE_COST_NODE 1.0f
+#endif
+#ifndef LMB_WIDE_COST_TRI
+#define LMB_WIDE_COST_TRI 1.2f   // measured on B200 (profiles/r01_sweep.md): the TriAccel test (3 x LDG.128, one divide) costs about a node visit
+#endif
 constexpr uint32_t kParallelGrain = 1u << 14;
 constexpr double kQSlack = 1.0 / 256.0;   // grid steps added around every quantised child box (see emit_node)
 
@@ -118,12 +126,11 @@ struct Builder {
         BinNode& node = nodes[ni];
         const uint32_t n = end - begin;
         node.box = bounds_of(&refs[begin], n);
-        node.count = 0; node.first = begin; node.left = 0;
+        node.count = 0; node.first = begin; node.left = 0; node.total = n;
         if (n == 1) { node.count = 1; return 0; }
         int axis; float pos, cost;
         uint32_t mid = 0;
         if (find_split(begin, end, node.box, axis, pos, cost)) {
-            if (n <= (uint32_t)kMaxLeaf && kCostTri * n <= cost) { node.count = n; return 0; }
             Ref* lo = &refs[begin]; Ref* hi = &refs[end];
             Ref* m = std::partition(lo, hi, [&](const Ref& r) { return 0.5f * (r.lo[axis] + r.hi[axis]) < pos; });
             mid = begin + (uint32_t)(m - lo);
@@ -157,7 +164,7 @@ struct Builder {
         const uint32_t n = (uint32_t)refs.size();
         nodes.resize(std::max<size_t>(1, 2 * (size_t)n));
         node_count = 1;
-        if (n == 0) { nodes[0].box.reset(); nodes[0].count = 0; nodes[0].left = 0; nodes[0].first = 0; return; }
+        if (n == 0) { nodes[0].box.reset(); nodes[0].count = 0; nodes[0].left = 0; nodes[0].first = 0; nodes[0].total = 0; return; }
         // Phase A: split the largest open ranges on this thread until there is enough parallel work.
         std::vector<Task> open;
         open.push_back({0, 0, n});
@@ -210,6 +217,7 @@ struct Emitter {
         const uint32_t nrefs = (uint32_t)B.refs.size();
         if (nrefs == 0) { out.nodes[0].e[0] = out.nodes[0].e[1] = out.nodes[0].e[2] = 127; return; }
         out.tris.reserve(nrefs); out.tri_index.reserve(nrefs);
+        plan();
         std::vector<Pending> st;
         st.push_back({0, 0, 1});
         const float root_area = std::max(B.nodes[0].box.half_area(), 1e-30f);
@@ -220,21 +228,71 @@ struct Emitter {
         }
     }
 
-    void emit_node(const Pending& p, std::vector<Pending>& st, float root_area) {
-        // 1. gather up to 8 children by repeatedly opening the internal child of largest area
-        uint32_t ch[8]; int n = 0;
-        const BinNode& root = B.nodes[p.bin];
-        if (root.count > 0) { ch[n++] = p.bin; }           // the whole tree is one leaf
-        else { ch[n++] = root.left; ch[n++] = root.left + 1; }
-        for (;;) {
-            int best = -1; float best_area = -1.f;
-            for (int i = 0; i < n; i++) {
-                const BinNode& c = B.nodes[ch[i]];
-                if (c.count == 0) { const float a = c.box.half_area(); if (a > best_area) { best_area = a; best = i; } }
+    // ---- SAH-optimal collapse (dynamic programme over the binary tree) ----
+    // cost[n][i-1], i = 1..7: cheapest way to represent subtree n as at most i wide-node slots.
+    //   i = 1: either one leaf slot (<= 3 triangles) or one internal slot (a new wide node with up to 8 slots)
+    //   i > 1: additionally the slots may be split between the two binary children.
+    struct Choice { uint8_t take[7]; uint8_t dist_k[7]; uint8_t int_k; };   // take: 0 leaf, 1 internal, 2 distribute, 3 as i-1
+    std::vector<float> cost;       // 7 per binary node
+    std::vector<Choice> choice;
+
+    void plan() {
+        const uint32_t nb = B.node_count.load();
+        cost.assign((size_t)nb * 7, 0.f);
+        choice.assign(nb, Choice());
+        const float inv_root = 1.0f / std::max(B.nodes[0].box.half_area(), 1e-30f);
+        for (uint32_t n = nb; n-- > 0;) {          // children have larger indices than their parent
+            const BinNode& N = B.nodes[n];
+            float* c = &cost[(size_t)n * 7];
+            Choice& ch = choice[n];
+            const float area = N.box.half_area() * inv_root;
+            const float leaf = N.total <= (uint32_t)kMaxLeaf ? area * N.total * LMB_WIDE_COST_TRI : INFINITY;
+            if (N.count > 0) {                     // binary leaf: nothing to distribute
+                for (int i = 0; i < 7; i++) { c[i] = leaf; ch.take[i] = 0; }
+                continue;
             }
-            if (best < 0 || n == 8) break;
-            const uint32_t l = B.nodes[ch[best]].left;
-            ch[best] = l; ch[n++] = l + 1;
+            const float* cl = &cost[(size_t)N.left * 7];
+            const float* cr = &cost[(size_t)(N.left + 1) * 7];
+            auto distribute = [&](int j, uint8_t& kbest) {   // best split of j slots (2..8) between the children
+                float best = INFINITY; kbest = 1;
+                for (int k = 1; k < j; k++) {
+                    if (k > 7 || j - k > 7) continue;
+                    const float v = cl[k - 1] + cr[j - k - 1];
+                    if (v < best) { best = v; kbest = (uint8_t)k; }
+                }
+                return best;
+            };
+            const float internal = distribute(8, ch.int_k) + area * LMB_WIDE_COST_NODE;
+            if (leaf <= internal) { c[0] = leaf; ch.take[0] = 0; } else { c[0] = internal; ch.take[0] = 1; }
+            for (int i = 2; i <= 7; i++) {
+                const float d = distribute(i, ch.dist_k[i - 1]);
+                if (d < c[i - 2]) { c[i - 1] = d; ch.take[i - 1] = 2; } else { c[i - 1] = c[i - 2]; ch.take[i - 1] = 3; }
+            }
+        }
+    }
+
+    // slots of subtree n when it may use at most i slots
+    void collect(uint32_t n, int i, uint32_t* out, bool* out_leaf, int& cnt) const {
+        for (;;) {
+            const uint8_t t = choice[n].take[i - 1];
+            if (t == 3) { i--; continue; }
+            if (t == 0) { out[cnt] = n; out_leaf[cnt++] = true; return; }
+            if (t == 1) { out[cnt] = n; out_leaf[cnt++] = false; return; }
+            const int k = choice[n].dist_k[i - 1];
+            collect(B.nodes[n].left, k, out, out_leaf, cnt);
+            n = B.nodes[n].left + 1; i = i - k;
+        }
+    }
+
+    void emit_node(const Pending& p, std::vector<Pending>& st, float root_area) {
+        // 1. the slots of this wide node as planned by the dynamic programme
+        uint32_t ch[8]; bool is_leaf[8]; int n = 0;
+        const BinNode& root = B.nodes[p.bin];
+        if (root.count > 0 || root.total <= 1) { ch[0] = p.bin; is_leaf[0] = true; n = 1; }   // the whole tree is one leaf
+        else {
+            const int k = choice[p.bin].int_k;
+            collect(root.left, k, ch, is_leaf, n);
+            collect(root.left + 1, 8 - k, ch, is_leaf, n);
         }
         // 2. node box + quantisation grid
         Box nb; nb.reset();
@@ -291,22 +349,22 @@ struct Emitter {
                 qh = std::max(0.0, std::min(255.0, qh));
                 node.qlo[a][s] = (uint8_t)ql; node.qhi[a][s] = (uint8_t)qh;
             }
-            if (c.count > 0) {
-                node.meta[s] = (uint8_t)((((1u << c.count) - 1u) << 5) | tri_off);
-                for (uint32_t k = 0; k < c.count; k++) {
+            if (is_leaf[i]) {
+                node.meta[s] = (uint8_t)((((1u << c.total) - 1u) << 5) | tri_off);
+                for (uint32_t k = 0; k < c.total; k++) {
                     const uint32_t id = B.refs[c.first + k].id;
                     out.tris.push_back(recs[id]);
                     out.tri_index.push_back(id);
                 }
-                tri_off += c.count;
-                sah += kCostTri * c.count * c.box.half_area() * inv_root;
+                tri_off += c.total;
+                sah += LMB_WIDE_COST_TRI * c.total * c.box.half_area() * inv_root;
             } else {
                 node.imask |= (uint8_t)(1u << s);
                 node.meta[s] = (uint8_t)(0x20u | (24u + s));
                 n_internal++;
             }
         }
-        sah += kCostNode * nb.half_area() * inv_root;
+        sah += LMB_WIDE_COST_NODE * nb.half_area() * inv_root;
         out.nodes[p.wide] = node;
         // 5. reserve the internal children (contiguous, slot order) and schedule them
         const uint32_t base = node.child_base;
@@ -314,7 +372,7 @@ struct Emitter {
         uint32_t rel = 0;
         for (int s = 0; s < 8; s++) {
             const int i = child_in_slot[s];
-            if (i < 0 || B.nodes[ch[i]].count > 0) continue;
+            if (i < 0 || is_leaf[i]) continue;
             st.push_back({ch[i], base + rel, p.depth + 1});
             rel++;
         }

@@ -9,6 +9,11 @@
 #ifndef LMB_TRACE_BLOCK
 #define LMB_TRACE_BLOCK 128
 #endif
+#ifndef LMB_TRACE_MIN_BLOCKS
+#define LMB_TRACE_MIN_BLOCKS 9     // resident blocks per SM the traversal kernels are compiled for (register cap)
+#endif
+
+#define LMB_NBUF 3
 
 namespace lmb200 {
 
@@ -29,9 +34,10 @@ struct Accel {
     int trace_blocks_per_sm = 4;
     double upload_seconds = 0;
     // staging for the host-pointer entry points
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    void* stage_rays[2] = {nullptr, nullptr};
-    void* stage_out[2] = {nullptr, nullptr};
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};      // copy-in, kernel, copy-out
+    void* stage_rays[LMB_NBUF] = {};
+    void* stage_out[LMB_NBUF] = {};
+    cudaEvent_t events[3 * LMB_NBUF] = {};
     uint64_t stage_cap = 0;
 
     ~Accel();

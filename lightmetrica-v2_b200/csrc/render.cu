@@ -540,10 +540,10 @@ struct ExtendIo {
         P.hit[P.eq[qi]] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
     }
 };
-__global__ void __launch_bounds__(LMB_TRACE_BLOCK)
+__global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
 k_extend(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter)
 {
-    __shared__ uint2 smem[LMB_SM_STACK * LMB_TRACE_BLOCK];
+    __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ExtendIo io{P, P.qcount[1]};
     TravCounters cnt;
     persistent_trace<false, false>(nodes, tris, io, counter, smem, cnt);
@@ -562,10 +562,10 @@ struct ShadowIo {
         }
     }
 };
-__global__ void __launch_bounds__(LMB_TRACE_BLOCK)
+__global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
 k_shadow(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter, float4* film)
 {
-    __shared__ uint2 smem[LMB_SM_STACK * LMB_TRACE_BLOCK];
+    __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ShadowIo io{P, P.qcount[2], film};
     TravCounters cnt;
     persistent_trace<true, false>(nodes, tris, io, counter, smem, cnt);
@@ -727,7 +727,7 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     if (p->mode != LMB200_MODE_PT && p->mode != LMB200_MODE_PTDIRECT) return set_error(LMB200_E_INVALID, "unknown render mode");
     if (p->sample_end < p->sample_begin) return set_error(LMB200_E_INVALID, "sample_end < sample_begin");
     const int64_t todo = p->sample_end - p->sample_begin;
-    uint32_t pool = p->pool_size > 0 ? (uint32_t)p->pool_size : (1u << 21);
+    uint32_t pool = p->pool_size > 0 ? (uint32_t)p->pool_size : (1u << 22);   // 4 Mi slots: best on B200 (profiles/r01_sweep.md)
     if ((int64_t)pool > todo) pool = (uint32_t)std::max<int64_t>(todo, 1);
     pool = (pool + 31u) & ~31u;
     int rc = ensure_pool(s, pool);

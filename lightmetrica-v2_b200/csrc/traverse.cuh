@@ -7,9 +7,8 @@
 //     slowest ray of its warp is done,
 //   * one thread per ray, (node-group, triangle-group) pairs in registers and a short stack of
 //     8-byte entries in shared memory (overflow to local memory),
-//   * triangle tests can be postponed (pushed back as a triangle group) while too few lanes of the
-//     warp have triangle work (LMB_TRI_POSTPONE_BELOW); measured on B200 this does not pay with
-//     <=3-triangle leaves (profiles/r01_sweep.md), so the default threshold is 0 = test at once.
+//   * triangle tests are batched across the warp (parked per lane until LMB_TRI_BATCH lanes have
+//     some), so the triangle code runs with many lanes instead of ~2.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -24,8 +23,8 @@ namespace lmb200 {
 #ifndef LMB_REFILL_BELOW
 #define LMB_REFILL_BELOW 26     // refill the warp when fewer lanes than this are active
 #endif
-#ifndef LMB_TRI_POSTPONE_BELOW
-#define LMB_TRI_POSTPONE_BELOW 0   // postpone triangle tests while fewer lanes than this have some
+#ifndef LMB_TRI_BATCH
+#define LMB_TRI_BATCH 12         // test parked triangles once this many lanes have some
 #endif
 
 struct TravCounters { uint32_t nodes, tris; };
@@ -89,6 +88,8 @@ __device__ __forceinline__ void lmb_child(const uint32_t nearx, const uint32_t n
 
 // Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 31..24 =
 // internal children in traversal priority order, bits 23..0 = triangles of hit leaf slots.
+// (A variant that collects slot-order hit bits and permutes them with a shared-memory table was
+// measured slower on B200: it needs 64 registers instead of 56, profiles/r01_sweep.md.)
 __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
                                                        const float ox, const float oy, const float oz,
                                                        const float idx, const float idy, const float idz,
@@ -136,7 +137,8 @@ struct Trav {
     float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tmax, hu, hv;
     uint32_t hid, oct_inv4;
     uint32_t one;      // lmb_one_bits()
-    uint2 ngroup;      // y: bits 31..24 pending internal children (priority order) | imask ; or a postponed triangle group (y < 2^24)
+    uint2 ngroup;      // x: child_base; y: bits 31..24 pending internal children (priority order) | imask
+    uint2 pend;        // parked triangle group: x = first triangle, y = 24-bit mask
     int sp;
 };
 
@@ -151,6 +153,7 @@ __device__ __forceinline__ void trav_init(Trav& T, const float4 ro, const float4
     T.oct_inv4 = (7u - oct) * 0x01010101u;
     T.hu = 0.f; T.hv = 0.f; T.hid = 0xffffffffu;
     T.ngroup = make_uint2(0u, 0x80000000u);   // root: node 0 (imask 0 resolves to relative index 0)
+    T.pend = make_uint2(0u, 0u);
     T.sp = 0;
 }
 
@@ -167,16 +170,19 @@ __device__ __forceinline__ uint2 trav_pop(Trav& T, const uint2* __restrict__ sme
     return T.sp < LMB_SM_STACK ? smem[T.sp * blockDim.x + threadIdx.x] : lstack[T.sp - LMB_SM_STACK];
 }
 
-// One traversal step of an active lane: open one node (or take a postponed triangle group), test
-// the pending triangles unless the warp decides to postpone them, fetch the next group.
+// One traversal step of an active lane: open the nearest pending node, then maybe test triangles.
+// Triangle work is batched across the warp: the triangles hit by a node test are parked in a
+// per-lane pending group (two registers) and tested only when at least LMB_TRI_BATCH lanes have
+// parked work, or when some lane must (it hit a second group, or it has nothing else left to do).
+// Incoherent rays reach a leaf on ~5 % of their node visits, so testing at once would run the
+// triangle code on ~80 % of the warp's steps with ~2 of 32 lanes active (ncu, profiles/).
 // Returns true when the ray is finished. Closest hit: tie on t -> larger triangle index wins, which
 // is what a linear scan with the reference's "reject t > maxT" rule yields (accel_naive.cpp:92-124).
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                           uint2* __restrict__ smem, uint2* __restrict__ lstack, TravCounters& cnt)
 {
-    uint2 tgroup;
-    bool fresh = false;   // tgroup comes from a node opened in this step (may be postponed once)
+    uint2 fresh = make_uint2(0u, 0u);
     if (T.ngroup.y & 0xff000000u) {
         const uint32_t hits_imask = T.ngroup.y;
         const uint32_t bit = 31u - __clz(hits_imask);
@@ -191,49 +197,42 @@ __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ no
                                                     T.idx < 0.f, T.idy < 0.f, T.idz < 0.f, T.oct_inv4, T.tmin, T.tmax, T.one);
         T.ngroup.x = __float_as_uint(n1.x);
         T.ngroup.y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
-        tgroup.x = __float_as_uint(n1.y);
-        tgroup.y = hitmask & 0x00ffffffu;
-        fresh = true;
-    } else {
-        tgroup = T.ngroup;                 // a postponed triangle group came off the stack
-        T.ngroup = make_uint2(0u, 0u);
+        fresh.x = __float_as_uint(n1.y);
+        fresh.y = hitmask & 0x00ffffffu;
     }
+    // next node group
+    if ((T.ngroup.y & 0xff000000u) == 0u && T.sp > 0) T.ngroup = trav_pop(T, smem, lstack);
+    const bool no_nodes = (T.ngroup.y & 0xff000000u) == 0u;
 
-    // triangle phase
+    // park the fresh triangles if the pending slot is free
+    const bool collide = T.pend.y != 0u && fresh.y != 0u;
+    if (T.pend.y == 0u) { T.pend = fresh; fresh.y = 0u; }
     {
         const unsigned lanes = __activemask();
-        const unsigned want = __ballot_sync(lanes, tgroup.y != 0u);
-        if (want) {
-            // Postpone only triangles of a node opened in THIS step (so the same group is never
-            // postponed twice: a group popped from the stack is always tested -> progress), and
-            // only while the lane still has boxes to test next (otherwise it would just pop them back).
-            const bool few = __popc(want) < LMB_TRI_POSTPONE_BELOW;
-            if (few && fresh && tgroup.y && (T.ngroup.y & 0xff000000u)) {
-                trav_push(T, smem, lstack, tgroup);
-            } else {
-                while (tgroup.y) {
-                    const uint32_t i = __ffs(tgroup.y) - 1;
-                    tgroup.y &= tgroup.y - 1;
-                    const float4* tp = tris + (size_t)(tgroup.x + i) * 3u;
-                    const float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
-                    if (COUNT) cnt.tris++;
-                    float t, u, v;
-                    if (triaccel_intersect(r0, r1, r2, T.ox, T.oy, T.oz, T.dx, T.dy, T.dz, T.tmin, T.tmax, t, u, v)) {
-                        if (ANY) { T.hid = 0u; return true; }
-                        const uint32_t id = __float_as_uint(r2.z);
-                        if (t < T.tmax || T.hid == 0xffffffffu || id > T.hid) { T.tmax = t; T.hu = u; T.hv = v; T.hid = id; }
-                    }
+        const unsigned want = __ballot_sync(lanes, T.pend.y != 0u);
+        const unsigned must = __ballot_sync(lanes, collide || (no_nodes && T.pend.y != 0u));
+        if (must != 0u || __popc(want) >= LMB_TRI_BATCH) {
+            while (T.pend.y) {
+                const uint32_t i = __ffs(T.pend.y) - 1;
+                T.pend.y &= T.pend.y - 1;
+                const float4* tp = tris + (size_t)(T.pend.x + i) * 3u;
+                const float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
+                if (COUNT) cnt.tris++;
+                float t, u, v;
+                if (triaccel_intersect(r0, r1, r2, T.ox, T.oy, T.oz, T.dx, T.dy, T.dz, T.tmin, T.tmax, t, u, v)) {
+                    if (ANY) { T.hid = 0u; return true; }
+                    const uint32_t id = __float_as_uint(r2.z);
+                    if (t < T.tmax || T.hid == 0xffffffffu || id > T.hid) { T.tmax = t; T.hu = u; T.hv = v; T.hid = id; }
                 }
             }
+            if (fresh.y) { T.pend = fresh; }      // the second group of a collision waits for the next batch
         }
     }
-
-    if ((T.ngroup.y & 0xff000000u) == 0u) {
-        if (T.sp == 0) return true;
-        T.ngroup = trav_pop(T, smem, lstack);
-    }
-    return false;
+    return no_nodes && T.pend.y == 0u;
 }
+
+// Shared memory a block needs (uint2 entries): the per-thread short stacks.
+#define LMB_TRAV_SMEM_UINT2(block) (LMB_SM_STACK * (block))
 
 // Persistent-warp driver. `Io` supplies rays and consumes results:
 //   uint64_t count() const;                          number of rays
@@ -290,7 +289,7 @@ __device__ __forceinline__ void persistent_trace(const float4* __restrict__ node
     }
 }
 
-// Whole-ray helper for single-ray callers (per-ray Accel3::Intersect path, debug kernels).
+// Whole-ray helper for single-ray callers (per-ray Accel3::Intersect path).
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ bool lmb_traverse(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                              const float4 ro, const float4 rd, Trav& T, uint2* __restrict__ smem, TravCounters& cnt)
