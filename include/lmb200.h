@@ -167,6 +167,7 @@ typedef struct lmb200_scene lmb200_scene;
 
 #define LMB200_MODE_PT        0   /* renderer::pt: emission on BSDF-sampled hits, no NEE */
 #define LMB200_MODE_PTDIRECT  1   /* renderer::ptdirect: NEE at every vertex incl. the camera vertex */
+#define LMB200_MODE_PTMIS     3   /* renderer::ptmis: NEE + BSDF-sampled emission, balance heuristic (renderer_ptmis.cpp:130-275) */
 #define LMB200_MODE_NORMAL    2   /* primary rays at pixel centres, |sn| as RGB (renderer_raycast.cpp:72-105 ray gen,
                                      plugin/renderer_normal/renderer_normal.cpp:62-75 shading) */
 

@@ -61,6 +61,7 @@ struct Pool {
     float4* vtx_p;                // p.xyz, w = tri (uint bits) ; camera vertex: tri = 0xffffffff
     float4* vtx_wi;               // wi.xyz, w = u
     float*  vtx_v;                // barycentric v
+    float4* prev;                 // ptmis: shading normal of the vertex the extend ray left from, w = pdf of the sampled direction
     // queues
     uint32_t* vq;                 // vertex queue (slot indices)
     uint32_t* eq;                 // extend queue (slot indices)
@@ -331,12 +332,27 @@ __global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg
                 float4 thr = P.thr[i];
                 const lmb200_primitive& prim = S.prims[S.tri_prim[tri]];
                 bool cont = true;
-                if (cfg.mode == LMB200_MODE_PT && prim.light >= 0 && nv + 1 >= cfg.min_verts) {
+                if (cfg.mode != LMB200_MODE_PTDIRECT && prim.light >= 0 && nv + 1 >= cfg.min_verts) {
                     // emission on hit (renderer_pt.cpp:183-194; light_area.cpp:105-115)
                     Geom g;
                     tri_geom(S, tri, h.y, h.z, o + d * h.x, g);
-                    if (to_local(g, neg(d)).z > 0.f)
-                        film_add(film, __float_as_int(thr.w), F3(thr.x, thr.y, thr.z) * ld3(S.lights[prim.light].Le));
+                    if (to_local(g, neg(d)).z > 0.f) {
+                        f3 C = F3(thr.x, thr.y, thr.z) * ld3(S.lights[prim.light].Le);
+                        if (cfg.mode == LMB200_MODE_PTMIS) {
+                            // balance heuristic against the light-sampling pdf (renderer_ptmis.cpp:247-260):
+                            // pdfPL / G(hit, previous vertex) * pdfL, G as renderutils.h:46-56
+                            const float4 pv = P.prev[i];
+                            f3 dd = o - g.p;
+                            const float d2 = dot(dd, dd), dl = sqrtf(d2);
+                            dd = F3(dd.x / dl, dd.y / dl, dd.z / dl);
+                            float G = fabsf(dot(g.sn, dd));
+                            if (nv > 1) G *= fabsf(dot(F3(pv.x, pv.y, pv.z), neg(dd)));   // the camera vertex is degenerated
+                            G = G / d2;
+                            const float pdfDL = S.light_inv_area[prim.light] / G * (1.0f / (float)S.num_lights);
+                            C = C * (pv.w / (pv.w + pdfDL));
+                        }
+                        film_add(film, __float_as_int(thr.w), C);
+                    }
                 }
                 // Russian roulette with the 4th uniform of this iteration's first block (renderer_pt.cpp:207-215)
                 const float4 ua = rng_block(cfg.seed, P.sample[i], (uint32_t)(2 * nv - 1));
@@ -377,8 +393,8 @@ __global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg
             if (sidx < cfg.sample_end) {
                 bool ok = true;
                 int pixel = -1;
-                if (cfg.mode == LMB200_MODE_PT) {
-                    // renderer::pt computes the raster position up front and drops the sample if it fails (renderer_pt.cpp:94-99)
+                if (cfg.mode != LMB200_MODE_PTDIRECT) {
+                    // renderer::pt / ptmis compute the raster position up front and drop the sample if it fails (renderer_pt.cpp:94-99)
                     const float4 u = rng_block(cfg.seed, sidx, 0u);
                     float rx, ry;
                     ok = raster_position(S, camera_dir(S, u.y, u.z), rx, ry);
@@ -413,7 +429,7 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
         bool emit = false;
         f3 C = F3(0, 0, 0), p = F3(0, 0, 0), pl = F3(0, 0, 0);
         int pixel = 0;
-        if (qi < nq && S.num_lights > 0) {
+        if (qi < nq && S.num_lights > 0 && (cfg.mode == LMB200_MODE_PTDIRECT || P.nverts[P.vq[qi]] + 1 >= cfg.min_verts)) {
             const uint32_t i = P.vq[qi];
             const int nv = P.nverts[i];
             const float4 vp = P.vtx_p[i];
@@ -432,11 +448,14 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
             const f3 ppL = normalize(gL.p - p);
             f3 fsE;
             Geom g;
-            if (is_sensor) { const float im = importance(S, ppL); fsE = F3(im, im, im); g.degenerated = true; }
+            float pdfB;      // pdf of sampling ppL from this vertex (ptmis)
+            if (is_sensor) { const float im = importance(S, ppL); fsE = F3(im, im, im); g.degenerated = true; pdfB = im; }
             else {
                 const float4 vw = P.vtx_wi[i];
                 tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
-                fsE = bsdf_eval(S.bsdfs[S.prims[S.tri_prim[tri]].bsdf], g, F3(vw.x, vw.y, vw.z), ppL);
+                const lmb200_bsdf& B = S.bsdfs[S.prims[S.tri_prim[tri]].bsdf];
+                fsE = bsdf_eval(B, g, F3(vw.x, vw.y, vw.z), ppL);
+                pdfB = cfg.mode == LMB200_MODE_PTMIS ? bsdf_pdf(B, g, F3(vw.x, vw.y, vw.z), ppL) : 0.f;
             }
             const f3 fsL = to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le);   // light_area.cpp:105-110
             f3 d = gL.p - p;                                                   // RenderUtils::GeometryTerm, renderutils.h:46-56
@@ -449,6 +468,10 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
             C = ((F3(thr.x, thr.y, thr.z) * fsE) * fsL) * G;
             if (!black(C)) {
                 C = C * (1.0f / pdfL / pdfPL);
+                if (cfg.mode == LMB200_MODE_PTMIS) {          // renderer_ptmis.cpp:163-170
+                    const float pdfDL = pdfPL / G * pdfL;
+                    C = C * (pdfDL / (pdfDL + pdfB));
+                }
                 pixel = __float_as_int(thr.w);
                 if (is_sensor) {                                               // renderer_ptdirect.cpp:165-170
                     float rx = 0.f, ry = 0.f;
@@ -489,7 +512,7 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
             const bool is_sensor = tri == LMB200_MISS;
             const f3 p = F3(vp.x, vp.y, vp.z);
             float4 thr = P.thr[i];
-            f3 wo = F3(0, 0, 0), fs;
+            f3 wo = F3(0, 0, 0), fs, sn_here = F3(0, 0, 0);
             float pdfD;
             bool ok = true;
             if (is_sensor) {
@@ -512,10 +535,12 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
                 bsdf_sample(B, g, wi, ub.x, ub.y, wo);
                 pdfD = bsdf_pdf(B, g, wi, wo);
                 fs = bsdf_eval(B, g, wi, wo);
+                sn_here = g.sn;
             }
             if (ok && !black(fs)) {
                 thr.x *= fs.x / pdfD; thr.y *= fs.y / pdfD; thr.z *= fs.z / pdfD;
                 P.thr[i] = thr;
+                if (cfg.mode == LMB200_MODE_PTMIS) P.prev[i] = make_float4(sn_here.x, sn_here.y, sn_here.z, pdfD);
                 P.ray_o[i] = make_float4(p.x, p.y, p.z, LMB_EPS_ISECT);       // scene3.cpp:461
                 P.ray_d[i] = make_float4(wo.x, wo.y, wo.z, LMB_FLT_MAX);
                 P.traced[i] = 1;
@@ -674,6 +699,7 @@ static int ensure_pool(Scene* s, uint32_t n)
     if ((rc = pool_alloc(s, &P.vtx_p, n))) return rc;
     if ((rc = pool_alloc(s, &P.vtx_wi, n))) return rc;
     if ((rc = pool_alloc(s, &P.vtx_v, n))) return rc;
+    if ((rc = pool_alloc(s, &P.prev, n))) return rc;
     if ((rc = pool_alloc(s, &P.vq, n))) return rc;
     if ((rc = pool_alloc(s, &P.eq, n))) return rc;
     if ((rc = pool_alloc(s, &P.sq_o, n))) return rc;
@@ -724,7 +750,8 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
         }
         return rc;
     }
-    if (p->mode != LMB200_MODE_PT && p->mode != LMB200_MODE_PTDIRECT) return set_error(LMB200_E_INVALID, "unknown render mode");
+    if (p->mode != LMB200_MODE_PT && p->mode != LMB200_MODE_PTDIRECT && p->mode != LMB200_MODE_PTMIS) return set_error(LMB200_E_INVALID, "unknown render mode");
+    const bool nee = p->mode != LMB200_MODE_PT;
     if (p->sample_end < p->sample_begin) return set_error(LMB200_E_INVALID, "sample_end < sample_begin");
     const int64_t todo = p->sample_end - p->sample_begin;
     uint32_t pool = p->pool_size > 0 ? (uint32_t)p->pool_size : (1u << 22);   // 4 Mi slots: best on B200 (profiles/r01_sweep.md)
@@ -755,13 +782,13 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
         cudaMemsetAsync(P.qcount, 0, 4 * sizeof(uint32_t), st);
         cudaMemsetAsync(s->accel.d_counter, 0, 2 * sizeof(unsigned long long), st);
         k_logic<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg, film);
-        if (cfg.mode == LMB200_MODE_PTDIRECT) k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
+        if (nee) k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
         k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
         k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel.d_nodes), reinterpret_cast<const float4*>(s->accel.d_tris), P, s->accel.d_counter);
-        if (cfg.mode == LMB200_MODE_PTDIRECT)
+        if (nee)
             k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel.d_nodes), reinterpret_cast<const float4*>(s->accel.d_tris), P, s->accel.d_counter + 1, film);
         k_stats<<<1, 1, 0, st>>>(P);
-        g_launch_count += (cfg.mode == LMB200_MODE_PTDIRECT) ? 6 : 4;
+        g_launch_count += nee ? 6 : 4;
         cudaMemcpyAsync(s->h_pinned, P.qcount, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(s->h_pinned) + 4, P.next_sample, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return cuda_fail(e, "wavefront iteration"); }

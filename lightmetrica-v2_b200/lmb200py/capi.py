@@ -7,7 +7,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("LMB200_LIB", os.path.join(_ROOT, "lib", "liblmb200.so"))   # override: tuning variants only
 
 MISS = 0xFFFFFFFF
-MODE_PT, MODE_PTDIRECT, MODE_NORMAL = 0, 1, 2
+MODE_PT, MODE_PTDIRECT, MODE_NORMAL, MODE_PTMIS = 0, 1, 2, 3
 BSDF_NULL, BSDF_DIFFUSE, BSDF_COOKTORRANCE = 0, 1, 2
 
 RAY_DTYPE = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"),

@@ -48,8 +48,9 @@ public:
         }
         if (mode == "pt") mode_ = LMB200_MODE_PT;
         else if (mode == "ptdirect") mode_ = LMB200_MODE_PTDIRECT;
+        else if (mode == "ptmis") mode_ = LMB200_MODE_PTMIS;
         else if (mode == "normal") mode_ = LMB200_MODE_NORMAL;
-        else { LM_LOG_ERROR("renderer::lmb200pt: unknown mode '" + mode + "' (pt | ptdirect | normal)"); return false; }
+        else { LM_LOG_ERROR("renderer::lmb200pt: unknown mode '" + mode + "' (pt | ptdirect | ptmis | normal)"); return false; }
         if (numGpus_ < 1) numGpus_ = 1;
         if (lmb200_device_count() < device_ + numGpus_ && !std::getenv("LMB200_DUMP_SCENE"))
         {

@@ -300,8 +300,20 @@ static void splat(const orc_pt_scene* S, float* film, float rx, float ry, v3 c) 
     f[0] += c.x; f[1] += c.y; f[2] += c.z;
 }
 
-/* One sample of renderer::pt (mode 0, renderer_pt.cpp:68-231) or renderer::ptdirect (mode 1,
- * renderer_ptdirect.cpp:76-282). RNG blocks: 0 = camera (x1,x2 = raster sample); iteration `it`
+/* RenderUtils::GeometryTerm (renderutils.h:46-56) */
+static float geometry_term(const geom_t* g1, const geom_t* g2)
+{
+    v3 d = vsub(g2->p, g1->p);
+    const float d2 = vdot(d, d), dl = sqrtf(d2);
+    float t = 1.0f;
+    d = V(d.x / dl, d.y / dl, d.z / dl);
+    if (!g1->degenerated) t *= fabsf(vdot(g1->sn, d));
+    if (!g2->degenerated) t *= fabsf(vdot(g2->sn, vneg(d)));
+    return t / d2;
+}
+
+/* One sample of renderer::pt (mode 0, renderer_pt.cpp:68-231), renderer::ptdirect (mode 1,
+ * renderer_ptdirect.cpp:76-282) or renderer::ptmis (mode 3, renderer_ptmis.cpp:79-290). RNG blocks: 0 = camera (x1,x2 = raster sample); iteration `it`
  * (= numVertices at loop top) uses block 2it-1 = (light pick, light u0, light u1, RR) and block
  * 2it = (bsdf u0, bsdf u1, component, -). */
 static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed, uint64_t sample,
@@ -316,7 +328,7 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
     init_wo = camera_dir(S, u[1], u[2]);
     memset(&geom, 0, sizeof(geom));
     geom.degenerated = 1; geom.p = ld3(S->d.camera.position);
-    if (mode == 0 && !raster_position(S, init_wo, &rx, &ry)) return;      /* renderer_pt.cpp:94-99 */
+    if (mode != 1 && !raster_position(S, init_wo, &rx, &ry)) return;      /* renderer_pt.cpp:94-99, renderer_ptmis.cpp:100-105 */
 
     for (;;) {
         float ua[4], ub[4];
@@ -326,7 +338,7 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
         rng_block(seed, sample, (uint32_t)(2 * num_verts - 1), ua);
         rng_block(seed, sample, (uint32_t)(2 * num_verts), ub);
 
-        if (mode == 1 && S->d.num_lights > 0) {   /* direct light sampling, renderer_ptdirect.cpp:123-177 */
+        if ((mode == 1 || (mode == 3 && num_verts + 1 >= min_verts)) && S->d.num_lights > 0) {   /* direct light sampling, renderer_ptdirect.cpp:123-177, renderer_ptmis.cpp:130-205 */
             const int nL = (int)S->d.num_lights;
             int li = (int)(ua[0] * (float)nL);
             geom_t gL;
@@ -352,7 +364,11 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
                 if (visible(S, geom.p, gL.p)) {
                     float prx = rx, pry = ry;
                     C = vmul(C, 1.0f / pdfL / pdfPL);
-                    C = V(C.x, C.y, C.z);
+                    if (mode == 3) {   /* MIS weight, renderer_ptmis.cpp:163-170 */
+                        const float pdfDL = pdfPL / geometry_term(&geom, &gL) * pdfL;
+                        const float pdfB = is_sensor ? importance(S, ppL) : bsdf_pdf(bsdf, &geom, wi, ppL);
+                        C = vmul(C, pdfDL / (pdfDL + pdfB));
+                    }
                     if (is_sensor) raster_position(S, ppL, &prx, &pry);              /* renderer_ptdirect.cpp:165-170 */
                     splat(S, film, prx, pry, C);
                 }
@@ -371,6 +387,7 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
         {   /* intersection, scene3.cpp:458-478 */
             float ray[8], tuv[3]; int32_t tri;
             const orc_prim* P;
+            geom_t prev = geom;
             v3 hp;
             ray[0] = geom.p.x; ray[1] = geom.p.y; ray[2] = geom.p.z; ray[3] = ORC_EPS_ISECT;
             ray[4] = wo.x; ray[5] = wo.y; ray[6] = wo.z; ray[7] = FLT_MAX;
@@ -380,8 +397,15 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
             hp = vadd(geom.p, vmul(wo, tuv[0]));
             P = &S->d.prims[S->d.tri_prim[tri]];
             tri_geom(S, (uint32_t)tri, tuv[1], tuv[2], hp, &geom);
-            if (mode == 0 && P->light >= 0 && num_verts + 1 >= min_verts) {          /* renderer_pt.cpp:183-194 */
-                if (to_local(&geom, vneg(wo)).z > 0.0f) splat(S, film, rx, ry, vmulv(thr, ld3(S->d.lights[P->light].Le)));
+            if (mode != 1 && P->light >= 0 && num_verts + 1 >= min_verts) {          /* renderer_pt.cpp:183-194 */
+                if (to_local(&geom, vneg(wo)).z > 0.0f) {
+                    v3 C = vmulv(thr, ld3(S->d.lights[P->light].Le));
+                    if (mode == 3) {   /* renderer_ptmis.cpp:247-260: balance heuristic against the light-sampling pdf */
+                        const float pdfDL = S->inv_area[P->light] / geometry_term(&geom, &prev) * (1.0f / (float)S->d.num_lights);
+                        C = vmul(C, pdfD / (pdfD + pdfDL));
+                    }
+                    splat(S, film, rx, ry, C);
+                }
             }
             if (ua[3] > 0.5f) break;                                                 /* renderer_pt.cpp:207-215 */
             thr = V(thr.x / 0.5f, thr.y / 0.5f, thr.z / 0.5f);

@@ -44,7 +44,7 @@ def accel_golden():
 
 def pt_golden():
     """Reference images of the Cornell-style box (configs[0] geometry at 48x48) rendered by the
-    reference's own renderer::pt / renderer::ptdirect with accel::qbvh and dSFMT, two seeds each
+    reference's own renderer::pt / renderer::ptdirect / renderer::ptmis with accel::qbvh and dSFMT, two seeds each
     (the second seed measures the Monte-Carlo noise floor)."""
     from lmb200py import scenedesc
     sc = scenedesc.cornell_box(48, 48, glossy_block=True)
@@ -52,7 +52,7 @@ def pt_golden():
     spp = 16384
     N = 48 * 48 * spp
     out = {}
-    for name in ("ptdirect", "pt"):
+    for name in ("ptdirect", "pt", "ptmis"):
         a, _ = R.render(name, N, seed=1, threads=8)
         b, _ = R.render(name, N, seed=2, threads=8)
         out[name + "_a"] = a
