@@ -210,6 +210,18 @@ int lmb200_render(lmb200_scene* s, const lmb200_render_params* p, float* film_rg
  * device 0 with ncclReduce, then rescaled). scenes[g] must hold the same scene on device g. */
 int lmb200_render_multi(lmb200_scene** scenes, int num_gpus, const lmb200_render_params* p, float* film_rgba_host, lmb200_render_stats* stats);
 
+/* Time-budgeted / progressive rendering: Scheduler_'s `render_time` and
+ * `progress_image_update_interval` (scheduler.cpp:54-57,108,191-255). Runs passes of pass_samples
+ * samples (the reference uses grain_size*1000; <=0: 10^7) until render_time seconds have elapsed
+ * (render_time <= 0: until [sample_begin,sample_end) is done). Every progress_interval seconds (> 0)
+ * `progress` receives the image so far (W*H*4 floats, rescaled by W*H/processed), the number of
+ * samples processed and a running tick count; a non-zero return stops the render. The final image
+ * is rescaled by W*H/processed (scheduler.cpp:288) and stats->samples = samples processed. */
+typedef int (*lmb200_progress_fn)(void* user, const float* film_rgba, int64_t samples_done, int64_t tick);
+int lmb200_render_timed(lmb200_scene** scenes, int num_gpus, const lmb200_render_params* p, double render_time,
+                        int64_t pass_samples, double progress_interval, lmb200_progress_fn progress, void* user,
+                        float* film_rgba_host, lmb200_render_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -919,86 +919,183 @@ int lmb200_render(lmb200_scene* h, const lmb200_render_params* p, float* film_ho
     return rc;
 }
 
-// Single-process multi-GPU: one host thread per device renders a contiguous slice of the sample
-// range into its own film; the films are summed to device 0 with one ncclReduce over NVLink
-// (replaces contexts.combine_each(film->Accumulate), scheduler.cpp:280-285), then rescaled.
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU / time-budgeted rendering in one process. A Session keeps one UNSCALED film per GPU that
+// accumulates over passes; films are combined only when an image is needed (progress tick, end):
+// one ncclReduce to device 0 over NVLink, replacing contexts.combine_each(film->Accumulate)
+// (scheduler.cpp:280-285), followed by the W*H/processed rescale (scheduler.cpp:288).
+namespace {
+
+typedef int (*fn_init_all)(void**, int, const int*);
+typedef int (*fn_void)(void);
+typedef int (*fn_reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+
+struct Session {
+    std::vector<Scene*> sc;
+    std::vector<int> devs;
+    std::vector<void*> films;
+    std::vector<cudaStream_t> streams;
+    std::vector<void*> comms;
+    void* scratch = nullptr;       // on device 0: reduced + rescaled copy that goes to the host
+    int64_t npx = 0;
+    fn_void gs = nullptr, ge = nullptr;
+    fn_reduce reduce = nullptr;
+    fn_destroy destroy = nullptr;
+    lmb200_render_stats total{};
+
+    int open(lmb200_scene** scenes, int n)
+    {
+        for (int g = 0; g < n; g++) {
+            Scene* s = reinterpret_cast<Scene*>(scenes[g]);
+            if (!s) return set_error(LMB200_E_INVALID, "null scene");
+            sc.push_back(s); devs.push_back(s->device);
+        }
+        npx = (int64_t)sc[0]->dev.width * sc[0]->dev.height;
+        films.assign(n, nullptr); streams.assign(n, nullptr); comms.assign(n, nullptr);
+        for (int g = 0; g < n; g++) {
+            cudaError_t e = cudaSetDevice(devs[g]);
+            if (e == cudaSuccess) e = cudaMalloc(&films[g], sizeof(float4) * (size_t)npx);
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&streams[g], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaMemsetAsync(films[g], 0, sizeof(float4) * (size_t)npx, streams[g]);
+            if (e != cudaSuccess) return cuda_fail(e, "session film");
+        }
+        cudaSetDevice(devs[0]);
+        cudaError_t e = cudaMalloc(&scratch, sizeof(float4) * (size_t)npx);
+        if (e != cudaSuccess) return cuda_fail(e, "session scratch");
+        if (n > 1) {
+            void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!lib) return set_error(LMB200_E_NCCL, std::string("cannot load libnccl: ") + dlerror());
+            fn_init_all init = (fn_init_all)dlsym(lib, "ncclCommInitAll");
+            gs = (fn_void)dlsym(lib, "ncclGroupStart"); ge = (fn_void)dlsym(lib, "ncclGroupEnd");
+            reduce = (fn_reduce)dlsym(lib, "ncclReduce");
+            destroy = (fn_destroy)dlsym(lib, "ncclCommDestroy");
+            if (!init || !gs || !ge || !reduce || !destroy) return set_error(LMB200_E_NCCL, "libnccl lacks required symbols");
+            if (init(comms.data(), n, devs.data()) != 0) return set_error(LMB200_E_NCCL, "ncclCommInitAll failed");
+        }
+        memset(&total, 0, sizeof(total));
+        return LMB200_OK;
+    }
+
+    // renders global samples [begin,end) of p, split contiguously over the GPUs, into the per-GPU films
+    int pass(const lmb200_render_params* p, int64_t begin, int64_t end)
+    {
+        const int n = (int)sc.size();
+        std::vector<int> rcs(n, 0);
+        std::vector<std::string> errs(n);
+        std::vector<lmb200_render_stats> st(n);
+        auto work = [&](int g) {
+            lmb200_render_params q = *p;
+            q.sample_begin = begin + (end - begin) * g / n;
+            q.sample_end = begin + (end - begin) * (g + 1) / n;
+            rcs[g] = render_dev(sc[g], &q, films[g], streams[g], &st[g]);
+            if (rcs[g]) errs[g] = g_last_error;
+        };
+        std::vector<std::thread> th;
+        for (int g = 1; g < n; g++) th.emplace_back(work, g);
+        work(0);
+        for (auto& t : th) t.join();
+        double secs = 0; int64_t iters = 0;
+        for (int g = 0; g < n; g++) {
+            if (rcs[g]) return set_error(rcs[g], errs[g]);
+            total.samples += st[g].samples; total.extend_rays += st[g].extend_rays; total.shadow_rays += st[g].shadow_rays;
+            total.launches += st[g].launches;
+            secs = std::max(secs, st[g].seconds); iters = std::max(iters, st[g].iterations);
+        }
+        total.seconds += secs; total.iterations += iters;
+        return LMB200_OK;
+    }
+
+    // sum of the films * scale -> host (the per-GPU films keep accumulating afterwards)
+    int gather(float scale, float* film_host)
+    {
+        const int n = (int)sc.size();
+        if (n > 1) {
+            gs();
+            int bad = 0;
+            for (int g = 0; g < n; g++) {
+                cudaSetDevice(devs[g]);
+                if (reduce(films[g], g == 0 ? scratch : films[g], (size_t)npx * 4, 7 /*ncclFloat32*/, 0 /*ncclSum*/, 0, comms[g], streams[g]) != 0) bad = 1;
+            }
+            ge();
+            if (bad) return set_error(LMB200_E_NCCL, "ncclReduce failed");
+            for (int g = 1; g < n; g++) { cudaSetDevice(devs[g]); cudaStreamSynchronize(streams[g]); }
+            cudaSetDevice(devs[0]);
+        } else {
+            cudaSetDevice(devs[0]);
+            cudaMemcpyAsync(scratch, films[0], sizeof(float4) * (size_t)npx, cudaMemcpyDeviceToDevice, streams[0]);
+        }
+        int rc = LMB200_OK;
+        if (scale != 1.0f) rc = lmb200_film_rescale_dev(scratch, npx, scale, streams[0]);
+        cudaError_t e = cudaMemcpyAsync(film_host, scratch, sizeof(float4) * (size_t)npx, cudaMemcpyDeviceToHost, streams[0]);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(streams[0]);
+        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "film readback");
+        return rc;
+    }
+
+    ~Session()
+    {
+        for (size_t g = 0; g < sc.size(); g++) {
+            cudaSetDevice(devs[g]);
+            if (comms[g] && destroy) destroy(comms[g]);
+            if (films[g]) cudaFree(films[g]);
+            if (streams[g]) cudaStreamDestroy(streams[g]);
+        }
+        if (scratch) { cudaSetDevice(devs[0]); cudaFree(scratch); }
+    }
+};
+
+}  // namespace
+
 int lmb200_render_multi(lmb200_scene** scenes, int num_gpus, const lmb200_render_params* p, float* film_host, lmb200_render_stats* stats)
 {
     if (!scenes || num_gpus < 1 || !p || !film_host) return set_error(LMB200_E_INVALID, "null argument");
-    if (num_gpus == 1) return lmb200_render(scenes[0], p, film_host, stats);
-    typedef int (*fn_init_all)(void**, int, const int*);
-    typedef int (*fn_void)(void);
-    typedef int (*fn_reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
-    typedef int (*fn_destroy)(void*);
-    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!lib) return set_error(LMB200_E_NCCL, std::string("cannot load libnccl: ") + dlerror());
-    fn_init_all nccl_init = (fn_init_all)dlsym(lib, "ncclCommInitAll");
-    fn_void nccl_gs = (fn_void)dlsym(lib, "ncclGroupStart"), nccl_ge = (fn_void)dlsym(lib, "ncclGroupEnd");
-    fn_reduce nccl_reduce = (fn_reduce)dlsym(lib, "ncclReduce");
-    fn_destroy nccl_destroy = (fn_destroy)dlsym(lib, "ncclCommDestroy");
-    if (!nccl_init || !nccl_gs || !nccl_ge || !nccl_reduce || !nccl_destroy) return set_error(LMB200_E_NCCL, "libnccl lacks required symbols");
+    Session S;
+    int rc = S.open(scenes, num_gpus);
+    if (!rc) rc = S.pass(p, p->sample_begin, p->sample_end);
+    if (!rc) rc = S.gather(p->mode == LMB200_MODE_NORMAL ? 1.0f : (float)S.npx / (float)p->num_samples, film_host);
+    if (!rc && stats) *stats = S.total;
+    return rc;
+}
 
-    std::vector<Scene*> sc(num_gpus);
-    std::vector<int> devs(num_gpus);
-    for (int g = 0; g < num_gpus; g++) { sc[g] = reinterpret_cast<Scene*>(scenes[g]); if (!sc[g]) return set_error(LMB200_E_INVALID, "null scene"); devs[g] = sc[g]->device; }
-    const int64_t npx = (int64_t)sc[0]->dev.width * sc[0]->dev.height;
-    std::vector<void*> films(num_gpus, nullptr);
-    std::vector<cudaStream_t> streams(num_gpus, nullptr);
-    std::vector<int> rcs(num_gpus, 0);
-    std::vector<std::string> errs(num_gpus);
-    std::vector<lmb200_render_stats> st(num_gpus);
-    const int64_t b = p->sample_begin, todo = p->sample_end - p->sample_begin;
-    auto work = [&](int g) {
-        cudaSetDevice(devs[g]);
-        cudaError_t e = cudaMalloc(&films[g], sizeof(float4) * (size_t)npx);
-        if (e != cudaSuccess) { rcs[g] = LMB200_E_CUDA; errs[g] = cudaGetErrorString(e); return; }
-        cudaStreamCreateWithFlags(&streams[g], cudaStreamNonBlocking);
-        cudaMemsetAsync(films[g], 0, sizeof(float4) * (size_t)npx, streams[g]);
+// Time-budgeted / progressive rendering (Scheduler_'s render_time and progress_image_update_interval,
+// scheduler.cpp:54-57,108,191-255): passes of `pass_samples` samples (the reference uses grain_size*1000)
+// until `render_time` seconds have elapsed (render_time <= 0: until p->num_samples are done); every
+// `progress_interval` seconds (> 0) the image so far, rescaled by W*H/processed, is handed to `progress`.
+// The final image is rescaled by W*H/processed and stats->samples holds the number processed.
+int lmb200_render_timed(lmb200_scene** scenes, int num_gpus, const lmb200_render_params* p, double render_time,
+                        int64_t pass_samples, double progress_interval, lmb200_progress_fn progress, void* user,
+                        float* film_host, lmb200_render_stats* stats)
+{
+    if (!scenes || num_gpus < 1 || !p || !film_host) return set_error(LMB200_E_INVALID, "null argument");
+    if (p->mode == LMB200_MODE_NORMAL) return lmb200_render_multi(scenes, num_gpus, p, film_host, stats);
+    if (pass_samples <= 0) pass_samples = 10000000;
+    Session S;
+    int rc = S.open(scenes, num_gpus);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto last_tick = t0;
+    int64_t done = 0, cursor = p->sample_begin;
+    int64_t ticks = 0;
+    while (!rc) {
+        int64_t n = pass_samples;
+        if (render_time <= 0) n = std::min<int64_t>(n, p->sample_end - cursor);
+        if (n <= 0) break;
         lmb200_render_params q = *p;
-        q.sample_begin = b + todo * g / num_gpus;
-        q.sample_end = b + todo * (g + 1) / num_gpus;
-        rcs[g] = render_dev(sc[g], &q, films[g], streams[g], &st[g]);
-        if (rcs[g]) errs[g] = g_last_error;
-    };
-    std::vector<std::thread> th;
-    for (int g = 1; g < num_gpus; g++) th.emplace_back(work, g);
-    work(0);
-    for (auto& t : th) t.join();
-    int rc = 0;
-    for (int g = 0; g < num_gpus; g++) if (rcs[g]) rc = set_error(rcs[g], errs[g]);
-    std::vector<void*> comms(num_gpus, nullptr);
-    if (!rc && nccl_init(comms.data(), num_gpus, devs.data()) != 0) rc = set_error(LMB200_E_NCCL, "ncclCommInitAll failed");
-    if (!rc) {
-        nccl_gs();
-        for (int g = 0; g < num_gpus; g++) {
-            cudaSetDevice(devs[g]);
-            if (nccl_reduce(films[g], films[g], (size_t)npx * 4, 7 /*ncclFloat32*/, 0 /*ncclSum*/, 0, comms[g], streams[g]) != 0) rc = set_error(LMB200_E_NCCL, "ncclReduce failed");
+        q.num_samples = n;
+        rc = S.pass(&q, cursor, cursor + n);
+        if (rc) break;
+        cursor += n; done += n;
+        const auto now = std::chrono::steady_clock::now();
+        if (progress && progress_interval > 0 && std::chrono::duration<double>(now - last_tick).count() > progress_interval) {
+            rc = S.gather((float)S.npx / (float)done, film_host);
+            if (!rc) { ticks++; if (progress(user, film_host, done, ticks) != 0) break; }
+            last_tick = now;
         }
-        nccl_ge();
-        for (int g = 0; g < num_gpus; g++) { cudaSetDevice(devs[g]); cudaStreamSynchronize(streams[g]); }
+        if (render_time > 0 && std::chrono::duration<double>(now - t0).count() > render_time) break;
     }
-    if (!rc) {
-        cudaSetDevice(devs[0]);
-        if (p->mode != LMB200_MODE_NORMAL) rc = lmb200_film_rescale_dev(films[0], npx, (float)npx / (float)p->num_samples, streams[0]);
-        cudaError_t e = cudaMemcpyAsync(film_host, films[0], sizeof(float4) * (size_t)npx, cudaMemcpyDeviceToHost, streams[0]);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(streams[0]);
-        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "film readback");
-    }
-    for (int g = 0; g < num_gpus; g++) {
-        cudaSetDevice(devs[g]);
-        if (comms[g]) nccl_destroy(comms[g]);
-        if (films[g]) cudaFree(films[g]);
-        if (streams[g]) cudaStreamDestroy(streams[g]);
-    }
-    if (stats && !rc) {
-        memset(stats, 0, sizeof(*stats));
-        for (int g = 0; g < num_gpus; g++) {
-            stats->samples += st[g].samples; stats->extend_rays += st[g].extend_rays; stats->shadow_rays += st[g].shadow_rays;
-            stats->iterations = std::max(stats->iterations, st[g].iterations); stats->launches += st[g].launches;
-            stats->seconds = std::max(stats->seconds, st[g].seconds);
-        }
-    }
+    if (!rc) rc = S.gather(done > 0 ? (float)S.npx / (float)done : 1.0f, film_host);
+    if (!rc && stats) { *stats = S.total; stats->samples = done; }
     return rc;
 }
 

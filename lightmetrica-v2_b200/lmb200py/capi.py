@@ -56,12 +56,14 @@ class RenderStats(C.Structure):
                 ("launches", C.c_uint64), ("seconds", C.c_double)]
 
 
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int64)
+
 EXPORTS = [
     "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build",
     "lmb200_accel_get_stats", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
     "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_arrays", "lmb200_accel_create_host_only",
     "lmb200_scene_create", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
-    "lmb200_render", "lmb200_render_multi",
+    "lmb200_render", "lmb200_render_multi", "lmb200_render_timed",
 ]
 
 _lib = None
@@ -101,6 +103,8 @@ def lib():
         L.lmb200_film_rescale_dev.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
         L.lmb200_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(RenderStats)]
         L.lmb200_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RenderParams), C.c_void_p, C.POINTER(RenderStats)]
+        L.lmb200_render_timed.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RenderParams), C.c_double, C.c_int64, C.c_double,
+                                          PROGRESS_FN, C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
     _lib = L
     return L
 

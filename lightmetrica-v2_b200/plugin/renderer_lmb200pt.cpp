@@ -3,7 +3,8 @@
 // mode "normal", for the primary-ray renderers (renderer_raycast.cpp, plugin/renderer_normal).
 // Selected from the scene YAML with
 //     renderer: {type: lmb200pt, params: {mode: ptdirect, num_samples: ..., max_num_vertices: -1,
-//                                         min_num_vertices: 0, num_gpus: 1, device: 0, pool_size: 0}}
+//                                         min_num_vertices: 0, num_gpus: 1, device: 0, pool_size: 0,
+//                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000}}
 // It reads the scene through the reference's interfaces (Scene3::PrimitiveAt, TriangleMesh::*,
 // BSDF::Reflectance/Glossiness, Light::Emittance, Sensor::GetFilm/GetProjectionMatrix), flattens
 // it into the POD arrays of include/lmb200.h and calls liblmb200.so; the film comes back through
@@ -42,6 +43,10 @@ public:
             numSamples_ = prop->ChildAs<long long>("num_samples", 10000000L);
             maxNumVertices_ = prop->ChildAs<int>("max_num_vertices", -1);
             minNumVertices_ = prop->ChildAs<int>("min_num_vertices", 0);
+            // scheduler.cpp:44-58: time budget and progressive output
+            if (prop->Child("render_time")) renderTime_ = prop->ChildAs<double>("render_time", -1.0);
+            if (prop->Child("progress_image_update_interval")) progressImageInterval_ = prop->ChildAs<double>("progress_image_update_interval", -1.0);
+            if (prop->Child("grain_size")) grainSize_ = prop->ChildAs<long long>("grain_size", 10000);
             if (prop->Child("num_gpus")) numGpus_ = prop->ChildAs<int>("num_gpus", 1);
             if (prop->Child("device")) device_ = prop->ChildAs<int>("device", 0);
             if (prop->Child("pool_size")) poolSize_ = prop->ChildAs<int>("pool_size", 0);
@@ -204,8 +209,20 @@ public:
         std::vector<float> rgba((size_t)W * H * 4, 0.f);
         lmb200_render_stats st;
         memset(&st, 0, sizeof(st));
-        const int rc = numGpus_ > 1 ? lmb200_render_multi(scenes.data(), numGpus_, &p, rgba.data(), &st)
-                                    : lmb200_render(scenes[0], &p, rgba.data(), &st);
+        int rc;
+        if (renderTime_ > 0 || progressImageInterval_ > 0)
+        {
+            // Scheduler_ semantics: passes of grain_size*1000 samples until render_time has elapsed,
+            // "progress_%010d" images every progress_image_update_interval seconds (scheduler.cpp:108,221-255)
+            ProgressCtx ctx{ film, W, H };
+            rc = lmb200_render_timed(scenes.data(), numGpus_, &p, renderTime_, grainSize_ * 1000, progressImageInterval_,
+                                     &Renderer_LMB200PT::OnProgress, &ctx, rgba.data(), &st);
+        }
+        else
+        {
+            rc = numGpus_ > 1 ? lmb200_render_multi(scenes.data(), numGpus_, &p, rgba.data(), &st)
+                              : lmb200_render(scenes[0], &p, rgba.data(), &st);
+        }
         for (auto* s : scenes) lmb200_scene_destroy(s);
         if (rc != LMB200_OK)
         {
@@ -216,13 +233,7 @@ public:
                     std::to_string(st.shadow_rays) + " shadow rays in " + std::to_string(st.seconds) + " s on " + std::to_string(numGpus_) + " GPU(s)");
 
         // ---- hand the image back through the Film interface (film.h) ----
-        film->Clear();
-        for (int y = 0; y < H; y++)
-            for (int x = 0; x < W; x++)
-            {
-                const float* c = &rgba[4 * ((size_t)y * W + x)];
-                film->SetPixel(x, y, SPD::FromRGB(Vec3(c[0], c[1], c[2])));
-            }
+        StoreFilm(film, W, H, rgba.data());
         {
             LM_LOG_INFO("Saving image");
             LM_LOG_INDENTER();
@@ -231,6 +242,30 @@ public:
     };
 
 private:
+
+    struct ProgressCtx { Film* film; int W, H; };
+
+    static void StoreFilm(Film* film, int W, int H, const float* rgba)
+    {
+        film->Clear();
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++)
+            {
+                const float* c = &rgba[4 * ((size_t)y * W + x)];
+                film->SetPixel(x, y, SPD::FromRGB(Vec3(c[0], c[1], c[2])));
+            }
+    }
+
+    static int OnProgress(void* user, const float* rgba, int64_t samplesDone, int64_t tick)
+    {
+        auto* ctx = static_cast<ProgressCtx*>(user);
+        StoreFilm(ctx->film, ctx->W, ctx->H, rgba);
+        char name[64];
+        snprintf(name, sizeof(name), "progress_%010lld", (long long)tick);   // scheduler.cpp:236-240
+        LM_LOG_INFO("Saving progress: " + std::string(name) + " (" + std::to_string(samplesDone) + " samples)");
+        ctx->film->Save(name);
+        return 0;
+    }
 
     // "lightmetrica/assets[/params]/<asset id>/params" of the loaded YAML, or nullptr
     auto AssetParams(const Asset* asset) const -> const PropertyNode*
@@ -294,6 +329,9 @@ private:
     int numGpus_ = 1;
     int device_ = 0;
     int poolSize_ = 0;
+    double renderTime_ = -1.0;
+    double progressImageInterval_ = -1.0;
+    long long grainSize_ = 10000;
 
 };
 

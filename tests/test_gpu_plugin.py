@@ -130,3 +130,16 @@ def test_renderer_plugin_rejects_unsupported_scene():
     R = ob.RefScene(sc, accel="qbvh")
     with pytest.raises(RuntimeError, match="renderer init failed"):
         R.render("lmb200pt", 100, extra={"mode": "bdpt"})
+
+
+def test_renderer_plugin_time_budget(tmp_path, monkeypatch):
+    """`render_time` + `progress_image_update_interval` from the YAML, as Scheduler_ reads them (scheduler.cpp:44-58):
+    the plugin renders until the budget is spent and writes progress_%010d images through Film::Save."""
+    monkeypatch.chdir(tmp_path)
+    sc = scenedesc.cornell_box(32, 32)
+    R = ob.RefScene(sc, accel="qbvh")
+    img, _ = R.render("lmb200pt", 1000, seed=1, in_tree=True,
+                      extra={"mode": "ptdirect", "render_time": 0.4, "progress_image_update_interval": 0.1, "grain_size": 200})
+    ref, _ = R.render("ptdirect", 32 * 32 * 1024, seed=1, threads=os.cpu_count() or 1)
+    assert abs(img.mean() - ref.mean()) / ref.mean() < 0.05      # far more than the 1000 samples of num_samples were taken
+    assert any(f.startswith("progress_") for f in os.listdir(tmp_path))

@@ -124,3 +124,35 @@ def test_render_multi_nccl_reduce():
     capi.check(L.lmb200_render_multi(arr, 2, C.byref(p), film.ctypes.data_as(C.c_void_p), C.byref(st)))
     assert st.samples == N
     assert np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
+
+
+def test_time_budget_and_progress():
+    """Scheduler_'s render_time / progress_image_update_interval semantics (scheduler.cpp:108,191-255): passes until
+    the time budget is spent, progress images rescaled by W*H/processed, final image rescaled by the processed count."""
+    sc = scenedesc.cornell_box(32, 32)
+    S = capi.Scene(sc)
+    L = capi.lib()
+    arr = (C.c_void_p * 1)(S.h_)
+    film = np.zeros((32, 32, 4), np.float32)
+    st = capi.RenderStats()
+    ticks = []
+
+    def on_progress(user, rgba, done, tick):
+        img = np.ctypeslib.as_array(rgba, shape=(32, 32, 4))
+        ticks.append((int(done), int(tick), float(img[..., :3].mean())))
+        return 0
+    cb = capi.PROGRESS_FN(on_progress)
+    p = S.params(capi.MODE_PTDIRECT, 1, seed=9)
+    capi.check(L.lmb200_render_timed(arr, 1, C.byref(p), 0.5, 200000, 0.1, cb, None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    assert st.samples >= 200000 and st.samples % 200000 == 0
+    assert len(ticks) >= 2 and [t[1] for t in ticks] == list(range(1, len(ticks) + 1))
+    assert all(ticks[i][0] < ticks[i + 1][0] for i in range(len(ticks) - 1))
+    ref, _ = S.render(capi.MODE_PTDIRECT, 32 * 32 * 2048, seed=1)
+    assert abs(film[..., :3].mean() - ref.mean()) / ref.mean() < 0.05
+    assert all(abs(t[2] - ref.mean()) / ref.mean() < 0.25 for t in ticks)
+    # without a time budget the call renders exactly [sample_begin, sample_end) and equals lmb200_render
+    N = 32 * 32 * 16
+    p = S.params(capi.MODE_PTDIRECT, N, seed=3)
+    capi.check(L.lmb200_render_timed(arr, 1, C.byref(p), -1.0, 5000, -1.0, capi.PROGRESS_FN(0), None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    one, _ = S.render(capi.MODE_PTDIRECT, N, seed=3)
+    assert st.samples == N and np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
