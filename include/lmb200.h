@@ -74,6 +74,16 @@ void lmb200_accel_destroy(lmb200_accel* a);
 int lmb200_accel_build(lmb200_accel* a, const float* verts, uint64_t ntris);
 int lmb200_accel_get_stats(const lmb200_accel* a, lmb200_accel_stats* out);
 
+/* Same, with a choice of builder. Both produce the same node/record format and therefore the same
+ * hits (the closest hit does not depend on the tree); they differ in build time and tree quality.
+ *   LMB200_BUILD_HOST_SAH  multi-threaded binned-SAH build on the host + SAH-optimal 8-wide collapse
+ *                          (what lmb200_accel_build does)
+ *   LMB200_BUILD_GPU_LBVH  Morton-order radix tree + collapse entirely on the device: milliseconds
+ *                          instead of seconds, lower tree quality */
+#define LMB200_BUILD_HOST_SAH 0
+#define LMB200_BUILD_GPU_LBVH 1
+int lmb200_accel_build_ex(lmb200_accel* a, const float* verts, uint64_t ntris, int builder);
+
 /* Replaces Accel3::Intersect (accel3.h:68; accel_qbvh.cpp:398-497) for a batch of n rays.
  * Closest hit with the reference's acceptance rule (reject t<tmin or t>tmax, triaccel.h:137);
  * on exact ties in t the triangle with the larger index wins (= accel::naive's scan order,
@@ -192,6 +202,8 @@ typedef struct lmb200_render_stats {
 
 /* Builds the accel (device) and uploads shading data. */
 lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* desc);
+/* Same with a choice of BVH builder (LMB200_BUILD_HOST_SAH / LMB200_BUILD_GPU_LBVH). */
+lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* desc, int builder);
 void lmb200_scene_destroy(lmb200_scene* s);
 lmb200_accel* lmb200_scene_accel(lmb200_scene* s);
 

@@ -137,6 +137,21 @@ void Accel::free_device()
 
 Accel::~Accel() { free_device(); }
 
+int mirror_to_host(Accel* a)
+{
+    if (!a->gpu_built || !a->bvh.nodes.empty()) return LMB200_OK;
+    cudaError_t e = cudaSetDevice(a->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t nn = a->bvh.stats.num_nodes, nt = a->bvh.stats.num_valid;
+    a->bvh.nodes.resize(nn);
+    a->bvh.tris.resize(nt);
+    if ((e = cudaMemcpy(a->bvh.nodes.data(), a->d_nodes, nn * sizeof(Node80), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "D2H nodes");
+    if (nt && (e = cudaMemcpy(a->bvh.tris.data(), a->d_tris, nt * sizeof(TriRecord), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "D2H tris");
+    a->bvh.tri_index.resize(nt);
+    for (size_t i = 0; i < nt; i++) a->bvh.tri_index[i] = a->bvh.tris[i].tri;
+    return LMB200_OK;
+}
+
 int Accel::upload()
 {
     const auto t0 = std::chrono::steady_clock::now();
@@ -263,8 +278,31 @@ int lmb200_accel_build(lmb200_accel* h, const float* verts, uint64_t ntris)
     if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27, as the reference's leaf encoding accel_qbvh.cpp:62-72)");
     build_bvh(verts, ntris, a->bvh, 0);
     a->built = true;
+    a->gpu_built = false;
     if (a->host_only) return LMB200_OK;
     return a->upload();
+}
+
+int lmb200_accel_build_ex(lmb200_accel* h, const float* verts, uint64_t ntris, int builder)
+{
+    if (builder == LMB200_BUILD_HOST_SAH) return lmb200_accel_build(h, verts, ntris);
+    if (builder != LMB200_BUILD_GPU_LBVH) return set_error(LMB200_E_INVALID, "unknown builder");
+    Accel* a = reinterpret_cast<Accel*>(h);
+    if (!a || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
+    if (a->host_only) return set_error(LMB200_E_STATE, "the GPU builder needs a device accel");
+    if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27)");
+    const int rc = build_bvh_gpu(a, verts, ntris);
+    if (rc) return rc;
+    a->built = true;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, a->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    a->num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false, false>, LMB_TRACE_BLOCK, 0);
+    a->trace_blocks_per_sm = occ > 0 ? occ : 4;
+    a->upload_seconds = 0;
+    return LMB200_OK;
 }
 
 int lmb200_accel_get_stats(const lmb200_accel* h, lmb200_accel_stats* out)
@@ -274,9 +312,9 @@ int lmb200_accel_get_stats(const lmb200_accel* h, lmb200_accel_stats* out)
     if (!a->built) return set_error(LMB200_E_STATE, "accel not built");
     out->num_triangles = a->bvh.stats.num_triangles;
     out->num_valid_triangles = a->bvh.stats.num_valid;
-    out->num_nodes = a->bvh.nodes.size();
-    out->node_bytes = a->bvh.nodes.size() * sizeof(Node80);
-    out->tri_bytes = a->bvh.tris.size() * sizeof(TriRecord);
+    out->num_nodes = a->gpu_built ? a->bvh.stats.num_nodes : a->bvh.nodes.size();
+    out->node_bytes = out->num_nodes * sizeof(Node80);
+    out->tri_bytes = (a->gpu_built ? a->bvh.stats.num_valid : a->bvh.tris.size()) * sizeof(TriRecord);
     out->build_seconds = a->bvh.stats.build_seconds;
     out->upload_seconds = a->upload_seconds;
     out->sah_cost = a->bvh.stats.sah_cost;
@@ -287,9 +325,10 @@ int lmb200_accel_get_stats(const lmb200_accel* h, lmb200_accel_stats* out)
 int lmb200_accel_host_arrays(const lmb200_accel* h, const void** nodes80, uint64_t* num_nodes,
                              const void** tris48, const uint32_t** tri_index, uint64_t* num_tris)
 {
-    const Accel* a = reinterpret_cast<const Accel*>(h);
+    Accel* a = const_cast<Accel*>(reinterpret_cast<const Accel*>(h));
     if (!a) return set_error(LMB200_E_INVALID, "null argument");
     if (!a->built) return set_error(LMB200_E_STATE, "accel not built");
+    if (const int rc = mirror_to_host(a)) return rc;
     if (nodes80) *nodes80 = a->bvh.nodes.data();
     if (num_nodes) *num_nodes = a->bvh.nodes.size();
     if (tris48) *tris48 = a->bvh.tris.data();

@@ -26,6 +26,7 @@ struct Accel {
     int device = -1;
     bool host_only = false;
     bool built = false;
+    bool gpu_built = false;     // built by build_bvh_gpu: bvh.nodes/tris mirror is filled on demand
     HostBVH bvh;
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
@@ -44,6 +45,9 @@ struct Accel {
     int upload();
     void free_device();
 };
+
+int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris);   // bvh_build_gpu.cu
+int mirror_to_host(Accel* a);                                            // accel.cu
 
 // n_dev != nullptr: the ray count is read from device memory (wavefront queues).
 int trace_closest_dev(Accel* a, const void* rays, void* hits, uint64_t n, const uint32_t* n_dev, cudaStream_t st, int slot);

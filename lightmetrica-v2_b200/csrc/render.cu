@@ -819,8 +819,11 @@ using namespace lmb200;
 
 extern "C" {
 
-lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d)
+lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d) { return lmb200_scene_create_ex(device, d, LMB200_BUILD_HOST_SAH); }
+
+lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int builder)
 {
+    if (builder != LMB200_BUILD_HOST_SAH && builder != LMB200_BUILD_GPU_LBVH) { set_error(LMB200_E_INVALID, "unknown builder"); return nullptr; }
     if (!d || (d->num_tris && (!d->verts || !d->tri_prim)) || !d->prims || !d->bsdfs) { set_error(LMB200_E_INVALID, "null scene field"); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error(LMB200_E_CUDA, "no CUDA device available (lmb200 has no CPU fallback)"); return nullptr; }
@@ -834,9 +837,7 @@ lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d)
     s->device = device;
     s->accel.device = device;
     cudaSetDevice(device);
-    build_bvh(d->verts, d->num_tris, s->accel.bvh, 0);
-    s->accel.built = true;
-    if (s->accel.upload()) { delete s; return nullptr; }
+    if (lmb200_accel_build_ex(reinterpret_cast<lmb200_accel*>(&s->accel), d->verts, d->num_tris, builder)) { delete s; return nullptr; }
     s->num_sms = s->accel.num_sms;
     DevScene& D = s->dev;
     int rc = 0;

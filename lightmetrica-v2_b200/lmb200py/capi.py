@@ -9,6 +9,7 @@ LIB_PATH = os.environ.get("LMB200_LIB", os.path.join(_ROOT, "lib", "liblmb200.so
 MISS = 0xFFFFFFFF
 MODE_PT, MODE_PTDIRECT, MODE_NORMAL, MODE_PTMIS = 0, 1, 2, 3
 BSDF_NULL, BSDF_DIFFUSE, BSDF_COOKTORRANCE = 0, 1, 2
+BUILD_HOST_SAH, BUILD_GPU_LBVH = 0, 1
 
 RAY_DTYPE = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"),
                       ("dx", "f4"), ("dy", "f4"), ("dz", "f4"), ("tmax", "f4")])
@@ -59,10 +60,10 @@ class RenderStats(C.Structure):
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int64)
 
 EXPORTS = [
-    "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build",
+    "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build", "lmb200_accel_build_ex",
     "lmb200_accel_get_stats", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
     "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_arrays", "lmb200_accel_create_host_only",
-    "lmb200_scene_create", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
+    "lmb200_scene_create", "lmb200_scene_create_ex", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
     "lmb200_render", "lmb200_render_multi", "lmb200_render_timed",
 ]
 
@@ -83,6 +84,7 @@ def lib():
     L.lmb200_accel_create_host_only.restype = C.c_void_p
     L.lmb200_accel_destroy.argtypes = [C.c_void_p]
     L.lmb200_accel_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.lmb200_accel_build_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     L.lmb200_accel_get_stats.argtypes = [C.c_void_p, C.POINTER(AccelStats)]
     L.lmb200_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.lmb200_trace_closest_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -96,6 +98,8 @@ def lib():
     if hasattr(L, "lmb200_scene_create"):
         L.lmb200_scene_create.restype = C.c_void_p
         L.lmb200_scene_create.argtypes = [C.c_int, C.POINTER(SceneDesc)]
+        L.lmb200_scene_create_ex.restype = C.c_void_p
+        L.lmb200_scene_create_ex.argtypes = [C.c_int, C.POINTER(SceneDesc), C.c_int]
         L.lmb200_scene_destroy.argtypes = [C.c_void_p]
         L.lmb200_scene_accel.restype = C.c_void_p
         L.lmb200_scene_accel.argtypes = [C.c_void_p]
@@ -143,10 +147,10 @@ class Accel:
         except Exception:
             pass
 
-    def build(self, verts):
+    def build(self, verts, builder=BUILD_HOST_SAH):
         verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 9)
         self._verts = verts
-        check(lib().lmb200_accel_build(self.h, _ptr(verts), verts.shape[0]))
+        check(lib().lmb200_accel_build_ex(self.h, _ptr(verts), verts.shape[0], builder))
         return self.stats()
 
     def stats(self):
@@ -183,10 +187,10 @@ class Accel:
 class Scene:
     """Mirror of the reference's Renderer interface (Initialize/Render, renderer.h:68-81) over a flattened scene."""
 
-    def __init__(self, scene, device=0):
+    def __init__(self, scene, device=0, builder=BUILD_HOST_SAH):
         self.desc, self.keep = scene.flatten()
         self.w, self.h = scene.camera["w"], scene.camera["h"]
-        self.h_ = lib().lmb200_scene_create(device, C.byref(self.desc))
+        self.h_ = lib().lmb200_scene_create_ex(device, C.byref(self.desc), builder)
         if not self.h_:
             raise LmbError(lib().lmb200_last_error().decode())
 

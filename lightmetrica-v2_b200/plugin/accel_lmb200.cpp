@@ -2,7 +2,7 @@
 // (/root/reference/src/liblightmetrica/accel/accel_qbvh.cpp et al.) through the reference's own
 // component mechanism: built as plugin/accel_lmb200.so, registered at dlopen time with
 // LM_COMPONENT_REGISTER_IMPL (component.h:660-667), selected from the scene YAML with
-//     accel: {type: lmb200, params: {device: 0}}
+//     accel: {type: lmb200, params: {device: 0, builder: host}}
 // All compute happens in liblmb200.so (CUDA, include/lmb200.h); this file only flattens the
 // scene the way the reference accels do and fills the Intersection the way they do.
 #include <lightmetrica/lightmetrica.h>
@@ -32,6 +32,14 @@ public:
     LM_IMPL_F(Initialize) = [this](const PropertyNode* prop) -> bool
     {
         device_ = (prop && prop->Child("device")) ? prop->ChildAs<int>("device", 0) : 0;
+        // builder: host (binned SAH on the host, default) | gpu (Morton radix tree on the device, ~100x faster to build)
+        builder_ = LMB200_BUILD_HOST_SAH;
+        if (prop && prop->Child("builder"))
+        {
+            const auto b = prop->ChildAs<std::string>("builder", "host");
+            if (b == "gpu") builder_ = LMB200_BUILD_GPU_LBVH;
+            else if (b != "host") { LM_LOG_ERROR("accel::lmb200: unknown builder '" + b + "' (host | gpu)"); return false; }
+        }
         if (accel_) { lmb200_accel_destroy(accel_); accel_ = nullptr; }
         accel_ = lmb200_accel_create(device_);
         if (!accel_)
@@ -47,7 +55,7 @@ public:
         const auto* scene = static_cast<const Scene3*>(scene_);
         std::vector<float> verts;
         lmb200plugin::FlattenTriangles(scene, verts, nullptr, primOfTri_, faceOfTri_, nullptr);
-        if (lmb200_accel_build(accel_, verts.data(), verts.size() / 9) != LMB200_OK)
+        if (lmb200_accel_build_ex(accel_, verts.data(), verts.size() / 9, builder_) != LMB200_OK)
         {
             LM_LOG_ERROR(std::string("accel::lmb200: ") + lmb200_last_error());
             return false;
@@ -92,6 +100,7 @@ public:
 private:
 
     int device_ = 0;
+    int builder_ = LMB200_BUILD_HOST_SAH;
     lmb200_accel* accel_ = nullptr;
     std::vector<uint32_t> primOfTri_;
     std::vector<uint32_t> faceOfTri_;

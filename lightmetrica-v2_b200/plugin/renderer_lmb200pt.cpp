@@ -4,7 +4,7 @@
 // Selected from the scene YAML with
 //     renderer: {type: lmb200pt, params: {mode: ptdirect, num_samples: ..., max_num_vertices: -1,
 //                                         min_num_vertices: 0, num_gpus: 1, device: 0, pool_size: 0,
-//                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000}}
+//                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000, builder: host}}
 // It reads the scene through the reference's interfaces (Scene3::PrimitiveAt, TriangleMesh::*,
 // BSDF::Reflectance/Glossiness, Light::Emittance, Sensor::GetFilm/GetProjectionMatrix), flattens
 // it into the POD arrays of include/lmb200.h and calls liblmb200.so; the film comes back through
@@ -50,6 +50,12 @@ public:
             if (prop->Child("num_gpus")) numGpus_ = prop->ChildAs<int>("num_gpus", 1);
             if (prop->Child("device")) device_ = prop->ChildAs<int>("device", 0);
             if (prop->Child("pool_size")) poolSize_ = prop->ChildAs<int>("pool_size", 0);
+            if (prop->Child("builder"))
+            {
+                const auto b = prop->ChildAs<std::string>("builder", "host");
+                if (b == "gpu") builder_ = LMB200_BUILD_GPU_LBVH;
+                else if (b != "host") { LM_LOG_ERROR("renderer::lmb200pt: unknown builder '" + b + "' (host | gpu)"); return false; }
+            }
         }
         if (mode == "pt") mode_ = LMB200_MODE_PT;
         else if (mode == "ptdirect") mode_ = LMB200_MODE_PTDIRECT;
@@ -185,7 +191,7 @@ public:
         std::vector<lmb200_scene*> scenes;
         for (int g = 0; g < numGpus_; g++)
         {
-            auto* s = lmb200_scene_create(device_ + g, &d);
+            auto* s = lmb200_scene_create_ex(device_ + g, &d, builder_);
             if (!s)
             {
                 LM_LOG_ERROR(std::string("renderer::lmb200pt: ") + lmb200_last_error());
@@ -329,6 +335,7 @@ private:
     int numGpus_ = 1;
     int device_ = 0;
     int poolSize_ = 0;
+    int builder_ = LMB200_BUILD_HOST_SAH;
     double renderTime_ = -1.0;
     double progressImageInterval_ = -1.0;
     long long grainSize_ = 10000;

@@ -156,3 +156,13 @@ def test_time_budget_and_progress():
     capi.check(L.lmb200_render_timed(arr, 1, C.byref(p), -1.0, 5000, -1.0, capi.PROGRESS_FN(0), None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
     one, _ = S.render(capi.MODE_PTDIRECT, N, seed=3)
     assert st.samples == N and np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
+
+
+def test_gpu_built_scene_renders_the_same_image():
+    """The renderer on a device-built BVH: same samples => same image (hits do not depend on the tree)."""
+    sc = scenedesc.config2_scene(30000, 64, 36, n_objects=40)
+    N = 64 * 36 * 32
+    a, sa = capi.Scene(sc, builder=capi.BUILD_HOST_SAH).render(capi.MODE_PTDIRECT, N, seed=2)
+    b, sb = capi.Scene(sc, builder=capi.BUILD_GPU_LBVH).render(capi.MODE_PTDIRECT, N, seed=2)
+    assert sa["extend_rays"] == sb["extend_rays"] and sa["shadow_rays"] == sb["shadow_rays"]
+    assert np.allclose(a, b, rtol=2e-4, atol=1e-5)
