@@ -62,9 +62,28 @@ def pt_golden():
     np.savez_compressed(os.path.join(HERE, "pt_cornell.npz"), spp=spp, **out)
 
 
+def config0_golden():
+    """BASELINE configs[0]: Cornell box, reference path tracers at 512x512, 64 spp on the CPU (the PR1
+    equivalence reference). Stored as 8x8 block means (64x64x3) so the fixture stays small; block means are
+    what the GPU test compares (per-pixel noise at 64 spp is ~40 %)."""
+    from lmb200py import scenedesc
+    sc = scenedesc.cornell_box(512, 512, glossy_block=True)
+    R = ob.RefScene(sc, "qbvh")
+    N = 512 * 512 * 64
+    out = {}
+    for name in ("ptdirect", "pt"):
+        for seed, tag in ((1, "a"), (2, "b")):
+            img, sec = R.render(name, N, seed=seed, threads=8)
+            out[f"{name}_{tag}"] = img.reshape(64, 8, 64, 8, 3).mean(axis=(1, 3)).astype(np.float32)
+            print(name, seed, "%.1f s" % sec, img.mean(axis=(0, 1)))
+    np.savez_compressed(os.path.join(HERE, "config0_cornell512_blockmeans.npz"), spp=64, **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["accel", "pt"]
     if "accel" in which:
         accel_golden()
     if "pt" in which:
         pt_golden()
+    if "config0" in which:
+        config0_golden()
