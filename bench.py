@@ -11,7 +11,8 @@ no data-path collective). One "step" = one pass of lmb200_trace_closest over the
             kernel) * rays / kernel time, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the CPU oracle on a bounded ray sample of the same scene (rank 0, N=1 only)
   path_tracing  secondary figure: wavefront ptdirect Msamples/s on the 1 M-triangle scene of
-                configs[2] at reduced spp, films summed over ranks with one NCCL reduce
+                configs[2] at reduced spp (128 instead of 1024), sample range sharded over ranks
+                (strong scaling), films summed with one NCCL reduce
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref: accel::qbvh through the
 real Accel3::Intersect, all host threads) on a bounded sample of the same workload.
@@ -46,7 +47,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=1_000_000, help="bounded CPU sample")
     ap.add_argument("--no-pt", action="store_true", help="skip the secondary path-tracing figure")
     ap.add_argument("--pt-tris", type=int, default=1_000_000)
-    ap.add_argument("--pt-spp", type=int, default=16)
+    ap.add_argument("--pt-spp", type=int, default=128)
     ap.add_argument("--pt-pool", type=int, default=0, help="wavefront pool size (0 = library default)")
     return ap.parse_args()
 
@@ -186,6 +187,8 @@ def run_reference(a):
 
 
 def main():
+    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO level
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     a = parse()
     if a.impl == "reference":
         run_reference(a)
@@ -367,7 +370,7 @@ def bench_pt(a, torch, dist, capi, world, rank, local, dev):
     S.close()
     return {"metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene", "value": N / (float(ms.item()) * 1e-3) / 1e6,
             "unit": "Msamples/s", "spp": a.pt_spp, "samples": N, "ms": float(ms.item()), "rays_per_sample": float(rays.item()) / N,
-            "mrays_per_s": float(rays.item()) / (float(ms.item()) * 1e-3) / 1e6, "film_reduce": "torch.distributed NCCL reduce" if world > 1 else "none (1 GPU)",
+            "mrays_per_s": float(rays.item()) / (float(ms.item()) * 1e-3) / 1e6, "film_reduce": "torch.distributed NCCL reduce" if world > 1 else "none (1 GPU)", "scaling": "strong (fixed image and spp, sample range sharded over ranks)",
             "mean_rgb": [float(x) for x in film[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None}
 
 
