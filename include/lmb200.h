@@ -125,6 +125,9 @@ lmb200_accel* lmb200_accel_create_host_only(void);
 #define LMB200_BSDF_NULL          0   /* bsdf_null.cpp:38-56: Type()==None, path ends */
 #define LMB200_BSDF_DIFFUSE       1   /* bsdf_diffuse.cpp:69-104 */
 #define LMB200_BSDF_COOKTORRANCE  2   /* bsdf_cooktorrance.cpp:73-120,187-225,276-293 (GGX) */
+#define LMB200_BSDF_REFLECT_ALL   3   /* bsdf_reflectall.cpp:57-105: perfect mirror (delta) */
+#define LMB200_BSDF_REFRACT_ALL   4   /* bsdf_refractall.cpp:59-140: refraction, mirror on total internal reflection (delta) */
+#define LMB200_BSDF_FLESNEL       5   /* bsdf_flesnel.cpp:59-160,222-240: Fresnel-weighted choice of the two (delta) */
 
 typedef struct lmb200_bsdf {
     int32_t type;
@@ -132,6 +135,7 @@ typedef struct lmb200_bsdf {
     float eta[3];
     float k[3];
     float roughness;
+    float eta1, eta2;   /* refract_all / flesnel: indices of refraction outside / inside (defaults 1, 2) */
 } lmb200_bsdf;
 
 /* One entry per scene primitive that owns triangles (primitive.h:57-84). */
@@ -145,9 +149,13 @@ typedef struct lmb200_primitive {
 
 /* light::area (light_area.cpp:47-115). The area CDF over the primitive's triangles is built
  * by the library exactly as TriangleUtils::CreateTriangleAreaDist (triangleutils.h:47-68). */
+#define LMB200_LIGHT_AREA   0
+#define LMB200_LIGHT_POINT  1   /* light_point.cpp:47-105: delta position, emits Le in every direction */
 typedef struct lmb200_light {
     float   Le[3];
-    int32_t primitive;
+    int32_t primitive;     /* area: the primitive whose mesh is sampled; point: the light's own primitive (no mesh) */
+    int32_t kind;
+    float   position[3];   /* point: world-space position */
 } lmb200_light;
 
 /* sensor::pinhole (sensor_pinhole.cpp:47-61): position = column 3 of the primitive transform,

@@ -204,10 +204,38 @@ __device__ __forceinline__ float ggx_D(float alpha, f3 H)
     const float t = alpha * alpha + tanH * tanH;
     return t1 / (LMB_PI * cosH * cosH * cosH * cosH * t * t);
 }
-__device__ __forceinline__ bool bsdf_sample(const lmb200_bsdf& B, const Geom& g, f3 wi, float u0, float u1, f3& wo)
+// Fresnel term of bsdf::flesnel (bsdf_flesnel.cpp:224-240)
+__device__ __forceinline__ float fresnel_term(f3 lwi, float etaI, float etaT)
+{
+    const float wiDotN = lwi.z, eta = etaI / etaT;
+    const float c2 = 1.0f - eta * eta * (1.0f - wiDotN * wiDotN);
+    if (c2 <= 0.f) return 1.0f;
+    const float ci = fabsf(wiDotN), ct = sqrtf(c2);
+    const float rhoS = (etaI * ci - etaT * ct) / (etaI * ci + etaT * ct);
+    const float rhoT = (etaI * ct - etaT * ci) / (etaI * ct + etaT * ci);
+    return (rhoS * rhoS + rhoT * rhoT) * 0.5f;
+}
+__device__ __forceinline__ bool is_specular(const lmb200_bsdf& B) { return B.type >= LMB200_BSDF_REFLECT_ALL && B.type <= LMB200_BSDF_FLESNEL; }
+
+__device__ __forceinline__ bool bsdf_sample(const lmb200_bsdf& B, const Geom& g, f3 wi, float u0, float u1, float ucomp, f3& wo)
 {
     const f3 lwi = to_local(g, wi);
+    if (B.type == LMB200_BSDF_REFRACT_ALL || B.type == LMB200_BSDF_FLESNEL) {
+        // bsdf_refractall.cpp:59-90, bsdf_flesnel.cpp:59-95: both sides of the surface
+        float etaI = B.eta1, etaT = B.eta2;
+        if (lwi.z < 0.f) { const float t = etaI; etaI = etaT; etaT = t; }
+        const float eta = etaI / etaT;
+        const float c2 = 1.0f - eta * eta * (1.0f - lwi.z * lwi.z);
+        const bool reflect = B.type == LMB200_BSDF_REFRACT_ALL ? (c2 <= 0.f) : (ucomp <= fresnel_term(lwi, etaI, etaT));
+        if (reflect) wo = to_world(g, F3(-lwi.x, -lwi.y, lwi.z));                // BSDFUtils::LocalReflect
+        else {
+            const float ct = sqrtf(c2) * (lwi.z > 0.f ? -1.0f : 1.0f);
+            wo = to_world(g, F3(-eta * lwi.x, -eta * lwi.y, ct));                 // BSDFUtils::LocalRefract
+        }
+        return true;
+    }
     if (lwi.z <= 0.f) return false;
+    if (B.type == LMB200_BSDF_REFLECT_ALL) { wo = to_world(g, F3(-lwi.x, -lwi.y, lwi.z)); return true; }   // bsdf_reflectall.cpp:57-68
     if (B.type == LMB200_BSDF_DIFFUSE) {
         float sx, sy;
         concentric_disk(u0, u1, sx, sy);
@@ -230,9 +258,18 @@ __device__ __forceinline__ bool bsdf_sample(const lmb200_bsdf& B, const Geom& g,
     }
     return false;
 }
-__device__ __forceinline__ float bsdf_pdf(const lmb200_bsdf& B, const Geom& g, f3 wi, f3 wo)
+__device__ __forceinline__ float bsdf_pdf(const lmb200_bsdf& B, const Geom& g, f3 wi, f3 wo, bool eval_delta)
 {
     const f3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (is_specular(B)) {
+        if (eval_delta) return 0.f;
+        if (B.type == LMB200_BSDF_REFLECT_ALL) return (lwi.z <= 0.f || lwo.z <= 0.f) ? 0.f : 1.f;   // bsdf_reflectall.cpp:70-85
+        if (B.type == LMB200_BSDF_REFRACT_ALL) return 1.f;                                            // bsdf_refractall.cpp:92-100
+        float etaI = B.eta1, etaT = B.eta2;                                                           // bsdf_flesnel.cpp:97-128
+        if (lwi.z < 0.f) { const float t = etaI; etaI = etaT; etaT = t; }
+        const float Fr = fresnel_term(lwi, etaI, etaT);
+        return lwi.z * lwo.z >= 0.f ? Fr : 1.0f - Fr;
+    }
     if (lwi.z <= 0.f || lwo.z <= 0.f) return 0.f;
     if (B.type == LMB200_BSDF_DIFFUSE) return LMB_INV_PI;
     if (B.type == LMB200_BSDF_COOKTORRANCE) {
@@ -242,9 +279,24 @@ __device__ __forceinline__ float bsdf_pdf(const lmb200_bsdf& B, const Geom& g, f
     }
     return 0.f;
 }
-__device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 wi, f3 wo)
+__device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 wi, f3 wo, bool eval_delta)
 {
     const f3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (is_specular(B)) {
+        if (eval_delta) return F3(0, 0, 0);
+        if (B.type == LMB200_BSDF_REFLECT_ALL) {                                                      // bsdf_reflectall.cpp:87-103
+            if (lwi.z <= 0.f || lwo.z <= 0.f) return F3(0, 0, 0);
+            return ld3(B.R) * snc(g, wi, wo);
+        }
+        float etaI = B.eta1, etaT = B.eta2;
+        if (lwi.z < 0.f) { const float t = etaI; etaI = etaT; etaT = t; }
+        const float eta = etaI / etaT;
+        const float Fr = B.type == LMB200_BSDF_FLESNEL ? fresnel_term(lwi, etaI, etaT) : 0.f;
+        if (lwi.z * lwo.z >= 0.f)        // reflection (total internal reflection for refract_all)
+            return ld3(B.R) * ((B.type == LMB200_BSDF_FLESNEL ? Fr : 1.0f) * snc(g, wi, wo));
+        // refraction, EL transport: eta^2 (bsdf_refractall.cpp:120-127, bsdf_flesnel.cpp:150-156)
+        return ld3(B.R) * ((B.type == LMB200_BSDF_FLESNEL ? 1.0f - Fr : 1.0f) * snc(g, wi, wo) * eta * eta);
+    }
     if (lwi.z <= 0.f || lwo.z <= 0.f) return F3(0, 0, 0);
     if (B.type == LMB200_BSDF_DIFFUSE) return (ld3(B.R) * LMB_INV_PI) * snc(g, wi, wo);
     if (B.type == LMB200_BSDF_COOKTORRANCE) {
@@ -273,6 +325,12 @@ __device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 
 // ---- light::area position sampling (triangleutils.h:71-122, dist.h:70-76, sampler.h:97-101) ----
 __device__ __forceinline__ void light_sample(const DevScene& S, int li, float u0, float u1, Geom& g)
 {
+    if (S.lights[li].kind == LMB200_LIGHT_POINT) {            // light_point.cpp:62-66
+        g.p = ld3(S.lights[li].position);
+        g.degenerated = true;
+        g.gn = g.sn = g.dpdu = g.dpdv = F3(0, 0, 0);
+        return;
+    }
     const lmb200_primitive& P = S.prims[S.lights[li].primitive];
     const float* cdf = S.light_cdf + S.light_cdf_off[li];
     const int n = (int)P.num_tris;
@@ -348,8 +406,9 @@ __global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg
                             float G = fabsf(dot(g.sn, dd));
                             if (nv > 1) G *= fabsf(dot(F3(pv.x, pv.y, pv.z), neg(dd)));   // the camera vertex is degenerated
                             G = G / d2;
-                            const float pdfDL = S.light_inv_area[prim.light] / G * (1.0f / (float)S.num_lights);
-                            C = C * (pv.w / (pv.w + pdfDL));
+                            const float pdfDL = pv.w < 0.f ? 0.f : S.light_inv_area[prim.light] / G * (1.0f / (float)S.num_lights);
+                            const float pdfBS = fabsf(pv.w);
+                            C = C * (pdfBS / (pdfBS + pdfDL));
                         }
                         film_add(film, __float_as_int(thr.w), C);
                     }
@@ -454,16 +513,17 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
                 const float4 vw = P.vtx_wi[i];
                 tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
                 const lmb200_bsdf& B = S.bsdfs[S.prims[S.tri_prim[tri]].bsdf];
-                fsE = bsdf_eval(B, g, F3(vw.x, vw.y, vw.z), ppL);
-                pdfB = cfg.mode == LMB200_MODE_PTMIS ? bsdf_pdf(B, g, F3(vw.x, vw.y, vw.z), ppL) : 0.f;
+                fsE = bsdf_eval(B, g, F3(vw.x, vw.y, vw.z), ppL, true);
+                pdfB = cfg.mode == LMB200_MODE_PTMIS ? bsdf_pdf(B, g, F3(vw.x, vw.y, vw.z), ppL, true) : 0.f;
             }
-            const f3 fsL = to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le);   // light_area.cpp:105-110
+            const f3 fsL = gL.degenerated ? ld3(S.lights[li].Le)                                   // light_point.cpp:95-98
+                                          : (to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le));   // light_area.cpp:105-110
             f3 d = gL.p - p;                                                   // RenderUtils::GeometryTerm, renderutils.h:46-56
             const float d2 = dot(d, d), dl = sqrtf(d2);
             d = F3(d.x / dl, d.y / dl, d.z / dl);
             float G = 1.0f;
             if (!is_sensor) G *= fabsf(dot(g.sn, d));
-            G *= fabsf(dot(gL.sn, neg(d)));
+            if (!gL.degenerated) G *= fabsf(dot(gL.sn, neg(d)));
             G = G / d2;
             C = ((F3(thr.x, thr.y, thr.z) * fsE) * fsL) * G;
             if (!black(C)) {
@@ -514,7 +574,7 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
             float4 thr = P.thr[i];
             f3 wo = F3(0, 0, 0), fs, sn_here = F3(0, 0, 0);
             float pdfD;
-            bool ok = true;
+            bool ok = true, specular_here = false;
             if (is_sensor) {
                 const float4 u = rng_block(cfg.seed, P.sample[i], 0u);
                 wo = camera_dir(S, u.y, u.z);
@@ -532,15 +592,17 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
                 tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
                 const lmb200_bsdf& B = S.bsdfs[S.prims[S.tri_prim[tri]].bsdf];
                 const float4 ub = rng_block(cfg.seed, P.sample[i], (uint32_t)(2 * nv));
-                bsdf_sample(B, g, wi, ub.x, ub.y, wo);
-                pdfD = bsdf_pdf(B, g, wi, wo);
-                fs = bsdf_eval(B, g, wi, wo);
+                bsdf_sample(B, g, wi, ub.x, ub.y, ub.z, wo);
+                pdfD = bsdf_pdf(B, g, wi, wo, false);
+                fs = bsdf_eval(B, g, wi, wo, false);
                 sn_here = g.sn;
+                specular_here = is_specular(B);
             }
             if (ok && !black(fs)) {
                 thr.x *= fs.x / pdfD; thr.y *= fs.y / pdfD; thr.z *= fs.z / pdfD;
                 P.thr[i] = thr;
-                if (cfg.mode == LMB200_MODE_PTMIS) P.prev[i] = make_float4(sn_here.x, sn_here.y, sn_here.z, pdfD);
+                // ptmis: a negative pdf marks a specular vertex (light sampling cannot reach it, renderer_ptmis.cpp:251-254)
+                if (cfg.mode == LMB200_MODE_PTMIS) P.prev[i] = make_float4(sn_here.x, sn_here.y, sn_here.z, specular_here ? -pdfD : pdfD);
                 P.ray_o[i] = make_float4(p.x, p.y, p.z, LMB_EPS_ISECT);       // scene3.cpp:461
                 P.ray_d[i] = make_float4(wo.x, wo.y, wo.z, LMB_FLT_MAX);
                 P.traced[i] = 1;
@@ -833,6 +895,8 @@ lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int
         const lmb200_primitive& P = d->prims[i];
         if (P.bsdf < 0 || (uint32_t)P.bsdf >= d->num_bsdfs || P.light >= (int32_t)d->num_lights || (uint64_t)P.first_tri + P.num_tris > d->num_tris) { set_error(LMB200_E_INVALID, "primitive out of range"); return nullptr; }
     }
+    for (uint32_t i = 0; i < d->num_bsdfs; i++)
+        if (d->bsdfs[i].type < LMB200_BSDF_NULL || d->bsdfs[i].type > LMB200_BSDF_FLESNEL) { set_error(LMB200_E_INVALID, "unknown bsdf type"); return nullptr; }
     Scene* s = new Scene;
     s->device = device;
     s->accel.device = device;
@@ -854,6 +918,9 @@ lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int
         if (d->lights[li].primitive < 0 || (uint32_t)d->lights[li].primitive >= d->num_prims) { set_error(LMB200_E_INVALID, "light primitive out of range"); delete s; return nullptr; }
         const lmb200_primitive& P = d->prims[d->lights[li].primitive];
         off.push_back((uint32_t)cdf.size());
+        if (d->lights[li].kind == LMB200_LIGHT_POINT) { cdf.push_back(0.f); cdf.push_back(1.f); inv_area.push_back(1.0f); continue; }   // pdf 1 (light_point.cpp:88-91)
+        if (d->lights[li].kind != LMB200_LIGHT_AREA) { set_error(LMB200_E_INVALID, "unknown light kind"); delete s; return nullptr; }
+        if (P.num_tris == 0) { set_error(LMB200_E_INVALID, "area light without triangles"); delete s; return nullptr; }
         const size_t base = cdf.size();
         cdf.push_back(0.f);
         float sum = 0.f;

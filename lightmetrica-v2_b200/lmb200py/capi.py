@@ -8,7 +8,8 @@ LIB_PATH = os.environ.get("LMB200_LIB", os.path.join(_ROOT, "lib", "liblmb200.so
 
 MISS = 0xFFFFFFFF
 MODE_PT, MODE_PTDIRECT, MODE_NORMAL, MODE_PTMIS = 0, 1, 2, 3
-BSDF_NULL, BSDF_DIFFUSE, BSDF_COOKTORRANCE = 0, 1, 2
+BSDF_NULL, BSDF_DIFFUSE, BSDF_COOKTORRANCE, BSDF_REFLECT_ALL, BSDF_REFRACT_ALL, BSDF_FLESNEL = 0, 1, 2, 3, 4, 5
+LIGHT_AREA, LIGHT_POINT = 0, 1
 BUILD_HOST_SAH, BUILD_GPU_LBVH = 0, 1
 
 RAY_DTYPE = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"),
@@ -23,7 +24,8 @@ class AccelStats(C.Structure):
 
 
 class Bsdf(C.Structure):
-    _fields_ = [("type", C.c_int32), ("R", C.c_float * 3), ("eta", C.c_float * 3), ("k", C.c_float * 3), ("roughness", C.c_float)]
+    _fields_ = [("type", C.c_int32), ("R", C.c_float * 3), ("eta", C.c_float * 3), ("k", C.c_float * 3), ("roughness", C.c_float),
+                ("eta1", C.c_float), ("eta2", C.c_float)]
 
 
 class Primitive(C.Structure):
@@ -31,7 +33,7 @@ class Primitive(C.Structure):
 
 
 class Light(C.Structure):
-    _fields_ = [("Le", C.c_float * 3), ("primitive", C.c_int32)]
+    _fields_ = [("Le", C.c_float * 3), ("primitive", C.c_int32), ("kind", C.c_int32), ("position", C.c_float * 3)]
 
 
 class Camera(C.Structure):

@@ -18,16 +18,24 @@ class Scene:
         self.meshes = []      # dict(verts (nv,3) f32, faces (nf,3) u32, normals (nv,3) f32 or None)
         self.nodes = []       # dict(mesh=int, bsdf=str or None, light=str or None)
         self.bsdfs = {}       # name -> dict(type='diffuse'|'cook_torrance', R, eta, k, roughness)
-        self.lights = {}      # name -> Le (3,)
+        self.lights = {}      # name -> Le (3,)   (light::area)
+        self.point_lights = {}   # name -> dict(Le, position)   (light::point)
         self.camera = None    # dict(eye, center, up, fov, w, h)
 
     # ---- construction helpers ----
     def add_bsdf(self, name, type="diffuse", R=(0.8, 0.8, 0.8), roughness=0.1,
-                 eta=(0.14, 0.129, 0.1585), k=(4.58625, 3.348125, 2.329375)):
-        self.bsdfs[name] = dict(type=type, R=tuple(R), roughness=float(roughness), eta=tuple(eta), k=tuple(k))
+                 eta=(0.14, 0.129, 0.1585), k=(4.58625, 3.348125, 2.329375), eta1=1.0, eta2=2.0):
+        """type: diffuse | cook_torrance | reflect_all | refract_all | flesnel"""
+        self.bsdfs[name] = dict(type=type, R=tuple(R), roughness=float(roughness), eta=tuple(eta), k=tuple(k),
+                                eta1=float(eta1), eta2=float(eta2))
 
     def add_light(self, name, Le):
         self.lights[name] = tuple(Le)
+
+    def add_point_light(self, name, Le, position):
+        """light::point (light_point.cpp:47-54) on a node of its own (no mesh)."""
+        self.point_lights[name] = dict(Le=tuple(Le), position=tuple(float(x) for x in position))
+        self.nodes.append(dict(mesh=None, bsdf=None, light=name))
 
     def add_mesh_tris(self, tris9, bsdf=None, light=None, normals=None):
         """tris9: (n,9) world-space triangles, stored unshared (3 vertices per face)."""
@@ -56,8 +64,13 @@ class Scene:
             out += [f"    {name}:", "      interface: bsdf", f"      type: {b['type']}", "      params:", f"        R: {v3(b['R'])}"]
             if b["type"] == "cook_torrance":
                 out += [f"        eta: {v3(b['eta'])}", f"        k: {v3(b['k'])}", f"        roughness: {b['roughness']!r}"]
+            if b["type"] in ("refract_all", "flesnel"):
+                out += [f"        eta1: {b['eta1']!r}", f"        eta2: {b['eta2']!r}"]
         for name, le in self.lights.items():
             out += [f"    {name}:", "      interface: light", "      type: area", "      params:", f"        Le: {v3(le)}"]
+        for name, pl in self.point_lights.items():
+            out += [f"    {name}:", "      interface: light", "      type: point", "      params:", f"        Le: {v3(pl['Le'])}",
+                    f"        position: {v3(pl['position'])}"]
         c = self.camera
         out += ["    film1:", "      interface: film", "      type: hdr", "      params:", f"        w: {c['w']}", f"        h: {c['h']}"]
         out += ["    cam:", "      interface: sensor", "      type: pinhole", "      params:", "        film: film1", f"        fov: {c['fov']!r}"]
@@ -66,6 +79,9 @@ class Scene:
         out += ["        - id: n_cam", "          sensor: cam", "          transform:", "            lookat:",
                 f"              eye: {v3(c['eye'])}", f"              center: {v3(c['center'])}", f"              up: {v3(c['up'])}"]
         for nd in self.nodes:
+            if nd["mesh"] is None:
+                out += [f"        - light: {nd['light']}"]
+                continue
             out += [f"        - mesh: mesh{nd['mesh']}"]
             if nd["bsdf"]:
                 out += [f"          bsdf: {nd['bsdf']}"]
@@ -82,7 +98,9 @@ class Scene:
         bs = (capi.Bsdf * (len(bs_names) + 1))()
         for i, n in enumerate(bs_names):
             b = self.bsdfs[n]
-            bs[i].type = capi.BSDF_DIFFUSE if b["type"] == "diffuse" else capi.BSDF_COOKTORRANCE
+            bs[i].type = {"diffuse": capi.BSDF_DIFFUSE, "cook_torrance": capi.BSDF_COOKTORRANCE, "reflect_all": capi.BSDF_REFLECT_ALL,
+                          "refract_all": capi.BSDF_REFRACT_ALL, "flesnel": capi.BSDF_FLESNEL}[b["type"]]
+            bs[i].eta1, bs[i].eta2 = b["eta1"], b["eta2"]
             bs[i].R = (C.c_float * 3)(*b["R"])
             bs[i].eta = (C.c_float * 3)(*b["eta"])
             bs[i].k = (C.c_float * 3)(*b["k"])
@@ -93,10 +111,17 @@ class Scene:
         prims[0].bsdf = null_idx
         prims[0].light = -1
         lights, verts, norms, tri_prim = [], [], [], []
-        any_normals = any(self.meshes[nd["mesh"]]["normals"] is not None for nd in self.nodes)
+        any_normals = any(nd["mesh"] is not None and self.meshes[nd["mesh"]]["normals"] is not None for nd in self.nodes)
         first = 0
         first_prim_of_light = {}
         for pi, nd in enumerate(self.nodes, start=1):
+            if nd["mesh"] is None:      # light::point node: a primitive without geometry
+                prims[pi].bsdf = null_idx
+                prims[pi].first_tri = first
+                prims[pi].light = len(lights)
+                pl = self.point_lights[nd["light"]]
+                lights.append((pl["Le"], pi, capi.LIGHT_POINT, pl["position"]))
+                continue
             m = self.meshes[nd["mesh"]]
             t = m["verts"][m["faces"].reshape(-1)].reshape(-1, 9)
             verts.append(t)
@@ -114,15 +139,17 @@ class Scene:
                 # distribution at Load): later primitives sharing the asset sample the first one's mesh.
                 bound = first_prim_of_light.setdefault(nd["light"], pi)
                 prims[pi].light = len(lights)
-                lights.append((self.lights[nd["light"]], bound))
+                lights.append((self.lights[nd["light"]], bound, capi.LIGHT_AREA, (0.0, 0.0, 0.0)))
             first += t.shape[0]
         verts = np.ascontiguousarray(np.concatenate(verts), np.float32) if verts else np.zeros((0, 9), np.float32)
         tri_prim = np.ascontiguousarray(np.concatenate(tri_prim), np.uint32) if tri_prim else np.zeros(0, np.uint32)
         norms = np.ascontiguousarray(np.concatenate(norms), np.float32) if any_normals else None
         ls = (capi.Light * max(1, len(lights)))()
-        for i, (le, pi) in enumerate(lights):
+        for i, (le, pi, kind, pos) in enumerate(lights):
             ls[i].Le = (C.c_float * 3)(*le)
             ls[i].primitive = pi
+            ls[i].kind = kind
+            ls[i].position = (C.c_float * 3)(*pos)
         c = self.camera
         vx, vy, vz = scenes.lookat(c["eye"], c["center"], c["up"])
         cam = capi.Camera()
@@ -218,4 +245,30 @@ def config2_scene(target_tris=1_000_000, w=1920, h=1080, seed=42, half=50.0, n_o
         # faces down: (b-a)x(c-a) = -y
         s.add_quad((cx - r, y, cz - r), (cx + r, y, cz - r), (cx + r, y, cz + r), (cx - r, y, cz + r), "lampb", f"lamp{k}")
     s.set_camera((0.0, half * 0.45, half * 1.05), (0.0, half * 0.1, 0.0), (0, 1, 0), 45.0, w, h)
+    return s
+
+
+def specular_box(w=64, h=64, point_light=True):
+    """Cornell-style box with a glass sphere (bsdf::flesnel), a mirror block (bsdf::reflect_all), a refract_all slab
+    and, optionally, a light::point besides the ceiling area light: exercises the delta BSDFs and the delta light."""
+    s = Scene()
+    s.add_bsdf("white", "diffuse", (0.75, 0.75, 0.75))
+    s.add_bsdf("red", "diffuse", (0.75, 0.25, 0.25))
+    s.add_bsdf("green", "diffuse", (0.25, 0.75, 0.25))
+    s.add_bsdf("glass", "flesnel", (1.0, 1.0, 1.0), eta1=1.0, eta2=1.5)
+    s.add_bsdf("mirror", "reflect_all", (0.9, 0.9, 0.9))
+    s.add_bsdf("slab", "refract_all", (0.95, 0.95, 1.0), eta1=1.0, eta2=1.3)
+    s.add_light("lamp", (17.0, 12.0, 4.0))
+    s.add_quad((-1, 0, -1), (-1, 0, 1), (1, 0, 1), (1, 0, -1), "white")
+    s.add_quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1), "white")
+    s.add_quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1), "white")
+    s.add_quad((-1, 0, -1), (-1, 2, -1), (-1, 2, 1), (-1, 0, 1), "red")
+    s.add_quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1), "green")
+    s.add_mesh_tris(scenes.sphere((0.4, 0.45, 0.3), 0.4, 24, 16), "glass")
+    _box(s, (-0.4, 0.6, -0.35), (0.3, 0.6, 0.3), 20.0, "mirror")
+    _box(s, (-0.45, 0.25, 0.55), (0.25, 0.25, 0.05), -10.0, "slab")
+    s.add_quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), "white", "lamp")
+    if point_light:
+        s.add_point_light("bulb", (1.5, 1.5, 2.0), (0.6, 1.5, 0.6))
+    s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h)
     return s

@@ -118,9 +118,23 @@ public:
             prims[i].light = -1;
             if (prim->light)
             {
-                if (std::string(prim->light->implName) != "Light_Area")
+                const std::string limpl = prim->light->implName;
+                if (limpl == "Light_Point")
                 {
-                    LM_LOG_ERROR(std::string("renderer::lmb200pt: unsupported light '") + prim->light->implName + "' (only light::area)");
+                    // light_point.cpp:47-105: position and Le through the Emitter interface
+                    SurfaceGeometry gp, gprev;
+                    prim->light->SamplePositionGivenPreviousPosition(Vec2(), gprev, gp);
+                    const auto Le = prim->light->EvaluateDirection(gp, SurfaceInteractionType::L, Vec3(), Vec3(0_f, 0_f, 1_f), TransportDirection::LE, false).ToRGB();
+                    lmb200_light L; memset(&L, 0, sizeof(L));
+                    L.Le[0] = Le.x; L.Le[1] = Le.y; L.Le[2] = Le.z; L.primitive = i; L.kind = LMB200_LIGHT_POINT;
+                    L.position[0] = gp.p.x; L.position[1] = gp.p.y; L.position[2] = gp.p.z;
+                    prims[i].light = (int)lights.size();
+                    lights.push_back(L);
+                    continue;
+                }
+                if (limpl != "Light_Area")
+                {
+                    LM_LOG_ERROR("renderer::lmb200pt: unsupported light '" + limpl + "' (light::area | light::point)");
                     return;
                 }
                 const auto Le = prim->light->Emittance().ToRGB();
@@ -129,7 +143,8 @@ public:
                 // distribution at Load): primitives sharing the asset all sample that first mesh.
                 auto bound = lightBound.find(prim->light);
                 if (bound == lightBound.end()) bound = lightBound.emplace(prim->light, i).first;
-                lmb200_light L; L.Le[0] = Le.x; L.Le[1] = Le.y; L.Le[2] = Le.z; L.primitive = bound->second;
+                lmb200_light L; memset(&L, 0, sizeof(L));
+                L.Le[0] = Le.x; L.Le[1] = Le.y; L.Le[2] = Le.z; L.primitive = bound->second; L.kind = LMB200_LIGHT_AREA;
                 prims[i].light = (int)lights.size();
                 lights.push_back(L);
             }
@@ -291,9 +306,26 @@ private:
         memset(&b, 0, sizeof(b));
         const std::string impl = bsdf->implName;
         if (impl == "BSDF_Null") { b.type = LMB200_BSDF_NULL; return true; }
+        if (impl == "BSDF_ReflectAll" || impl == "BSDF_RefractAll" || impl == "BSDF_Flesnel")
+        {
+            // delta BSDFs expose neither R nor the indices of refraction through the interface
+            // (bsdf_reflectall.cpp:48-51, bsdf_refractall.cpp:46-52): read the YAML the asset was loaded from
+            const auto* sp = AssetParams(bsdf);
+            if (!sp)
+            {
+                LM_LOG_ERROR("renderer::lmb200pt: cannot reach the scene tree to read the parameters of '" + bsdf->ID() + "' (" + impl + ")");
+                return false;
+            }
+            const Vec3 R = sp->ChildAs<Vec3>("R", Vec3());
+            b.R[0] = R.x; b.R[1] = R.y; b.R[2] = R.z;
+            b.eta1 = sp->ChildAs<Float>("eta1", 1_f);
+            b.eta2 = sp->ChildAs<Float>("eta2", 2_f);
+            b.type = impl == "BSDF_ReflectAll" ? LMB200_BSDF_REFLECT_ALL : impl == "BSDF_RefractAll" ? LMB200_BSDF_REFRACT_ALL : LMB200_BSDF_FLESNEL;
+            return true;
+        }
         if (impl != "BSDF_Diffuse" && impl != "BSDF_CookTorrance")
         {
-            LM_LOG_ERROR("renderer::lmb200pt: unsupported BSDF '" + impl + "' (diffuse | cook_torrance | null)");
+            LM_LOG_ERROR("renderer::lmb200pt: unsupported BSDF '" + impl + "' (diffuse | cook_torrance | reflect_all | refract_all | flesnel | null)");
             return false;
         }
         const auto* ap = AssetParams(bsdf);

@@ -33,9 +33,9 @@ int orc_closest_one(const orc_scene* s, const float* ray, int use_bvh, float* tu
 int orc_any_one(const orc_scene* s, const float* ray);
 
 /* Same field layout as include/lmb200.h (restated here; the oracle does not include product headers). */
-typedef struct { int32_t type; float R[3], eta[3], k[3], roughness; } orc_bsdf;
+typedef struct { int32_t type; float R[3], eta[3], k[3], roughness, eta1, eta2; } orc_bsdf;
 typedef struct { int32_t bsdf, light; uint32_t first_tri, num_tris; int32_t has_normals; } orc_prim;
-typedef struct { float Le[3]; int32_t primitive; } orc_light;
+typedef struct { float Le[3]; int32_t primitive; int32_t kind; float position[3]; } orc_light;
 typedef struct { float position[3], vx[3], vy[3], vz[3], fov; int32_t width, height; } orc_camera;
 typedef struct {
     uint64_t num_tris; const float* verts; const float* normals; const uint32_t* tri_prim;
@@ -185,10 +185,39 @@ static float ggx_D(float alpha, v3 H)   /* bsdf_cooktorrance.cpp:187-198 */
 }
 /* Sample wo (returns 0 if no direction is produced, in which case the reference leaves wo
  * untouched (zero) and the pdf / fs evaluate to 0). */
-static int bsdf_sample(const orc_bsdf* B, const geom_t* g, v3 wi, float u0, float u1, v3* wo)
+/* Fresnel term of bsdf::flesnel (bsdf_flesnel.cpp:224-240) */
+static float fresnel_term(v3 lwi, float etaI, float etaT)
+{
+    const float wiDotN = lwi.z, eta = etaI / etaT;
+    const float c2 = 1.0f - eta * eta * (1.0f - wiDotN * wiDotN);
+    if (c2 <= 0.0f) return 1.0f;
+    {
+        const float ci = fabsf(wiDotN), ct = sqrtf(c2);
+        const float rhoS = (etaI * ci - etaT * ct) / (etaI * ci + etaT * ct);
+        const float rhoT = (etaI * ct - etaT * ci) / (etaI * ct + etaT * ci);
+        return (rhoS * rhoS + rhoT * rhoT) * 0.5f;
+    }
+}
+static int is_specular(const orc_bsdf* B) { return B->type >= 3 && B->type <= 5; }
+
+static int bsdf_sample(const orc_bsdf* B, const geom_t* g, v3 wi, float u0, float u1, float ucomp, v3* wo)
 {
     const v3 lwi = to_local(g, wi);
+    if (B->type == 4 || B->type == 5) {   /* refract_all (bsdf_refractall.cpp:59-90), flesnel (bsdf_flesnel.cpp:59-95): both sides */
+        float etaI = B->eta1, etaT = B->eta2, eta, c2;
+        if (lwi.z < 0.0f) { const float t = etaI; etaI = etaT; etaT = t; }
+        eta = etaI / etaT;
+        c2 = 1.0f - eta * eta * (1.0f - lwi.z * lwi.z);
+        if (B->type == 4 ? (c2 <= 0.0f) : (ucomp <= fresnel_term(lwi, etaI, etaT))) {
+            *wo = to_world(g, V(-lwi.x, -lwi.y, lwi.z));            /* BSDFUtils::LocalReflect */
+        } else {
+            const float ct = sqrtf(c2) * (lwi.z > 0.0f ? -1.0f : 1.0f);
+            *wo = to_world(g, V(-eta * lwi.x, -eta * lwi.y, ct));     /* BSDFUtils::LocalRefract */
+        }
+        return 1;
+    }
     if (lwi.z <= 0.0f) return 0;
+    if (B->type == 3) { *wo = to_world(g, V(-lwi.x, -lwi.y, lwi.z)); return 1; }   /* bsdf_reflectall.cpp:57-68 */
     if (B->type == 1) {            /* bsdf_diffuse.cpp:69-79 */
         float sx, sy;
         concentric_disk(u0, u1, &sx, &sy);
@@ -211,9 +240,20 @@ static int bsdf_sample(const orc_bsdf* B, const geom_t* g, v3 wi, float u0, floa
     }
     return 0;
 }
-static float bsdf_pdf(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo)   /* projected solid angle */
+static float bsdf_pdf(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval_delta)   /* projected solid angle */
 {
     const v3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (is_specular(B)) {
+        if (eval_delta) return 0.0f;
+        if (B->type == 3) return (lwi.z <= 0.0f || lwo.z <= 0.0f) ? 0.0f : 1.0f;       /* bsdf_reflectall.cpp:70-85 */
+        if (B->type == 4) return 1.0f;                                                  /* bsdf_refractall.cpp:92-100 */
+        {                                                                               /* bsdf_flesnel.cpp:97-128 */
+            float etaI = B->eta1, etaT = B->eta2, Fr;
+            if (lwi.z < 0.0f) { const float t = etaI; etaI = etaT; etaT = t; }
+            Fr = fresnel_term(lwi, etaI, etaT);
+            return lwi.z * lwo.z >= 0.0f ? Fr : 1.0f - Fr;
+        }
+    }
     if (lwi.z <= 0.0f || lwo.z <= 0.0f) return 0.0f;
     if (B->type == 1) return ORC_INV_PI;   /* bsdf_diffuse.cpp:81-91 */
     if (B->type == 2) {                    /* bsdf_cooktorrance.cpp:91-103 */
@@ -223,9 +263,26 @@ static float bsdf_pdf(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo)   /* pro
     }
     return 0.0f;
 }
-static v3 bsdf_eval(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo)
+static v3 bsdf_eval(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval_delta)
 {
     const v3 lwi = to_local(g, wi), lwo = to_local(g, wo);
+    if (is_specular(B)) {
+        float etaI = B->eta1, etaT = B->eta2;
+        if (eval_delta) return V(0, 0, 0);
+        if (B->type == 3) {                                                            /* bsdf_reflectall.cpp:87-103 */
+            if (lwi.z <= 0.0f || lwo.z <= 0.0f) return V(0, 0, 0);
+            return vmul(ld3(B->R), snc(g, wi, wo));
+        }
+        if (lwi.z < 0.0f) { const float t = etaI; etaI = etaT; etaT = t; }
+        {
+            const float eta = etaI / etaT;
+            const float Fr = B->type == 5 ? fresnel_term(lwi, etaI, etaT) : 0.0f;
+            if (lwi.z * lwo.z >= 0.0f)      /* reflection (total internal reflection for refract_all) */
+                return vmul(ld3(B->R), (B->type == 5 ? Fr : 1.0f) * snc(g, wi, wo));
+            /* refraction, EL transport: radiance scaling eta^2 (bsdf_refractall.cpp:120-127, bsdf_flesnel.cpp:150-156) */
+            return vmul(ld3(B->R), (B->type == 5 ? 1.0f - Fr : 1.0f) * snc(g, wi, wo) * eta * eta);
+        }
+    }
     if (lwi.z <= 0.0f || lwo.z <= 0.0f) return V(0, 0, 0);
     if (B->type == 1) {                    /* bsdf_diffuse.cpp:93-104 */
         return vmul(vmul(ld3(B->R), ORC_INV_PI), snc(g, wi, wo));
@@ -260,6 +317,12 @@ static void light_sample(const orc_pt_scene* S, int li, float u0, float u1, geom
     const orc_light* L = &S->d.lights[li];
     const orc_prim* P = &S->d.prims[L->primitive];
     const float* cdf = S->cdf[li];
+    if (L->kind == 1) {            /* light::point, light_point.cpp:62-66 */
+        memset(g, 0, sizeof(*g));
+        g->degenerated = 1;
+        g->p = ld3(L->position);
+        return;
+    }
     const int n = (int)P->num_tris;
     int lo = 0, hi = n + 1, i;
     float u2x, s, bx, by;
@@ -350,12 +413,13 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
             pdfPL = S->inv_area[li];                                                 /* light_area.cpp:100-103 */
             ppL = vnorm(vsub(gL.p, geom.p));
             if (is_sensor) { const float im = importance(S, ppL); fsE = V(im, im, im); }
-            else fsE = bsdf_eval(bsdf, &geom, wi, ppL);
-            fsL = to_local(&gL, vneg(ppL)).z <= 0.0f ? V(0, 0, 0) : ld3(S->d.lights[li].Le);   /* light_area.cpp:105-110 */
+            else fsE = bsdf_eval(bsdf, &geom, wi, ppL, 1);
+            if (S->d.lights[li].kind == 1) fsL = ld3(S->d.lights[li].Le);                      /* light_point.cpp:95-98 */
+            else fsL = to_local(&gL, vneg(ppL)).z <= 0.0f ? V(0, 0, 0) : ld3(S->d.lights[li].Le);   /* light_area.cpp:105-110 */
             d = vsub(gL.p, geom.p); d2 = vdot(d, d); dl = sqrtf(d2); d = V(d.x / dl, d.y / dl, d.z / dl);   /* renderutils.h:46-56 */
             G = 1.0f;
             if (!geom.degenerated) G *= fabsf(vdot(geom.sn, d));
-            G *= fabsf(vdot(gL.sn, vneg(d)));
+            if (!gL.degenerated) G *= fabsf(vdot(gL.sn, vneg(d)));
             G = G / d2;
             C = vmul(vmulv(vmulv(thr, fsE), fsL), G);
             if (!vblack(C)) {
@@ -366,7 +430,7 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
                     C = vmul(C, 1.0f / pdfL / pdfPL);
                     if (mode == 3) {   /* MIS weight, renderer_ptmis.cpp:163-170 */
                         const float pdfDL = pdfPL / geometry_term(&geom, &gL) * pdfL;
-                        const float pdfB = is_sensor ? importance(S, ppL) : bsdf_pdf(bsdf, &geom, wi, ppL);
+                        const float pdfB = is_sensor ? importance(S, ppL) : bsdf_pdf(bsdf, &geom, wi, ppL, 1);
                         C = vmul(C, pdfDL / (pdfDL + pdfB));
                     }
                     if (is_sensor) raster_position(S, ppL, &prx, &pry);              /* renderer_ptdirect.cpp:165-170 */
@@ -376,11 +440,11 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
         }
 
         if (is_sensor) wo = init_wo;
-        else { wo = V(0, 0, 0); bsdf_sample(bsdf, &geom, wi, ub[0], ub[1], &wo); }
-        pdfD = is_sensor ? importance(S, wo) : bsdf_pdf(bsdf, &geom, wi, wo);
+        else { wo = V(0, 0, 0); bsdf_sample(bsdf, &geom, wi, ub[0], ub[1], ub[2], &wo); }
+        pdfD = is_sensor ? importance(S, wo) : bsdf_pdf(bsdf, &geom, wi, wo, 0);
         if (mode == 1 && is_sensor) { if (!raster_position(S, wo, &rx, &ry)) break; }   /* renderer_ptdirect.cpp:200-208 */
         if (is_sensor) { const float im = importance(S, wo); fs = V(im, im, im); }
-        else fs = bsdf_eval(bsdf, &geom, wi, wo);
+        else fs = bsdf_eval(bsdf, &geom, wi, wo, 0);
         if (vblack(fs)) break;
         thr = vmulv(thr, V(fs.x / pdfD, fs.y / pdfD, fs.z / pdfD));
 
@@ -401,7 +465,9 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
                 if (to_local(&geom, vneg(wo)).z > 0.0f) {
                     v3 C = vmulv(thr, ld3(S->d.lights[P->light].Le));
                     if (mode == 3) {   /* renderer_ptmis.cpp:247-260: balance heuristic against the light-sampling pdf */
-                        const float pdfDL = S->inv_area[P->light] / geometry_term(&geom, &prev) * (1.0f / (float)S->d.num_lights);
+                        /* (type & S) > 0 ? 0 : ... : a specular previous vertex cannot be reached by light sampling */
+                        const float pdfDL = (!is_sensor && is_specular(bsdf)) ? 0.0f
+                            : S->inv_area[P->light] / geometry_term(&geom, &prev) * (1.0f / (float)S->d.num_lights);
                         C = vmul(C, pdfD / (pdfD + pdfDL));
                     }
                     splat(S, film, rx, ry, C);
@@ -429,7 +495,9 @@ orc_pt_scene* orc_pt_scene_create(const orc_scene_desc* d)
     S->inv_area = (float*)calloc(d->num_lights ? d->num_lights : 1, sizeof(float));
     for (li = 0; li < d->num_lights; li++) {     /* TriangleUtils::CreateTriangleAreaDist, triangleutils.h:47-68 */
         const orc_prim* P = &d->prims[d->lights[li].primitive];
-        float* cdf = (float*)malloc(sizeof(float) * (P->num_tris + 1));
+        float* cdf;
+        if (d->lights[li].kind == 1) { S->cdf[li] = NULL; S->inv_area[li] = 1.0f; continue; }   /* point: pdf 1 (light_point.cpp:88-91) */
+        cdf = (float*)malloc(sizeof(float) * (P->num_tris + 1));
         float sum = 0.0f, inv;
         uint32_t i;
         cdf[0] = 0.0f;

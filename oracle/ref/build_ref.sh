@@ -29,7 +29,11 @@ src/liblightmetrica/renderer/renderer_ptmis.cpp
 src/liblightmetrica/asset/bsdf/bsdf_diffuse.cpp
 src/liblightmetrica/asset/bsdf/bsdf_cooktorrance.cpp
 src/liblightmetrica/asset/bsdf/bsdf_null.cpp
+src/liblightmetrica/asset/bsdf/bsdf_reflectall.cpp
+src/liblightmetrica/asset/bsdf/bsdf_refractall.cpp
+src/liblightmetrica/asset/bsdf/bsdf_flesnel.cpp
 src/liblightmetrica/asset/light/light_area.cpp
+src/liblightmetrica/asset/light/light_point.cpp
 src/liblightmetrica/asset/sensor/sensor_pinhole.cpp
 src/liblightmetrica/asset/trianglemesh/trianglemesh_raw.cpp
 src/liblightmetrica/random.cpp

@@ -143,3 +143,17 @@ def test_renderer_plugin_time_budget(tmp_path, monkeypatch):
     ref, _ = R.render("ptdirect", 32 * 32 * 1024, seed=1, threads=os.cpu_count() or 1)
     assert abs(img.mean() - ref.mean()) / ref.mean() < 0.05      # far more than the 1000 samples of num_samples were taken
     assert any(f.startswith("progress_") for f in os.listdir(tmp_path))
+
+
+def test_renderer_plugin_delta_bsdfs_and_point_light():
+    """A scene with bsdf::flesnel / reflect_all / refract_all and a light::point through the plugin (parameters read
+    from the YAML tree and the Emitter interface) against the reference's renderer::ptdirect."""
+    sc = scenedesc.specular_box(32, 32)
+    N = 32 * 32 * 2048
+    R = ob.RefScene(sc, accel="qbvh")
+    ours, _ = R.render("lmb200pt", N, seed=1, extra={"mode": "ptdirect"}, in_tree=True)
+    ra, _ = R.render("ptdirect", N, seed=1, threads=os.cpu_count() or 1)
+    rb, _ = R.render("ptdirect", N, seed=2, threads=os.cpu_count() or 1)
+    floor = rel_rmse(ra, rb)
+    assert rel_rmse(ours, ra) < 1.25 * floor, (rel_rmse(ours, ra), floor)
+    assert np.allclose(ours.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.03)

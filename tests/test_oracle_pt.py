@@ -87,3 +87,20 @@ def test_port_vs_reference_live_glossy_scene():
     floor = rel_rmse(ra, rb)
     assert rel_rmse(img, ra) < 1.3 * floor, (rel_rmse(img, ra), floor)
     assert np.allclose(img.mean(axis=(0, 1)), ra.mean(axis=(0, 1)), rtol=0.02)
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mode,name", [(1, "ptdirect"), (3, "ptmis")])
+def test_port_vs_reference_live_delta_bsdfs_and_point_light(mode, name):
+    """bsdf::flesnel / reflect_all / refract_all and light::point against the live reference
+    (bsdf_flesnel.cpp, bsdf_reflectall.cpp, bsdf_refractall.cpp, light_point.cpp)."""
+    sc = scenedesc.specular_box(32, 32)
+    N = 32 * 32 * 2048
+    img, _ = ob.PortPT(sc).render(mode, N, seed=1)
+    R = ob.RefScene(sc)
+    ra, _ = R.render(name, N, seed=1, threads=4)
+    rb, _ = R.render(name, N, seed=2, threads=4)
+    floor = rel_rmse(ra, rb)
+    assert not np.isnan(img).any()
+    assert rel_rmse(img, ra) < 1.3 * floor, (rel_rmse(img, ra), floor)
+    assert np.allclose(img.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.03)
