@@ -52,10 +52,10 @@ trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     if (ANY) {
         BatchIoAny io{rays, reinterpret_cast<uint8_t*>(out), n};
-        persistent_trace<true, COUNT>(nodes, tris, io, counter, smem, cnt);
+        persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
     } else {
         BatchIoClosest io{rays, reinterpret_cast<float4*>(out), n};
-        persistent_trace<false, COUNT>(nodes, tris, io, counter, smem, cnt);
+        persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
     }
     if (COUNT) {
         const unsigned lane = threadIdx.x & 31u;
@@ -72,7 +72,7 @@ __global__ void trace_one_kernel(const float4* __restrict__ nodes, const float4*
     if (threadIdx.x != 0) return;
     Trav T;
     TravCounters cnt;
-    const bool hit = lmb_traverse<false, false>(nodes, tris, ray[0], ray[1], T, smem, cnt);
+    const bool hit = lmb_traverse<false, false, 32>(nodes, tris, ray[0], ray[1], T, smem, cnt);
     out[0] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
 }
 

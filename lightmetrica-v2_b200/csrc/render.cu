@@ -633,7 +633,7 @@ k_extend(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ExtendIo io{P, P.qcount[1]};
     TravCounters cnt;
-    persistent_trace<false, false>(nodes, tris, io, counter, smem, cnt);
+    persistent_trace<false, false, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
 }
 
 // shadow: any hit over the shadow queue, unoccluded contributions are splatted (film_hdr.cpp:218-223)
@@ -655,7 +655,7 @@ k_shadow(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ShadowIo io{P, P.qcount[2], film};
     TravCounters cnt;
-    persistent_trace<true, false>(nodes, tris, io, counter, smem, cnt);
+    persistent_trace<true, false, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
 }
 
 __global__ void k_stats(Pool P)

@@ -66,13 +66,13 @@ __device__ __forceinline__ uint32_t lmb_sign_extend_s8x4(uint32_t x)
     return r;
 }
 
-template <int J>
+template <int SLOT>
 __device__ __forceinline__ void lmb_child(const uint32_t nearx, const uint32_t neary, const uint32_t nearz,
                                           const uint32_t farx, const uint32_t fary, const uint32_t farz,
                                           const float sx, const float sy, const float sz, const float bx, const float by, const float bz,
-                                          const float tmin, const float tmax, const uint32_t one,
-                                          const uint32_t child_bits4, const uint32_t bit_index4, uint32_t& hitmask)
+                                          const float tmin, const float tmax, const uint32_t one, uint32_t& hits8)
 {
+    constexpr int J = SLOT & 3;
     const float tnx = fmaf(lmb_q2m<J>(nearx, one), sx, bx);
     const float tny = fmaf(lmb_q2m<J>(neary, one), sy, by);
     const float tnz = fmaf(lmb_q2m<J>(nearz, one), sz, bz);
@@ -81,20 +81,15 @@ __device__ __forceinline__ void lmb_child(const uint32_t nearx, const uint32_t n
     const float tfz = fmaf(lmb_q2m<J>(farz, one), sz, bz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
-    const uint32_t idx5 = (bit_index4 >> (8 * J)) & 0xffu;
-    if (tn <= tf) hitmask |= bits << idx5;
+    if (tn <= tf) hits8 |= (1u << SLOT);
 }
 
-// Intersects the 8 quantised child boxes of one node. Returns the hit mask: bits 31..24 =
-// internal children in traversal priority order, bits 23..0 = triangles of hit leaf slots.
-// (A variant that collects slot-order hit bits and permutes them with a shared-memory table was
-// measured slower on B200: it needs 64 registers instead of 56, profiles/r01_sweep.md.)
-__device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
+// Intersects the 8 quantised child boxes of one node; bit s of the result = slot s was hit. Empty slots
+// carry an inverted box (qlo = 255 > qhi = 0) and a zero meta byte, so they never contribute.
+__device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const float4 n2, const float4 n3, const float4 n4,
                                                        const float ox, const float oy, const float oz,
                                                        const float idx, const float idy, const float idz,
-                                                       const bool negx, const bool negy, const bool negz,
-                                                       const uint32_t oct_inv4, const float tmin, const float tmax, const uint32_t one)
+                                                       const float tmin, const float tmax, const uint32_t one)
 {
     const uint32_t ew = __float_as_uint(n0.w);
     // grid step * 2^15 (exponent bytes are biased; the builder keeps e + 15 <= 254)
@@ -104,38 +99,49 @@ __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const fl
     const float bx = fmaf(n0.x - ox, idx, -sx);
     const float by = fmaf(n0.y - oy, idy, -sy);
     const float bz = fmaf(n0.z - oz, idz, -sz);
-
-    uint32_t hitmask = 0;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = __float_as_uint(half == 0 ? n1.z : n1.w);
-        const uint32_t qlox = __float_as_uint(half == 0 ? n2.x : n2.y);
-        const uint32_t qloy = __float_as_uint(half == 0 ? n2.z : n2.w);
-        const uint32_t qloz = __float_as_uint(half == 0 ? n3.x : n3.y);
-        const uint32_t qhix = __float_as_uint(half == 0 ? n3.z : n3.w);
-        const uint32_t qhiy = __float_as_uint(half == 0 ? n4.x : n4.y);
-        const uint32_t qhiz = __float_as_uint(half == 0 ? n4.z : n4.w);
+    const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
+    uint32_t hits8 = 0;
+    {
+        const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
+        const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
         const uint32_t nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
         const uint32_t neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
         const uint32_t nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
-        // internal slots carry 24+s in their low 5 bits (both bits 3 and 4 set): flip the slot
-        // number by the ray octant so that the highest set bit is the nearest child
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = lmb_sign_extend_s8x4(is_inner4 << 3);    // 0xff per inner byte
-        const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        lmb_child<0>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
-        lmb_child<1>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
-        lmb_child<2>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
-        lmb_child<3>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, child_bits4, bit_index4, hitmask);
+        lmb_child<0>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
+        lmb_child<1>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
+        lmb_child<2>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
+        lmb_child<3>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
     }
-    return hitmask;
+    {
+        const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
+        const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
+        const uint32_t nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
+        const uint32_t neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
+        const uint32_t nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
+        lmb_child<4>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
+        lmb_child<5>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
+        lmb_child<6>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
+        lmb_child<7>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
+    }
+    return hits8;
+}
+
+// Moves bit s of an 8-bit mask to bit s ^ o (o = 7 - ray octant) with three masked delta swaps, turning
+// the slot-order hit mask into traversal-priority order (highest bit = nearest child). `pm` holds the
+// three swap masks of the ray: byte 0 = 0x55 if o&1, byte 1 = 0x33 if o&2, byte 2 = 0x0f if o&4 (else 0).
+__device__ __forceinline__ uint32_t lmb_xor_permute8(uint32_t x, uint32_t pm)
+{
+    uint32_t t;
+    t = ((x >> 1) ^ x) & (pm & 0xffu);          x ^= t ^ (t << 1);
+    t = ((x >> 2) ^ x) & ((pm >> 8) & 0xffu);   x ^= t ^ (t << 2);
+    t = ((x >> 4) ^ x) & ((pm >> 16) & 0xffu);  x ^= t ^ (t << 4);
+    return x;
 }
 
 // Per-lane traversal state. hid == 0xffffffff <=> no hit yet (triangle ids are < 2^27).
 struct Trav {
     float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tmax, hu, hv;
-    uint32_t hid, oct_inv4;
+    uint32_t hid, oct_inv4;   // oct_inv4: bits 2..0 = 7 - octant, bits 31..8 = the three swap masks of lmb_xor_permute8
     uint32_t one;      // lmb_one_bits()
     uint2 ngroup;      // x: child_base; y: bits 31..24 pending internal children (priority order) | imask
     uint2 pend;        // parked triangle group: x = first triangle, y = 24-bit mask
@@ -150,24 +156,29 @@ __device__ __forceinline__ void trav_init(Trav& T, const float4 ro, const float4
     T.idx = lmb_safe_inv(rd.x); T.idy = lmb_safe_inv(rd.y); T.idz = lmb_safe_inv(rd.z);
     // signs taken from the clamped reciprocal so that -0.0 picks the same near/far planes it scales
     const uint32_t oct = (T.idx < 0.f ? 1u : 0u) | (T.idy < 0.f ? 2u : 0u) | (T.idz < 0.f ? 4u : 0u);
-    T.oct_inv4 = (7u - oct) * 0x01010101u;
+    const uint32_t oi = 7u - oct;
+    T.oct_inv4 = oi | ((oi & 1u) ? 0x5500u : 0u) | ((oi & 2u) ? 0x330000u : 0u) | ((oi & 4u) ? 0x0f000000u : 0u);
     T.hu = 0.f; T.hv = 0.f; T.hid = 0xffffffffu;
     T.ngroup = make_uint2(0u, 0x80000000u);   // root: node 0 (imask 0 resolves to relative index 0)
     T.pend = make_uint2(0u, 0u);
     T.sp = 0;
 }
 
-// shared-memory stack: entry e of thread t lives at smem[e * blockDim.x + t] (conflict-free)
+// shared-memory stack: entry e of thread t lives at smem[e * STRIDE + t] (conflict-free). `smem` is the
+// calling thread's own column (block base + threadIdx.x) and STRIDE the compile-time block size, so a
+// push/pop is one address computation instead of re-deriving the thread index every time.
+template <int STRIDE>
 __device__ __forceinline__ void trav_push(Trav& T, uint2* __restrict__ smem, uint2* __restrict__ lstack, const uint2 v)
 {
-    if (T.sp < LMB_SM_STACK) smem[T.sp * blockDim.x + threadIdx.x] = v;
+    if (T.sp < LMB_SM_STACK) smem[T.sp * STRIDE] = v;
     else lstack[T.sp - LMB_SM_STACK] = v;
     T.sp++;
 }
+template <int STRIDE>
 __device__ __forceinline__ uint2 trav_pop(Trav& T, const uint2* __restrict__ smem, const uint2* __restrict__ lstack)
 {
     T.sp--;
-    return T.sp < LMB_SM_STACK ? smem[T.sp * blockDim.x + threadIdx.x] : lstack[T.sp - LMB_SM_STACK];
+    return T.sp < LMB_SM_STACK ? smem[T.sp * STRIDE] : lstack[T.sp - LMB_SM_STACK];
 }
 
 // One traversal step of an active lane: open the nearest pending node, then maybe test triangles.
@@ -178,37 +189,46 @@ __device__ __forceinline__ uint2 trav_pop(Trav& T, const uint2* __restrict__ sme
 // triangle code on ~80 % of the warp's steps with ~2 of 32 lanes active (ncu, profiles/).
 // Returns true when the ray is finished. Closest hit: tie on t -> larger triangle index wins, which
 // is what a linear scan with the reference's "reject t > maxT" rule yields (accel_naive.cpp:92-124).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, int STRIDE>
 __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                          uint2* __restrict__ smem, uint2* __restrict__ lstack, TravCounters& cnt)
+                                          uint2* __restrict__ smem, uint2* __restrict__ lstack, TravCounters& cnt, const unsigned lanes)
 {
+    // `lanes`: the lanes of this warp that execute this step together (the caller's ballot of active lanes)
     uint2 fresh = make_uint2(0u, 0u);
     if (T.ngroup.y & 0xff000000u) {
         const uint32_t hits_imask = T.ngroup.y;
         const uint32_t bit = 31u - __clz(hits_imask);
         T.ngroup.y &= ~(1u << bit);
-        if (T.ngroup.y & 0xff000000u) trav_push(T, smem, lstack, T.ngroup);
+        if (T.ngroup.y & 0xff000000u) trav_push<STRIDE>(T, smem, lstack, T.ngroup);
         const uint32_t slot = (bit - 24u) ^ (T.oct_inv4 & 7u);
         const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot) & 0xffu);
         const float4* np = nodes + (size_t)(T.ngroup.x + rel) * 5u;
         const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
         if (COUNT) cnt.nodes++;
-        const uint32_t hitmask = lmb_intersect_node(n0, n1, n2, n3, n4, T.ox, T.oy, T.oz, T.idx, T.idy, T.idz,
-                                                    T.idx < 0.f, T.idy < 0.f, T.idz < 0.f, T.oct_inv4, T.tmin, T.tmax, T.one);
+        const uint32_t hits8 = lmb_intersect_node(n0, n2, n3, n4, T.ox, T.oy, T.oz, T.idx, T.idy, T.idz, T.tmin, T.tmax, T.one);
+        const uint32_t imask = __float_as_uint(n0.w) >> 24;
         T.ngroup.x = __float_as_uint(n1.x);
-        T.ngroup.y = (hitmask & 0xff000000u) | (__float_as_uint(n0.w) >> 24);
+        T.ngroup.y = (lmb_xor_permute8(hits8 & imask, T.oct_inv4 >> 8) << 24) | imask;
+        // triangles of the hit leaf slots (rare: ~5 % of the node visits of an incoherent ray):
+        // meta byte = unary count << 5 | offset into the node's triangle block
+        uint32_t leaf = hits8 & ~imask;
         fresh.x = __float_as_uint(n1.y);
-        fresh.y = hitmask & 0x00ffffffu;
+        while (leaf) {
+            const uint32_t sl = __ffs(leaf) - 1;
+            leaf &= leaf - 1;
+            const uint32_t word = __float_as_uint(sl < 4u ? n1.z : n1.w);
+            const uint32_t mb = (word >> ((sl & 3u) * 8u)) & 0xffu;
+            fresh.y |= (mb >> 5) << (mb & 31u);
+        }
     }
     // next node group
-    if ((T.ngroup.y & 0xff000000u) == 0u && T.sp > 0) T.ngroup = trav_pop(T, smem, lstack);
+    if ((T.ngroup.y & 0xff000000u) == 0u && T.sp > 0) T.ngroup = trav_pop<STRIDE>(T, smem, lstack);
     const bool no_nodes = (T.ngroup.y & 0xff000000u) == 0u;
 
     // park the fresh triangles if the pending slot is free
     const bool collide = T.pend.y != 0u && fresh.y != 0u;
     if (T.pend.y == 0u) { T.pend = fresh; fresh.y = 0u; }
     {
-        const unsigned lanes = __activemask();
         const unsigned want = __ballot_sync(lanes, T.pend.y != 0u);
         const unsigned must = __ballot_sync(lanes, collide || (no_nodes && T.pend.y != 0u));
         if (must != 0u || __popc(want) >= LMB_TRI_BATCH) {
@@ -238,10 +258,11 @@ __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ no
 //   uint64_t count() const;                          number of rays
 //   void load(uint64_t i, float4& ro, float4& rd);   ray i
 //   void store(uint64_t i, const Trav& T);           result of ray i (T.hid == 0xffffffff: miss)
-template <bool ANY, bool COUNT, typename Io>
+template <bool ANY, bool COUNT, int STRIDE, typename Io>
 __device__ __forceinline__ void persistent_trace(const float4* __restrict__ nodes, const float4* __restrict__ tris, Io& io,
-                                                 unsigned long long* __restrict__ counter, uint2* __restrict__ smem, TravCounters& cnt)
+                                                 unsigned long long* __restrict__ counter, uint2* __restrict__ smem_block, TravCounters& cnt)
 {
+    uint2* const smem = smem_block + threadIdx.x;     // this thread's stack column
     const uint64_t n = io.count();
     const unsigned lane = threadIdx.x & 31u;
     uint2 lstack[LMB_LOCAL_STACK];
@@ -275,14 +296,15 @@ __device__ __forceinline__ void persistent_trace(const float4* __restrict__ node
         if (!__any_sync(0xffffffffu, active)) break;
 
         // ---- traverse until enough lanes have finished to make a refill worthwhile ----
+        unsigned live = __ballot_sync(0xffffffffu, active);
         for (;;) {
             if (active) {
-                if (trav_step<ANY, COUNT>(T, nodes, tris, smem, lstack, cnt)) {
+                if (trav_step<ANY, COUNT, STRIDE>(T, nodes, tris, smem, lstack, cnt, live)) {
                     io.store(ray_index, T);
                     active = false;
                 }
             }
-            const unsigned live = __ballot_sync(0xffffffffu, active);
+            live = __ballot_sync(0xffffffffu, active);
             if (live == 0u) break;
             if (!exhausted && __popc(live) < LMB_REFILL_BELOW) break;
         }
@@ -290,13 +312,14 @@ __device__ __forceinline__ void persistent_trace(const float4* __restrict__ node
 }
 
 // Whole-ray helper for single-ray callers (per-ray Accel3::Intersect path).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, int STRIDE>
 __device__ __forceinline__ bool lmb_traverse(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                             const float4 ro, const float4 rd, Trav& T, uint2* __restrict__ smem, TravCounters& cnt)
+                                             const float4 ro, const float4 rd, Trav& T, uint2* __restrict__ smem_block, TravCounters& cnt)
 {
+    uint2* const smem = smem_block + threadIdx.x;
     uint2 lstack[LMB_LOCAL_STACK];
     trav_init(T, ro, rd);
-    while (!trav_step<ANY, COUNT>(T, nodes, tris, smem, lstack, cnt)) {}
+    while (!trav_step<ANY, COUNT, STRIDE>(T, nodes, tris, smem, lstack, cnt, __activemask())) {}
     return T.hid != 0xffffffffu;
 }
 
