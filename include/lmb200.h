@@ -212,7 +212,16 @@ typedef struct lmb200_render_stats {
 lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* desc);
 /* Same with a choice of BVH builder (LMB200_BUILD_HOST_SAH / LMB200_BUILD_GPU_LBVH). */
 lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* desc, int builder);
+/* Same, but traversal uses an accel that is already built on a device over the SAME triangle list (same
+ * order); the scene borrows it and never frees it. Lets renderer::lmb200pt reuse the BVH of accel::lmb200
+ * when the YAML selected both. */
+lmb200_scene* lmb200_scene_create_shared(const lmb200_scene_desc* desc, lmb200_accel* accel);
 void lmb200_scene_destroy(lmb200_scene* s);
+
+/* Process-wide lookup table (owner address -> accel) through which the two plugins, loaded RTLD_LOCAL by the
+ * host (component.cpp:127-164), find each other's objects. put(owner, NULL) removes the entry. */
+void lmb200_registry_put(const void* owner, lmb200_accel* accel);
+lmb200_accel* lmb200_registry_get(const void* owner);
 lmb200_accel* lmb200_scene_accel(lmb200_scene* s);
 
 /* Accumulates UNSCALED splats of the given sample range into film_dev: W*H float4 (rgb + pad,

@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <dlfcn.h>
@@ -701,7 +703,9 @@ __global__ void k_normal_shade(DevScene S, const float4* hits, float4* film)
 
 struct Scene {
     int device = 0;
-    Accel accel;
+    Accel own_accel;                 // used unless a built accel is shared in (lmb200_scene_create_shared)
+    Accel* accel = &own_accel;
+    unsigned long long* d_counter = nullptr;   // work counters of this scene's traversal launches ([0] extend, [1] shadow)
     DevScene dev{};
     std::vector<void*> allocs;
     // pool (lazily sized)
@@ -716,6 +720,7 @@ struct Scene {
         cudaSetDevice(device);
         for (void* p : pool_allocs) cudaFree(p);
         for (void* p : allocs) cudaFree(p);
+        if (d_counter) cudaFree(d_counter);
         if (h_pinned) cudaFreeHost(h_pinned);
     }
 };
@@ -784,7 +789,7 @@ static int render_normal(Scene* s, float4* film, cudaStream_t st)
     if ((e = cudaMalloc(&rays, sizeof(float4) * 2 * (size_t)npx)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(rays)");
     if ((e = cudaMalloc(&hits, sizeof(float4) * (size_t)npx)) != cudaSuccess) { cudaFree(rays); return cuda_fail(e, "cudaMalloc(hits)"); }
     k_normal_raygen<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, rays); g_launch_count++;
-    rc = trace_closest_dev(&s->accel, rays, hits, (uint64_t)npx, nullptr, st, 0);
+    rc = trace_closest_dev(s->accel, rays, hits, (uint64_t)npx, nullptr, st, 0);
     if (!rc) { k_normal_shade<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, hits, film); g_launch_count++; }
     e = cudaStreamSynchronize(st);
     cudaFree(rays); cudaFree(hits);
@@ -838,17 +843,17 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
     const int logic_blocks = s->num_sms * 8;
-    const int trace_blocks = s->accel.num_sms * s->accel.trace_blocks_per_sm;
+    const int trace_blocks = s->accel->num_sms * s->accel->trace_blocks_per_sm;
     int64_t iters = 0;
     for (;;) {
         cudaMemsetAsync(P.qcount, 0, 4 * sizeof(uint32_t), st);
-        cudaMemsetAsync(s->accel.d_counter, 0, 2 * sizeof(unsigned long long), st);
+        cudaMemsetAsync(s->d_counter, 0, 2 * sizeof(unsigned long long), st);
         k_logic<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg, film);
         if (nee) k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
         k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
-        k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel.d_nodes), reinterpret_cast<const float4*>(s->accel.d_tris), P, s->accel.d_counter);
+        k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel->d_nodes), reinterpret_cast<const float4*>(s->accel->d_tris), P, s->d_counter);
         if (nee)
-            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel.d_nodes), reinterpret_cast<const float4*>(s->accel.d_tris), P, s->accel.d_counter + 1, film);
+            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel->d_nodes), reinterpret_cast<const float4*>(s->accel->d_tris), P, s->d_counter + 1, film);
         k_stats<<<1, 1, 0, st>>>(P);
         g_launch_count += nee ? 6 : 4;
         cudaMemcpyAsync(s->h_pinned, P.qcount, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
@@ -881,9 +886,22 @@ using namespace lmb200;
 
 extern "C" {
 
-lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d) { return lmb200_scene_create_ex(device, d, LMB200_BUILD_HOST_SAH); }
+static lmb200_scene* scene_create(int device, const lmb200_scene_desc* d, int builder, Accel* shared);
 
-lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int builder)
+lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d) { return scene_create(device, d, LMB200_BUILD_HOST_SAH, nullptr); }
+
+lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int builder) { return scene_create(device, d, builder, nullptr); }
+
+lmb200_scene* lmb200_scene_create_shared(const lmb200_scene_desc* d, lmb200_accel* accel)
+{
+    Accel* a = reinterpret_cast<Accel*>(accel);
+    if (!a || !d) { set_error(LMB200_E_INVALID, "null argument"); return nullptr; }
+    if (!a->built || a->host_only || !a->d_nodes) { set_error(LMB200_E_STATE, "shared accel is not built on a device"); return nullptr; }
+    if (a->bvh.stats.num_triangles != d->num_tris) { set_error(LMB200_E_INVALID, "shared accel was built over a different triangle list"); return nullptr; }
+    return scene_create(a->device, d, LMB200_BUILD_HOST_SAH, a);
+}
+
+static lmb200_scene* scene_create(int device, const lmb200_scene_desc* d, int builder, Accel* shared)
 {
     if (builder != LMB200_BUILD_HOST_SAH && builder != LMB200_BUILD_GPU_LBVH) { set_error(LMB200_E_INVALID, "unknown builder"); return nullptr; }
     if (!d || (d->num_tris && (!d->verts || !d->tri_prim)) || !d->prims || !d->bsdfs) { set_error(LMB200_E_INVALID, "null scene field"); return nullptr; }
@@ -899,10 +917,14 @@ lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int
         if (d->bsdfs[i].type < LMB200_BSDF_NULL || d->bsdfs[i].type > LMB200_BSDF_FLESNEL) { set_error(LMB200_E_INVALID, "unknown bsdf type"); return nullptr; }
     Scene* s = new Scene;
     s->device = device;
-    s->accel.device = device;
     cudaSetDevice(device);
-    if (lmb200_accel_build_ex(reinterpret_cast<lmb200_accel*>(&s->accel), d->verts, d->num_tris, builder)) { delete s; return nullptr; }
-    s->num_sms = s->accel.num_sms;
+    if (shared) s->accel = shared;
+    else {
+        s->own_accel.device = device;
+        if (lmb200_accel_build_ex(reinterpret_cast<lmb200_accel*>(&s->own_accel), d->verts, d->num_tris, builder)) { delete s; return nullptr; }
+    }
+    if (cudaMalloc(&s->d_counter, 4 * sizeof(unsigned long long)) != cudaSuccess) { set_error(LMB200_E_CUDA, "cudaMalloc(scene counters)"); delete s; return nullptr; }
+    s->num_sms = s->accel->num_sms;
     DevScene& D = s->dev;
     int rc = 0;
     rc |= dev_upload(s, d->verts, 9 * d->num_tris, &D.verts);
@@ -953,7 +975,24 @@ lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int
 
 void lmb200_scene_destroy(lmb200_scene* s) { delete reinterpret_cast<Scene*>(s); }
 
-lmb200_accel* lmb200_scene_accel(lmb200_scene* s) { return s ? reinterpret_cast<lmb200_accel*>(&reinterpret_cast<Scene*>(s)->accel) : nullptr; }
+lmb200_accel* lmb200_scene_accel(lmb200_scene* s) { return s ? reinterpret_cast<lmb200_accel*>(reinterpret_cast<Scene*>(s)->accel) : nullptr; }
+
+// Process-wide registry so that two plugins loaded RTLD_LOCAL can find each other's objects:
+// accel::lmb200 publishes its device BVH under its component address, renderer::lmb200pt looks it up.
+namespace { std::mutex g_reg_mu; std::map<const void*, lmb200_accel*> g_registry; }
+
+void lmb200_registry_put(const void* owner, lmb200_accel* accel)
+{
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    if (accel) g_registry[owner] = accel; else g_registry.erase(owner);
+}
+
+lmb200_accel* lmb200_registry_get(const void* owner)
+{
+    std::lock_guard<std::mutex> lock(g_reg_mu);
+    auto it = g_registry.find(owner);
+    return it == g_registry.end() ? nullptr : it->second;
+}
 
 int lmb200_render_dev(lmb200_scene* h, const lmb200_render_params* p, void* film_dev, void* stream, lmb200_render_stats* stats)
 {

@@ -65,7 +65,7 @@ EXPORTS = [
     "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build", "lmb200_accel_build_ex",
     "lmb200_accel_get_stats", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
     "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_arrays", "lmb200_accel_create_host_only",
-    "lmb200_scene_create", "lmb200_scene_create_ex", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
+    "lmb200_scene_create", "lmb200_scene_create_ex", "lmb200_scene_create_shared", "lmb200_registry_put", "lmb200_registry_get", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
     "lmb200_render", "lmb200_render_multi", "lmb200_render_timed",
 ]
 
@@ -102,6 +102,11 @@ def lib():
         L.lmb200_scene_create.argtypes = [C.c_int, C.POINTER(SceneDesc)]
         L.lmb200_scene_create_ex.restype = C.c_void_p
         L.lmb200_scene_create_ex.argtypes = [C.c_int, C.POINTER(SceneDesc), C.c_int]
+        L.lmb200_scene_create_shared.restype = C.c_void_p
+        L.lmb200_scene_create_shared.argtypes = [C.POINTER(SceneDesc), C.c_void_p]
+        L.lmb200_registry_put.argtypes = [C.c_void_p, C.c_void_p]
+        L.lmb200_registry_get.restype = C.c_void_p
+        L.lmb200_registry_get.argtypes = [C.c_void_p]
         L.lmb200_scene_destroy.argtypes = [C.c_void_p]
         L.lmb200_scene_accel.restype = C.c_void_p
         L.lmb200_scene_accel.argtypes = [C.c_void_p]

@@ -25,6 +25,7 @@ public:
     ~Accel_LMB200()
     {
         // runs before dlclose (component.h:640-646): CUDA resources are released here
+        lmb200_registry_put(static_cast<const Accel*>(this), nullptr);
         if (accel_) { lmb200_accel_destroy(accel_); accel_ = nullptr; }
     }
 
@@ -60,6 +61,8 @@ public:
             LM_LOG_ERROR(std::string("accel::lmb200: ") + lmb200_last_error());
             return false;
         }
+        // publish the device BVH so that renderer::lmb200pt can reuse it instead of building its own
+        lmb200_registry_put(static_cast<const Accel*>(this), accel_);
         lmb200_accel_stats st;
         if (lmb200_accel_get_stats(accel_, &st) == LMB200_OK)
         {
@@ -91,11 +94,6 @@ public:
             (int)faceOfTri_[h.tri]);
         return true;
     };
-
-public:
-
-    // Used by renderer::lmb200pt to reuse the device BVH when the YAML selected this accel.
-    lmb200_accel* Handle() const { return accel_; }
 
 private:
 

@@ -203,10 +203,19 @@ public:
         }
 
         // ---- render ----
+        // If the YAML selected accel::lmb200 too, its device BVH (same triangle list, same order) is reused
+        // on its device; other GPUs build their own replica.
+        lmb200_accel* sharedAccel = lmb200_registry_get(scene->GetAccel());
         std::vector<lmb200_scene*> scenes;
         for (int g = 0; g < numGpus_; g++)
         {
-            auto* s = lmb200_scene_create_ex(device_ + g, &d, builder_);
+            lmb200_scene* s = nullptr;
+            if (g == 0 && sharedAccel)
+            {
+                s = lmb200_scene_create_shared(&d, sharedAccel);
+                if (s) LM_LOG_INFO("renderer::lmb200pt: reusing the BVH of accel::lmb200");
+            }
+            if (!s) s = lmb200_scene_create_ex(device_ + g, &d, builder_);
             if (!s)
             {
                 LM_LOG_ERROR(std::string("renderer::lmb200pt: ") + lmb200_last_error());

@@ -174,3 +174,35 @@ def test_gpu_built_scene_renders_the_same_image():
     b, sb = capi.Scene(sc, builder=capi.BUILD_GPU_LBVH).render(capi.MODE_PTDIRECT, N, seed=2)
     assert sa["extend_rays"] == sb["extend_rays"] and sa["shadow_rays"] == sb["shadow_rays"]
     assert np.allclose(a, b, rtol=2e-4, atol=1e-5)
+
+
+def test_scene_sharing_a_prebuilt_accel():
+    """lmb200_scene_create_shared: the renderer borrows an accel built over the same triangle list (what
+    renderer::lmb200pt does when the YAML also selected accel::lmb200) and renders the same image."""
+    sc = scenedesc.cornell_box(48, 48, glossy_block=True)
+    L = capi.lib()
+    own = capi.Scene(sc)
+    N = 48 * 48 * 32
+    a, _ = own.render(capi.MODE_PTDIRECT, N, seed=4)
+    desc, keep = sc.flatten()
+    A = capi.Accel(0)
+    A.build(keep["verts"], builder=capi.BUILD_GPU_LBVH)
+    h = L.lmb200_scene_create_shared(C.byref(desc), A.h)
+    assert h, L.lmb200_last_error()
+    assert L.lmb200_scene_accel(h) == A.h
+    film = np.zeros((48, 48, 4), np.float32)
+    st = capi.RenderStats()
+    p = own.params(capi.MODE_PTDIRECT, N, seed=4)
+    capi.check(L.lmb200_render(h, C.byref(p), film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    L.lmb200_scene_destroy(h)
+    assert np.allclose(film[..., :3], a, rtol=2e-4, atol=1e-5)
+    assert len(A.trace_closest(np.array([[0, 1, 4, 1e-4, 0, 0, -1, 3e38]], np.float32))) == 1     # the accel outlives the scene
+    # mismatching triangle list is refused
+    B = capi.Accel(0)
+    B.build(keep["verts"][:10])
+    assert not L.lmb200_scene_create_shared(C.byref(desc), B.h)
+    # registry round trip
+    L.lmb200_registry_put(12345, A.h)
+    assert L.lmb200_registry_get(12345) == A.h
+    L.lmb200_registry_put(12345, None)
+    assert not L.lmb200_registry_get(12345)

@@ -118,3 +118,38 @@ def test_builder_edge_cases():
     rays = np.array([[0.2, 0.2, 1, 0, 0, 0, -1, 3.4e38]], np.float32)
     tuv, tri = ob.wide_closest(nodes, tris, rays)
     assert tri[0] == 39      # tie rule: larger index wins
+
+
+def test_error_paths_without_a_device():
+    """Error behaviour of the C ABI (nothing throws, codes + lmb200_last_error): bad arguments and wrong state."""
+    L = capi.lib()
+    A = capi.Accel(host_only=True)
+    # not built yet
+    st = capi.AccelStats()
+    assert L.lmb200_accel_get_stats(A.h, C.byref(st)) == -3            # LMB200_E_STATE
+    assert b"not built" in L.lmb200_last_error()
+    # null arguments
+    assert L.lmb200_accel_build(A.h, None, 5) == -1                    # LMB200_E_INVALID
+    assert L.lmb200_accel_build(None, None, 0) == -1
+    assert L.lmb200_accel_get_stats(None, C.byref(st)) == -1
+    # unknown builder / GPU builder on a host-only accel
+    verts = scenes.soup(10, seed=1, extent=1.0, edge=0.3)
+    assert L.lmb200_accel_build_ex(A.h, verts.ctypes.data_as(C.c_void_p), 10, 7) == -1
+    assert L.lmb200_accel_build_ex(A.h, verts.ctypes.data_as(C.c_void_p), 10, capi.BUILD_GPU_LBVH) == -3
+    # too many triangles (2^27 limit of the leaf encoding): rejected before touching the data
+    assert L.lmb200_accel_build(A.h, verts.ctypes.data_as(C.c_void_p), 1 << 27) == -1
+    # a host-only accel cannot trace
+    A.build(verts)
+    rays = np.zeros((1, 8), np.float32)
+    hits = np.zeros(1, capi.HIT_DTYPE)
+    assert L.lmb200_trace_closest(A.h, rays.ctypes.data_as(C.c_void_p), hits.ctypes.data_as(C.c_void_p), 1) == -3
+    assert L.lmb200_trace_closest_one(A.h, rays.ctypes.data_as(C.c_void_p), hits.ctypes.data_as(C.c_void_p)) == -3
+    assert L.lmb200_trace_closest_dev(A.h, None, None, 1, None) == -1
+    # scene creation validates its description before any CUDA call
+    assert L.lmb200_scene_create(0, None) is None
+    from lmb200py import scenedesc
+    d, keep = scenedesc.cornell_box(8, 8).flatten()
+    d.num_lights = 1
+    keep["ls"][0].primitive = 99
+    assert L.lmb200_scene_create(0, C.byref(d)) is None
+    assert L.lmb200_last_error() != b""
