@@ -23,8 +23,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "smsp__cycles_active.avg"]
 
 
-def launches():
-    p = os.path.join(G, "launches.csv")
+def launches(fname="launches.csv", suffix="launches", cmd="python bench.py --rays 16777216 --steps 2 --warmup 3 --cpu-rays 100000"):
+    p = os.path.join(G, fname)
     if not os.path.exists(p):
         return
     txt = open(p).read().splitlines()
@@ -40,9 +40,9 @@ def launches():
         agg[k][0] += 1
         agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
-    with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as f:
+    with open(os.path.join(OUT, f"{tag}_{suffix}.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised: compare shares)\n\n")
-        f.write("command: `python bench.py --rays 16777216 --steps 2 --warmup 3 --cpu-rays 100000`\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
+        f.write(f"command: `{cmd}`\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"| `{k}` | {v[0]} | {v[1]:.3f} | {100 * v[1] / tot:.1f}% |\n")
         f.write(f"\ntotal {tot:.1f} ms over {sum(v[0] for v in agg.values())} launches\n")
@@ -67,6 +67,7 @@ def full(rep, name):
 
 os.makedirs(OUT, exist_ok=True)
 launches()
+launches("launches_default.csv", "launches_default_cmd", "python bench.py --steps 2 --warmup 1   (first 600 launches)")
 t = full("prof_trace.ncu-rep", "trace_kernel")
 full("prof_extend.ncu-rep", "k_extend")
 if t:
