@@ -151,20 +151,34 @@ typedef struct lmb200_primitive {
  * by the library exactly as TriangleUtils::CreateTriangleAreaDist (triangleutils.h:47-68). */
 #define LMB200_LIGHT_AREA   0
 #define LMB200_LIGHT_POINT  1   /* light_point.cpp:47-105: delta position, emits Le in every direction */
+#define LMB200_LIGHT_DIRECTIONAL 2   /* light_directional.cpp:92-215: delta direction; sampled on the virtual disk of the
+                                        scene's bounding sphere; never hit by extend rays (no emitter shape registered) */
+#define LMB200_LIGHT_ENV    3   /* light_env.cpp:96-275 with a constant Le (its envmap branch cannot load in the reference,
+                                   :107-113): direction uniform on the sphere. Direct-light sampling only: accepted by
+                                   LMB200_MODE_PTDIRECT; the reference's pt / ptmis dereference a null primitive when an
+                                   extend ray escapes to the env emitter shape (scene3.cpp:463-475, renderer_pt.cpp:183),
+                                   so lmb200_render* rejects those modes with LMB200_ERR_INVALID */
 typedef struct lmb200_light {
     float   Le[3];
-    int32_t primitive;     /* area: the primitive whose mesh is sampled; point: the light's own primitive (no mesh) */
+    int32_t primitive;     /* area: the primitive whose mesh is sampled; others: the light's own primitive (no mesh) */
     int32_t kind;
     float   position[3];   /* point: world-space position */
+    float   direction[3];  /* directional: Mat3(transform) * normalize(direction), the direction light travels (light_directional.cpp:103) */
 } lmb200_light;
 
 /* sensor::pinhole (sensor_pinhole.cpp:47-61): position = column 3 of the primitive transform,
- * vx,vy,vz = columns 0..2, fov in radians (vertical), aspect = W/H. */
+ * vx,vy,vz = columns 0..2, fov in radians (vertical), aspect = W/H.
+ * sensor::thinlens (sensor_thinlens.cpp:44-68) adds the aperture radius and the focal distance; the lens point of a
+ * sample is position + lens_radius * concentric_disk(u2) in the (vx,vy) plane (:87-106). */
+#define LMB200_CAMERA_PINHOLE  0
+#define LMB200_CAMERA_THINLENS 1
 typedef struct lmb200_camera {
     float position[3];
     float vx[3], vy[3], vz[3];
     float fov;
     int32_t width, height;
+    int32_t kind;
+    float lens_radius, focal_distance;   /* thinlens only */
 } lmb200_camera;
 
 typedef struct lmb200_scene_desc {
@@ -179,6 +193,8 @@ typedef struct lmb200_scene_desc {
     uint32_t num_lights;
     const lmb200_light* lights;
     lmb200_camera camera;
+    float sphere_center[3];    /* Scene3::GetSphereBound() (scene3.cpp:56-78): bounding sphere of all mesh vertices and the */
+    float sphere_radius;       /* sensor position, radius grown by 1 %. Read by directional / env lights only. */
 } lmb200_scene_desc;
 
 typedef struct lmb200_scene lmb200_scene;

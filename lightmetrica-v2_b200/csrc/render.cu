@@ -48,6 +48,11 @@ struct DevScene {
     float pos[3], vx[3], vy[3], vz[3];
     float tan_fov, aspect;
     int width, height;
+    int cam_kind;              // LMB200_CAMERA_*
+    float lens_radius, focal_distance;
+    // Scene3::GetSphereBound (directional / env lights)
+    float sph_c[3], sph_r;
+    int has_env;
 };
 
 struct Pool {
@@ -144,20 +149,41 @@ __device__ __forceinline__ void tri_geom(const DevScene& S, uint32_t tri, float 
     basis(g.sn, g.dpdu, g.dpdv);
 }
 
-// ---- sensor::pinhole (sensor_pinhole.cpp:79-90, 137-154, 165-185) ----
-__device__ __forceinline__ bool raster_position(const DevScene& S, f3 wo, float& rx, float& ry)
+// ---- sensor::pinhole (sensor_pinhole.cpp:79-90, 137-154, 165-185) and sensor::thinlens
+//      (sensor_thinlens.cpp:87-106, 150-176, 186-222); p = the sensor vertex (pinhole position / lens point) ----
+__device__ __forceinline__ bool sensor_eye(const DevScene& S, f3 p, f3 wo, f3& e)
 {
-    const f3 e = F3(dot(ld3(S.vx), wo), dot(ld3(S.vy), wo), dot(ld3(S.vz), wo));
-    if (e.z >= 0.f) return false;
+    if (S.cam_kind == LMB200_CAMERA_THINLENS) {
+        const f3 nvz = neg(ld3(S.vz));
+        const float c = dot(nvz, wo);
+        if (c <= 0.f) return false;
+        const float tf = S.focal_distance / c;
+        const f3 Pf = p + wo * tf;                                  // intersection with the focal plane
+        const f3 wo0 = normalize(Pf - ld3(S.pos));                  // direction before refraction
+        e = F3(dot(ld3(S.vx), wo0), dot(ld3(S.vy), wo0), dot(ld3(S.vz), wo0));
+    } else {
+        e = F3(dot(ld3(S.vx), wo), dot(ld3(S.vy), wo), dot(ld3(S.vz), wo));
+    }
+    return e.z < 0.f;
+}
+__device__ __forceinline__ bool raster_from_eye(const DevScene& S, f3 e, float& rx, float& ry)
+{
     rx = (-e.x / e.z / S.tan_fov / S.aspect + 1.0f) * 0.5f;
     ry = (-e.y / e.z / S.tan_fov + 1.0f) * 0.5f;
     return !(rx < 0.f || rx > 1.f || ry < 0.f || ry > 1.f);
 }
-__device__ __forceinline__ float importance(const DevScene& S, f3 wo)
+__device__ __forceinline__ bool raster_position(const DevScene& S, f3 p, f3 wo, float& rx, float& ry)
 {
+    f3 e;
+    if (!sensor_eye(S, p, wo, e)) return false;
+    return raster_from_eye(S, e, rx, ry);
+}
+__device__ __forceinline__ float importance(const DevScene& S, f3 p, f3 wo)
+{
+    f3 e;
     float rx, ry;
-    if (!raster_position(S, wo, rx, ry)) return 0.f;
-    const float cosT = -dot(ld3(S.vz), wo), inv = 1.0f / cosT;
+    if (!sensor_eye(S, p, wo, e) || !raster_from_eye(S, e, rx, ry)) return 0.f;
+    const float cosT = -e.z, inv = 1.0f / cosT;
     const float A = S.tan_fov * S.tan_fov * S.aspect * 4.0f;
     return inv * inv * inv / A;
 }
@@ -167,6 +193,26 @@ __device__ __forceinline__ f3 camera_dir(const DevScene& S, float u0, float u1)
     const f3 e = normalize(F3(S.aspect * S.tan_fov * x, S.tan_fov * y, -1.0f));
     return (ld3(S.vx) * e.x + ld3(S.vy) * e.y) + ld3(S.vz) * e.z;
 }
+__device__ __forceinline__ void concentric_disk(float u0, float u1, float& sx, float& sy);
+// Sensor::SamplePositionAndDirection split in two: the sensor vertex for lens sample (l0,l1) ...
+__device__ __forceinline__ f3 camera_point(const DevScene& S, float l0, float l1)
+{
+    if (S.cam_kind != LMB200_CAMERA_THINLENS) return ld3(S.pos);
+    float lx, ly;
+    concentric_disk(l0, l1, lx, ly);
+    lx *= S.lens_radius; ly *= S.lens_radius;
+    return (ld3(S.pos) + ld3(S.vx) * lx) + ld3(S.vy) * ly;
+}
+// ... and the direction through raster sample (u0,u1) leaving from the sensor vertex p
+__device__ __forceinline__ f3 camera_wo(const DevScene& S, float u0, float u1, f3 p)
+{
+    const f3 dir = camera_dir(S, u0, u1);
+    if (S.cam_kind != LMB200_CAMERA_THINLENS) return dir;
+    const float tf = S.focal_distance / dot(neg(ld3(S.vz)), dir);
+    const f3 Pf = ld3(S.pos) + dir * tf;
+    return normalize(Pf - p);
+}
+#define LMB_LENS_BLOCK 0xffffffffu   // Philox block of the lens sample (the second Next2D of renderer_pt.cpp:86)
 __device__ __forceinline__ int pixel_index(const DevScene& S, float rx, float ry)   // film_hdr.cpp:218-223
 {
     int px = (int)(rx * (float)S.width), py = (int)(ry * (float)S.height);
@@ -324,14 +370,57 @@ __device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 
     return F3(0, 0, 0);
 }
 
-// ---- light::area position sampling (triangleutils.h:71-122, dist.h:70-76, sampler.h:97-101) ----
-__device__ __forceinline__ void light_sample(const DevScene& S, int li, float u0, float u1, Geom& g)
+// ---- emitter shape of light::directional / light::env (light_directional.cpp:52-73, light_env.cpp:56-77;
+//      SphereBound::Intersect with minT=0, maxT=Inf, bound.h:125-167) ----
+__device__ __forceinline__ bool emitter_shape_hit(const DevScene& S, f3 o, f3 d, Geom& g)
 {
-    if (S.lights[li].kind == LMB200_LIGHT_POINT) {            // light_point.cpp:62-66
+    const f3 center = ld3(S.sph_c);
+    const f3 oo = o - center;
+    const float a = dot(d, d), b = 2.0f * dot(oo, d), c = dot(oo, oo) - S.sph_r * S.sph_r;
+    const float det = b * b - 4.0f * a * c;
+    if (det < 0.f) return false;
+    const float e = sqrtf(det), denom = 2.0f * a;
+    const float t0 = (-b - e) / denom, t1 = (-b + e) / denom;
+    if (t0 > LMB_FLT_MAX || t1 < 0.f) return false;
+    float t = t0;
+    if (t < 0.f) { t = t1; if (t > LMB_FLT_MAX) return false; }
+    g.degenerated = false;
+    g.gn = g.sn = neg(d);
+    basis(g.sn, g.dpdu, g.dpdv);
+    const f3 p = o + d * t;
+    const f3 cc = center + d * S.sph_r;
+    g.p = (cc + g.dpdu * dot(g.dpdu, p - cc)) + g.dpdv * dot(g.dpdv, p - cc);
+    return true;
+}
+
+// ---- Light::SamplePositionGivenPreviousPosition + its area pdf (evalDelta=false) from the vertex at `from` ----
+// light::area: triangleutils.h:71-122, dist.h:70-76, sampler.h:97-101, light_area.cpp:100-103
+__device__ __forceinline__ bool light_sample(const DevScene& S, int li, f3 from, float u0, float u1, Geom& g, float& pdfPL)
+{
+    const int kind = S.lights[li].kind;
+    if (kind == LMB200_LIGHT_POINT) {            // light_point.cpp:62-66, 88-91
         g.p = ld3(S.lights[li].position);
         g.degenerated = true;
         g.gn = g.sn = g.dpdu = g.dpdv = F3(0, 0, 0);
-        return;
+        pdfPL = 1.0f;
+        return true;
+    }
+    if (kind == LMB200_LIGHT_DIRECTIONAL || kind == LMB200_LIGHT_ENV) {
+        f3 d;
+        float pdfSA = 1.0f;                      // light_directional.cpp:176-180
+        if (kind == LMB200_LIGHT_DIRECTIONAL) d = neg(ld3(S.lights[li].direction));   // light_directional.cpp:131-145
+        else {                                   // light_env.cpp:129-146, Sampler::UniformSampleSphere (sampler.h:79-85)
+            const float z = 1.0f - 2.0f * u0, r = sqrtf(fmaxf(0.f, 1.0f - z * z)), phi = 2.0f * LMB_PI * u1;
+            d = F3(r * cosf(phi), r * sinf(phi), z);
+            pdfSA = LMB_INV_PI * 0.25f;          // light_env.cpp:185-189
+        }
+        if (!emitter_shape_hit(S, from, d, g)) return false;
+        // PDFVal(SolidAngle).ConvertToArea(geomPrev, geom), probability.h:59-71
+        f3 w = g.p - from;
+        const float d2 = dot(w, w), dl = sqrtf(d2);
+        w = F3(w.x / dl, w.y / dl, w.z / dl);
+        pdfPL = pdfSA * fabsf(dot(g.sn, neg(w))) / d2;
+        return true;
     }
     const lmb200_primitive& P = S.prims[S.lights[li].primitive];
     const float* cdf = S.light_cdf + S.light_cdf_off[li];
@@ -348,6 +437,8 @@ __device__ __forceinline__ void light_sample(const DevScene& S, int li, float u0
     g.gn = normalize(cross(p2 - p1, p3 - p1));
     g.sn = g.gn;
     basis(g.sn, g.dpdu, g.dpdv);
+    pdfPL = S.light_inv_area[li];
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -454,18 +545,23 @@ __global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg
             if (sidx < cfg.sample_end) {
                 bool ok = true;
                 int pixel = -1;
+                f3 cp = ld3(S.pos);
+                if (S.cam_kind == LMB200_CAMERA_THINLENS) {
+                    const float4 ul = rng_block(cfg.seed, sidx, LMB_LENS_BLOCK);
+                    cp = camera_point(S, ul.x, ul.y);
+                }
                 if (cfg.mode != LMB200_MODE_PTDIRECT) {
                     // renderer::pt / ptmis compute the raster position up front and drop the sample if it fails (renderer_pt.cpp:94-99)
                     const float4 u = rng_block(cfg.seed, sidx, 0u);
                     float rx, ry;
-                    ok = raster_position(S, camera_dir(S, u.y, u.z), rx, ry);
+                    ok = raster_position(S, cp, camera_wo(S, u.y, u.z, cp), rx, ry);
                     if (ok) pixel = pixel_index(S, rx, ry);
                 }
                 if (ok && !(cfg.max_verts != -1 && 1 >= cfg.max_verts)) {
                     P.sample[i] = sidx;
                     P.nverts[i] = 1;
                     P.thr[i] = make_float4(1.f, 1.f, 1.f, __int_as_float(pixel));
-                    P.vtx_p[i] = make_float4(S.pos[0], S.pos[1], S.pos[2], __uint_as_float(LMB200_MISS));
+                    P.vtx_p[i] = make_float4(cp.x, cp.y, cp.z, __uint_as_float(LMB200_MISS));
                     alive = true;
                 } else {
                     P.nverts[i] = 0;   // sample consumed without a path; the slot is refilled next iteration
@@ -502,15 +598,15 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
             const int li = min(max((int)(ua.x * (float)nL), 0), nL - 1);      // scene3.cpp:508-513
             const float pdfL = 1.0f / (float)nL;                               // scene3.cpp:526-530
             Geom gL;
-            light_sample(S, li, ua.y, ua.z, gL);
-            const float pdfPL = S.light_inv_area[li];                          // light_area.cpp:100-103
+            float pdfPL = 1.0f;
             p = F3(vp.x, vp.y, vp.z);
+            const bool sampled = light_sample(S, li, p, ua.y, ua.z, gL, pdfPL);
             pl = gL.p;
             const f3 ppL = normalize(gL.p - p);
             f3 fsE;
             Geom g;
             float pdfB;      // pdf of sampling ppL from this vertex (ptmis)
-            if (is_sensor) { const float im = importance(S, ppL); fsE = F3(im, im, im); g.degenerated = true; pdfB = im; }
+            if (is_sensor) { const float im = importance(S, p, ppL); fsE = F3(im, im, im); g.degenerated = true; pdfB = im; }
             else {
                 const float4 vw = P.vtx_wi[i];
                 tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
@@ -518,8 +614,10 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
                 fsE = bsdf_eval(B, g, F3(vw.x, vw.y, vw.z), ppL, true);
                 pdfB = cfg.mode == LMB200_MODE_PTMIS ? bsdf_pdf(B, g, F3(vw.x, vw.y, vw.z), ppL, true) : 0.f;
             }
-            const f3 fsL = gL.degenerated ? ld3(S.lights[li].Le)                                   // light_point.cpp:95-98
-                                          : (to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le));   // light_area.cpp:105-110
+            // light_point.cpp:95-98, light_directional.cpp:182-185, light_env.cpp:191-208 emit Le in every direction;
+            // light::area only on its front side (light_area.cpp:105-110)
+            const f3 fsL = S.lights[li].kind != LMB200_LIGHT_AREA ? ld3(S.lights[li].Le)
+                                          : (to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le));
             f3 d = gL.p - p;                                                   // RenderUtils::GeometryTerm, renderutils.h:46-56
             const float d2 = dot(d, d), dl = sqrtf(d2);
             d = F3(d.x / dl, d.y / dl, d.z / dl);
@@ -528,7 +626,7 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
             if (!gL.degenerated) G *= fabsf(dot(gL.sn, neg(d)));
             G = G / d2;
             C = ((F3(thr.x, thr.y, thr.z) * fsE) * fsL) * G;
-            if (!black(C)) {
+            if (sampled && !black(C)) {
                 C = C * (1.0f / pdfL / pdfPL);
                 if (cfg.mode == LMB200_MODE_PTMIS) {          // renderer_ptmis.cpp:163-170
                     const float pdfDL = pdfPL / G * pdfL;
@@ -537,7 +635,7 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
                 pixel = __float_as_int(thr.w);
                 if (is_sensor) {                                               // renderer_ptdirect.cpp:165-170
                     float rx = 0.f, ry = 0.f;
-                    raster_position(S, ppL, rx, ry);
+                    raster_position(S, p, ppL, rx, ry);
                     pixel = pixel_index(S, rx, ry);
                 }
                 emit = true;
@@ -579,12 +677,12 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
             bool ok = true, specular_here = false;
             if (is_sensor) {
                 const float4 u = rng_block(cfg.seed, P.sample[i], 0u);
-                wo = camera_dir(S, u.y, u.z);
-                const float im = importance(S, wo);
+                wo = camera_wo(S, u.y, u.z, p);
+                const float im = importance(S, p, wo);
                 pdfD = im; fs = F3(im, im, im);
                 if (cfg.mode == LMB200_MODE_PTDIRECT) {
                     float rx, ry;
-                    ok = raster_position(S, wo, rx, ry);                       // renderer_ptdirect.cpp:200-208
+                    ok = raster_position(S, p, wo, rx, ry);                    // renderer_ptdirect.cpp:200-208
                     if (ok) thr.w = __int_as_float(pixel_index(S, rx, ry));
                 }
             } else {
@@ -679,8 +777,10 @@ __global__ void k_normal_raygen(DevScene S, float4* rays)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S.width * S.height) return;
     const int x = i % S.width, y = i / S.width;
-    const f3 wo = camera_dir(S, ((float)x + 0.5f) / (float)S.width, ((float)y + 0.5f) / (float)S.height);
-    rays[2 * i] = make_float4(S.pos[0], S.pos[1], S.pos[2], LMB_EPS_ISECT);
+    // thin lens: the lens centre (lens sample (.5,.5)), i.e. the in-focus pinhole image
+    const f3 cp = camera_point(S, 0.5f, 0.5f);
+    const f3 wo = camera_wo(S, ((float)x + 0.5f) / (float)S.width, ((float)y + 0.5f) / (float)S.height, cp);
+    rays[2 * i] = make_float4(cp.x, cp.y, cp.z, LMB_EPS_ISECT);
     rays[2 * i + 1] = make_float4(wo.x, wo.y, wo.z, LMB_FLT_MAX);
 }
 __global__ void k_normal_shade(DevScene S, const float4* hits, float4* film)
@@ -819,6 +919,9 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     }
     if (p->mode != LMB200_MODE_PT && p->mode != LMB200_MODE_PTDIRECT && p->mode != LMB200_MODE_PTMIS) return set_error(LMB200_E_INVALID, "unknown render mode");
     const bool nee = p->mode != LMB200_MODE_PT;
+    if (s->dev.has_env && p->mode != LMB200_MODE_PTDIRECT)
+        return set_error(LMB200_E_INVALID, "light::env is direct-light sampled only: use mode ptdirect (the reference's pt / ptmis dereference a null "
+                                           "primitive when a ray escapes to the env emitter shape, scene3.cpp:463-475 + renderer_pt.cpp:183)");
     if (p->sample_end < p->sample_begin) return set_error(LMB200_E_INVALID, "sample_end < sample_begin");
     const int64_t todo = p->sample_end - p->sample_begin;
     uint32_t pool = p->pool_size > 0 ? (uint32_t)p->pool_size : (1u << 22);   // 4 Mi slots: best on B200 (profiles/r01_sweep.md)
@@ -940,8 +1043,12 @@ static lmb200_scene* scene_create(int device, const lmb200_scene_desc* d, int bu
         if (d->lights[li].primitive < 0 || (uint32_t)d->lights[li].primitive >= d->num_prims) { set_error(LMB200_E_INVALID, "light primitive out of range"); delete s; return nullptr; }
         const lmb200_primitive& P = d->prims[d->lights[li].primitive];
         off.push_back((uint32_t)cdf.size());
-        if (d->lights[li].kind == LMB200_LIGHT_POINT) { cdf.push_back(0.f); cdf.push_back(1.f); inv_area.push_back(1.0f); continue; }   // pdf 1 (light_point.cpp:88-91)
-        if (d->lights[li].kind != LMB200_LIGHT_AREA) { set_error(LMB200_E_INVALID, "unknown light kind"); delete s; return nullptr; }
+        const int kind = d->lights[li].kind;
+        if (kind == LMB200_LIGHT_POINT || kind == LMB200_LIGHT_DIRECTIONAL || kind == LMB200_LIGHT_ENV) {   // no mesh to sample
+            if (kind != LMB200_LIGHT_POINT && !(d->sphere_radius > 0.f)) { set_error(LMB200_E_INVALID, "directional / env lights need lmb200_scene_desc::sphere_radius > 0"); delete s; return nullptr; }
+            cdf.push_back(0.f); cdf.push_back(1.f); inv_area.push_back(1.0f); continue;
+        }
+        if (kind != LMB200_LIGHT_AREA) { set_error(LMB200_E_INVALID, "unknown light kind"); delete s; return nullptr; }
         if (P.num_tris == 0) { set_error(LMB200_E_INVALID, "area light without triangles"); delete s; return nullptr; }
         const size_t base = cdf.size();
         cdf.push_back(0.f);
@@ -970,6 +1077,12 @@ static lmb200_scene* scene_create(int device, const lmb200_scene_desc* d, int bu
     D.tan_fov = std::tan(d->camera.fov * 0.5f);
     D.width = d->camera.width; D.height = d->camera.height;
     D.aspect = (float)d->camera.width / (float)d->camera.height;
+    D.cam_kind = d->camera.kind;
+    D.lens_radius = d->camera.lens_radius; D.focal_distance = d->camera.focal_distance;
+    for (int k = 0; k < 3; k++) D.sph_c[k] = d->sphere_center[k];
+    D.sph_r = d->sphere_radius;
+    D.has_env = 0;
+    for (uint32_t li = 0; li < d->num_lights; li++) if (d->lights[li].kind == LMB200_LIGHT_ENV) D.has_env = 1;
     return reinterpret_cast<lmb200_scene*>(s);
 }
 

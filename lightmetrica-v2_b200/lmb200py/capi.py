@@ -9,7 +9,8 @@ LIB_PATH = os.environ.get("LMB200_LIB", os.path.join(_ROOT, "lib", "liblmb200.so
 MISS = 0xFFFFFFFF
 MODE_PT, MODE_PTDIRECT, MODE_NORMAL, MODE_PTMIS = 0, 1, 2, 3
 BSDF_NULL, BSDF_DIFFUSE, BSDF_COOKTORRANCE, BSDF_REFLECT_ALL, BSDF_REFRACT_ALL, BSDF_FLESNEL = 0, 1, 2, 3, 4, 5
-LIGHT_AREA, LIGHT_POINT = 0, 1
+LIGHT_AREA, LIGHT_POINT, LIGHT_DIRECTIONAL, LIGHT_ENV = 0, 1, 2, 3
+CAMERA_PINHOLE, CAMERA_THINLENS = 0, 1
 BUILD_HOST_SAH, BUILD_GPU_LBVH = 0, 1
 
 RAY_DTYPE = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"),
@@ -33,12 +34,14 @@ class Primitive(C.Structure):
 
 
 class Light(C.Structure):
-    _fields_ = [("Le", C.c_float * 3), ("primitive", C.c_int32), ("kind", C.c_int32), ("position", C.c_float * 3)]
+    _fields_ = [("Le", C.c_float * 3), ("primitive", C.c_int32), ("kind", C.c_int32), ("position", C.c_float * 3),
+                ("direction", C.c_float * 3)]
 
 
 class Camera(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("vx", C.c_float * 3), ("vy", C.c_float * 3), ("vz", C.c_float * 3),
-                ("fov", C.c_float), ("width", C.c_int32), ("height", C.c_int32)]
+                ("fov", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("kind", C.c_int32), ("lens_radius", C.c_float), ("focal_distance", C.c_float)]
 
 
 class SceneDesc(C.Structure):
@@ -46,7 +49,7 @@ class SceneDesc(C.Structure):
                 ("num_prims", C.c_uint32), ("prims", C.POINTER(Primitive)),
                 ("num_bsdfs", C.c_uint32), ("bsdfs", C.POINTER(Bsdf)),
                 ("num_lights", C.c_uint32), ("lights", C.POINTER(Light)),
-                ("camera", Camera)]
+                ("camera", Camera), ("sphere_center", C.c_float * 3), ("sphere_radius", C.c_float)]
 
 
 class RenderParams(C.Structure):

@@ -20,7 +20,9 @@ class Scene:
         self.bsdfs = {}       # name -> dict(type='diffuse'|'cook_torrance', R, eta, k, roughness)
         self.lights = {}      # name -> Le (3,)   (light::area)
         self.point_lights = {}   # name -> dict(Le, position)   (light::point)
-        self.camera = None    # dict(eye, center, up, fov, w, h)
+        self.dir_lights = {}     # name -> dict(Le, direction)  (light::directional)
+        self.env_lights = {}     # name -> Le                   (light::env, constant)
+        self.camera = None    # dict(eye, center, up, fov, w, h[, lens_radius, focal_distance])
 
     # ---- construction helpers ----
     def add_bsdf(self, name, type="diffuse", R=(0.8, 0.8, 0.8), roughness=0.1,
@@ -37,6 +39,16 @@ class Scene:
         self.point_lights[name] = dict(Le=tuple(Le), position=tuple(float(x) for x in position))
         self.nodes.append(dict(mesh=None, bsdf=None, light=name))
 
+    def add_directional_light(self, name, Le, direction):
+        """light::directional (light_directional.cpp:100-105) on a node of its own; `direction` is where the light travels."""
+        self.dir_lights[name] = dict(Le=tuple(Le), direction=tuple(float(x) for x in direction))
+        self.nodes.append(dict(mesh=None, bsdf=None, light=name))
+
+    def add_env_light(self, name, Le):
+        """light::env with a constant Le (light_env.cpp:103-121) on a node of its own."""
+        self.env_lights[name] = tuple(Le)
+        self.nodes.append(dict(mesh=None, bsdf=None, light=name))
+
     def add_mesh_tris(self, tris9, bsdf=None, light=None, normals=None):
         """tris9: (n,9) world-space triangles, stored unshared (3 vertices per face)."""
         tris9 = np.ascontiguousarray(tris9, np.float32).reshape(-1, 9)
@@ -50,8 +62,10 @@ class Scene:
         a, b, c, d = (np.asarray(x, np.float32) for x in (a, b, c, d))
         self.add_mesh_tris(np.stack([np.concatenate([a, b, c]), np.concatenate([a, c, d])]), bsdf, light)
 
-    def set_camera(self, eye, center, up, fov, w, h):
-        self.camera = dict(eye=tuple(eye), center=tuple(center), up=tuple(up), fov=float(fov), w=int(w), h=int(h))
+    def set_camera(self, eye, center, up, fov, w, h, lens_radius=None, focal_distance=1.0):
+        """sensor::pinhole, or sensor::thinlens when lens_radius is given (sensor_thinlens.cpp:44-68)."""
+        self.camera = dict(eye=tuple(eye), center=tuple(center), up=tuple(up), fov=float(fov), w=int(w), h=int(h),
+                           lens_radius=None if lens_radius is None else float(lens_radius), focal_distance=float(focal_distance))
 
     # ---- consumers ----
     def to_yaml(self, mesh_handles, accel="qbvh", renderer="ptdirect", renderer_params=None):
@@ -71,9 +85,18 @@ class Scene:
         for name, pl in self.point_lights.items():
             out += [f"    {name}:", "      interface: light", "      type: point", "      params:", f"        Le: {v3(pl['Le'])}",
                     f"        position: {v3(pl['position'])}"]
+        for name, dl in self.dir_lights.items():
+            out += [f"    {name}:", "      interface: light", "      type: directional", "      params:", f"        Le: {v3(dl['Le'])}",
+                    f"        direction: {v3(dl['direction'])}"]
+        for name, le in self.env_lights.items():
+            out += [f"    {name}:", "      interface: light", "      type: env", "      params:", f"        Le: {v3(le)}"]
         c = self.camera
         out += ["    film1:", "      interface: film", "      type: hdr", "      params:", f"        w: {c['w']}", f"        h: {c['h']}"]
-        out += ["    cam:", "      interface: sensor", "      type: pinhole", "      params:", "        film: film1", f"        fov: {c['fov']!r}"]
+        if c.get("lens_radius") is None:
+            out += ["    cam:", "      interface: sensor", "      type: pinhole", "      params:", "        film: film1", f"        fov: {c['fov']!r}"]
+        else:
+            out += ["    cam:", "      interface: sensor", "      type: thinlens", "      params:", "        film: film1", f"        fov: {c['fov']!r}",
+                    f"        lens_radius: {c['lens_radius']!r}", f"        focal_distance: {c['focal_distance']!r}"]
         out += ["  accel:", f"    type: {accel}"]
         out += ["  scene:", "    type: scene3", "    params:", "      sensor: n_cam", "      nodes:"]
         out += ["        - id: n_cam", "          sensor: cam", "          transform:", "            lookat:",
@@ -115,12 +138,21 @@ class Scene:
         first = 0
         first_prim_of_light = {}
         for pi, nd in enumerate(self.nodes, start=1):
-            if nd["mesh"] is None:      # light::point node: a primitive without geometry
+            if nd["mesh"] is None:      # point / directional / env light node: a primitive without geometry
                 prims[pi].bsdf = null_idx
                 prims[pi].first_tri = first
                 prims[pi].light = len(lights)
-                pl = self.point_lights[nd["light"]]
-                lights.append((pl["Le"], pi, capi.LIGHT_POINT, pl["position"]))
+                z3 = (0.0, 0.0, 0.0)
+                if nd["light"] in self.point_lights:
+                    pl = self.point_lights[nd["light"]]
+                    lights.append((pl["Le"], pi, capi.LIGHT_POINT, pl["position"], z3))
+                elif nd["light"] in self.dir_lights:
+                    dl = self.dir_lights[nd["light"]]
+                    dv = np.asarray(dl["direction"], np.float32)
+                    dv = dv / np.sqrt(np.float32(dv @ dv))      # Math::Normalize at load (light_directional.cpp:103)
+                    lights.append((dl["Le"], pi, capi.LIGHT_DIRECTIONAL, z3, tuple(float(x) for x in dv)))
+                else:
+                    lights.append((self.env_lights[nd["light"]], pi, capi.LIGHT_ENV, z3, z3))
                 continue
             m = self.meshes[nd["mesh"]]
             t = m["verts"][m["faces"].reshape(-1)].reshape(-1, 9)
@@ -139,17 +171,18 @@ class Scene:
                 # distribution at Load): later primitives sharing the asset sample the first one's mesh.
                 bound = first_prim_of_light.setdefault(nd["light"], pi)
                 prims[pi].light = len(lights)
-                lights.append((self.lights[nd["light"]], bound, capi.LIGHT_AREA, (0.0, 0.0, 0.0)))
+                lights.append((self.lights[nd["light"]], bound, capi.LIGHT_AREA, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0)))
             first += t.shape[0]
         verts = np.ascontiguousarray(np.concatenate(verts), np.float32) if verts else np.zeros((0, 9), np.float32)
         tri_prim = np.ascontiguousarray(np.concatenate(tri_prim), np.uint32) if tri_prim else np.zeros(0, np.uint32)
         norms = np.ascontiguousarray(np.concatenate(norms), np.float32) if any_normals else None
         ls = (capi.Light * max(1, len(lights)))()
-        for i, (le, pi, kind, pos) in enumerate(lights):
+        for i, (le, pi, kind, pos, dirn) in enumerate(lights):
             ls[i].Le = (C.c_float * 3)(*le)
             ls[i].primitive = pi
             ls[i].kind = kind
             ls[i].position = (C.c_float * 3)(*pos)
+            ls[i].direction = (C.c_float * 3)(*dirn)
         c = self.camera
         vx, vy, vz = scenes.lookat(c["eye"], c["center"], c["up"])
         cam = capi.Camera()
@@ -159,7 +192,20 @@ class Scene:
         cam.vz = (C.c_float * 3)(*vz)
         cam.fov = float(np.radians(np.float32(c["fov"])))
         cam.width, cam.height = c["w"], c["h"]
+        if c.get("lens_radius") is not None:
+            cam.kind = capi.CAMERA_THINLENS
+            cam.lens_radius, cam.focal_distance = c["lens_radius"], c["focal_distance"]
+        # Scene3::GetSphereBound (scene3.cpp:56-78): AABB of every mesh vertex and the sensor position; centre = mid point,
+        # radius = |centre - max| * 1.01
+        pts = [np.asarray(c["eye"], np.float32)[None, :]] + [self.meshes[nd["mesh"]]["verts"] for nd in self.nodes if nd["mesh"] is not None]
+        allp = np.concatenate(pts).astype(np.float32)
+        bmin, bmax = allp.min(axis=0), allp.max(axis=0)
+        centre = ((bmax + bmin) * np.float32(0.5)).astype(np.float32)
+        dd = (centre - bmax).astype(np.float32)
+        radius = np.float32(np.sqrt(np.float32(dd @ dd))) * np.float32(1.01)
         d = capi.SceneDesc()
+        d.sphere_center = (C.c_float * 3)(*[float(x) for x in centre])
+        d.sphere_radius = float(radius)
         d.num_tris = verts.shape[0]
         d.verts = verts.ctypes.data_as(C.c_void_p)
         d.normals = norms.ctypes.data_as(C.c_void_p) if norms is not None else None
@@ -194,7 +240,7 @@ def _box(scene, center, half, angle_deg, bsdf):
     scene.add_mesh_tris(np.stack(tris), bsdf)
 
 
-def cornell_box(w=512, h=512, glossy_block=False):
+def cornell_box(w=512, h=512, glossy_block=False, thinlens=False):
     """Cornell-style box, 36 triangles: 5 walls, 2 blocks, 1 ceiling light (config 0 of BASELINE.json)."""
     s = Scene()
     s.add_bsdf("white", "diffuse", (0.75, 0.75, 0.75))
@@ -210,7 +256,10 @@ def cornell_box(w=512, h=512, glossy_block=False):
     _box(s, (-0.35, 0.6, -0.3), (0.3, 0.6, 0.3), 18.0, "white")                  # tall block
     _box(s, (0.4, 0.3, 0.3), (0.3, 0.3, 0.3), -17.0, "metal" if glossy_block else "white")   # short block
     s.add_quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), "white", "lamp")  # light, faces down
-    s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h)
+    if thinlens:   # sensor::thinlens focused on the front face of the short block
+        s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h, lens_radius=0.2, focal_distance=3.6)
+    else:
+        s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h)
     return s
 
 
@@ -271,4 +320,30 @@ def specular_box(w=64, h=64, point_light=True):
     if point_light:
         s.add_point_light("bulb", (1.5, 1.5, 2.0), (0.6, 1.5, 0.6))
     s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h)
+    return s
+
+
+def outdoor_scene(w=64, h=36, light="directional", thinlens=False):
+    """Open scene (ground + a few objects, no enclosure) lit by light::directional, light::env (constant Le) or both,
+    optionally seen through sensor::thinlens focused on the middle object: exercises the bounding-sphere emitter shapes
+    (geom.infinite) and the lens sampling."""
+    if light == "cornell":
+        return cornell_box(w, h, glossy_block=True, thinlens=thinlens)
+    s = Scene()
+    s.add_bsdf("ground", "diffuse", (0.6, 0.55, 0.5))
+    s.add_bsdf("red", "diffuse", (0.7, 0.2, 0.2))
+    s.add_bsdf("blue", "diffuse", (0.2, 0.3, 0.7))
+    s.add_bsdf("metal", "cook_torrance", (1.0, 1.0, 1.0), roughness=0.3)
+    s.add_quad((-6, 0, -6), (-6, 0, 6), (6, 0, 6), (6, 0, -6), "ground")
+    s.add_mesh_tris(scenes.sphere((0.0, 0.8, 0.0), 0.8, 20, 14), "red")
+    _box(s, (-1.9, 0.6, -1.2), (0.5, 0.6, 0.5), 25.0, "blue")
+    s.add_mesh_tris(scenes.torus((1.9, 0.45, 1.0), 0.7, 0.25, 20, 10), "metal")
+    if light in ("directional", "both"):
+        s.add_directional_light("sun", (3.0, 2.8, 2.5), (-0.4, -1.0, -0.3))
+    if light in ("env", "both"):
+        s.add_env_light("sky", (0.5, 0.6, 0.8))
+    if thinlens:
+        s.set_camera((0.0, 2.0, 6.0), (0.0, 0.7, 0.0), (0, 1, 0), 35.0, w, h, lens_radius=0.25, focal_distance=6.1)
+    else:
+        s.set_camera((0.0, 2.0, 6.0), (0.0, 0.7, 0.0), (0, 1, 0), 35.0, w, h)
     return s

@@ -9,8 +9,8 @@
 // BSDF::Reflectance/Glossiness, Light::Emittance, Sensor::GetFilm/GetProjectionMatrix), flattens
 // it into the POD arrays of include/lmb200.h and calls liblmb200.so; the film comes back through
 // Film::SetPixel and is written with Film::Save, exactly where the reference renderers save
-// (renderer_pt.cpp:236-241). Scenes using assets outside the supported set (delta BSDFs, textures,
-// point/directional/env lights, non-pinhole sensors) are rejected with an error, never mis-rendered.
+// (renderer_pt.cpp:236-241). Scenes using assets outside the supported set (textured BSDFs, light::env
+// outside mode ptdirect, unknown plugins) are rejected with an error, never mis-rendered.
 #include <lightmetrica/lightmetrica.h>
 #include <vector>
 #include <map>
@@ -132,9 +132,39 @@ public:
                     lights.push_back(L);
                     continue;
                 }
+                if (limpl == "Light_Directional" || limpl == "Light_EnvLight")
+                {
+                    // light_directional.cpp:147-162 / light_env.cpp:148-168: the sampled direction of a directional light is
+                    // its (transformed, normalised) direction_; Le through EvaluateDirection (constant for light::env, whose
+                    // envmap branch cannot load: light_env.cpp:107-113)
+                    SurfaceGeometry gp;
+                    Vec3 wo;
+                    prim->light->SamplePositionAndDirection(Vec2(0.5_f, 0.5_f), Vec2(0.5_f, 0.5_f), gp, wo);
+                    const auto Le = prim->light->EvaluateDirection(gp, SurfaceInteractionType::L, Vec3(), wo, TransportDirection::LE, false).ToRGB();
+                    lmb200_light L; memset(&L, 0, sizeof(L));
+                    L.Le[0] = Le.x; L.Le[1] = Le.y; L.Le[2] = Le.z; L.primitive = i;
+                    if (limpl == "Light_Directional")
+                    {
+                        L.kind = LMB200_LIGHT_DIRECTIONAL;
+                        L.direction[0] = wo.x; L.direction[1] = wo.y; L.direction[2] = wo.z;
+                    }
+                    else
+                    {
+                        L.kind = LMB200_LIGHT_ENV;
+                        if (mode_ == LMB200_MODE_PT || mode_ == LMB200_MODE_PTMIS)
+                        {
+                            LM_LOG_ERROR("renderer::lmb200pt: light::env is supported in mode ptdirect only (renderer::pt / ptmis of the reference "
+                                         "dereference a null primitive when a ray escapes to the env emitter shape)");
+                            return;
+                        }
+                    }
+                    prims[i].light = (int)lights.size();
+                    lights.push_back(L);
+                    continue;
+                }
                 if (limpl != "Light_Area")
                 {
-                    LM_LOG_ERROR("renderer::lmb200pt: unsupported light '" + limpl + "' (light::area | light::point)");
+                    LM_LOG_ERROR("renderer::lmb200pt: unsupported light '" + limpl + "' (light::area | light::point | light::directional | light::env)");
                     return;
                 }
                 const auto Le = prim->light->Emittance().ToRGB();
@@ -150,14 +180,21 @@ public:
             }
         }
 
-        // ---- sensor::pinhole (sensor_pinhole.cpp:47-61) ----
-        if (std::string(sensorPrim->sensor->implName) != "Sensor_Pinhole")
+        // ---- sensor::pinhole (sensor_pinhole.cpp:47-61) / sensor::thinlens (sensor_thinlens.cpp:44-68) ----
+        const std::string simpl = sensorPrim->sensor->implName;
+        if (simpl != "Sensor_Pinhole" && simpl != "Sensor_ThinLens")
         {
-            LM_LOG_ERROR(std::string("renderer::lmb200pt: unsupported sensor '") + sensorPrim->sensor->implName + "' (only sensor::pinhole)");
+            LM_LOG_ERROR("renderer::lmb200pt: unsupported sensor '" + simpl + "' (sensor::pinhole | sensor::thinlens)");
             return;
         }
         lmb200_scene_desc d;
         memset(&d, 0, sizeof(d));
+        {
+            // Scene3::GetSphereBound (scene3.cpp:56-78), the virtual-disk geometry of directional / env lights
+            const auto sb = scene->GetSphereBound();
+            d.sphere_center[0] = sb.center.x; d.sphere_center[1] = sb.center.y; d.sphere_center[2] = sb.center.z;
+            d.sphere_radius = sb.radius;
+        }
         {
             const Vec3 pos(sensorPrim->transform * Vec4(0_f, 0_f, 0_f, 1_f));
             const Vec3 vx(sensorPrim->transform[0]), vy(sensorPrim->transform[1]), vz(sensorPrim->transform[2]);
@@ -173,6 +210,29 @@ public:
             else d.camera.fov = 2_f * std::atan(1_f / sensorPrim->sensor->GetProjectionMatrix(1_f, 2_f)[1][1]);
             d.camera.width = film->Width();
             d.camera.height = film->Height();
+            d.camera.kind = LMB200_CAMERA_PINHOLE;
+            if (simpl == "Sensor_ThinLens")
+            {
+                d.camera.kind = LMB200_CAMERA_THINLENS;
+                if (const auto* ap = AssetParams(sensorPrim->sensor))
+                {
+                    d.camera.lens_radius = ap->ChildAs<Float>("lens_radius", 0.1_f);      // sensor_thinlens.cpp:64-65
+                    d.camera.focal_distance = ap->ChildAs<Float>("focal_distance", 1_f);
+                }
+                else
+                {
+                    // not reachable through the YAML tree: recover both from one sample through the Sensor interface.
+                    // Lens sample (1,.5) maps to lensUV = (radius, 0) (sampler.h:44-60), raster centre to rayDir = -vz,
+                    // so p = pos + R vx and wo ~ -(F vz + R vx)  (sensor_thinlens.cpp:87-106)
+                    SurfaceGeometry gp;
+                    Vec3 wo;
+                    sensorPrim->sensor->SamplePositionAndDirection(Vec2(0.5_f, 0.5_f), Vec2(1_f, 0.5_f), gp, wo);
+                    const Float R = Math::Dot(gp.p - pos, vx) / Math::Dot(vx, vx);
+                    d.camera.lens_radius = R;
+                    d.camera.focal_distance = R * Math::Dot(wo, -vz) / Math::Dot(wo, -vx);
+                    LM_LOG_WARN("renderer::lmb200pt: thin-lens parameters recovered through the Sensor interface (asset params not reachable)");
+                }
+            }
         }
         d.num_tris = verts.size() / 9;
         d.verts = verts.data();
@@ -193,6 +253,8 @@ public:
                 const uint64_t hdr[5] = { d.num_tris, d.num_prims, d.num_bsdfs, d.num_lights, d.normals ? 1u : 0u };
                 fwrite(hdr, sizeof(hdr), 1, f);
                 fwrite(&d.camera, sizeof(d.camera), 1, f);
+                fwrite(d.sphere_center, sizeof(float), 3, f);
+                fwrite(&d.sphere_radius, sizeof(float), 1, f);
                 fwrite(d.verts, sizeof(float), 9 * d.num_tris, f);
                 fwrite(d.tri_prim, sizeof(uint32_t), d.num_tris, f);
                 fwrite(d.prims, sizeof(lmb200_primitive), d.num_prims, f);

@@ -35,14 +35,15 @@ int orc_any_one(const orc_scene* s, const float* ray);
 /* Same field layout as include/lmb200.h (restated here; the oracle does not include product headers). */
 typedef struct { int32_t type; float R[3], eta[3], k[3], roughness, eta1, eta2; } orc_bsdf;
 typedef struct { int32_t bsdf, light; uint32_t first_tri, num_tris; int32_t has_normals; } orc_prim;
-typedef struct { float Le[3]; int32_t primitive; int32_t kind; float position[3]; } orc_light;
-typedef struct { float position[3], vx[3], vy[3], vz[3], fov; int32_t width, height; } orc_camera;
+typedef struct { float Le[3]; int32_t primitive; int32_t kind; float position[3]; float direction[3]; } orc_light;   /* kind: 0 area, 1 point, 2 directional, 3 env */
+typedef struct { float position[3], vx[3], vy[3], vz[3], fov; int32_t width, height; int32_t kind; float lens_radius, focal_distance; } orc_camera;   /* kind: 0 pinhole, 1 thinlens */
 typedef struct {
     uint64_t num_tris; const float* verts; const float* normals; const uint32_t* tri_prim;
     uint32_t num_prims; const orc_prim* prims;
     uint32_t num_bsdfs; const orc_bsdf* bsdfs;
     uint32_t num_lights; const orc_light* lights;
     orc_camera camera;
+    float sphere_center[3], sphere_radius;   /* Scene3::GetSphereBound (scene3.cpp:56-78), used by directional / env lights */
 } orc_scene_desc;
 
 typedef struct {
@@ -118,34 +119,71 @@ static void tri_geom(const orc_pt_scene* S, uint32_t tri, float b0, float b1, v3
     basis(g->sn, &g->dpdu, &g->dpdv);
 }
 
-/* ---- sensor::pinhole (src/liblightmetrica/asset/sensor/sensor_pinhole.cpp) ---- */
-static int raster_position(const orc_pt_scene* S, v3 wo, float* rx, float* ry)   /* :165-185 */
+/* ---- sensor::pinhole (src/liblightmetrica/asset/sensor/sensor_pinhole.cpp) and
+ *      sensor::thinlens (src/liblightmetrica/asset/sensor/sensor_thinlens.cpp); p = the sensor vertex (lens point) ---- */
+static int sensor_eye(const orc_pt_scene* S, v3 p, v3 wo, v3* e)
 {
     const orc_camera* c = &S->d.camera;
-    const v3 e = V(vdot(ld3(c->vx), wo), vdot(ld3(c->vy), wo), vdot(ld3(c->vz), wo));
-    if (e.z >= 0.0f) return 0;
+    if (c->kind == 1) {                      /* sensor_thinlens.cpp:186-209 */
+        const v3 nvz = vneg(ld3(c->vz));
+        v3 Pf, woOrig;
+        float tf;
+        if (vdot(nvz, wo) <= 0.0f) return 0;
+        tf = c->focal_distance / vdot(nvz, wo);
+        Pf = vadd(p, vmul(wo, tf));          /* intersection with the focal plane */
+        woOrig = vnorm(vsub(Pf, ld3(c->position)));   /* direction before refraction */
+        *e = V(vdot(ld3(c->vx), woOrig), vdot(ld3(c->vy), woOrig), vdot(ld3(c->vz), woOrig));
+    } else {                                 /* sensor_pinhole.cpp:165-175 */
+        *e = V(vdot(ld3(c->vx), wo), vdot(ld3(c->vy), wo), vdot(ld3(c->vz), wo));
+    }
+    return e->z < 0.0f;
+}
+static int raster_position(const orc_pt_scene* S, v3 p, v3 wo, float* rx, float* ry)   /* pinhole :165-185, thinlens :186-222 */
+{
+    v3 e;
+    if (!sensor_eye(S, p, wo, &e)) return 0;
     *rx = (-e.x / e.z / S->tan_fov / S->aspect + 1.0f) * 0.5f;
     *ry = (-e.y / e.z / S->tan_fov + 1.0f) * 0.5f;
     if (*rx < 0.0f || *rx > 1.0f || *ry < 0.0f || *ry > 1.0f) return 0;
     return 1;
 }
-static float importance(const orc_pt_scene* S, v3 wo)   /* :137-154 */
+static float importance(const orc_pt_scene* S, v3 p, v3 wo)   /* pinhole :137-154, thinlens :150-176 */
 {
-    const orc_camera* c = &S->d.camera;
     float rx, ry;
-    if (!raster_position(S, wo, &rx, &ry)) return 0.0f;
+    v3 e;
+    if (!raster_position(S, p, wo, &rx, &ry)) return 0.0f;
+    sensor_eye(S, p, wo, &e);
     {
-        const float cosT = -vdot(ld3(c->vz), wo), inv = 1.0f / cosT;
+        const float cosT = -e.z, inv = 1.0f / cosT;
         const float A = S->tan_fov * S->tan_fov * S->aspect * 4.0f;
         return inv * inv * inv / A;
     }
 }
-static v3 camera_dir(const orc_pt_scene* S, float u0, float u1)   /* :79-90 */
+static v3 camera_dir(const orc_pt_scene* S, float u0, float u1)   /* sensor_pinhole.cpp:79-90 */
 {
     const orc_camera* c = &S->d.camera;
     const float x = 2.0f * u0 - 1.0f, y = 2.0f * u1 - 1.0f;
     const v3 e = vnorm(V(S->aspect * S->tan_fov * x, S->tan_fov * y, -1.0f));
     return vadd(vadd(vmul(ld3(c->vx), e.x), vmul(ld3(c->vy), e.y)), vmul(ld3(c->vz), e.z));
+}
+static void concentric_disk(float u0, float u1, float* sx, float* sy);
+/* Sensor::SamplePositionAndDirection: u = raster sample, (l0,l1) = lens sample (ignored by the pinhole) */
+static v3 camera_sample(const orc_pt_scene* S, float u0, float u1, float l0, float l1, v3* p)
+{
+    const orc_camera* c = &S->d.camera;
+    const v3 dir = camera_dir(S, u0, u1);
+    *p = ld3(c->position);
+    if (c->kind == 1) {                      /* sensor_thinlens.cpp:87-106 */
+        float lx, ly, tf;
+        v3 Pf;
+        concentric_disk(l0, l1, &lx, &ly);
+        lx *= c->lens_radius; ly *= c->lens_radius;
+        *p = vadd(vadd(ld3(c->position), vmul(ld3(c->vx), lx)), vmul(ld3(c->vy), ly));
+        tf = c->focal_distance / vdot(vneg(ld3(c->vz)), dir);
+        Pf = vadd(ld3(c->position), vmul(dir, tf));
+        return vnorm(vsub(Pf, *p));
+    }
+    return dir;
 }
 
 /* ---- BSDFs ---- */
@@ -311,18 +349,66 @@ static v3 bsdf_eval(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval_d
     return V(0, 0, 0);
 }
 
-/* ---- light::area (src/liblightmetrica/asset/light/light_area.cpp, include/lightmetrica/triangleutils.h) ---- */
-static void light_sample(const orc_pt_scene* S, int li, float u0, float u1, geom_t* g)   /* triangleutils.h:71-122 */
+/* EmitterShape_{DirectionalLight,EnvLight}::Intersect with minT=0, maxT=Inf (light_directional.cpp:52-73,
+ * light_env.cpp:56-77; SphereBound::Intersect, bound.h:125-167): the point where the ray leaves the scene's
+ * bounding sphere, moved onto the virtual disk perpendicular to d. */
+static int emitter_shape_hit(const orc_pt_scene* S, v3 o, v3 d, geom_t* g)
+{
+    const v3 center = ld3(S->d.sphere_center);
+    const float radius = S->d.sphere_radius;
+    const v3 oo = vsub(o, center);
+    const float a = vdot(d, d), b = 2.0f * vdot(oo, d), c = vdot(oo, oo) - radius * radius;
+    const float det = b * b - 4.0f * a * c;
+    float e, denom, t0, t1, t;
+    v3 p, cc;
+    if (det < 0.0f) return 0;
+    e = sqrtf(det); denom = 2.0f * a;
+    t0 = (-b - e) / denom; t1 = (-b + e) / denom;
+    if (t0 > FLT_MAX || t1 < 0.0f) return 0;
+    t = t0;
+    if (t < 0.0f) { t = t1; if (t > FLT_MAX) return 0; }
+    g->degenerated = 0;
+    g->gn = vneg(d); g->sn = g->gn;
+    basis(g->sn, &g->dpdu, &g->dpdv);
+    p = vadd(o, vmul(d, t));
+    cc = vadd(center, vmul(d, radius));
+    g->p = vadd(vadd(cc, vmul(g->dpdu, vdot(g->dpdu, vsub(p, cc)))), vmul(g->dpdv, vdot(g->dpdv, vsub(p, cc))));
+    return 1;
+}
+
+/* Light::SamplePositionGivenPreviousPosition + EvaluatePositionGivenPreviousPositionPDF(evalDelta=false) from the
+ * vertex at `from`. Returns 0 when no position is produced (the reference's LM_UNREACHABLE branches).
+ * light::area: light_area.cpp:67-103, triangleutils.h:71-122; light::point: light_point.cpp:62-66,88-91;
+ * light::directional: light_directional.cpp:131-145,176-180; light::env: light_env.cpp:129-146,185-189. */
+static int light_sample(const orc_pt_scene* S, int li, v3 from, float u0, float u1, geom_t* g, float* pdfPL)
 {
     const orc_light* L = &S->d.lights[li];
     const orc_prim* P = &S->d.prims[L->primitive];
     const float* cdf = S->cdf[li];
-    if (L->kind == 1) {            /* light::point, light_point.cpp:62-66 */
+    if (L->kind == 1) {            /* light::point */
         memset(g, 0, sizeof(*g));
         g->degenerated = 1;
         g->p = ld3(L->position);
-        return;
+        *pdfPL = 1.0f;
+        return 1;
     }
+    if (L->kind == 2 || L->kind == 3) {
+        v3 d, w;
+        float d2, pdfSA = 1.0f;
+        if (L->kind == 2) d = vneg(ld3(L->direction));
+        else {                     /* Sampler::UniformSampleSphere, sampler.h:79-85 */
+            const float z = 1.0f - 2.0f * u0, r = sqrtf(fmaxf(0.0f, 1.0f - z * z)), phi = 2.0f * ORC_PI * u1;
+            d = V(r * cosf(phi), r * sinf(phi), z);
+            pdfSA = ORC_INV_PI * 0.25f;
+        }
+        if (!emitter_shape_hit(S, from, d, g)) return 0;
+        /* PDFVal(SolidAngle, pdfSA).ConvertToArea(geomPrev, geom), probability.h:59-71 */
+        w = vsub(g->p, from); d2 = vdot(w, w);
+        { const float dl = sqrtf(d2); w = V(w.x / dl, w.y / dl, w.z / dl); }
+        *pdfPL = pdfSA * fabsf(vdot(g->sn, vneg(w))) / d2;
+        return 1;
+    }
+    {
     const int n = (int)P->num_tris;
     int lo = 0, hi = n + 1, i;
     float u2x, s, bx, by;
@@ -339,6 +425,9 @@ static void light_sample(const orc_pt_scene* S, int li, float u0, float u1, geom
         g->gn = vnorm(vcross(vsub(p2, p1), vsub(p3, p1)));
         g->sn = g->gn;
         basis(g->sn, &g->dpdu, &g->dpdv);
+    }
+    *pdfPL = S->inv_area[li];                                    /* light_area.cpp:100-103 */
+    return 1;
     }
 }
 
@@ -387,11 +476,13 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
     geom_t geom;
     int is_sensor = 1, num_verts = 1;
     const orc_bsdf* bsdf = NULL;
+    float ul[4] = {0.5f, 0.5f, 0.0f, 0.0f};
     rng_block(seed, sample, 0u, u);
-    init_wo = camera_dir(S, u[1], u[2]);
+    if (S->d.camera.kind == 1) rng_block(seed, sample, 0xffffffffu, ul);   /* lens sample (the second Next2D of renderer_pt.cpp:86) */
     memset(&geom, 0, sizeof(geom));
-    geom.degenerated = 1; geom.p = ld3(S->d.camera.position);
-    if (mode != 1 && !raster_position(S, init_wo, &rx, &ry)) return;      /* renderer_pt.cpp:94-99, renderer_ptmis.cpp:100-105 */
+    geom.degenerated = 1;
+    init_wo = camera_sample(S, u[1], u[2], ul[0], ul[1], &geom.p);
+    if (mode != 1 && !raster_position(S, geom.p, init_wo, &rx, &ry)) return;      /* renderer_pt.cpp:94-99, renderer_ptmis.cpp:100-105 */
 
     for (;;) {
         float ua[4], ub[4];
@@ -409,12 +500,11 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
             float pdfL, pdfPL, G, d2, dl;
             if (li < 0) li = 0; if (li > nL - 1) li = nL - 1;                       /* scene3.cpp:508-513 */
             pdfL = 1.0f / (float)nL;                                                 /* scene3.cpp:526-530 */
-            light_sample(S, li, ua[1], ua[2], &gL);
-            pdfPL = S->inv_area[li];                                                 /* light_area.cpp:100-103 */
+            if (!light_sample(S, li, geom.p, ua[1], ua[2], &gL, &pdfPL)) goto nee_done;
             ppL = vnorm(vsub(gL.p, geom.p));
-            if (is_sensor) { const float im = importance(S, ppL); fsE = V(im, im, im); }
+            if (is_sensor) { const float im = importance(S, geom.p, ppL); fsE = V(im, im, im); }
             else fsE = bsdf_eval(bsdf, &geom, wi, ppL, 1);
-            if (S->d.lights[li].kind == 1) fsL = ld3(S->d.lights[li].Le);                      /* light_point.cpp:95-98 */
+            if (S->d.lights[li].kind != 0) fsL = ld3(S->d.lights[li].Le);   /* light_point.cpp:95-98, light_directional.cpp:182-185, light_env.cpp:191-208 (constant Le) */
             else fsL = to_local(&gL, vneg(ppL)).z <= 0.0f ? V(0, 0, 0) : ld3(S->d.lights[li].Le);   /* light_area.cpp:105-110 */
             d = vsub(gL.p, geom.p); d2 = vdot(d, d); dl = sqrtf(d2); d = V(d.x / dl, d.y / dl, d.z / dl);   /* renderutils.h:46-56 */
             G = 1.0f;
@@ -430,20 +520,21 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
                     C = vmul(C, 1.0f / pdfL / pdfPL);
                     if (mode == 3) {   /* MIS weight, renderer_ptmis.cpp:163-170 */
                         const float pdfDL = pdfPL / geometry_term(&geom, &gL) * pdfL;
-                        const float pdfB = is_sensor ? importance(S, ppL) : bsdf_pdf(bsdf, &geom, wi, ppL, 1);
+                        const float pdfB = is_sensor ? importance(S, geom.p, ppL) : bsdf_pdf(bsdf, &geom, wi, ppL, 1);
                         C = vmul(C, pdfDL / (pdfDL + pdfB));
                     }
-                    if (is_sensor) raster_position(S, ppL, &prx, &pry);              /* renderer_ptdirect.cpp:165-170 */
+                    if (is_sensor) raster_position(S, geom.p, ppL, &prx, &pry);      /* renderer_ptdirect.cpp:165-170 */
                     splat(S, film, prx, pry, C);
                 }
             }
         }
+nee_done:
 
         if (is_sensor) wo = init_wo;
         else { wo = V(0, 0, 0); bsdf_sample(bsdf, &geom, wi, ub[0], ub[1], ub[2], &wo); }
-        pdfD = is_sensor ? importance(S, wo) : bsdf_pdf(bsdf, &geom, wi, wo, 0);
-        if (mode == 1 && is_sensor) { if (!raster_position(S, wo, &rx, &ry)) break; }   /* renderer_ptdirect.cpp:200-208 */
-        if (is_sensor) { const float im = importance(S, wo); fs = V(im, im, im); }
+        pdfD = is_sensor ? importance(S, geom.p, wo) : bsdf_pdf(bsdf, &geom, wi, wo, 0);
+        if (mode == 1 && is_sensor) { if (!raster_position(S, geom.p, wo, &rx, &ry)) break; }   /* renderer_ptdirect.cpp:200-208 */
+        if (is_sensor) { const float im = importance(S, geom.p, wo); fs = V(im, im, im); }
         else fs = bsdf_eval(bsdf, &geom, wi, wo, 0);
         if (vblack(fs)) break;
         thr = vmulv(thr, V(fs.x / pdfD, fs.y / pdfD, fs.z / pdfD));
@@ -496,7 +587,7 @@ orc_pt_scene* orc_pt_scene_create(const orc_scene_desc* d)
     for (li = 0; li < d->num_lights; li++) {     /* TriangleUtils::CreateTriangleAreaDist, triangleutils.h:47-68 */
         const orc_prim* P = &d->prims[d->lights[li].primitive];
         float* cdf;
-        if (d->lights[li].kind == 1) { S->cdf[li] = NULL; S->inv_area[li] = 1.0f; continue; }   /* point: pdf 1 (light_point.cpp:88-91) */
+        if (d->lights[li].kind != 0) { S->cdf[li] = NULL; S->inv_area[li] = 1.0f; continue; }   /* only light::area samples a mesh */
         cdf = (float*)malloc(sizeof(float) * (P->num_tris + 1));
         float sum = 0.0f, inv;
         uint32_t i;
@@ -558,10 +649,11 @@ void orc_render_normal(const orc_pt_scene* S, float* film, int32_t* tri_out)
     for (y = 0; y < H; y++) {
         int x;
         for (x = 0; x < W; x++) {
-            const v3 wo = camera_dir(S, ((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+            v3 cp;   /* thin lens: the lens centre (u2 = (.5,.5)), i.e. the in-focus pinhole image */
+            const v3 wo = camera_sample(S, ((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H, 0.5f, 0.5f, &cp);
             float ray[8], tuv[3]; int32_t tri;
             float* f = film + 4 * ((size_t)y * W + x);
-            ray[0] = S->d.camera.position[0]; ray[1] = S->d.camera.position[1]; ray[2] = S->d.camera.position[2]; ray[3] = ORC_EPS_ISECT;
+            ray[0] = cp.x; ray[1] = cp.y; ray[2] = cp.z; ray[3] = ORC_EPS_ISECT;
             ray[4] = wo.x; ray[5] = wo.y; ray[6] = wo.z; ray[7] = FLT_MAX;
             orc_closest_one(S->accel, ray, 1, tuv, &tri);
             if (tri_out) tri_out[(size_t)y * W + x] = tri;

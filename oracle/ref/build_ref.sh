@@ -34,7 +34,10 @@ src/liblightmetrica/asset/bsdf/bsdf_refractall.cpp
 src/liblightmetrica/asset/bsdf/bsdf_flesnel.cpp
 src/liblightmetrica/asset/light/light_area.cpp
 src/liblightmetrica/asset/light/light_point.cpp
+src/liblightmetrica/asset/light/light_directional.cpp
+src/liblightmetrica/asset/light/light_env.cpp
 src/liblightmetrica/asset/sensor/sensor_pinhole.cpp
+src/liblightmetrica/asset/sensor/sensor_thinlens.cpp
 src/liblightmetrica/asset/trianglemesh/trianglemesh_raw.cpp
 src/liblightmetrica/random.cpp
 "

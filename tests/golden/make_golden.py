@@ -79,6 +79,29 @@ def config0_golden():
     np.savez_compressed(os.path.join(HERE, "config0_cornell512_blockmeans.npz"), spp=64, **out)
 
 
+OUTDOOR_CASES = [("directional", False, "ptdirect"), ("env", False, "ptdirect"), ("both", True, "ptdirect"),
+                 ("directional", True, "ptmis"), ("directional", True, "pt"), ("cornell", True, "pt")]
+
+
+def outdoor_golden():
+    """Reference images of the open scene lit by light::directional / light::env and seen through sensor::pinhole or
+    sensor::thinlens (scenedesc.outdoor_scene at 48x27), two dSFMT seeds each. renderer::pt sees nothing of a directional
+    light (delta direction, never hit): its golden image pins exactly that (all zero)."""
+    from lmb200py import scenedesc
+    spp = 8192
+    out = {}
+    for light, thin, name in OUTDOOR_CASES:
+        sc = scenedesc.outdoor_scene(48, 27, light, thin)
+        R = ob.RefScene(sc, "qbvh")
+        N = 48 * 27 * spp
+        key = f"{light}_{'thinlens' if thin else 'pinhole'}_{name}"
+        a, _ = R.render(name, N, seed=1, threads=8)
+        b, _ = R.render(name, N, seed=2, threads=8)
+        out[key + "_a"], out[key + "_b"] = a, b
+        print(key, "mean", a.mean(axis=(0, 1)), "two-seed relRMSE", float(np.sqrt(np.mean((a - b) ** 2)) / max(np.mean(a), 1e-30)))
+    np.savez_compressed(os.path.join(HERE, "pt_outdoor.npz"), spp=spp, **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["accel", "pt"]
     if "accel" in which:
@@ -87,3 +110,5 @@ if __name__ == "__main__":
         pt_golden()
     if "config0" in which:
         config0_golden()
+    if "outdoor" in which:
+        outdoor_golden()

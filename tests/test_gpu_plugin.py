@@ -157,3 +157,19 @@ def test_renderer_plugin_delta_bsdfs_and_point_light():
     floor = rel_rmse(ra, rb)
     assert rel_rmse(ours, ra) < 1.25 * floor, (rel_rmse(ours, ra), floor)
     assert np.allclose(ours.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.03)
+
+
+def test_renderer_plugin_thinlens_directional_env():
+    """sensor::thinlens + light::directional + light::env (constant) through the plugin against the reference's own
+    renderer::ptdirect on the same YAML; and the env light refused in mode pt (the reference crashes there)."""
+    sc = scenedesc.outdoor_scene(32, 18, "both", True)
+    N = 32 * 18 * 2048
+    R = ob.RefScene(sc, accel="qbvh")
+    ours, _ = R.render("lmb200pt", N, seed=1, extra={"mode": "ptdirect"}, in_tree=True)
+    ra, _ = R.render("ptdirect", N, seed=1, threads=os.cpu_count() or 1)
+    rb, _ = R.render("ptdirect", N, seed=2, threads=os.cpu_count() or 1)
+    floor = rel_rmse(ra, rb)
+    assert rel_rmse(ours, ra) < 1.25 * floor, (rel_rmse(ours, ra), floor)
+    assert np.allclose(ours.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.03)
+    refused, _ = R.render("lmb200pt", 1000, seed=1, extra={"mode": "pt"}, in_tree=True)
+    assert refused.max() == 0        # Render logs the error and returns without touching the film

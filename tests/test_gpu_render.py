@@ -206,3 +206,60 @@ def test_scene_sharing_a_prebuilt_accel():
     assert L.lmb200_registry_get(12345) == A.h
     L.lmb200_registry_put(12345, None)
     assert not L.lmb200_registry_get(12345)
+
+
+OUTDOOR_CASES = [("directional", False, capi.MODE_PTDIRECT, "ptdirect"), ("env", False, capi.MODE_PTDIRECT, "ptdirect"),
+                 ("both", True, capi.MODE_PTDIRECT, "ptdirect"), ("directional", True, capi.MODE_PTMIS, "ptmis"),
+                 ("directional", True, capi.MODE_PT, "pt"), ("cornell", True, capi.MODE_PT, "pt")]
+
+
+@pytest.mark.parametrize("light,thin,mode,name", OUTDOOR_CASES)
+def test_directional_env_thinlens_same_samples_as_oracle_and_reference_images(light, thin, mode, name):
+    """light::directional / light::env (bounding-sphere emitter shapes) and sensor::thinlens on the device:
+    (1) same seed => the oracle's image and ray counts; (2) converged => the reference's own image
+    (tests/golden/pt_outdoor.npz) within 1.25x its two-seed noise floor."""
+    sc = scenedesc.outdoor_scene(48, 27, light, thin)
+    S = capi.Scene(sc)
+    N = 48 * 27 * 32
+    port, counts = ob.PortPT(sc).render(mode, N, seed=7)
+    gpu, st = S.render(mode, N, seed=7, pool=1 << 14)
+    assert not np.isnan(gpu).any()
+    assert abs(st["extend_rays"] - counts[0]) <= max(4, 1e-4 * counts[0])
+    assert abs(st["shadow_rays"] - counts[1]) <= max(4, 1e-4 * counts[1])
+    gold = np.load(os.path.join(GOLD, "pt_outdoor.npz"))
+    key = f"{light}_{'thinlens' if thin else 'pinhole'}_{name}"
+    ra, rb = gold[key + "_a"], gold[key + "_b"]
+    if light == "directional" and name == "pt":
+        assert gpu.max() == 0 and ra.max() == 0 and st["shadow_rays"] == 0     # a delta-direction light is never hit
+        return
+    close = np.abs(gpu - port) <= 2e-3 + 1e-3 * np.abs(port)
+    assert close.all(axis=2).mean() >= 0.999
+    assert rel_rmse(gpu, port) < 1e-3, rel_rmse(gpu, port)
+    spp = int(gold["spp"])
+    img, _ = S.render(mode, 48 * 27 * spp, seed=11)
+    floor = rel_rmse(ra, rb)
+    assert rel_rmse(img, ra) < 1.25 * floor, (rel_rmse(img, ra), floor)
+    assert rel_rmse(img, rb) < 1.25 * floor, (rel_rmse(img, rb), floor)
+    ref_mean = 0.5 * (ra + rb).mean(axis=(0, 1))
+    assert np.allclose(img.mean(axis=(0, 1)), ref_mean, rtol=0.02 if mode == capi.MODE_PT else 0.006)
+
+
+def test_env_light_is_rejected_outside_ptdirect():
+    """renderer::pt / ptmis of the reference crash on light::env (null primitive on escape); we refuse instead."""
+    sc = scenedesc.outdoor_scene(16, 9, "env", False)
+    S = capi.Scene(sc)
+    for mode in (capi.MODE_PT, capi.MODE_PTMIS):
+        with pytest.raises(capi.LmbError, match="light::env"):
+            S.render(mode, 100)
+    img, _ = S.render(capi.MODE_PTDIRECT, 16 * 9 * 16)
+    assert img.mean() > 0
+
+
+def test_normal_renderer_thinlens_uses_lens_centre():
+    a = scenedesc.outdoor_scene(64, 36, "directional", False)
+    b = scenedesc.outdoor_scene(64, 36, "directional", True)
+    ga, _ = capi.Scene(a).render(capi.MODE_NORMAL, 0)
+    gb, _ = capi.Scene(b).render(capi.MODE_NORMAL, 0)
+    pb, _ = ob.PortPT(b).render_normal()
+    assert np.abs(gb - pb).max() <= 1e-6
+    assert (np.abs(ga - gb).max(axis=2) > 1e-3).mean() < 0.02      # same picture up to rounding at silhouettes

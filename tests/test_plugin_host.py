@@ -39,11 +39,26 @@ def test_no_gpu_fails_loudly():
         R.render("lmb200pt", 100)
 
 
+def _read_dump(path):
+    import ctypes as C
+    import numpy as np
+    with open(path, "rb") as f:
+        nt, npr, nb, nl, has_n = (int(x) for x in np.frombuffer(f.read(40), np.uint64))
+        cam = capi.Camera.from_buffer_copy(f.read(C.sizeof(capi.Camera)))
+        sphere = np.frombuffer(f.read(16), np.float32)
+        verts = np.frombuffer(f.read(36 * nt), np.float32).reshape(-1, 9)
+        tri_prim = np.frombuffer(f.read(4 * nt), np.uint32)
+        prims = (capi.Primitive * npr).from_buffer_copy(f.read(C.sizeof(capi.Primitive) * npr))
+        bsdfs = (capi.Bsdf * nb).from_buffer_copy(f.read(C.sizeof(capi.Bsdf) * nb))
+        lights = (capi.Light * nl).from_buffer_copy(f.read(C.sizeof(capi.Light) * nl))
+    return dict(nt=nt, npr=npr, nb=nb, nl=nl, has_n=has_n, cam=cam, sphere=sphere, verts=verts, tri_prim=tri_prim,
+                prims=prims, bsdfs=bsdfs, lights=lights)
+
+
 def test_renderer_plugin_scene_extraction(tmp_path, monkeypatch):
     """What renderer::lmb200pt reads through the reference's interfaces (Scene3::PrimitiveAt,
     TriangleMesh, BSDF::Reflectance/Glossiness, YAML eta/k, Light::Emittance, pinhole transform/fov)
     equals the scene that was described. Uses the plugin's LMB200_DUMP_SCENE aid, so no GPU is needed."""
-    import ctypes as C
     import numpy as np
     dump = str(tmp_path / "scene.bin")
     monkeypatch.setenv("LMB200_DUMP_SCENE", dump)
@@ -52,14 +67,8 @@ def test_renderer_plugin_scene_extraction(tmp_path, monkeypatch):
     R = ob.RefScene(sc, accel="qbvh")
     # Render returns void (renderer.h:81): without a device it logs the CUDA error and returns after the dump
     R.render("lmb200pt", 10, extra={"mode": "ptdirect"}, in_tree=True)
-    with open(dump, "rb") as f:
-        nt, npr, nb, nl, has_n = (int(x) for x in np.frombuffer(f.read(40), np.uint64))
-        cam = capi.Camera.from_buffer_copy(f.read(C.sizeof(capi.Camera)))
-        verts = np.frombuffer(f.read(36 * nt), np.float32).reshape(-1, 9)
-        tri_prim = np.frombuffer(f.read(4 * nt), np.uint32)
-        prims = (capi.Primitive * npr).from_buffer_copy(f.read(C.sizeof(capi.Primitive) * npr))
-        bsdfs = (capi.Bsdf * nb).from_buffer_copy(f.read(C.sizeof(capi.Bsdf) * nb))
-        lights = (capi.Light * nl).from_buffer_copy(f.read(C.sizeof(capi.Light) * nl))
+    D = _read_dump(dump)
+    nt, npr, nl, has_n, cam, verts, tri_prim, prims, bsdfs, lights = (D[k] for k in ("nt", "npr", "nl", "has_n", "cam", "verts", "tri_prim", "prims", "bsdfs", "lights"))
     d, keep = sc.flatten()
     assert (nt, npr, nl, has_n) == (d.num_tris, d.num_prims, d.num_lights, 0)
     assert np.array_equal(verts, keep["verts"]) and np.array_equal(tri_prim, keep["tri_prim"])
@@ -77,3 +86,31 @@ def test_renderer_plugin_scene_extraction(tmp_path, monkeypatch):
     for k in ("position", "vx", "vy", "vz"):
         assert np.allclose(list(getattr(cam, k)), list(getattr(d.camera, k)), atol=1e-3)
     assert abs(cam.fov - d.camera.fov) < 1e-6 and (cam.width, cam.height) == (32, 24)
+    assert cam.kind == capi.CAMERA_PINHOLE
+    # Scene3::GetSphereBound as restated by Scene.flatten()
+    assert np.allclose(D["sphere"][:3], list(d.sphere_center), atol=1e-5) and abs(D["sphere"][3] - d.sphere_radius) < 1e-4 * d.sphere_radius
+
+
+def test_renderer_plugin_extracts_thinlens_directional_env(tmp_path, monkeypatch):
+    """sensor::thinlens (lens radius / focal distance), light::directional (transformed, normalised direction) and light::env
+    (constant Le) as the plugin reads them through the reference's Sensor / Light interfaces and the YAML tree."""
+    import numpy as np
+    dump = str(tmp_path / "scene.bin")
+    monkeypatch.setenv("LMB200_DUMP_SCENE", dump)
+    load_plugins()
+    sc = scenedesc.outdoor_scene(32, 18, light="both", thinlens=True)
+    R = ob.RefScene(sc, accel="qbvh")
+    R.render("lmb200pt", 10, extra={"mode": "ptdirect"}, in_tree=True)
+    D = _read_dump(dump)
+    d, keep = sc.flatten()
+    cam, lights = D["cam"], D["lights"]
+    assert cam.kind == capi.CAMERA_THINLENS and cam.lens_radius == np.float32(0.25) and cam.focal_distance == np.float32(6.1)
+    assert D["nl"] == 2
+    kinds = {lights[i].kind: lights[i] for i in range(2)}
+    sun, sky = kinds[capi.LIGHT_DIRECTIONAL], kinds[capi.LIGHT_ENV]
+    want = [x for x in keep["ls"] if x.kind == capi.LIGHT_DIRECTIONAL][0]
+    assert np.allclose(list(sun.direction), list(want.direction), atol=1e-3)      # rsqrt-normalised in the reference
+    assert abs(np.linalg.norm(list(sun.direction)) - 1) < 1e-3
+    assert np.allclose(list(sun.Le), [3.0, 2.8, 2.5]) and np.allclose(list(sky.Le), [0.5, 0.6, 0.8])
+    assert sun.primitive == want.primitive
+    assert np.allclose(D["sphere"][:3], list(d.sphere_center), atol=1e-5) and abs(D["sphere"][3] - d.sphere_radius) < 1e-4 * d.sphere_radius
