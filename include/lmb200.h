@@ -136,7 +136,17 @@ typedef struct lmb200_bsdf {
     float k[3];
     float roughness;
     float eta1, eta2;   /* refract_all / flesnel: indices of refraction outside / inside (defaults 1, 2) */
+    int32_t texR;       /* diffuse / cook_torrance "TexR" (bsdf_diffuse.cpp:48-53,102, bsdf_cooktorrance.cpp:50-55):
+                           0 = use R, k > 0 = R is textures[k-1] evaluated at the hit's interpolated uv */
 } lmb200_bsdf;
+
+/* A texture as texture::bitmap holds it (texture_bitmap.cpp:140-160): width*height RGB texels, row-major; evaluated with
+ * x = clamp(int(fract(u)*width), 0, width-1), y likewise, texel y*width+x (:162-168). Other Texture implementations
+ * are baked into this form by the host (renderer::lmb200pt param texture_resolution). */
+typedef struct lmb200_texture {
+    int32_t width, height;
+    const float* rgb;   /* 3 floats / texel */
+} lmb200_texture;
 
 /* One entry per scene primitive that owns triangles (primitive.h:57-84). */
 typedef struct lmb200_primitive {
@@ -195,6 +205,10 @@ typedef struct lmb200_scene_desc {
     lmb200_camera camera;
     float sphere_center[3];    /* Scene3::GetSphereBound() (scene3.cpp:56-78): bounding sphere of all mesh vertices and the */
     float sphere_radius;       /* sensor position, radius grown by 1 %. Read by directional / env lights only. */
+    const float* uvs;          /* 6 floats / triangle: the three vertices' texture coordinates (TriangleMesh::Texcoords, */
+                               /* intersectionutils.h:107-115), or NULL when no BSDF is textured (uv = 0 for meshes without) */
+    uint32_t num_textures;
+    const lmb200_texture* textures;
 } lmb200_scene_desc;
 
 typedef struct lmb200_scene lmb200_scene;

@@ -53,6 +53,10 @@ struct DevScene {
     // Scene3::GetSphereBound (directional / env lights)
     float sph_c[3], sph_r;
     int has_env;
+    // TexR textures (texture_bitmap.cpp layout): all texels concatenated, tex_info[k] = (width, height, first texel, 0)
+    const float* uvs;          // 6 floats / tri or nullptr
+    const float* tex_rgb;
+    const int4* tex_info;
 };
 
 struct Pool {
@@ -327,7 +331,24 @@ __device__ __forceinline__ float bsdf_pdf(const lmb200_bsdf& B, const Geom& g, f
     }
     return 0.f;
 }
-__device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 wi, f3 wo, bool eval_delta)
+// R of bsdf::diffuse / bsdf::cook_torrance: the constant, or TexR evaluated at the interpolated texture coordinates
+// (intersectionutils.h:107-115; Texture_Bitmap::Evaluate, texture_bitmap.cpp:162-168; bsdf_diffuse.cpp:102)
+__device__ __forceinline__ f3 bsdf_R(const DevScene& S, const lmb200_bsdf& B, uint32_t tri, float b0, float b1)
+{
+    if (B.texR <= 0) return ld3(B.R);
+    float u = 0.f, v = 0.f;
+    if (S.uvs) {
+        const float* t = S.uvs + 6 * (size_t)tri;
+        u = t[0] * (1.0f - b0 - b1) + t[2] * b0 + t[4] * b1;
+        v = t[1] * (1.0f - b0 - b1) + t[3] * b0 + t[5] * b1;
+    }
+    const int4 ti = S.tex_info[B.texR - 1];
+    const int x = min(max((int)((u - floorf(u)) * (float)ti.x), 0), ti.x - 1);
+    const int y = min(max((int)((v - floorf(v)) * (float)ti.y), 0), ti.y - 1);
+    return ld3(S.tex_rgb + 3 * ((size_t)ti.z + (size_t)ti.x * (size_t)y + (size_t)x));
+}
+// Rr = bsdf_R(...) of the vertex (only diffuse / cook_torrance read it)
+__device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, f3 Rr, const Geom& g, f3 wi, f3 wo, bool eval_delta)
 {
     const f3 lwi = to_local(g, wi), lwo = to_local(g, wo);
     if (is_specular(B)) {
@@ -346,7 +367,7 @@ __device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 
         return ld3(B.R) * ((B.type == LMB200_BSDF_FLESNEL ? 1.0f - Fr : 1.0f) * snc(g, wi, wo) * eta * eta);
     }
     if (lwi.z <= 0.f || lwo.z <= 0.f) return F3(0, 0, 0);
-    if (B.type == LMB200_BSDF_DIFFUSE) return (ld3(B.R) * LMB_INV_PI) * snc(g, wi, wo);
+    if (B.type == LMB200_BSDF_DIFFUSE) return (Rr * LMB_INV_PI) * snc(g, wi, wo);
     if (B.type == LMB200_BSDF_COOKTORRANCE) {
         const f3 H = normalize(lwi + lwo);
         const float D = ggx_D(B.roughness, H);
@@ -365,7 +386,7 @@ __device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, const Geom& g, f3 
             F[i] = (rP + rS) * 0.5f;
         }
         const float s = D * G / (4.0f * lwi.z) / lwo.z * snc(g, wi, wo);
-        return F3(B.R[0] * F[0] * s, B.R[1] * F[1] * s, B.R[2] * F[2] * s);
+        return F3(Rr.x * F[0] * s, Rr.y * F[1] * s, Rr.z * F[2] * s);
     }
     return F3(0, 0, 0);
 }
@@ -611,7 +632,7 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
                 const float4 vw = P.vtx_wi[i];
                 tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
                 const lmb200_bsdf& B = S.bsdfs[S.prims[S.tri_prim[tri]].bsdf];
-                fsE = bsdf_eval(B, g, F3(vw.x, vw.y, vw.z), ppL, true);
+                fsE = bsdf_eval(B, bsdf_R(S, B, tri, vw.w, P.vtx_v[i]), g, F3(vw.x, vw.y, vw.z), ppL, true);
                 pdfB = cfg.mode == LMB200_MODE_PTMIS ? bsdf_pdf(B, g, F3(vw.x, vw.y, vw.z), ppL, true) : 0.f;
             }
             // light_point.cpp:95-98, light_directional.cpp:182-185, light_env.cpp:191-208 emit Le in every direction;
@@ -694,7 +715,7 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
                 const float4 ub = rng_block(cfg.seed, P.sample[i], (uint32_t)(2 * nv));
                 bsdf_sample(B, g, wi, ub.x, ub.y, ub.z, wo);
                 pdfD = bsdf_pdf(B, g, wi, wo, false);
-                fs = bsdf_eval(B, g, wi, wo, false);
+                fs = bsdf_eval(B, bsdf_R(S, B, tri, vw.w, P.vtx_v[i]), g, wi, wo, false);
                 sn_here = g.sn;
                 specular_here = is_specular(B);
             }
@@ -1036,6 +1057,27 @@ static lmb200_scene* scene_create(int device, const lmb200_scene_desc* d, int bu
     rc |= dev_upload(s, d->prims, d->num_prims, &D.prims);
     rc |= dev_upload(s, d->bsdfs, d->num_bsdfs, &D.bsdfs);
     rc |= dev_upload(s, d->lights, d->num_lights, &D.lights);
+    // TexR textures: concatenated texels + (width, height, first texel) per texture
+    D.uvs = nullptr; D.tex_rgb = nullptr; D.tex_info = nullptr;
+    {
+        bool textured = false;
+        for (uint32_t b = 0; b < d->num_bsdfs; b++) {
+            if (d->bsdfs[b].texR < 0 || (uint32_t)d->bsdfs[b].texR > d->num_textures) { set_error(LMB200_E_INVALID, "bsdf texR out of range"); delete s; return nullptr; }
+            textured = textured || d->bsdfs[b].texR > 0;
+        }
+        if (textured) {
+            std::vector<float> texels; std::vector<int4> info;
+            for (uint32_t t = 0; t < d->num_textures; t++) {
+                const lmb200_texture& T = d->textures[t];
+                if (T.width <= 0 || T.height <= 0 || !T.rgb) { set_error(LMB200_E_INVALID, "empty texture"); delete s; return nullptr; }
+                info.push_back(make_int4(T.width, T.height, (int)(texels.size() / 3), 0));
+                texels.insert(texels.end(), T.rgb, T.rgb + 3 * (size_t)T.width * (size_t)T.height);
+            }
+            rc |= dev_upload(s, texels.data(), texels.size(), &D.tex_rgb);
+            rc |= dev_upload(s, info.data(), info.size(), &D.tex_info);
+            if (d->uvs) rc |= dev_upload(s, d->uvs, 6 * d->num_tris, &D.uvs);
+        }
+    }
     // area CDFs exactly as TriangleUtils::CreateTriangleAreaDist + Distribution1D::Normalize
     // (triangleutils.h:47-68, dist.h:44-60); Length uses the _mm_dp_ps summation order
     std::vector<float> cdf; std::vector<uint32_t> off; std::vector<float> inv_area;

@@ -26,7 +26,11 @@ class AccelStats(C.Structure):
 
 class Bsdf(C.Structure):
     _fields_ = [("type", C.c_int32), ("R", C.c_float * 3), ("eta", C.c_float * 3), ("k", C.c_float * 3), ("roughness", C.c_float),
-                ("eta1", C.c_float), ("eta2", C.c_float)]
+                ("eta1", C.c_float), ("eta2", C.c_float), ("texR", C.c_int32)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("rgb", C.c_void_p)]
 
 
 class Primitive(C.Structure):
@@ -49,7 +53,8 @@ class SceneDesc(C.Structure):
                 ("num_prims", C.c_uint32), ("prims", C.POINTER(Primitive)),
                 ("num_bsdfs", C.c_uint32), ("bsdfs", C.POINTER(Bsdf)),
                 ("num_lights", C.c_uint32), ("lights", C.POINTER(Light)),
-                ("camera", Camera), ("sphere_center", C.c_float * 3), ("sphere_radius", C.c_float)]
+                ("camera", Camera), ("sphere_center", C.c_float * 3), ("sphere_radius", C.c_float),
+                ("uvs", C.c_void_p), ("num_textures", C.c_uint32), ("textures", C.POINTER(Texture))]
 
 
 class RenderParams(C.Structure):

@@ -22,14 +22,30 @@ class Scene:
         self.point_lights = {}   # name -> dict(Le, position)   (light::point)
         self.dir_lights = {}     # name -> dict(Le, direction)  (light::directional)
         self.env_lights = {}     # name -> Le                   (light::env, constant)
+        self.textures = {}       # name -> dict(scale, color1, color2)   (texture::checker, plugin/texture_checker)
+        self.tex_res = 256       # resolution textures are baked at for the POD scene (a multiple of every checker scale => exact)
         self.camera = None    # dict(eye, center, up, fov, w, h[, lens_radius, focal_distance])
 
     # ---- construction helpers ----
     def add_bsdf(self, name, type="diffuse", R=(0.8, 0.8, 0.8), roughness=0.1,
-                 eta=(0.14, 0.129, 0.1585), k=(4.58625, 3.348125, 2.329375), eta1=1.0, eta2=2.0):
-        """type: diffuse | cook_torrance | reflect_all | refract_all | flesnel"""
+                 eta=(0.14, 0.129, 0.1585), k=(4.58625, 3.348125, 2.329375), eta1=1.0, eta2=2.0, texR=None):
+        """type: diffuse | cook_torrance | reflect_all | refract_all | flesnel; texR = name of a texture replacing R
+        (diffuse / cook_torrance, bsdf_diffuse.cpp:48-53)"""
         self.bsdfs[name] = dict(type=type, R=tuple(R), roughness=float(roughness), eta=tuple(eta), k=tuple(k),
-                                eta1=float(eta1), eta2=float(eta2))
+                                eta1=float(eta1), eta2=float(eta2), texR=texR)
+
+    def add_texture(self, name, scale=8.0, color1=(1.0, 0.0, 0.0), color2=(1.0, 1.0, 1.0)):
+        """texture::checker (plugin/texture_checker/texture_checker.cpp:38-52)."""
+        self.textures[name] = dict(scale=float(scale), color1=tuple(color1), color2=tuple(color2))
+
+    def bake_texture(self, name):
+        """(res, res, 3) float32: the texture evaluated at texel centres, the form lmb200_texture carries."""
+        t = self.textures[name]
+        res = self.tex_res
+        c = ((np.arange(res, dtype=np.float32) + np.float32(0.5)) / np.float32(res)).astype(np.float32)
+        iu = (c * np.float32(t["scale"])).astype(np.int32)
+        even = ((iu[None, :] + iu[:, None]) % 2) == 0                      # [y, x]
+        return np.where(even[..., None], np.asarray(t["color1"], np.float32), np.asarray(t["color2"], np.float32)).astype(np.float32)
 
     def add_light(self, name, Le):
         self.lights[name] = tuple(Le)
@@ -49,18 +65,21 @@ class Scene:
         self.env_lights[name] = tuple(Le)
         self.nodes.append(dict(mesh=None, bsdf=None, light=name))
 
-    def add_mesh_tris(self, tris9, bsdf=None, light=None, normals=None):
-        """tris9: (n,9) world-space triangles, stored unshared (3 vertices per face)."""
+    def add_mesh_tris(self, tris9, bsdf=None, light=None, normals=None, uvs=None):
+        """tris9: (n,9) world-space triangles, stored unshared (3 vertices per face); uvs: (3n,2) texture coordinates."""
         tris9 = np.ascontiguousarray(tris9, np.float32).reshape(-1, 9)
         n = tris9.shape[0]
         m = dict(verts=tris9.reshape(-1, 3).copy(), faces=np.arange(3 * n, dtype=np.uint32).reshape(-1, 3),
-                 normals=None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3))
+                 normals=None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3),
+                 uvs=None if uvs is None else np.ascontiguousarray(uvs, np.float32).reshape(-1, 2))
         self.meshes.append(m)
         self.nodes.append(dict(mesh=len(self.meshes) - 1, bsdf=bsdf, light=light))
 
-    def add_quad(self, a, b, c, d, bsdf=None, light=None):
+    def add_quad(self, a, b, c, d, bsdf=None, light=None, uv=False):
+        """uv=True: texture coordinates (0,0),(1,0),(1,1),(0,1) at a,b,c,d."""
         a, b, c, d = (np.asarray(x, np.float32) for x in (a, b, c, d))
-        self.add_mesh_tris(np.stack([np.concatenate([a, b, c]), np.concatenate([a, c, d])]), bsdf, light)
+        uvs = np.array([[0, 0], [1, 0], [1, 1], [0, 0], [1, 1], [0, 1]], np.float32) if uv else None
+        self.add_mesh_tris(np.stack([np.concatenate([a, b, c]), np.concatenate([a, c, d])]), bsdf, light, uvs=uvs)
 
     def set_camera(self, eye, center, up, fov, w, h, lens_radius=None, focal_distance=1.0):
         """sensor::pinhole, or sensor::thinlens when lens_radius is given (sensor_thinlens.cpp:44-68)."""
@@ -74,8 +93,12 @@ class Scene:
         out = ["lightmetrica:", "  version: 1.1.0", "  assets:"]
         for i, h in enumerate(mesh_handles):
             out += [f"    mesh{i}:", "      interface: trianglemesh", "      type: mem", "      params:", f"        handle: {h}"]
+        for name, t in self.textures.items():
+            out += [f"    {name}:", "      interface: texture", "      type: checker", "      params:", f"        scale: {t['scale']!r}",
+                    f"        color1: {v3(t['color1'])}", f"        color2: {v3(t['color2'])}"]
         for name, b in self.bsdfs.items():
-            out += [f"    {name}:", "      interface: bsdf", f"      type: {b['type']}", "      params:", f"        R: {v3(b['R'])}"]
+            out += [f"    {name}:", "      interface: bsdf", f"      type: {b['type']}", "      params:",
+                    f"        TexR: {b['texR']}" if b.get("texR") else f"        R: {v3(b['R'])}"]
             if b["type"] == "cook_torrance":
                 out += [f"        eta: {v3(b['eta'])}", f"        k: {v3(b['k'])}", f"        roughness: {b['roughness']!r}"]
             if b["type"] in ("refract_all", "flesnel"):
@@ -118,6 +141,7 @@ class Scene:
     def flatten(self):
         """Returns (SceneDesc, keepalive) in the reference's primitive order: primitive 0 is the camera node."""
         bs_names = list(self.bsdfs.keys())
+        tex_names = list(self.textures.keys())
         bs = (capi.Bsdf * (len(bs_names) + 1))()
         for i, n in enumerate(bs_names):
             b = self.bsdfs[n]
@@ -128,13 +152,15 @@ class Scene:
             bs[i].eta = (C.c_float * 3)(*b["eta"])
             bs[i].k = (C.c_float * 3)(*b["k"])
             bs[i].roughness = b["roughness"]
+            bs[i].texR = (tex_names.index(b["texR"]) + 1) if b.get("texR") else 0
         null_idx = len(bs_names)          # nodes without a bsdf get bsdf::null (scene3.cpp:315-319)
         bs[null_idx].type = capi.BSDF_NULL
         prims = (capi.Primitive * (len(self.nodes) + 1))()
         prims[0].bsdf = null_idx
         prims[0].light = -1
-        lights, verts, norms, tri_prim = [], [], [], []
+        lights, verts, norms, tri_prim, uvs = [], [], [], [], []
         any_normals = any(nd["mesh"] is not None and self.meshes[nd["mesh"]]["normals"] is not None for nd in self.nodes)
+        any_uvs = bool(tex_names)
         first = 0
         first_prim_of_light = {}
         for pi, nd in enumerate(self.nodes, start=1):
@@ -159,6 +185,9 @@ class Scene:
             verts.append(t)
             if any_normals:
                 norms.append(m["normals"][m["faces"].reshape(-1)].reshape(-1, 9) if m["normals"] is not None else np.zeros_like(t))
+            if any_uvs:
+                mu = m.get("uvs")
+                uvs.append(mu[m["faces"].reshape(-1)].reshape(-1, 6) if mu is not None else np.zeros((t.shape[0], 6), np.float32))
             tri_prim.append(np.full(t.shape[0], pi, np.uint32))
             prims[pi].bsdf = bs_names.index(nd["bsdf"]) if nd["bsdf"] else null_idx
             prims[pi].light = -1
@@ -217,7 +246,16 @@ class Scene:
         d.num_lights = len(lights)
         d.lights = C.cast(ls, C.POINTER(capi.Light))
         d.camera = cam
-        keep = dict(verts=verts, norms=norms, tri_prim=tri_prim, prims=prims, bs=bs, ls=ls)
+        uvs = np.ascontiguousarray(np.concatenate(uvs), np.float32) if (any_uvs and uvs) else None
+        baked = [np.ascontiguousarray(self.bake_texture(n)) for n in tex_names]
+        tx = (capi.Texture * max(1, len(baked)))()
+        for i, b in enumerate(baked):
+            tx[i].height, tx[i].width = b.shape[0], b.shape[1]
+            tx[i].rgb = b.ctypes.data_as(C.c_void_p)
+        d.uvs = uvs.ctypes.data_as(C.c_void_p) if uvs is not None else None
+        d.num_textures = len(baked)
+        d.textures = C.cast(tx, C.POINTER(capi.Texture))
+        keep = dict(verts=verts, norms=norms, tri_prim=tri_prim, prims=prims, bs=bs, ls=ls, uvs=uvs, baked=baked, tx=tx)
         return d, keep
 
 
@@ -329,6 +367,8 @@ def outdoor_scene(w=64, h=36, light="directional", thinlens=False):
     (geom.infinite) and the lens sampling."""
     if light == "cornell":
         return cornell_box(w, h, glossy_block=True, thinlens=thinlens)
+    if light == "textured":
+        return textured_box(w, h)
     s = Scene()
     s.add_bsdf("ground", "diffuse", (0.6, 0.55, 0.5))
     s.add_bsdf("red", "diffuse", (0.7, 0.2, 0.2))
@@ -346,4 +386,26 @@ def outdoor_scene(w=64, h=36, light="directional", thinlens=False):
         s.set_camera((0.0, 2.0, 6.0), (0.0, 0.7, 0.0), (0, 1, 0), 35.0, w, h, lens_radius=0.25, focal_distance=6.1)
     else:
         s.set_camera((0.0, 2.0, 6.0), (0.0, 0.7, 0.0), (0, 1, 0), 35.0, w, h)
+    return s
+
+
+def textured_box(w=48, h=48):
+    """Cornell-style box whose floor and back wall carry checker textures (TexR on bsdf::diffuse and on
+    bsdf::cook_torrance); the checker scales divide Scene.tex_res, so the baked textures are exact."""
+    s = Scene()
+    s.add_texture("tiles", 8.0, (0.8, 0.2, 0.2), (0.9, 0.9, 0.9))
+    s.add_texture("stripes", 4.0, (0.2, 0.3, 0.8), (0.8, 0.8, 0.3))
+    s.add_bsdf("white", "diffuse", (0.75, 0.75, 0.75))
+    s.add_bsdf("floor", "diffuse", texR="tiles")
+    s.add_bsdf("back", "cook_torrance", roughness=0.3, texR="stripes")
+    s.add_bsdf("red", "diffuse", (0.75, 0.25, 0.25))
+    s.add_light("lamp", (17.0, 12.0, 4.0))
+    s.add_quad((-1, 0, -1), (-1, 0, 1), (1, 0, 1), (1, 0, -1), "floor", uv=True)
+    s.add_quad((-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1), "white")
+    s.add_quad((-1, 0, -1), (1, 0, -1), (1, 2, -1), (-1, 2, -1), "back", uv=True)
+    s.add_quad((-1, 0, -1), (-1, 2, -1), (-1, 2, 1), (-1, 0, 1), "red")
+    s.add_quad((1, 0, -1), (1, 0, 1), (1, 2, 1), (1, 2, -1), "white")
+    _box(s, (0.3, 0.3, 0.2), (0.3, 0.3, 0.3), -17.0, "floor")       # textured BSDF on a mesh without texcoords: uv = 0
+    s.add_quad((-0.25, 1.98, -0.25), (0.25, 1.98, -0.25), (0.25, 1.98, 0.25), (-0.25, 1.98, 0.25), "white", "lamp")
+    s.set_camera((0, 1, 4.2), (0, 1, 0), (0, 1, 0), 40.0, w, h)
     return s

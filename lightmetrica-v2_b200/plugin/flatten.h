@@ -13,12 +13,14 @@ namespace lmb200plugin {
 using namespace lightmetrica_v2;
 
 // prims (optional): one lmb200_primitive per scene primitive with first_tri/num_tris/has_normals filled.
+// uvs (optional): 6 floats per triangle, TriangleMesh::Texcoords of the three vertices (0 for meshes without).
 inline void FlattenTriangles(const Scene3* scene, std::vector<float>& verts, std::vector<float>* normals,
                              std::vector<uint32_t>& primOfTri, std::vector<uint32_t>& faceOfTri,
-                             std::vector<lmb200_primitive>* prims)
+                             std::vector<lmb200_primitive>* prims, std::vector<float>* uvs = nullptr)
 {
     verts.clear(); primOfTri.clear(); faceOfTri.clear();
     if (normals) normals->clear();
+    if (uvs) uvs->clear();
     const int np = scene->NumPrimitives();
     if (prims) prims->assign((size_t)np, lmb200_primitive{0, -1, 0u, 0u, 0});
     for (int i = 0; i < np; i++)
@@ -30,6 +32,7 @@ inline void FlattenTriangles(const Scene3* scene, std::vector<float>& verts, std
         const auto* ps = mesh->Positions();
         const auto* ns = mesh->Normals();
         const auto* faces = mesh->Faces();
+        const auto* tc = uvs ? mesh->Texcoords() : nullptr;
         const int nf = mesh->NumFaces();
         for (int j = 0; j < nf; j++)
         {
@@ -44,6 +47,12 @@ inline void FlattenTriangles(const Scene3* scene, std::vector<float>& verts, std
                     Vec3 n;
                     if (ns) n = prim->normalTransform * Vec3(ns[3 * idx[k]], ns[3 * idx[k] + 1], ns[3 * idx[k] + 2]);
                     normals->push_back(n.x); normals->push_back(n.y); normals->push_back(n.z);
+                }
+                if (uvs)
+                {
+                    // intersectionutils.h:107-115
+                    uvs->push_back(tc ? tc[2 * idx[k]] : 0.f);
+                    uvs->push_back(tc ? tc[2 * idx[k] + 1] : 0.f);
                 }
             }
             primOfTri.push_back((uint32_t)i);

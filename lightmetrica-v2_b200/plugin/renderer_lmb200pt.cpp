@@ -4,7 +4,8 @@
 // Selected from the scene YAML with
 //     renderer: {type: lmb200pt, params: {mode: ptdirect, num_samples: ..., max_num_vertices: -1,
 //                                         min_num_vertices: 0, num_gpus: 1, device: 0, pool_size: 0,
-//                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000, builder: host}}
+//                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000, builder: host,
+//                                         texture_resolution: 1024}}
 // It reads the scene through the reference's interfaces (Scene3::PrimitiveAt, TriangleMesh::*,
 // BSDF::Reflectance/Glossiness, Light::Emittance, Sensor::GetFilm/GetProjectionMatrix), flattens
 // it into the POD arrays of include/lmb200.h and calls liblmb200.so; the film comes back through
@@ -50,6 +51,7 @@ public:
             if (prop->Child("num_gpus")) numGpus_ = prop->ChildAs<int>("num_gpus", 1);
             if (prop->Child("device")) device_ = prop->ChildAs<int>("device", 0);
             if (prop->Child("pool_size")) poolSize_ = prop->ChildAs<int>("pool_size", 0);
+            if (prop->Child("texture_resolution")) textureResolution_ = prop->ChildAs<int>("texture_resolution", 1024);
             if (prop->Child("builder"))
             {
                 const auto b = prop->ChildAs<std::string>("builder", "host");
@@ -79,10 +81,12 @@ public:
         auto* film = static_cast<const Sensor*>(sensorPrim->emitter)->GetFilm();   // renderer_pt.cpp:67
 
         // ---- flatten geometry ----
-        std::vector<float> verts, normals;
+        std::vector<float> verts, normals, uvs;
         std::vector<uint32_t> primOfTri, faceOfTri;
         std::vector<lmb200_primitive> prims;
-        lmb200plugin::FlattenTriangles(scene, verts, &normals, primOfTri, faceOfTri, &prims);
+        lmb200plugin::FlattenTriangles(scene, verts, &normals, primOfTri, faceOfTri, &prims, &uvs);
+        curScene_ = scene;
+        textures_.clear(); textureData_.clear(); textureIndex_.clear();
         bool anyNormals = false;
         for (const auto& p : prims) anyNormals = anyNormals || p.has_normals;
 
@@ -244,6 +248,10 @@ public:
         d.bsdfs = bsdfs.data();
         d.num_lights = (uint32_t)lights.size();
         d.lights = lights.data();
+        for (size_t t = 0; t < textures_.size(); t++) textures_[t].rgb = textureData_[t].data();
+        d.num_textures = (uint32_t)textures_.size();
+        d.textures = textures_.empty() ? nullptr : textures_.data();
+        d.uvs = textures_.empty() ? nullptr : uvs.data();
 
         if (const char* dump = std::getenv("LMB200_DUMP_SCENE"))
         {
@@ -260,6 +268,15 @@ public:
                 fwrite(d.prims, sizeof(lmb200_primitive), d.num_prims, f);
                 fwrite(d.bsdfs, sizeof(lmb200_bsdf), d.num_bsdfs, f);
                 fwrite(d.lights, sizeof(lmb200_light), d.num_lights, f);
+                const uint64_t tail[2] = { d.num_textures, d.uvs ? 1u : 0u };
+                fwrite(tail, sizeof(tail), 1, f);
+                for (uint32_t t = 0; t < d.num_textures; t++)
+                {
+                    const int32_t wh[2] = { d.textures[t].width, d.textures[t].height };
+                    fwrite(wh, sizeof(wh), 1, f);
+                    fwrite(d.textures[t].rgb, sizeof(float), 3 * (size_t)wh[0] * wh[1], f);
+                }
+                if (d.uvs) fwrite(d.uvs, sizeof(float), 6 * d.num_tris, f);
                 fclose(f);
             }
         }
@@ -372,7 +389,7 @@ private:
         return a ? a->Child("params") : nullptr;
     }
 
-    auto ConvertBSDF(const BSDF* bsdf, lmb200_bsdf& b) const -> bool
+    auto ConvertBSDF(const BSDF* bsdf, lmb200_bsdf& b) -> bool
     {
         memset(&b, 0, sizeof(b));
         const std::string impl = bsdf->implName;
@@ -402,11 +419,42 @@ private:
         const auto* ap = AssetParams(bsdf);
         if (ap && ap->Child("TexR"))
         {
-            LM_LOG_ERROR("renderer::lmb200pt: textured reflectance (TexR) is not supported");
-            return false;
+            // bsdf_diffuse.cpp:48-53 / bsdf_cooktorrance.cpp:50-55: R comes from a texture asset. The Texture interface only
+            // has Evaluate(uv) (texture.h:55), so the texture is baked at texel centres of a texture_resolution^2 grid and looked
+            // up on the device the way texture::bitmap does (texture_bitmap.cpp:162-168): exact for bitmaps whose size
+            // divides the resolution, an approximation along the edges of procedural textures otherwise.
+            const auto id = ap->ChildAs<std::string>("TexR", "");
+            auto* assets = const_cast<Assets*>(curScene_->GetAssets());
+            const auto* tex = assets ? static_cast<const Texture*>(assets->AssetByIDAndType(id, "texture", nullptr)) : nullptr;
+            if (!tex)
+            {
+                LM_LOG_ERROR("renderer::lmb200pt: cannot resolve texture '" + id + "' of BSDF '" + bsdf->ID() + "'");
+                return false;
+            }
+            auto it = textureIndex_.find(tex);
+            if (it == textureIndex_.end())
+            {
+                const int res = textureResolution_ > 0 ? textureResolution_ : 1024;
+                std::vector<float> data((size_t)res * res * 3);
+                for (int y = 0; y < res; y++)
+                    for (int x = 0; x < res; x++)
+                    {
+                        const Vec3 c = tex->Evaluate(Vec2(((Float)x + 0.5_f) / (Float)res, ((Float)y + 0.5_f) / (Float)res));
+                        float* o = &data[3 * ((size_t)res * y + x)];
+                        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+                    }
+                lmb200_texture t; t.width = res; t.height = res; t.rgb = nullptr;   // rgb is bound after all textures are baked
+                textures_.push_back(t);
+                textureData_.push_back(std::move(data));
+                it = textureIndex_.emplace(tex, (int)textures_.size()).first;
+            }
+            b.texR = it->second;
         }
-        const auto R = bsdf->Reflectance().ToRGB();
-        b.R[0] = R.x; b.R[1] = R.y; b.R[2] = R.z;
+        else
+        {
+            const auto R = bsdf->Reflectance().ToRGB();
+            b.R[0] = R.x; b.R[1] = R.y; b.R[2] = R.z;
+        }
         if (impl == "BSDF_Diffuse") { b.type = LMB200_BSDF_DIFFUSE; return true; }
         b.type = LMB200_BSDF_COOKTORRANCE;
         b.roughness = bsdf->Glossiness();                           // bsdf_cooktorrance.cpp:157-162
@@ -438,6 +486,11 @@ private:
     int numGpus_ = 1;
     int device_ = 0;
     int poolSize_ = 0;
+    int textureResolution_ = 1024;
+    const Scene3* curScene_ = nullptr;                    // valid during Render
+    std::vector<lmb200_texture> textures_;                 // baked TexR textures of the scene being rendered
+    std::vector<std::vector<float>> textureData_;
+    std::map<const Texture*, int> textureIndex_;           // texture -> index + 1
     int builder_ = LMB200_BUILD_HOST_SAH;
     double renderTime_ = -1.0;
     double progressImageInterval_ = -1.0;

@@ -256,7 +256,10 @@ class RefScene:
             ps = np.ascontiguousarray(m["verts"], np.float32)
             fs = np.ascontiguousarray(m["faces"], np.uint32)
             ns = None if m["normals"] is None else np.ascontiguousarray(m["normals"], np.float32)
-            handles.append(L.ref_register_mesh(_p(ps), ps.shape[0], _p(ns) if ns is not None else None, None, _p(fs), fs.shape[0]))
+            ts = None if m.get("uvs") is None else np.ascontiguousarray(m["uvs"], np.float32)
+            self._keep.append((ps, fs, ns, ts))
+            handles.append(L.ref_register_mesh(_p(ps), ps.shape[0], _p(ns) if ns is not None else None,
+                                               _p(ts) if ts is not None else None, _p(fs), fs.shape[0]))
         self.scene = scene
         self.handles = handles
         self.accel = accel

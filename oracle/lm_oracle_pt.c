@@ -33,7 +33,8 @@ int orc_closest_one(const orc_scene* s, const float* ray, int use_bvh, float* tu
 int orc_any_one(const orc_scene* s, const float* ray);
 
 /* Same field layout as include/lmb200.h (restated here; the oracle does not include product headers). */
-typedef struct { int32_t type; float R[3], eta[3], k[3], roughness, eta1, eta2; } orc_bsdf;
+typedef struct { int32_t type; float R[3], eta[3], k[3], roughness, eta1, eta2; int32_t texR; } orc_bsdf;   /* texR: 0 none, k>0 = textures[k-1] */
+typedef struct { int32_t width, height; const float* rgb; } orc_texture;
 typedef struct { int32_t bsdf, light; uint32_t first_tri, num_tris; int32_t has_normals; } orc_prim;
 typedef struct { float Le[3]; int32_t primitive; int32_t kind; float position[3]; float direction[3]; } orc_light;   /* kind: 0 area, 1 point, 2 directional, 3 env */
 typedef struct { float position[3], vx[3], vy[3], vz[3], fov; int32_t width, height; int32_t kind; float lens_radius, focal_distance; } orc_camera;   /* kind: 0 pinhole, 1 thinlens */
@@ -44,6 +45,8 @@ typedef struct {
     uint32_t num_lights; const orc_light* lights;
     orc_camera camera;
     float sphere_center[3], sphere_radius;   /* Scene3::GetSphereBound (scene3.cpp:56-78), used by directional / env lights */
+    const float* uvs;                        /* 6 floats / triangle or NULL */
+    uint32_t num_textures; const orc_texture* textures;
 } orc_scene_desc;
 
 typedef struct {
@@ -93,7 +96,7 @@ static void rng_block(uint64_t seed, uint64_t sample, uint32_t block, float u[4]
 }
 
 /* ---- surface geometry (include/lightmetrica/intersectionutils.h:59-135, subset used by the estimators) ---- */
-typedef struct { v3 p, gn, sn, dpdu, dpdv; int degenerated; } geom_t;
+typedef struct { v3 p, gn, sn, dpdu, dpdv; int degenerated; float uvx, uvy; } geom_t;
 
 static void basis(v3 a, v3* b, v3* c)   /* Math::OrthonormalBasis, math.h:2355-2360 */
 {
@@ -117,7 +120,24 @@ static void tri_geom(const orc_pt_scene* S, uint32_t tri, float b0, float b1, v3
         if (isnan(g->sn.x) || isnan(g->sn.y) || isnan(g->sn.z)) g->sn = g->gn;
     } else g->sn = g->gn;
     basis(g->sn, &g->dpdu, &g->dpdv);
+    g->uvx = g->uvy = 0.0f;
+    if (S->d.uvs) {   /* intersectionutils.h:107-115 */
+        const float* t = S->d.uvs + 6 * (size_t)tri;
+        g->uvx = t[0] * (1.0f - b0 - b1) + t[2] * b0 + t[4] * b1;
+        g->uvy = t[1] * (1.0f - b0 - b1) + t[3] * b0 + t[5] * b1;
+    }
 }
+
+/* Texture_Bitmap::Evaluate (src/liblightmetrica/asset/texture/texture_bitmap.cpp:162-168) */
+static v3 tex_eval(const orc_texture* T, float u, float v)
+{
+    int x = (int)((u - floorf(u)) * (float)T->width), y = (int)((v - floorf(v)) * (float)T->height);
+    if (x < 0) x = 0; if (x > T->width - 1) x = T->width - 1;
+    if (y < 0) y = 0; if (y > T->height - 1) y = T->height - 1;
+    return ld3(T->rgb + 3 * ((size_t)T->width * y + x));
+}
+/* R of bsdf::diffuse / bsdf::cook_torrance: constant or TexR at geom.uv (bsdf_diffuse.cpp:102, bsdf_cooktorrance.cpp:118) */
+static v3 bsdf_R(const orc_pt_scene* S, const void* B_, const geom_t* g);
 
 /* ---- sensor::pinhole (src/liblightmetrica/asset/sensor/sensor_pinhole.cpp) and
  *      sensor::thinlens (src/liblightmetrica/asset/sensor/sensor_thinlens.cpp); p = the sensor vertex (lens point) ---- */
@@ -301,7 +321,13 @@ static float bsdf_pdf(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval
     }
     return 0.0f;
 }
-static v3 bsdf_eval(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval_delta)
+static v3 bsdf_R(const orc_pt_scene* S, const void* B_, const geom_t* g)
+{
+    const orc_bsdf* B = (const orc_bsdf*)B_;
+    if (B->texR > 0 && (uint32_t)B->texR <= S->d.num_textures) return tex_eval(&S->d.textures[B->texR - 1], g->uvx, g->uvy);
+    return ld3(B->R);
+}
+static v3 bsdf_eval(const orc_pt_scene* S, const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval_delta)
 {
     const v3 lwi = to_local(g, wi), lwo = to_local(g, wo);
     if (is_specular(B)) {
@@ -323,7 +349,7 @@ static v3 bsdf_eval(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval_d
     }
     if (lwi.z <= 0.0f || lwo.z <= 0.0f) return V(0, 0, 0);
     if (B->type == 1) {                    /* bsdf_diffuse.cpp:93-104 */
-        return vmul(vmul(ld3(B->R), ORC_INV_PI), snc(g, wi, wo));
+        return vmul(vmul(bsdf_R(S, B, g), ORC_INV_PI), snc(g, wi, wo));
     }
     if (B->type == 2) {                    /* bsdf_cooktorrance.cpp:105-120, 276-293 */
         const v3 H = vnorm(vadd(lwi, lwo));
@@ -343,7 +369,8 @@ static v3 bsdf_eval(const orc_bsdf* B, const geom_t* g, v3 wi, v3 wo, int eval_d
         }
         {
             const float s = D * G / (4.0f * lwi.z) / lwo.z * snc(g, wi, wo);
-            return V(B->R[0] * F[0] * s, B->R[1] * F[1] * s, B->R[2] * F[2] * s);
+            const v3 R = bsdf_R(S, B, g);
+            return V(R.x * F[0] * s, R.y * F[1] * s, R.z * F[2] * s);
         }
     }
     return V(0, 0, 0);
@@ -503,7 +530,7 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
             if (!light_sample(S, li, geom.p, ua[1], ua[2], &gL, &pdfPL)) goto nee_done;
             ppL = vnorm(vsub(gL.p, geom.p));
             if (is_sensor) { const float im = importance(S, geom.p, ppL); fsE = V(im, im, im); }
-            else fsE = bsdf_eval(bsdf, &geom, wi, ppL, 1);
+            else fsE = bsdf_eval(S, bsdf, &geom, wi, ppL, 1);
             if (S->d.lights[li].kind != 0) fsL = ld3(S->d.lights[li].Le);   /* light_point.cpp:95-98, light_directional.cpp:182-185, light_env.cpp:191-208 (constant Le) */
             else fsL = to_local(&gL, vneg(ppL)).z <= 0.0f ? V(0, 0, 0) : ld3(S->d.lights[li].Le);   /* light_area.cpp:105-110 */
             d = vsub(gL.p, geom.p); d2 = vdot(d, d); dl = sqrtf(d2); d = V(d.x / dl, d.y / dl, d.z / dl);   /* renderutils.h:46-56 */
@@ -535,7 +562,7 @@ nee_done:
         pdfD = is_sensor ? importance(S, geom.p, wo) : bsdf_pdf(bsdf, &geom, wi, wo, 0);
         if (mode == 1 && is_sensor) { if (!raster_position(S, geom.p, wo, &rx, &ry)) break; }   /* renderer_ptdirect.cpp:200-208 */
         if (is_sensor) { const float im = importance(S, geom.p, wo); fs = V(im, im, im); }
-        else fs = bsdf_eval(bsdf, &geom, wi, wo, 0);
+        else fs = bsdf_eval(S, bsdf, &geom, wi, wo, 0);
         if (vblack(fs)) break;
         thr = vmulv(thr, V(fs.x / pdfD, fs.y / pdfD, fs.z / pdfD));
 

@@ -40,6 +40,7 @@ src/liblightmetrica/asset/sensor/sensor_pinhole.cpp
 src/liblightmetrica/asset/sensor/sensor_thinlens.cpp
 src/liblightmetrica/asset/trianglemesh/trianglemesh_raw.cpp
 src/liblightmetrica/random.cpp
+plugin/texture_checker/texture_checker.cpp
 "
 OBJS=""
 pids=()
@@ -48,7 +49,9 @@ for s in $SRCS; do
   o="$BUILD/$n.o"
   OBJS="$OBJS $o"
   if [ ! -f "$o" ] || [ "$REF/$s" -nt "$o" ]; then
-    ( sed -E 's/^\s*#pragma (region|endregion).*$//' "$REF/$s" > "$BUILD/$n.cpp" && $CXX $CXXFLAGS -c "$BUILD/$n.cpp" -o "$o" ; rm -f "$BUILD/$n.cpp" ) &
+    # sources from the reference's plugin/ tree include <lightmetrica/lightmetrica.h> instead of the pch: give them the std headers
+    EXTRA=""; case "$s" in plugin/*) EXTRA="-include $HERE/shim/pch.h" ;; esac
+    ( sed -E 's/^\s*#pragma (region|endregion).*$//' "$REF/$s" > "$BUILD/$n.cpp" && $CXX $CXXFLAGS $EXTRA -c "$BUILD/$n.cpp" -o "$o" ; rm -f "$BUILD/$n.cpp" ) &
     pids+=($!)
   fi
 done

@@ -80,7 +80,8 @@ def config0_golden():
 
 
 OUTDOOR_CASES = [("directional", False, "ptdirect"), ("env", False, "ptdirect"), ("both", True, "ptdirect"),
-                 ("directional", True, "ptmis"), ("directional", True, "pt"), ("cornell", True, "pt")]
+                 ("directional", True, "ptmis"), ("directional", True, "pt"), ("cornell", True, "pt"),
+                 ("textured", False, "ptdirect")]
 
 
 def outdoor_golden():

@@ -173,3 +173,24 @@ def test_renderer_plugin_thinlens_directional_env():
     assert np.allclose(ours.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.03)
     refused, _ = R.render("lmb200pt", 1000, seed=1, extra={"mode": "pt"}, in_tree=True)
     assert refused.max() == 0        # Render logs the error and returns without touching the film
+
+
+def test_renderer_plugin_textured_bsdfs():
+    """TexR (texture::checker from the reference's plugin tree) on bsdf::diffuse and bsdf::cook_torrance through the
+    plugin — texture baked by the plugin via Texture::Evaluate, texcoords via TriangleMesh::Texcoords — against the
+    reference's renderer::ptdirect on the same YAML."""
+    sc = scenedesc.textured_box(32, 32)
+    N = 32 * 32 * 2048
+    R = ob.RefScene(sc, accel="qbvh")
+    ours, _ = R.render("lmb200pt", N, seed=1, extra={"mode": "ptdirect", "texture_resolution": 256}, in_tree=True)
+    ra, _ = R.render("ptdirect", N, seed=1, threads=os.cpu_count() or 1)
+    rb, _ = R.render("ptdirect", N, seed=2, threads=os.cpu_count() or 1)
+    # the glossy textured wall throws fireflies at this spp (one pixel can carry the whole RMSE): compare with the 1 % largest
+    # per-pixel errors trimmed on both sides of the inequality
+    def trimmed(a, b):
+        e = ((a - b) ** 2).sum(axis=2).ravel()
+        keep = np.sort(e)[: int(0.99 * e.size)]
+        return float(np.sqrt(keep.mean() / 3) / np.mean(b))
+    floor = trimmed(ra, rb)
+    assert trimmed(ours, ra) < 1.25 * floor, (trimmed(ours, ra), floor)
+    assert np.allclose(ours.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.03)

@@ -210,7 +210,8 @@ def test_scene_sharing_a_prebuilt_accel():
 
 OUTDOOR_CASES = [("directional", False, capi.MODE_PTDIRECT, "ptdirect"), ("env", False, capi.MODE_PTDIRECT, "ptdirect"),
                  ("both", True, capi.MODE_PTDIRECT, "ptdirect"), ("directional", True, capi.MODE_PTMIS, "ptmis"),
-                 ("directional", True, capi.MODE_PT, "pt"), ("cornell", True, capi.MODE_PT, "pt")]
+                 ("directional", True, capi.MODE_PT, "pt"), ("cornell", True, capi.MODE_PT, "pt"),
+                 ("textured", False, capi.MODE_PTDIRECT, "ptdirect")]
 
 
 @pytest.mark.parametrize("light,thin,mode,name", OUTDOOR_CASES)

@@ -107,7 +107,8 @@ def test_port_vs_reference_live_delta_bsdfs_and_point_light(mode, name):
 
 
 OUTDOOR_CASES = [("directional", False, 1, "ptdirect"), ("env", False, 1, "ptdirect"), ("both", True, 1, "ptdirect"),
-                 ("directional", True, 3, "ptmis"), ("directional", True, 0, "pt"), ("cornell", True, 0, "pt")]
+                 ("directional", True, 3, "ptmis"), ("directional", True, 0, "pt"), ("cornell", True, 0, "pt"),
+                 ("textured", False, 1, "ptdirect")]
 
 
 @pytest.mark.parametrize("light,thin,mode,name", OUTDOOR_CASES)

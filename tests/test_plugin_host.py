@@ -51,8 +51,14 @@ def _read_dump(path):
         prims = (capi.Primitive * npr).from_buffer_copy(f.read(C.sizeof(capi.Primitive) * npr))
         bsdfs = (capi.Bsdf * nb).from_buffer_copy(f.read(C.sizeof(capi.Bsdf) * nb))
         lights = (capi.Light * nl).from_buffer_copy(f.read(C.sizeof(capi.Light) * nl))
+        ntex, has_uv = (int(x) for x in np.frombuffer(f.read(16), np.uint64))
+        textures = []
+        for _ in range(ntex):
+            tw, th = (int(x) for x in np.frombuffer(f.read(8), np.int32))
+            textures.append(np.frombuffer(f.read(12 * tw * th), np.float32).reshape(th, tw, 3))
+        uvs = np.frombuffer(f.read(24 * nt), np.float32).reshape(-1, 6) if has_uv else None
     return dict(nt=nt, npr=npr, nb=nb, nl=nl, has_n=has_n, cam=cam, sphere=sphere, verts=verts, tri_prim=tri_prim,
-                prims=prims, bsdfs=bsdfs, lights=lights)
+                prims=prims, bsdfs=bsdfs, lights=lights, textures=textures, uvs=uvs)
 
 
 def test_renderer_plugin_scene_extraction(tmp_path, monkeypatch):
@@ -114,3 +120,26 @@ def test_renderer_plugin_extracts_thinlens_directional_env(tmp_path, monkeypatch
     assert np.allclose(list(sun.Le), [3.0, 2.8, 2.5]) and np.allclose(list(sky.Le), [0.5, 0.6, 0.8])
     assert sun.primitive == want.primitive
     assert np.allclose(D["sphere"][:3], list(d.sphere_center), atol=1e-5) and abs(D["sphere"][3] - d.sphere_radius) < 1e-4 * d.sphere_radius
+
+
+def test_renderer_plugin_bakes_textures(tmp_path, monkeypatch):
+    """TexR on bsdf::diffuse / bsdf::cook_torrance: the plugin resolves the texture asset through Scene::GetAssets, bakes
+    Texture::Evaluate at texel centres (texture_resolution) and flattens TriangleMesh::Texcoords per triangle."""
+    import numpy as np
+    dump = str(tmp_path / "scene.bin")
+    monkeypatch.setenv("LMB200_DUMP_SCENE", dump)
+    load_plugins()
+    sc = scenedesc.textured_box(16, 16)
+    R = ob.RefScene(sc, accel="qbvh")
+    R.render("lmb200pt", 10, extra={"mode": "ptdirect", "texture_resolution": sc.tex_res}, in_tree=True)
+    D = _read_dump(dump)
+    d, keep = sc.flatten()
+    assert len(D["textures"]) == 2 and D["uvs"] is not None
+    assert np.array_equal(D["uvs"], keep["uvs"])
+    got_tex = {D["bsdfs"][D["prims"][i].bsdf].texR for i in range(D["npr"])}
+    assert got_tex == {0, 1, 2}
+    for i in range(D["npr"]):
+        a, b = D["bsdfs"][D["prims"][i].bsdf], keep["bs"][keep["prims"][i].bsdf]
+        assert (a.texR > 0) == (b.texR > 0)
+        if a.texR > 0:
+            assert np.array_equal(D["textures"][a.texR - 1], keep["baked"][b.texR - 1])
