@@ -163,6 +163,15 @@ def run_reference(a):
             r = R.intersect(rays, threads=cores)
             return r["seconds"]
         sample = f"{n} rays per step, accel::qbvh via Accel3::Intersect (oracle/_ref), build {build_s:.0f} s not timed"
+        # the other CPU accels the north star names: nanort (vendored header, called as accel::nanort calls it; speed only,
+        # its wrapper is broken in the reference) and Embree 2.8.0 (un-vendored dependency, not installable offline)
+        try:
+            NR = ob.RefNanort(verts)
+            nr = NR.trace(scenes.random_rays(n, lo, hi, seed=7), threads=cores, want_hits=False)
+            others = {"nanort_mrays_s": n / nr["seconds"] / 1e6, "nanort_build_s": NR.build_seconds, "embree": "n/a (not installable offline)"}
+            del NR
+        except Exception as e:      # noqa: BLE001
+            others = {"nanort": f"failed: {e}"}
     else:
         P = ob.PortScene(verts)
         kind = "port"
@@ -172,6 +181,7 @@ def run_reference(a):
             t0 = time.perf_counter()
             P.closest(rays)
             return time.perf_counter() - t0
+        others = {}
         sample = f"{n} rays per step, oracle/lm_oracle.c (OpenMP); oracle/_ref not present"
     for k in range(a.warmup):
         step(k)
@@ -181,7 +191,7 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, **others),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

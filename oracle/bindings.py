@@ -63,6 +63,11 @@ def ref():
         L.ref_render.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.ref_film_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ref_num_primitives.argtypes = [C.c_void_p]
+        L.ref_nanort_create.restype = C.c_void_p
+        L.ref_nanort_create.argtypes = [C.c_void_p, C.c_ulonglong, C.POINTER(C.c_double)]
+        L.ref_nanort_destroy.argtypes = [C.c_void_p]
+        L.ref_nanort_trace.restype = C.c_double
+        L.ref_nanort_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p]
         _ref = L
     return _ref
 
@@ -186,6 +191,32 @@ class RefSoup:
         sec = C.c_double()
         ref().ref_intersect_batch(self.s, n, _p(rays), threads, _p(prim), _p(face), _p(tuv), _p(geom), C.byref(sec))
         return dict(prim=prim, face=face, tuv=tuv, geom=geom, seconds=sec.value)
+
+
+class RefNanort:
+    """nanort (the reference's vendored third-party tracer) called as accel::nanort calls it — a THROUGHPUT baseline only:
+    its triangle test is not TriAccel and the reference's own wrapper is broken (oracle/ref/nanort_bench.cpp)."""
+
+    def __init__(self, verts):
+        v = np.ascontiguousarray(verts, np.float32).reshape(-1, 9)
+        sec = C.c_double()
+        self.h = ref().ref_nanort_create(_p(v), v.shape[0], C.byref(sec))
+        if not self.h:
+            raise RuntimeError("nanort build failed")
+        self.build_seconds = sec.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref().ref_nanort_destroy(self.h)
+            self.h = None
+
+    def trace(self, rays, threads=1, want_hits=True):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        face = np.zeros(n, np.int32) if want_hits else None
+        t = np.zeros(n, np.float32) if want_hits else None
+        sec = ref().ref_nanort_trace(self.h, _p(rays), n, threads, _p(face) if want_hits else None, _p(t) if want_hits else None)
+        return dict(face=face, t=t, seconds=sec)
 
 
 def ref_triaccel_records(verts):

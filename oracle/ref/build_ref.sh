@@ -55,7 +55,7 @@ for s in $SRCS; do
     pids+=($!)
   fi
 done
-for s in runtime host_shims harness; do
+for s in runtime host_shims harness nanort_bench; do
   o="$BUILD/shim_$s.o"
   OBJS="$OBJS $o"
   if [ ! -f "$o" ] || [ "$HERE/$s.cpp" -nt "$o" ] || [ "$HERE/host_shims.h" -nt "$o" ]; then
