@@ -10,8 +10,8 @@ no data-path collective). One "step" = one pass of lmb200_trace_closest over the
   roofline  algorithmic bytes per ray (48 + nodes/ray*80 + tris/ray*48, counted by the instrumented
             kernel) * rays / kernel time, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the CPU oracle on a bounded ray sample of the same scene (rank 0, N=1 only)
-  path_tracing  secondary figure: wavefront ptdirect Msamples/s on the 1 M-triangle scene of
-                configs[2] at reduced spp (128 instead of 1024), sample range sharded over ranks
+  path_tracing  secondary figure: wavefront ptdirect Msamples/s on configs[2] at full size (1 M-triangle
+                scene, 1920x1080, 1024 spp = 2.1 G samples), sample range sharded over ranks
                 (strong scaling), films summed with one NCCL reduce
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref: accel::qbvh through the
@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=1_000_000, help="bounded CPU sample")
     ap.add_argument("--no-pt", action="store_true", help="skip the secondary path-tracing figure")
     ap.add_argument("--pt-tris", type=int, default=1_000_000)
-    ap.add_argument("--pt-spp", type=int, default=128)
+    ap.add_argument("--pt-spp", type=int, default=1024)
     ap.add_argument("--pt-pool", type=int, default=0, help="wavefront pool size (0 = library default)")
     return ap.parse_args()
 
@@ -316,7 +316,7 @@ def main():
         if world == 1:
             cpu = base
 
-    # ---- secondary: path-traced samples/s on the configs[2] scene (reduced spp), NCCL film reduce ----
+    # ---- secondary: path-traced samples/s on configs[2] (full size by default), NCCL film reduce ----
     pt = None
     if not a.no_pt:
         pt = bench_pt(a, torch, dist, capi, world, rank, local, dev)
@@ -342,7 +342,7 @@ def main():
 
 
 def bench_pt(a, torch, dist, capi, world, rank, local, dev):
-    """ptdirect on the 1M-triangle mesh scene (BASELINE configs[2] geometry/materials/lights) at pt_spp samples per pixel,
+    """ptdirect on the 1M-triangle mesh scene (BASELINE configs[2] geometry/materials/lights) at pt_spp samples per pixel (1024 = the config),
     sample range sharded contiguously over ranks, films summed with one NCCL reduce, then rescaled."""
     from lmb200py import scenedesc, distributed
     sc = scenedesc.config2_scene(a.pt_tris, 1920, 1080)

@@ -835,6 +835,9 @@ struct Scene {
     std::vector<void*> pool_allocs;
     void* h_pinned = nullptr;   // 8 x u64 readback
     int num_sms = 148;
+    // k_shadow runs on its own stream beside k_bsdf / k_extend of the same iteration (tail filling)
+    cudaStream_t shadow_stream = nullptr;
+    cudaEvent_t ev_nee = nullptr, ev_shadow = nullptr;
 
     ~Scene()
     {
@@ -843,6 +846,9 @@ struct Scene {
         for (void* p : allocs) cudaFree(p);
         if (d_counter) cudaFree(d_counter);
         if (h_pinned) cudaFreeHost(h_pinned);
+        if (shadow_stream) cudaStreamDestroy(shadow_stream);
+        if (ev_nee) cudaEventDestroy(ev_nee);
+        if (ev_shadow) cudaEventDestroy(ev_shadow);
     }
 };
 
@@ -953,6 +959,11 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     Pool& P = s->pool;
     if (!s->h_pinned && (e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
     volatile unsigned long long* hp = reinterpret_cast<volatile unsigned long long*>(s->h_pinned);
+    if (!s->shadow_stream) {
+        if ((e = cudaStreamCreateWithFlags(&s->shadow_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+        cudaEventCreateWithFlags(&s->ev_nee, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->ev_shadow, cudaEventDisableTiming);
+    }
 
     RenderCfg cfg;
     cfg.mode = p->mode; cfg.max_verts = p->max_num_vertices; cfg.min_verts = p->min_num_vertices;
@@ -973,11 +984,18 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
         cudaMemsetAsync(P.qcount, 0, 4 * sizeof(uint32_t), st);
         cudaMemsetAsync(s->d_counter, 0, 2 * sizeof(unsigned long long), st);
         k_logic<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg, film);
-        if (nee) k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
+        if (nee) {
+            // the shadow rays of this iteration are traced on a second stream while the main stream goes on with
+            // k_bsdf and k_extend: the two persistent traversal kernels fill each other's tails
+            k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
+            cudaEventRecord(s->ev_nee, st);
+            cudaStreamWaitEvent(s->shadow_stream, s->ev_nee, 0);
+            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(reinterpret_cast<const float4*>(s->accel->d_nodes), reinterpret_cast<const float4*>(s->accel->d_tris), P, s->d_counter + 1, film);
+            cudaEventRecord(s->ev_shadow, s->shadow_stream);
+        }
         k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
         k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel->d_nodes), reinterpret_cast<const float4*>(s->accel->d_tris), P, s->d_counter);
-        if (nee)
-            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel->d_nodes), reinterpret_cast<const float4*>(s->accel->d_tris), P, s->d_counter + 1, film);
+        if (nee) cudaStreamWaitEvent(st, s->ev_shadow, 0);
         k_stats<<<1, 1, 0, st>>>(P);
         g_launch_count += nee ? 6 : 4;
         cudaMemcpyAsync(s->h_pinned, P.qcount, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
