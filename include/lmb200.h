@@ -228,6 +228,14 @@ typedef struct lmb200_render_params {
     int32_t  min_num_vertices;   /* renderer_pt.cpp:60 */
     uint64_t seed;               /* counter-based RNG key; same seed => same image at any GPU count */
     int32_t  pool_size;          /* wavefront size in paths, 0 = default */
+    /* Optional tile partitioning (off = all zero). tile = raster sub-rectangle {x0, y0, x1, y1} in [0,1]^2: the camera
+     * samples of THIS call are drawn uniformly inside it (raster sample u -> x0 + u.x (x1-x0), y0 + u.y (y1-y0)) instead
+     * of over the whole image. Rendering tiles of area a_k with a_k * num_samples samples each gives the same expected
+     * image as whole-image sampling (stratified over tiles: a different sampling pattern, statistically identical);
+     * splats of camera-vertex light sampling still land anywhere, so films are summed as usual. */
+    float    tile[4];
+    int32_t  tile_partition;     /* lmb200_render_multi / _timed only: 1 = GPU g of n draws its raster positions in the
+                                    horizontal strip [g/n, (g+1)/n) of the image (default 0: every GPU samples the whole image) */
 } lmb200_render_params;
 
 typedef struct lmb200_render_stats {

@@ -88,6 +88,7 @@ struct RenderCfg {
     unsigned long long seed;
     unsigned long long sample_end;
     uint32_t pool;
+    float tile_x0, tile_y0, tile_sx, tile_sy;   // raster sample u -> (x0 + u.x sx, y0 + u.y sy); whole image = (0, 0, 1, 1)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg
                     // renderer::pt / ptmis compute the raster position up front and drop the sample if it fails (renderer_pt.cpp:94-99)
                     const float4 u = rng_block(cfg.seed, sidx, 0u);
                     float rx, ry;
-                    ok = raster_position(S, cp, camera_wo(S, u.y, u.z, cp), rx, ry);
+                    ok = raster_position(S, cp, camera_wo(S, cfg.tile_x0 + u.y * cfg.tile_sx, cfg.tile_y0 + u.z * cfg.tile_sy, cp), rx, ry);
                     if (ok) pixel = pixel_index(S, rx, ry);
                 }
                 if (ok && !(cfg.max_verts != -1 && 1 >= cfg.max_verts)) {
@@ -698,7 +699,7 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
             bool ok = true, specular_here = false;
             if (is_sensor) {
                 const float4 u = rng_block(cfg.seed, P.sample[i], 0u);
-                wo = camera_wo(S, u.y, u.z, p);
+                wo = camera_wo(S, cfg.tile_x0 + u.y * cfg.tile_sx, cfg.tile_y0 + u.z * cfg.tile_sy, p);
                 const float im = importance(S, p, wo);
                 pdfD = im; fs = F3(im, im, im);
                 if (cfg.mode == LMB200_MODE_PTDIRECT) {
@@ -968,6 +969,13 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     RenderCfg cfg;
     cfg.mode = p->mode; cfg.max_verts = p->max_num_vertices; cfg.min_verts = p->min_num_vertices;
     cfg.seed = p->seed; cfg.sample_end = (unsigned long long)p->sample_end; cfg.pool = pool;
+    cfg.tile_x0 = 0.f; cfg.tile_y0 = 0.f; cfg.tile_sx = 1.f; cfg.tile_sy = 1.f;
+    if (p->tile[0] != 0.f || p->tile[1] != 0.f || p->tile[2] != 0.f || p->tile[3] != 0.f) {
+        if (!(p->tile[0] >= 0.f && p->tile[1] >= 0.f && p->tile[2] <= 1.f && p->tile[3] <= 1.f && p->tile[2] > p->tile[0] && p->tile[3] > p->tile[1]))
+            return set_error(LMB200_E_INVALID, "tile must satisfy 0 <= x0 < x1 <= 1 and 0 <= y0 < y1 <= 1");
+        cfg.tile_x0 = p->tile[0]; cfg.tile_y0 = p->tile[1];
+        cfg.tile_sx = p->tile[2] - p->tile[0]; cfg.tile_sy = p->tile[3] - p->tile[1];
+    }
 
     cudaMemsetAsync(P.nverts, 0, sizeof(int) * pool, st);
     cudaMemsetAsync(P.traced, 0, pool, st);
@@ -1269,6 +1277,16 @@ struct Session {
             lmb200_render_params q = *p;
             q.sample_begin = begin + (end - begin) * g / n;
             q.sample_end = begin + (end - begin) * (g + 1) / n;
+            if (p->tile_partition && n > 1) {
+                // GPU g owns the horizontal strip [g/n, (g+1)/n) of the raster (of the caller's tile, if any): equal areas
+                // and equal sample counts, so the summed film has the expected value of whole-image sampling
+                const bool whole = p->tile[0] == 0.f && p->tile[1] == 0.f && p->tile[2] == 0.f && p->tile[3] == 0.f;
+                const float x0 = whole ? 0.f : p->tile[0], x1 = whole ? 1.f : p->tile[2];
+                const float y0 = whole ? 0.f : p->tile[1], y1 = whole ? 1.f : p->tile[3];
+                q.tile[0] = x0; q.tile[2] = x1;
+                q.tile[1] = y0 + (y1 - y0) * (float)g / (float)n;
+                q.tile[3] = g + 1 == n ? y1 : y0 + (y1 - y0) * (float)(g + 1) / (float)n;
+            }
             rcs[g] = render_dev(sc[g], &q, films[g], streams[g], &st[g]);
             if (rcs[g]) errs[g] = g_last_error;
         };

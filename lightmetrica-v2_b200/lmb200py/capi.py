@@ -59,7 +59,8 @@ class SceneDesc(C.Structure):
 
 class RenderParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("num_samples", C.c_int64), ("sample_begin", C.c_int64), ("sample_end", C.c_int64),
-                ("max_num_vertices", C.c_int32), ("min_num_vertices", C.c_int32), ("seed", C.c_uint64), ("pool_size", C.c_int32)]
+                ("max_num_vertices", C.c_int32), ("min_num_vertices", C.c_int32), ("seed", C.c_uint64), ("pool_size", C.c_int32),
+                ("tile", C.c_float * 4), ("tile_partition", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -220,8 +221,11 @@ class Scene:
         except Exception:
             pass
 
-    def params(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None, pool=0):
+    def params(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None, pool=0, tile=None, tile_partition=False):
         p = RenderParams()
+        if tile is not None:
+            p.tile = (C.c_float * 4)(*tile)
+        p.tile_partition = 1 if tile_partition else 0
         p.mode, p.num_samples, p.sample_begin = mode, num_samples, begin
         p.sample_end = num_samples if end is None else end
         p.max_num_vertices, p.min_num_vertices, p.seed, p.pool_size = max_verts, min_verts, seed, pool

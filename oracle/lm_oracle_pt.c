@@ -496,7 +496,7 @@ static float geometry_term(const geom_t* g1, const geom_t* g2)
  * (= numVertices at loop top) uses block 2it-1 = (light pick, light u0, light u1, RR) and block
  * 2it = (bsdf u0, bsdf u1, component, -). */
 static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed, uint64_t sample,
-                        float* film, int64_t* n_extend, int64_t* n_shadow)
+                        const float* tile, float* film, int64_t* n_extend, int64_t* n_shadow)
 {
     float u[4], rx = 0.0f, ry = 0.0f;
     v3 init_wo, thr = V(1, 1, 1), wi = V(0, 0, 0);
@@ -508,7 +508,8 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
     if (S->d.camera.kind == 1) rng_block(seed, sample, 0xffffffffu, ul);   /* lens sample (the second Next2D of renderer_pt.cpp:86) */
     memset(&geom, 0, sizeof(geom));
     geom.degenerated = 1;
-    init_wo = camera_sample(S, u[1], u[2], ul[0], ul[1], &geom.p);
+    /* optional tile partitioning: the raster sample is drawn inside tile = {x0, y0, x1, y1} (whole image: 0,0,1,1) */
+    init_wo = camera_sample(S, tile[0] + u[1] * (tile[2] - tile[0]), tile[1] + u[2] * (tile[3] - tile[1]), ul[0], ul[1], &geom.p);
     if (mode != 1 && !raster_position(S, geom.p, init_wo, &rx, &ry)) return;      /* renderer_pt.cpp:94-99, renderer_ptmis.cpp:100-105 */
 
     for (;;) {
@@ -647,8 +648,17 @@ void orc_pt_scene_destroy(orc_pt_scene* S)
 /* Renders global sample indices [begin,end) of a num_samples job into film (W*H*4 floats, zeroed by
  * the caller), UNSCALED; threads accumulate into private films that are summed at the end, as
  * Scheduler_::Process does (scheduler.cpp:157-164, 280-285). counts[0]=extend rays, [1]=shadow rays. */
+void orc_pt_render_tile(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
+                        int64_t begin, int64_t end, const float* tile, float* film, int64_t* counts);
 void orc_pt_render(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
                    int64_t begin, int64_t end, float* film, int64_t* counts)
+{
+    const float whole[4] = {0.0f, 0.0f, 1.0f, 1.0f};
+    orc_pt_render_tile(S, mode, max_verts, min_verts, seed, begin, end, whole, film, counts);
+}
+/* Same with the camera samples drawn inside the raster rectangle tile = {x0, y0, x1, y1} (include/lmb200.h, tile partitioning). */
+void orc_pt_render_tile(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
+                        int64_t begin, int64_t end, const float* tile, float* film, int64_t* counts)
 {
     const size_t npx = (size_t)S->d.camera.width * S->d.camera.height;
     int64_t ne = 0, ns = 0;
@@ -658,7 +668,7 @@ void orc_pt_render(const orc_pt_scene* S, int mode, int max_verts, int min_verts
         int64_t i;
         size_t k;
 #pragma omp for schedule(dynamic, 4096)
-        for (i = begin; i < end; i++) sample_path(S, mode, max_verts, min_verts, seed, (uint64_t)i, local, &ne, &ns);
+        for (i = begin; i < end; i++) sample_path(S, mode, max_verts, min_verts, seed, (uint64_t)i, tile, local, &ne, &ns);
 #pragma omp critical
         for (k = 0; k < npx * 4; k++) film[k] += local[k];
         free(local);

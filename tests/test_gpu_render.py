@@ -264,3 +264,54 @@ def test_normal_renderer_thinlens_uses_lens_centre():
     pb, _ = ob.PortPT(b).render_normal()
     assert np.abs(gb - pb).max() <= 1e-6
     assert (np.abs(ga - gb).max(axis=2) > 1e-3).mean() < 0.02      # same picture up to rounding at silhouettes
+
+
+def test_tile_partitioning_matches_oracle_and_whole_image_sampling():
+    """Optional tile partitioning (include/lmb200.h lmb200_render_params::tile): camera samples drawn inside a raster
+    rectangle. Same samples as the oracle per tile; the whole tile is the same sample set as no tile; strips with
+    their share of the samples sum to the whole-image estimate within Monte-Carlo noise (diffuse box: no fireflies)."""
+    sc = scenedesc.cornell_box(48, 48)
+    S = capi.Scene(sc)
+    P = ob.PortPT(sc)
+    N = 48 * 48 * 128
+    full, _ = S.render(capi.MODE_PTDIRECT, N, seed=3)
+    same, _ = S.render(capi.MODE_PTDIRECT, N, seed=3, tile=(0, 0, 1, 1))
+    assert np.allclose(full, same, rtol=2e-4, atol=1e-5)
+    parts = []
+    for k in range(4):
+        t = (0.0, k / 4, 1.0, (k + 1) / 4)
+        g, st = S.render(capi.MODE_PTDIRECT, N, seed=3, begin=N * k // 4, end=N * (k + 1) // 4, tile=t)
+        p, counts = P.render(capi.MODE_PTDIRECT, N, seed=3, begin=N * k // 4, end=N * (k + 1) // 4, tile=t)
+        assert abs(st["extend_rays"] - counts[0]) <= 4 and abs(st["shadow_rays"] - counts[1]) <= 4
+        assert rel_rmse(g, p) < 1e-3
+        parts.append(g)
+    other, _ = S.render(capi.MODE_PTDIRECT, N, seed=4)
+    floor = rel_rmse(full, other)
+    assert rel_rmse(sum(parts), full) < 1.25 * floor
+    assert np.allclose(sum(parts).mean(axis=(0, 1)), full.mean(axis=(0, 1)), rtol=0.02)
+    # pt has no camera-vertex light splats: a strip's film is empty outside the strip
+    top, _ = S.render(capi.MODE_PT, N, seed=3, begin=0, end=N // 4, tile=(0, 0, 1, 0.25))
+    assert top[12:].max() == 0 and top[:12].max() > 0
+    with pytest.raises(capi.LmbError, match="tile"):
+        S.render(capi.MODE_PT, N, tile=(0.5, 0, 0.25, 1))
+
+
+def test_render_multi_tile_partitioning():
+    """lmb200_render_multi with tile_partition = 1: GPU g samples strip g; the summed film matches whole-image sampling
+    statistically."""
+    L = capi.lib()
+    if L.lmb200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = scenedesc.cornell_box(48, 48, glossy_block=True)
+    N = 48 * 48 * 256
+    scenes_ = [capi.Scene(sc, device=g) for g in range(2)]
+    one, _ = scenes_[0].render(capi.MODE_PTDIRECT, N, seed=3)
+    two, _ = scenes_[0].render(capi.MODE_PTDIRECT, N, seed=4)
+    arr = (C.c_void_p * 2)(*[s.h_ for s in scenes_])
+    p = scenes_[0].params(capi.MODE_PTDIRECT, N, seed=3, tile_partition=True)
+    film = np.zeros((48, 48, 4), np.float32)
+    st = capi.RenderStats()
+    capi.check(L.lmb200_render_multi(arr, 2, C.byref(p), film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    assert st.samples == N
+    assert rel_rmse(film[..., :3], one) < 1.25 * rel_rmse(two, one)
+    assert np.allclose(film[..., :3].mean(axis=(0, 1)), one.mean(axis=(0, 1)), rtol=0.02)

@@ -142,3 +142,23 @@ def test_thinlens_blurs_out_of_focus_only():
     ib, _ = ob.PortPT(b).render(1, N, seed=2)
     assert np.allclose(ia.mean(), ib.mean(), rtol=0.03)
     assert rel_rmse(ia, ib) > 0.05
+
+
+def test_tile_partitioning_port_is_statistically_the_whole_image():
+    """Optional tile partitioning: camera samples of shard k drawn inside strip k of the raster. The whole
+    tile (0,0,1,1) is the same sample set as no tile; four strips with a quarter of the samples each sum to an image with the
+    same expectation as whole-image sampling (ptdirect's camera-vertex light splats still land anywhere)."""
+    sc = scenedesc.cornell_box(32, 32)
+    P = ob.PortPT(sc)
+    N = 32 * 32 * 256
+    full, _ = P.render(1, N, seed=3)
+    same, _ = P.render(1, N, seed=3, tile=(0, 0, 1, 1))
+    assert np.allclose(full, same, rtol=1e-5, atol=1e-6)      # same paths; thread-private films are summed in arbitrary order
+    strips = sum(P.render(1, N, seed=3, begin=N * k // 4, end=N * (k + 1) // 4, tile=(0, k / 4, 1, (k + 1) / 4))[0] for k in range(4))
+    other, _ = P.render(1, N, seed=4)
+    floor = rel_rmse(full, other)
+    assert rel_rmse(strips, full) < 1.25 * floor
+    assert np.allclose(strips.mean(axis=(0, 1)), full.mean(axis=(0, 1)), rtol=0.02)
+    # a strip's own camera rays stay inside it: with pt (no light sampling from the camera vertex) nothing lands outside
+    top, _ = P.render(0, N, seed=3, begin=0, end=N // 4, tile=(0, 0, 1, 0.25))
+    assert top[8:].max() == 0 and top[:8].max() > 0
