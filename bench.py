@@ -287,11 +287,7 @@ def main():
     b_ray = 48.0 + npr.value * 80.0 + tpr.value * 48.0
     mean_kernel_s = float(np.mean(kernel_ms)) * 1e-3
     achieved = b_ray * a.rays / mean_kernel_s / 1e9
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+    peak, peak_src = hbm_peak()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -341,12 +337,55 @@ def main():
         dist.destroy_process_group()
 
 
+def hbm_peak():
+    """(GB/s, source): the measured HBM copy bandwidth of this pool's B200s if the driver wrote it, else the recipe's fallback."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def incoherent_on_scene(a, torch, dist, capi, S, verts, world, dev, stream):
+    """The north star's target figure: incoherent closest-hit Mrays/s per GPU on the 1M-triangle (mesh) scene — 16 Mi random
+    rays (origins uniform in the scene AABB, directions uniform on the sphere) against the BVH the path tracer just used."""
+    from lmb200py import scenes
+    L = capi.lib()
+    acc = L.lmb200_scene_accel(S.h_)
+    lo, hi = scenes.bounds(verts)
+    n = 1 << 24
+    rays = gen_rays_device(torch, n, [float(x) for x in lo], [float(x) for x in hi], 7, dev)
+    hits = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        capi.check(L.lmb200_trace_closest_dev(acc, rays.data_ptr(), hits.data_ptr(), n, stream))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        capi.check(L.lmb200_trace_closest_dev(acc, rays.data_ptr(), hits.data_ptr(), n, stream))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    npr, tpr = C.c_double(), C.c_double()
+    capi.check(L.lmb200_trace_count_dev(acc, rays.data_ptr(), 1 << 22, C.byref(npr), C.byref(tpr)))
+    bpr = 48 + 80 * npr.value + 48 * tpr.value
+    rate = n / (float(ms.item()) * 1e-3)
+    peak = hbm_peak()[0]
+    return {"value": world * rate / 1e6, "unit": "Mrays/s", "per_gpu": rate / 1e6, "rays_per_gpu": n, "triangles": int(len(verts)),
+            "nodes_per_ray": npr.value, "tris_per_ray": tpr.value, "bytes_per_ray": bpr,
+            "roofline_frac": rate * bpr / 1e9 / peak, "hit_fraction": float((hits[:, 3].view(torch.int32) != -1).float().mean().item()),
+            "target": ">= 1000 Mrays/s per GPU"}
+
+
 def bench_pt(a, torch, dist, capi, world, rank, local, dev):
     """ptdirect on the 1M-triangle mesh scene (BASELINE configs[2] geometry/materials/lights) at pt_spp samples per pixel (1024 = the config),
     sample range sharded contiguously over ranks, films summed with one NCCL reduce, then rescaled."""
     from lmb200py import scenedesc, distributed
     sc = scenedesc.config2_scene(a.pt_tris, 1920, 1080)
     S = capi.Scene(sc, device=local)
+    _k = S.keep
     W, H = 1920, 1080
     N = W * H * a.pt_spp
     film = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
@@ -377,8 +416,10 @@ def bench_pt(a, torch, dist, capi, world, rank, local, dev):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    target = incoherent_on_scene(a, torch, dist, capi, S, _k["verts"], world, dev, stream)
     S.close()
-    return {"metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene", "value": N / (float(ms.item()) * 1e-3) / 1e6,
+    return {"incoherent_1m_tri_mesh": target,
+            "metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene", "value": N / (float(ms.item()) * 1e-3) / 1e6,
             "unit": "Msamples/s", "spp": a.pt_spp, "samples": N, "ms": float(ms.item()), "rays_per_sample": float(rays.item()) / N,
             "mrays_per_s": float(rays.item()) / (float(ms.item()) * 1e-3) / 1e6, "film_reduce": "torch.distributed NCCL reduce" if world > 1 else "none (1 GPU)", "scaling": "strong (fixed image and spp, sample range sharded over ranks)",
             "mean_rgb": [float(x) for x in film[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None}
