@@ -193,12 +193,26 @@ def run_reference(a):
             "data": "synthetic", "config": cfg,
             "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, **others),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's ORIGINAL stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
-    # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO level
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    # stdout carries exactly one JSON line: keep the real stdout aside and point fd 1 at stderr, so that whatever
+    # libraries write to stdout (NCCL prints its version banner there) cannot end up next to it
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
@@ -331,7 +345,7 @@ def main():
                 "cpu_baseline": cpu, "parity": parity,
                 "bvh": {"nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
                 "path_tracing": pt}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
