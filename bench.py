@@ -228,6 +228,8 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device: lmb200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = capi.lib()
@@ -314,6 +316,7 @@ def main():
     cpu = None
     parity = None
     if rank == 0:
+        os.sched_setaffinity(0, all_cpus)      # the CPU baseline gets every host core (its OpenMP team starts here)
         n_chk = min(a.cpu_rays, a.rays) if world == 1 else min(100_000, a.rays)
         step_dev()
         torch.cuda.synchronize()
@@ -337,7 +340,7 @@ def main():
                 "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(a),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.rays * 32, "d2h_bytes_per_step": a.rays * 16,
-                        "api": "lmb200_trace_closest(host pinned rays -> host pinned hits)"},
+                        "api": "lmb200_trace_closest(host pinned rays -> host pinned hits)", "host_affinity": numa},
                 "gpu_launches": launches, "clocks": clock_info,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": npr.value, "tris_per_ray": tpr.value,
@@ -349,6 +352,26 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(torch, index):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs local to its GPU's PCIe root: with 8 ranks on a
+    two-socket box the host side of the e2e copies otherwise crosses the socket interconnect. Best effort; returns a note."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (no local CPUs in the allowed set)"
+        os.sched_setaffinity(0, cpus)
+        return f"cpus {txt} (local to GPU {bdf})"
+    except Exception as e:      # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
 
 
 def hbm_peak():
