@@ -23,7 +23,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "smsp__cycles_active.avg"]
 
 
-def launches(fname="launches.csv", suffix="launches", cmd="python bench.py --rays 16777216 --steps 2 --warmup 3 --cpu-rays 100000"):
+def launches(fname="launches.csv", suffix="launches", cmd="python bench.py --rays 16777216 --steps 2 --warmup 3 --cpu-rays 100000 --pt-spp 32"):
     p = os.path.join(G, fname)
     if not os.path.exists(p):
         return
