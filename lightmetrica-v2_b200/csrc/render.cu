@@ -104,8 +104,19 @@ __device__ __forceinline__ f3 operator*(f3 a, f3 b) { return F3(a.x * b.x, a.y *
 __device__ __forceinline__ f3 neg(f3 a) { return F3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ f3 cross(f3 a, f3 b) { return F3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-__device__ __forceinline__ f3 normalize(f3 a) { const float l = sqrtf(dot(a, a)); return F3(a.x / l, a.y / l, a.z / l); }
+// v * (1 / |v|): one IEEE square root, one IEEE division, three multiplications — the same sequence as the oracle's vnorm, so
+// both sides produce identical bits (the reference itself normalises with the 12-bit SSE rsqrt, math.h:1872-1875)
+__device__ __forceinline__ f3 normalize(f3 a) { const float inv = 1.0f / sqrtf(dot(a, a)); return F3(a.x * inv, a.y * inv, a.z * inv); }
 __device__ __forceinline__ bool black(f3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+
+// Radiometric scalars (BSDF values, pdfs, geometry terms, MIS weights, throughput) use the hardware reciprocal / square root
+// (2 ulp) instead of the IEEE sequences: they scale pixel values by 1 +- 2^-22 and never touch ray geometry. Everything that
+// decides WHERE a path goes — camera rays, surface frames, sampled directions, light points, shadow rays, raster positions,
+// the Fresnel coin of bsdf::flesnel — stays on the correctly rounded operations, so the device takes the same paths as the
+// oracle, sample for sample (tests/test_gpu_render.py::test_same_samples_as_oracle).
+__device__ __forceinline__ float qdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float qsqrt(float a) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ f3 qnormalize(f3 a) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(dot(a, a))); return a * r; }
 
 // Philox4x32-10, counter (sample_lo, sample_hi, block, 0), key (seed_lo, seed_hi) -> 4 uniforms in [0,1)
 __device__ __forceinline__ float4 rng_block(unsigned long long seed, unsigned long long sample, uint32_t block)
@@ -188,9 +199,9 @@ __device__ __forceinline__ float importance(const DevScene& S, f3 p, f3 wo)
     f3 e;
     float rx, ry;
     if (!sensor_eye(S, p, wo, e) || !raster_from_eye(S, e, rx, ry)) return 0.f;
-    const float cosT = -e.z, inv = 1.0f / cosT;
+    const float cosT = -e.z, inv = qdiv(1.0f, cosT);
     const float A = S.tan_fov * S.tan_fov * S.aspect * 4.0f;
-    return inv * inv * inv / A;
+    return qdiv(inv * inv * inv, A);
 }
 __device__ __forceinline__ f3 camera_dir(const DevScene& S, float u0, float u1)
 {
@@ -245,27 +256,31 @@ __device__ __forceinline__ void concentric_disk(float u0, float u1, float& sx, f
         if (vx < vy) { r = -vx; theta = (LMB_PI * 0.25f) * (4.0f + vy / vx); }
         else { r = -vy; theta = (LMB_PI * 0.25f) * (6.0f - vx / vy); }
     }
-    sx = r * cosf(theta); sy = r * sinf(theta);
+    float sn_, cs_;
+    sincosf(theta, &sn_, &cs_);      // same values as sinf / cosf, one argument reduction
+    sx = r * cs_; sy = r * sn_;
 }
 __device__ __forceinline__ float ggx_D(float alpha, f3 H)
 {
     const float cosH = H.z;
     if (cosH <= 0.f) return 0.f;
     const float s2 = 1.0f - cosH * cosH;
-    const float tanH = s2 <= 0.f ? 0.f : sqrtf(s2) / cosH;
+    const float tanH = s2 <= 0.f ? 0.f : qdiv(qsqrt(s2), cosH);
     const float t1 = alpha * alpha;
     const float t = alpha * alpha + tanH * tanH;
-    return t1 / (LMB_PI * cosH * cosH * cosH * cosH * t * t);
+    return qdiv(t1, LMB_PI * cosH * cosH * cosH * cosH * t * t);
 }
-// Fresnel term of bsdf::flesnel (bsdf_flesnel.cpp:224-240)
+// Fresnel term of bsdf::flesnel (bsdf_flesnel.cpp:224-240). EXACT = correctly rounded (the reflect / refract coin of the sampler),
+// otherwise radiometric (pdf and value).
+template <bool EXACT>
 __device__ __forceinline__ float fresnel_term(f3 lwi, float etaI, float etaT)
 {
     const float wiDotN = lwi.z, eta = etaI / etaT;
     const float c2 = 1.0f - eta * eta * (1.0f - wiDotN * wiDotN);
     if (c2 <= 0.f) return 1.0f;
-    const float ci = fabsf(wiDotN), ct = sqrtf(c2);
-    const float rhoS = (etaI * ci - etaT * ct) / (etaI * ci + etaT * ct);
-    const float rhoT = (etaI * ct - etaT * ci) / (etaI * ct + etaT * ci);
+    const float ci = fabsf(wiDotN), ct = EXACT ? sqrtf(c2) : qsqrt(c2);
+    const float rhoS = EXACT ? (etaI * ci - etaT * ct) / (etaI * ci + etaT * ct) : qdiv(etaI * ci - etaT * ct, etaI * ci + etaT * ct);
+    const float rhoT = EXACT ? (etaI * ct - etaT * ci) / (etaI * ct + etaT * ci) : qdiv(etaI * ct - etaT * ci, etaI * ct + etaT * ci);
     return (rhoS * rhoS + rhoT * rhoT) * 0.5f;
 }
 __device__ __forceinline__ bool is_specular(const lmb200_bsdf& B) { return B.type >= LMB200_BSDF_REFLECT_ALL && B.type <= LMB200_BSDF_FLESNEL; }
@@ -279,7 +294,7 @@ __device__ __forceinline__ bool bsdf_sample(const lmb200_bsdf& B, const Geom& g,
         if (lwi.z < 0.f) { const float t = etaI; etaI = etaT; etaT = t; }
         const float eta = etaI / etaT;
         const float c2 = 1.0f - eta * eta * (1.0f - lwi.z * lwi.z);
-        const bool reflect = B.type == LMB200_BSDF_REFRACT_ALL ? (c2 <= 0.f) : (ucomp <= fresnel_term(lwi, etaI, etaT));
+        const bool reflect = B.type == LMB200_BSDF_REFRACT_ALL ? (c2 <= 0.f) : (ucomp <= fresnel_term<true>(lwi, etaI, etaT));
         if (reflect) wo = to_world(g, F3(-lwi.x, -lwi.y, lwi.z));                // BSDFUtils::LocalReflect
         else {
             const float ct = sqrtf(c2) * (lwi.z > 0.f ? -1.0f : 1.0f);
@@ -302,7 +317,9 @@ __device__ __forceinline__ bool bsdf_sample(const lmb200_bsdf& B, const Geom& g,
         const float den = sqrtf(1.0f - (1.0f - a * a) * v0);
         const float cosT = sqrtf(1.0f - v0) / den, sinT = a * (sqrtf(v0) / den);
         const float phi = LMB_PI * (2.0f * v1 - 1.0f);
-        const f3 H = F3(sinT * cosf(phi), sinT * sinf(phi), cosT);
+        float sp, cp;
+        sincosf(phi, &sp, &cp);
+        const f3 H = F3(sinT * cp, sinT * sp, cosT);
         const f3 nwi = neg(lwi);
         const f3 lwo = nwi - H * (2.0f * dot(nwi, H));
         if (lwo.z <= 0.f) return false;
@@ -320,15 +337,15 @@ __device__ __forceinline__ float bsdf_pdf(const lmb200_bsdf& B, const Geom& g, f
         if (B.type == LMB200_BSDF_REFRACT_ALL) return 1.f;                                            // bsdf_refractall.cpp:92-100
         float etaI = B.eta1, etaT = B.eta2;                                                           // bsdf_flesnel.cpp:97-128
         if (lwi.z < 0.f) { const float t = etaI; etaI = etaT; etaT = t; }
-        const float Fr = fresnel_term(lwi, etaI, etaT);
+        const float Fr = fresnel_term<false>(lwi, etaI, etaT);
         return lwi.z * lwo.z >= 0.f ? Fr : 1.0f - Fr;
     }
     if (lwi.z <= 0.f || lwo.z <= 0.f) return 0.f;
     if (B.type == LMB200_BSDF_DIFFUSE) return LMB_INV_PI;
     if (B.type == LMB200_BSDF_COOKTORRANCE) {
-        const f3 H = normalize(lwi + lwo);
+        const f3 H = qnormalize(lwi + lwo);
         const float D = ggx_D(B.roughness, H);
-        return D * H.z / (4.0f * dot(lwo, H)) / lwo.z;
+        return qdiv(qdiv(D * H.z, 4.0f * dot(lwo, H)), lwo.z);
     }
     return 0.f;
 }
@@ -361,7 +378,7 @@ __device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, f3 Rr, const Geom&
         float etaI = B.eta1, etaT = B.eta2;
         if (lwi.z < 0.f) { const float t = etaI; etaI = etaT; etaT = t; }
         const float eta = etaI / etaT;
-        const float Fr = B.type == LMB200_BSDF_FLESNEL ? fresnel_term(lwi, etaI, etaT) : 0.f;
+        const float Fr = B.type == LMB200_BSDF_FLESNEL ? fresnel_term<false>(lwi, etaI, etaT) : 0.f;
         if (lwi.z * lwo.z >= 0.f)        // reflection (total internal reflection for refract_all)
             return ld3(B.R) * ((B.type == LMB200_BSDF_FLESNEL ? Fr : 1.0f) * snc(g, wi, wo));
         // refraction, EL transport: eta^2 (bsdf_refractall.cpp:120-127, bsdf_flesnel.cpp:150-156)
@@ -370,23 +387,23 @@ __device__ __forceinline__ f3 bsdf_eval(const lmb200_bsdf& B, f3 Rr, const Geom&
     if (lwi.z <= 0.f || lwo.z <= 0.f) return F3(0, 0, 0);
     if (B.type == LMB200_BSDF_DIFFUSE) return (Rr * LMB_INV_PI) * snc(g, wi, wo);
     if (B.type == LMB200_BSDF_COOKTORRANCE) {
-        const f3 H = normalize(lwi + lwo);
+        const f3 H = qnormalize(lwi + lwo);
         const float D = ggx_D(B.roughness, H);
         const float woH = fabsf(dot(lwo, H));
         // sic: the reference uses wo.H for both masking terms (bsdf_cooktorrance.cpp:281-283)
-        const float G = fminf(1.0f, fminf(2.0f * H.z * lwo.z / woH, 2.0f * H.z * lwi.z / woH));
+        const float G = fminf(1.0f, fminf(qdiv(2.0f * H.z * lwo.z, woH), qdiv(2.0f * H.z * lwi.z, woH)));
         const float c = dot(lwi, H);
         float F[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const float eta = B.eta[i], k = B.k[i];
             const float tmp = (eta * eta + k * k) * (c * c);
-            const float rP = (tmp - eta * (2.0f * c) + 1.0f) / (tmp + eta * (2.0f * c) + 1.0f);
+            const float rP = qdiv(tmp - eta * (2.0f * c) + 1.0f, tmp + eta * (2.0f * c) + 1.0f);
             const float tmpF = eta * eta + k * k;
-            const float rS = (tmpF - eta * (2.0f * c) + c * c) / (tmpF + eta * (2.0f * c) + c * c);
+            const float rS = qdiv(tmpF - eta * (2.0f * c) + c * c, tmpF + eta * (2.0f * c) + c * c);
             F[i] = (rP + rS) * 0.5f;
         }
-        const float s = D * G / (4.0f * lwi.z) / lwo.z * snc(g, wi, wo);
+        const float s = qdiv(qdiv(D * G, 4.0f * lwi.z), lwo.z) * snc(g, wi, wo);
         return F3(Rr.x * F[0] * s, Rr.y * F[1] * s, Rr.z * F[2] * s);
     }
     return F3(0, 0, 0);
@@ -433,15 +450,17 @@ __device__ __forceinline__ bool light_sample(const DevScene& S, int li, f3 from,
         if (kind == LMB200_LIGHT_DIRECTIONAL) d = neg(ld3(S.lights[li].direction));   // light_directional.cpp:131-145
         else {                                   // light_env.cpp:129-146, Sampler::UniformSampleSphere (sampler.h:79-85)
             const float z = 1.0f - 2.0f * u0, r = sqrtf(fmaxf(0.f, 1.0f - z * z)), phi = 2.0f * LMB_PI * u1;
-            d = F3(r * cosf(phi), r * sinf(phi), z);
+            float sp, cp;
+            sincosf(phi, &sp, &cp);
+            d = F3(r * cp, r * sp, z);
             pdfSA = LMB_INV_PI * 0.25f;          // light_env.cpp:185-189
         }
         if (!emitter_shape_hit(S, from, d, g)) return false;
         // PDFVal(SolidAngle).ConvertToArea(geomPrev, geom), probability.h:59-71
         f3 w = g.p - from;
-        const float d2 = dot(w, w), dl = sqrtf(d2);
-        w = F3(w.x / dl, w.y / dl, w.z / dl);
-        pdfPL = pdfSA * fabsf(dot(g.sn, neg(w))) / d2;
+        const float d2 = dot(w, w);
+        w = qnormalize(w);
+        pdfPL = qdiv(pdfSA * fabsf(dot(g.sn, neg(w))), d2);
         return true;
     }
     const lmb200_primitive& P = S.prims[S.lights[li].primitive];
@@ -516,14 +535,14 @@ __global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg
                             // pdfPL / G(hit, previous vertex) * pdfL, G as renderutils.h:46-56
                             const float4 pv = P.prev[i];
                             f3 dd = o - g.p;
-                            const float d2 = dot(dd, dd), dl = sqrtf(d2);
-                            dd = F3(dd.x / dl, dd.y / dl, dd.z / dl);
+                            const float d2 = dot(dd, dd);
+                            dd = qnormalize(dd);
                             float G = fabsf(dot(g.sn, dd));
                             if (nv > 1) G *= fabsf(dot(F3(pv.x, pv.y, pv.z), neg(dd)));   // the camera vertex is degenerated
-                            G = G / d2;
-                            const float pdfDL = pv.w < 0.f ? 0.f : S.light_inv_area[prim.light] / G * (1.0f / (float)S.num_lights);
+                            G = qdiv(G, d2);
+                            const float pdfDL = pv.w < 0.f ? 0.f : qdiv(S.light_inv_area[prim.light], G) * qdiv(1.0f, (float)S.num_lights);
                             const float pdfBS = fabsf(pv.w);
-                            C = C * (pdfBS / (pdfBS + pdfDL));
+                            C = C * qdiv(pdfBS, pdfBS + pdfDL);
                         }
                         film_add(film, __float_as_int(thr.w), C);
                     }
@@ -641,18 +660,18 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
             const f3 fsL = S.lights[li].kind != LMB200_LIGHT_AREA ? ld3(S.lights[li].Le)
                                           : (to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le));
             f3 d = gL.p - p;                                                   // RenderUtils::GeometryTerm, renderutils.h:46-56
-            const float d2 = dot(d, d), dl = sqrtf(d2);
-            d = F3(d.x / dl, d.y / dl, d.z / dl);
+            const float d2 = dot(d, d);
+            d = qnormalize(d);
             float G = 1.0f;
             if (!is_sensor) G *= fabsf(dot(g.sn, d));
             if (!gL.degenerated) G *= fabsf(dot(gL.sn, neg(d)));
-            G = G / d2;
+            G = qdiv(G, d2);
             C = ((F3(thr.x, thr.y, thr.z) * fsE) * fsL) * G;
             if (sampled && !black(C)) {
-                C = C * (1.0f / pdfL / pdfPL);
+                C = C * qdiv(qdiv(1.0f, pdfL), pdfPL);
                 if (cfg.mode == LMB200_MODE_PTMIS) {          // renderer_ptmis.cpp:163-170
-                    const float pdfDL = pdfPL / G * pdfL;
-                    C = C * (pdfDL / (pdfDL + pdfB));
+                    const float pdfDL = qdiv(pdfPL, G) * pdfL;
+                    C = C * qdiv(pdfDL, pdfDL + pdfB);
                 }
                 pixel = __float_as_int(thr.w);
                 if (is_sensor) {                                               // renderer_ptdirect.cpp:165-170
@@ -721,7 +740,8 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
                 specular_here = is_specular(B);
             }
             if (ok && !black(fs)) {
-                thr.x *= fs.x / pdfD; thr.y *= fs.y / pdfD; thr.z *= fs.z / pdfD;
+                const float ipdf = qdiv(1.0f, pdfD);
+                thr.x *= fs.x * ipdf; thr.y *= fs.y * ipdf; thr.z *= fs.z * ipdf;
                 P.thr[i] = thr;
                 // ptmis: a negative pdf marks a specular vertex (light sampling cannot reach it, renderer_ptmis.cpp:251-254)
                 if (cfg.mode == LMB200_MODE_PTMIS) P.prev[i] = make_float4(sn_here.x, sn_here.y, sn_here.z, specular_here ? -pdfD : pdfD);

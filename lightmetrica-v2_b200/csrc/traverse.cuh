@@ -36,7 +36,7 @@ __device__ __forceinline__ float lmb_safe_inv(float d)
     // both make the slab of a zero component span everything iff the origin lies inside it.
     const float tiny = 1.0e-30f;
     const float c = fabsf(d) < tiny ? copysignf(tiny, d) : d;
-    return 1.0f / c;
+    return __fdiv_rn(1.0f, c);      // explicitly IEEE: the traversal must not depend on the unit's -prec-div setting
 }
 
 // 0x3F800000 read from constant memory: ptxas cannot fold it, so PRMT takes it as its register /

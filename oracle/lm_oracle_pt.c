@@ -70,7 +70,8 @@ static v3 vmul(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }
 static v3 vmulv(v3 a, v3 b) { return V(a.x * b.x, a.y * b.y, a.z * b.z); }
 static float vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static v3 vcross(v3 a, v3 b) { return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-static v3 vnorm(v3 a) { const float l = sqrtf(vdot(a, a)); return V(a.x / l, a.y / l, a.z / l); }
+/* v * (1 / |v|), every operation individually rounded: the exact sequence of the CUDA renderer's normalize() */
+static v3 vnorm(v3 a) { const float inv = 1.0f / sqrtf(vdot(a, a)); return V(a.x * inv, a.y * inv, a.z * inv); }
 static v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
 static int vblack(v3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }   /* SPD::Black, spectrum.h */
 static v3 ld3(const float* p) { return V(p[0], p[1], p[2]); }
