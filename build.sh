@@ -13,6 +13,7 @@ for f in accel render bvh_build_gpu; do
   if [ -f "$SRC/$f.cu" ]; then
     if [ ! -f "$OUT/obj/$f.o" ] || [ -n "$(find "$SRC" "$ROOT/include" -newer "$OUT/obj/$f.o" -type f | head -1)" ]; then
       $NVCC $NVFLAGS -c "$SRC/$f.cu" -o "$OUT/obj/$f.o" 2> "$OUT/obj/$f.ptxas.log" || { cat "$OUT/obj/$f.ptxas.log"; exit 1; }
+      sed -i '/Compile time = /d' "$OUT/obj/$f.ptxas.log"      # keep the tracked register / spill report stable across builds
     fi
   fi
 done
