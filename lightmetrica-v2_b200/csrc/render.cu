@@ -194,11 +194,13 @@ __device__ __forceinline__ bool raster_position(const DevScene& S, f3 p, f3 wo, 
     if (!sensor_eye(S, p, wo, e)) return false;
     return raster_from_eye(S, e, rx, ry);
 }
-__device__ __forceinline__ float importance(const DevScene& S, f3 p, f3 wo)
+// Importance(wo) together with the raster position it is defined over (0 and inside = false outside the frustum): callers need
+// both, and the raster position costs five IEEE divisions
+__device__ __forceinline__ float importance_raster(const DevScene& S, f3 p, f3 wo, float& rx, float& ry, bool& inside)
 {
     f3 e;
-    float rx, ry;
-    if (!sensor_eye(S, p, wo, e) || !raster_from_eye(S, e, rx, ry)) return 0.f;
+    inside = sensor_eye(S, p, wo, e) && raster_from_eye(S, e, rx, ry);
+    if (!inside) return 0.f;
     const float cosT = -e.z, inv = qdiv(1.0f, cosT);
     const float A = S.tan_fov * S.tan_fov * S.aspect * 4.0f;
     return qdiv(inv * inv * inv, A);
@@ -647,7 +649,9 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
             f3 fsE;
             Geom g;
             float pdfB;      // pdf of sampling ppL from this vertex (ptmis)
-            if (is_sensor) { const float im = importance(S, p, ppL); fsE = F3(im, im, im); g.degenerated = true; pdfB = im; }
+            float srx = 0.f, sry = 0.f;      // raster position of ppL (camera vertex)
+            bool inside = false;
+            if (is_sensor) { const float im = importance_raster(S, p, ppL, srx, sry, inside); fsE = F3(im, im, im); g.degenerated = true; pdfB = im; }
             else {
                 const float4 vw = P.vtx_wi[i];
                 tri_geom(S, tri, vw.w, P.vtx_v[i], p, g);
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
                                           : (to_local(gL, neg(ppL)).z <= 0.f ? F3(0, 0, 0) : ld3(S.lights[li].Le));
             f3 d = gL.p - p;                                                   // RenderUtils::GeometryTerm, renderutils.h:46-56
             const float d2 = dot(d, d);
-            d = qnormalize(d);
+            d = ppL;
             float G = 1.0f;
             if (!is_sensor) G *= fabsf(dot(g.sn, d));
             if (!gL.degenerated) G *= fabsf(dot(gL.sn, neg(d)));
@@ -674,11 +678,7 @@ __global__ void __launch_bounds__(256) k_nee(DevScene S, Pool P, RenderCfg cfg)
                     C = C * qdiv(pdfDL, pdfDL + pdfB);
                 }
                 pixel = __float_as_int(thr.w);
-                if (is_sensor) {                                               // renderer_ptdirect.cpp:165-170
-                    float rx = 0.f, ry = 0.f;
-                    raster_position(S, p, ppL, rx, ry);
-                    pixel = pixel_index(S, rx, ry);
-                }
+                if (is_sensor) pixel = pixel_index(S, srx, sry);             // renderer_ptdirect.cpp:165-170 (C != 0 => inside)
                 emit = true;
             }
         }
@@ -719,11 +719,12 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
             if (is_sensor) {
                 const float4 u = rng_block(cfg.seed, P.sample[i], 0u);
                 wo = camera_wo(S, cfg.tile_x0 + u.y * cfg.tile_sx, cfg.tile_y0 + u.z * cfg.tile_sy, p);
-                const float im = importance(S, p, wo);
+                float rx = 0.f, ry = 0.f;
+                bool inside;
+                const float im = importance_raster(S, p, wo, rx, ry, inside);
                 pdfD = im; fs = F3(im, im, im);
                 if (cfg.mode == LMB200_MODE_PTDIRECT) {
-                    float rx, ry;
-                    ok = raster_position(S, p, wo, rx, ry);                    // renderer_ptdirect.cpp:200-208
+                    ok = inside;                                               // renderer_ptdirect.cpp:200-208
                     if (ok) thr.w = __int_as_float(pixel_index(S, rx, ry));
                 }
             } else {
