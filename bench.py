@@ -344,7 +344,11 @@ def main():
                 "gpu_launches": launches, "clocks": clock_info,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": npr.value, "tris_per_ray": tpr.value,
-                             "kernel": "lmb200::trace_kernel<false,false>", "kernel_ms": mean_kernel_s * 1e3},
+                             "kernel": "lmb200::trace_kernel<false,false>", "kernel_ms": mean_kernel_s * 1e3,
+                             # second ceiling, informational: node fetches/s against the rate at which a fetch-only kernel reads random
+                             # 80-byte records on a B200 (81.4 G/s, measured once with scripts/micro/l1_wavefront.cu, profiles/r01_sweep.md)
+                             "node_fetches_per_s": npr.value * a.rays / mean_kernel_s, "record_fetch_ceiling_per_s": 81.4e9,
+                             "frac_of_fetch_ceiling": npr.value * a.rays / mean_kernel_s / 81.4e9},
                 "cpu_baseline": cpu, "parity": parity,
                 "bvh": {"nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
                 "path_tracing": pt}
