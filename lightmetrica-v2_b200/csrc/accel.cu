@@ -2,6 +2,7 @@
 // Replaces Accel::Build / Accel3::Intersect of the reference's in-tree accels
 // (/root/reference/src/liblightmetrica/accel/accel_qbvh.cpp:152-497) for ray BATCHES.
 #include "internal.h"
+#include <cstdlib>
 #include "traverse.cuh"
 
 #include <chrono>
@@ -177,6 +178,9 @@ int Accel::upload()
 }
 
 // Host-buffer trace: a three-stage pipeline (H2D copy | kernel | D2H copy) over three streams and
+#ifndef LMB_E2E_CHUNK_LOG2
+#define LMB_E2E_CHUNK_LOG2 23      // rays per pipeline chunk (tuning override: env LMB200_E2E_CHUNK_LOG2)
+#endif
 // LMB_NBUF staging buffers, so that with pinned host memory the PCIe traffic of chunk k+1 and k-1
 // overlaps the kernel of chunk k.
 template <bool ANY>
@@ -189,7 +193,8 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     const size_t out_elem = ANY ? 1 : sizeof(lmb200_hit);
-    const uint64_t chunk = std::min<uint64_t>(n, 1ull << 23);
+    static const int chunk_log2 = [] { const char* e = getenv("LMB200_E2E_CHUNK_LOG2"); const int v = e ? atoi(e) : 0; return v >= 16 && v <= 26 ? v : LMB_E2E_CHUNK_LOG2; }();
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << chunk_log2);
     for (int i = 0; i < 3; i++) {
         if (!a->streams[i] && (e = cudaStreamCreateWithFlags(&a->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
     }
