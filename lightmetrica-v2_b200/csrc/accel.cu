@@ -130,7 +130,7 @@ void Accel::free_device()
         if (stage_out[i]) cudaFree(stage_out[i]);
         stage_rays[i] = stage_out[i] = nullptr;
     }
-    for (int i = 0; i < 3; i++) { if (streams[i]) cudaStreamDestroy(streams[i]); streams[i] = nullptr; }
+    for (int i = 0; i < 4; i++) { if (streams[i]) cudaStreamDestroy(streams[i]); streams[i] = nullptr; }
     for (int i = 0; i < 3 * LMB_NBUF; i++) { if (events[i]) cudaEventDestroy(events[i]); events[i] = nullptr; }
     stage_cap = 0;
     d_nodes = d_tris = nullptr; d_counter = nullptr;
@@ -195,7 +195,7 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
     const size_t out_elem = ANY ? 1 : sizeof(lmb200_hit);
     static const int chunk_log2 = [] { const char* e = getenv("LMB200_E2E_CHUNK_LOG2"); const int v = e ? atoi(e) : 0; return v >= 16 && v <= 26 ? v : LMB_E2E_CHUNK_LOG2; }();
     const uint64_t chunk = std::min<uint64_t>(n, 1ull << chunk_log2);
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 4; i++) {
         if (!a->streams[i] && (e = cudaStreamCreateWithFlags(&a->streams[i], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
     }
     for (int i = 0; i < 3 * LMB_NBUF; i++) {
@@ -211,7 +211,9 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
         }
         a->stage_cap = chunk;
     }
-    cudaStream_t s_in = a->streams[0], s_k = a->streams[1], s_out = a->streams[2];
+    // kernels of consecutive chunks go to two alternating streams (own work counters: slots 2 and 3), so that the next
+    // chunk's persistent blocks move in while the previous chunk's last rays drain
+    cudaStream_t s_in = a->streams[0], s_out = a->streams[2];
     uint64_t c = 0;
     for (uint64_t off = 0; off < n; off += chunk, c++) {
         const int b = (int)(c % LMB_NBUF);
@@ -220,16 +222,18 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
         if (c >= LMB_NBUF) cudaStreamWaitEvent(s_in, ev_out, 0);        // buffer b is free again
         if ((e = cudaMemcpyAsync(a->stage_rays[b], rays + off, m * sizeof(lmb200_ray), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D rays");
         cudaEventRecord(ev_in, s_in);
+        cudaStream_t s_k = a->streams[(c & 1) ? 3 : 1];
+        const int slot = (c & 1) ? 3 : 2;
         cudaStreamWaitEvent(s_k, ev_in, 0);
-        const int rc = ANY ? trace_any_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, 2)
-                           : trace_closest_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, 2);
+        const int rc = ANY ? trace_any_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot)
+                           : trace_closest_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot);
         if (rc) return rc;
         cudaEventRecord(ev_k, s_k);
         cudaStreamWaitEvent(s_out, ev_k, 0);
         if ((e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + off * out_elem, a->stage_out[b], m * out_elem, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return cuda_fail(e, "D2H hits");
         cudaEventRecord(ev_out, s_out);
     }
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 4; i++) {
         if ((e = cudaStreamSynchronize(a->streams[i])) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
     }
     return LMB200_OK;

@@ -35,7 +35,7 @@ struct Accel {
     int trace_blocks_per_sm = 4;
     double upload_seconds = 0;
     // staging for the host-pointer entry points
-    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};      // copy-in, kernel, copy-out
+    cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};      // copy-in, kernel (even chunks), copy-out, kernel (odd chunks)
     void* stage_rays[LMB_NBUF] = {};
     void* stage_out[LMB_NBUF] = {};
     cudaEvent_t events[3 * LMB_NBUF] = {};
