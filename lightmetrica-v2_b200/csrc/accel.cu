@@ -179,7 +179,7 @@ int Accel::upload()
 
 // Host-buffer trace: a three-stage pipeline (H2D copy | kernel | D2H copy) over three streams and
 #ifndef LMB_E2E_CHUNK_LOG2
-#define LMB_E2E_CHUNK_LOG2 23      // rays per pipeline chunk (tuning override: env LMB200_E2E_CHUNK_LOG2)
+#define LMB_E2E_CHUNK_LOG2 22      // rays per pipeline chunk (tuning override: env LMB200_E2E_CHUNK_LOG2); 2^23: 1068, 2^22: 1104, 2^21: 1082 Mrays/s
 #endif
 // LMB_NBUF staging buffers, so that with pinned host memory the PCIe traffic of chunk k+1 and k-1
 // overlaps the kernel of chunk k.
