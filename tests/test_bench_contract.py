@@ -33,3 +33,29 @@ def test_reference_arm_prints_one_json_line():
 
 def test_reference_arm_non_zero_rank_is_silent():
     assert run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_lmb200_arm_json_contract_small():
+    """The product arm on a reduced workload: one JSON line with every key of the bench contract, parity spot check clean."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "2", "--warmup", "3", "--rays", "2097152",
+                        "--tris", "200000", "--cpu-rays", "50000", "--pt-tris", "50000", "--pt-spp", "2"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout[:2000]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity", "path_tracing"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["dtype"] == "f32"
+    assert d["value"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.05
+    assert d["e2e"]["h2d_bytes_per_step"] == 2097152 * 32 and d["e2e"]["d2h_bytes_per_step"] == 2097152 * 16
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["gpu_launches"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["parity"]["index_mismatches"] == 0 and d["parity"]["tuv_bit_mismatches"] == 0
+    assert d["path_tracing"]["value"] > 0 and d["path_tracing"]["incoherent_1m_tri_mesh"]["value"] > 0
