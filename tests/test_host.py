@@ -28,6 +28,33 @@ def test_struct_sizes():
     assert capi.RAY_DTYPE.itemsize == 32 and capi.HIT_DTYPE.itemsize == 16
 
 
+def test_ctypes_mirrors_match_the_header(tmp_path):
+    """The ctypes structures of lmb200py/capi.py (which the oracle port shares through Scene.flatten) have the sizes and field
+    offsets a C compiler gives the structs of include/lmb200.h."""
+    import subprocess
+    pairs = [("lmb200_bsdf", capi.Bsdf), ("lmb200_texture", capi.Texture), ("lmb200_primitive", capi.Primitive), ("lmb200_light", capi.Light),
+             ("lmb200_camera", capi.Camera), ("lmb200_scene_desc", capi.SceneDesc), ("lmb200_render_params", capi.RenderParams),
+             ("lmb200_render_stats", capi.RenderStats), ("lmb200_accel_stats", capi.AccelStats)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lmb200.h"', 'int main(void) {']
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "sizes.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    for (cname, ct), line in zip(pairs, out):
+        toks = line.split()
+        assert toks[0] == cname
+        assert int(toks[1]) == C.sizeof(ct), (cname, toks[1], C.sizeof(ct))
+        offs = [int(t) for t in toks[2:]]
+        assert offs == [getattr(ct, f).offset for f, _ in ct._fields_], cname
+
+
 def test_no_device_fails_loudly(have_gpu):
     if have_gpu:
         pytest.skip("GPU present")
