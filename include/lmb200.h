@@ -73,6 +73,12 @@ void lmb200_accel_destroy(lmb200_accel* a);
  * (Vec3(prim->transform * Vec4(p,1)), accel_qbvh.cpp:182-184). ntris may be 0. */
 int lmb200_accel_build(lmb200_accel* a, const float* verts, uint64_t ntris);
 int lmb200_accel_get_stats(const lmb200_accel* a, lmb200_accel_stats* out);
+/* CUDA ordinal the accel lives on (-1: host-only accel). */
+int lmb200_accel_device(const lmb200_accel* a);
+/* A copy of a built accel on another GPU (device-to-device copy of the flattened arrays; no rebuild). The reference has
+ * one Accel per Scene (scene.h:79); a multi-GPU render needs the same BVH resident on every device. The caller owns
+ * the replica and destroys it with lmb200_accel_destroy. */
+lmb200_accel* lmb200_accel_replicate(const lmb200_accel* a, int device);
 
 /* Same, with a choice of builder. Both produce the same node/record format and therefore the same
  * hits (the closest hit does not depend on the tree); they differ in build time and tree quality.
@@ -244,6 +250,7 @@ typedef struct lmb200_render_stats {
     int64_t  iterations;
     uint64_t launches;
     double   seconds;            /* device time of the wavefront loop (CUDA events) */
+    double   reduce_seconds;     /* lmb200_render_multi / _timed: device time of the NCCL film reductions; else 0 */
 } lmb200_render_stats;
 
 /* Builds the accel (device) and uploads shading data. */

@@ -138,6 +138,17 @@ void Accel::free_device()
 
 Accel::~Accel() { free_device(); }
 
+// The traversal stack holds one entry per level of the wide tree (the not yet visited siblings of the node a ray
+// descended into): LMB_SM_STACK entries in shared memory + LMB_LOCAL_STACK in local memory, pushed without a bounds
+// check. A tree deeper than that is refused here instead of corrupting a thread's state on the device.
+static int check_depth(int max_depth)
+{
+    if (max_depth > LMB_SM_STACK + LMB_LOCAL_STACK)
+        return set_error(LMB200_E_STATE, "BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack capacity of " +
+                                             std::to_string(LMB_SM_STACK + LMB_LOCAL_STACK) + " levels");
+    return LMB200_OK;
+}
+
 int mirror_to_host(Accel* a)
 {
     if (!a->gpu_built || !a->bvh.nodes.empty()) return LMB200_OK;
@@ -164,7 +175,7 @@ int Accel::upload()
     const size_t tb = std::max<size_t>(bvh.tris.size(), 1) * sizeof(TriRecord);
     if ((e = cudaMalloc(&d_nodes, nb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(nodes)");
     if ((e = cudaMalloc(&d_tris, tb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tris)");
-    if (!d_counter && (e = cudaMalloc(&d_counter, 4 * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
+    if (!d_counter && (e = cudaMalloc(&d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
     if ((e = cudaMemcpy(d_nodes, bvh.nodes.data(), nb, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(nodes)");
     if (!bvh.tris.empty() && (e = cudaMemcpy(d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tris)");
     cudaDeviceProp prop;
@@ -214,29 +225,33 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
     // kernels of consecutive chunks go to two alternating streams (own work counters: slots 2 and 3), so that the next
     // chunk's persistent blocks move in while the previous chunk's last rays drain
     cudaStream_t s_in = a->streams[0], s_out = a->streams[2];
+    // a failure in the middle of the pipeline must not return while earlier chunks are still in flight on the
+    // caller's buffers: every exit path drains the four streams first
+    int rc = LMB200_OK;
     uint64_t c = 0;
-    for (uint64_t off = 0; off < n; off += chunk, c++) {
+    for (uint64_t off = 0; off < n && !rc; off += chunk, c++) {
         const int b = (int)(c % LMB_NBUF);
         cudaEvent_t ev_in = a->events[3 * b], ev_k = a->events[3 * b + 1], ev_out = a->events[3 * b + 2];
         const uint64_t m = std::min(chunk, n - off);
-        if (c >= LMB_NBUF) cudaStreamWaitEvent(s_in, ev_out, 0);        // buffer b is free again
-        if ((e = cudaMemcpyAsync(a->stage_rays[b], rays + off, m * sizeof(lmb200_ray), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return cuda_fail(e, "H2D rays");
-        cudaEventRecord(ev_in, s_in);
+        if (c >= LMB_NBUF && (e = cudaStreamWaitEvent(s_in, ev_out, 0)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamWaitEvent"); break; }   // buffer b is free again
+        if ((e = cudaMemcpyAsync(a->stage_rays[b], rays + off, m * sizeof(lmb200_ray), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { rc = cuda_fail(e, "H2D rays"); break; }
+        if ((e = cudaEventRecord(ev_in, s_in)) != cudaSuccess) { rc = cuda_fail(e, "cudaEventRecord"); break; }
         cudaStream_t s_k = a->streams[(c & 1) ? 3 : 1];
         const int slot = (c & 1) ? 3 : 2;
-        cudaStreamWaitEvent(s_k, ev_in, 0);
-        const int rc = ANY ? trace_any_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot)
-                           : trace_closest_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot);
-        if (rc) return rc;
-        cudaEventRecord(ev_k, s_k);
-        cudaStreamWaitEvent(s_out, ev_k, 0);
-        if ((e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + off * out_elem, a->stage_out[b], m * out_elem, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return cuda_fail(e, "D2H hits");
-        cudaEventRecord(ev_out, s_out);
+        if ((e = cudaStreamWaitEvent(s_k, ev_in, 0)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamWaitEvent"); break; }
+        rc = ANY ? trace_any_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot)
+                 : trace_closest_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot);
+        if (rc) break;
+        if ((e = cudaEventRecord(ev_k, s_k)) != cudaSuccess) { rc = cuda_fail(e, "cudaEventRecord"); break; }
+        if ((e = cudaStreamWaitEvent(s_out, ev_k, 0)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamWaitEvent"); break; }
+        if ((e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + off * out_elem, a->stage_out[b], m * out_elem, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) { rc = cuda_fail(e, "D2H hits"); break; }
+        if ((e = cudaEventRecord(ev_out, s_out)) != cudaSuccess) { rc = cuda_fail(e, "cudaEventRecord"); break; }
     }
     for (int i = 0; i < 4; i++) {
-        if ((e = cudaStreamSynchronize(a->streams[i])) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+        e = cudaStreamSynchronize(a->streams[i]);
+        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
-    return LMB200_OK;
+    return rc;
 }
 
 }  // namespace lmb200
@@ -286,8 +301,10 @@ int lmb200_accel_build(lmb200_accel* h, const float* verts, uint64_t ntris)
     if (!a || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
     if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27, as the reference's leaf encoding accel_qbvh.cpp:62-72)");
     build_bvh(verts, ntris, a->bvh, 0);
-    a->built = true;
+    a->built = false;
     a->gpu_built = false;
+    if (const int rc = check_depth(a->bvh.stats.max_depth)) return rc;
+    a->built = true;
     if (a->host_only) return LMB200_OK;
     return a->upload();
 }
@@ -300,7 +317,9 @@ int lmb200_accel_build_ex(lmb200_accel* h, const float* verts, uint64_t ntris, i
     if (!a || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
     if (a->host_only) return set_error(LMB200_E_STATE, "the GPU builder needs a device accel");
     if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27)");
-    const int rc = build_bvh_gpu(a, verts, ntris);
+    a->built = false;
+    int rc = build_bvh_gpu(a, verts, ntris);
+    if (!rc) rc = check_depth(a->bvh.stats.max_depth);
     if (rc) return rc;
     a->built = true;
     cudaDeviceProp prop;
@@ -312,6 +331,44 @@ int lmb200_accel_build_ex(lmb200_accel* h, const float* verts, uint64_t ntris, i
     a->trace_blocks_per_sm = occ > 0 ? occ : 4;
     a->upload_seconds = 0;
     return LMB200_OK;
+}
+
+int lmb200_accel_device(const lmb200_accel* h)
+{
+    const Accel* a = reinterpret_cast<const Accel*>(h);
+    return a && !a->host_only ? a->device : -1;
+}
+
+// Replica of a built device accel on another GPU: the node and record arrays are copied device to device (over
+// NVLink where the GPUs are peers), so an N-GPU render builds the BVH once instead of N times.
+lmb200_accel* lmb200_accel_replicate(const lmb200_accel* h, int device)
+{
+    const Accel* src = reinterpret_cast<const Accel*>(h);
+    if (!src || !src->built || src->host_only || !src->d_nodes) { set_error(LMB200_E_STATE, "replicate: source accel is not built on a device"); return nullptr; }
+    Accel* a = reinterpret_cast<Accel*>(lmb200_accel_create(device));
+    if (!a) return nullptr;
+    const size_t nn = src->gpu_built ? (size_t)src->bvh.stats.num_nodes : src->bvh.nodes.size();
+    const size_t nt = src->gpu_built ? (size_t)src->bvh.stats.num_valid : src->bvh.tris.size();
+    const size_t nb = nn * sizeof(Node80), tb = std::max<size_t>(nt, 1) * sizeof(TriRecord);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_nodes, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_tris, tb);
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemcpyPeer(a->d_nodes, device, src->d_nodes, src->device, nb);
+    if (e == cudaSuccess && nt) e = cudaMemcpyPeer(a->d_tris, device, src->d_tris, src->device, nt * sizeof(TriRecord));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cuda_fail(e, "lmb200_accel_replicate"); delete a; return nullptr; }
+    a->bvh.stats = src->bvh.stats;
+    for (int k = 0; k < 3; k++) { a->bvh.scene_lo[k] = src->bvh.scene_lo[k]; a->bvh.scene_hi[k] = src->bvh.scene_hi[k]; }
+    a->gpu_built = true;          // host mirror is filled on demand from the device arrays
+    a->built = true;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { cuda_fail(e, "cudaGetDeviceProperties"); delete a; return nullptr; }
+    a->num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false, false>, LMB_TRACE_BLOCK, 0);
+    a->trace_blocks_per_sm = occ > 0 ? occ : 4;
+    return reinterpret_cast<lmb200_accel*>(a);
 }
 
 int lmb200_accel_get_stats(const lmb200_accel* h, lmb200_accel_stats* out)
@@ -386,7 +443,7 @@ int lmb200_trace_closest_dev(lmb200_accel* h, const void* rays_dev, void* hits_d
     if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    return trace_closest_dev(a, rays_dev, hits_dev, n, nullptr, reinterpret_cast<cudaStream_t>(stream), 0);
+    return trace_closest_dev(a, rays_dev, hits_dev, n, nullptr, reinterpret_cast<cudaStream_t>(stream), a->ring_slot());
 }
 
 int lmb200_trace_any_dev(lmb200_accel* h, const void* rays_dev, void* occ_dev, uint64_t n, void* stream)
@@ -396,7 +453,7 @@ int lmb200_trace_any_dev(lmb200_accel* h, const void* rays_dev, void* occ_dev, u
     if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    return trace_any_dev(a, rays_dev, occ_dev, n, nullptr, reinterpret_cast<cudaStream_t>(stream), 0);
+    return trace_any_dev(a, rays_dev, occ_dev, n, nullptr, reinterpret_cast<cudaStream_t>(stream), a->ring_slot());
 }
 
 int lmb200_trace_count_dev(lmb200_accel* h, const void* rays_dev, uint64_t n, double* nodes_per_ray, double* tris_per_ray)
@@ -411,7 +468,7 @@ int lmb200_trace_count_dev(lmb200_accel* h, const void* rays_dev, uint64_t n, do
     if ((e = cudaMalloc(&scratch, n * sizeof(lmb200_hit))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
     if ((e = cudaMalloc(&work, 2 * sizeof(unsigned long long))) != cudaSuccess) { cudaFree(scratch); return cuda_fail(e, "cudaMalloc(work)"); }
     cudaMemset(work, 0, 2 * sizeof(unsigned long long));
-    int rc = launch_trace<false, true>(a, rays_dev, scratch, n, nullptr, 0, work, 0);
+    int rc = launch_trace<false, true>(a, rays_dev, scratch, n, nullptr, 0, work, a->ring_slot());
     unsigned long long hw[2] = {0, 0};
     if (!rc) {
         e = cudaMemcpy(hw, work, sizeof(hw), cudaMemcpyDeviceToHost);

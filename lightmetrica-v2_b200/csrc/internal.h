@@ -14,6 +14,11 @@
 #endif
 
 #define LMB_NBUF 3
+// work counters of an accel's persistent trace launches: [0],[1] reserved, [2],[3] the staging streams of the host-buffer
+// calls, [4 .. 4+LMB_COUNTER_RING) handed out round-robin to the *_dev entry points, so that calls in flight on
+// different streams (or on several scenes sharing one BVH) never share a counter
+#define LMB_COUNTER_RING 60
+#define LMB_NUM_COUNTERS (4 + LMB_COUNTER_RING)
 
 namespace lmb200 {
 
@@ -30,7 +35,9 @@ struct Accel {
     HostBVH bvh;
     void* d_nodes = nullptr;
     void* d_tris = nullptr;
-    unsigned long long* d_counter = nullptr;   // work counters: [0],[1] callers' slots, [2],[3] staging streams
+    unsigned long long* d_counter = nullptr;   // LMB_NUM_COUNTERS work counters (see above)
+    std::atomic<unsigned> ring{0};
+    int ring_slot() { return 4 + (int)(ring.fetch_add(1) % LMB_COUNTER_RING); }
     int num_sms = 148;
     int trace_blocks_per_sm = 4;
     double upload_seconds = 0;

@@ -24,6 +24,7 @@
 #include <thread>
 #include <vector>
 #include <dlfcn.h>
+#include <nccl.h>      // types and enum values only: libnccl is dlopen'ed at run time, the library has no link-time dependency on it
 
 namespace lmb200 {
 
@@ -815,21 +816,21 @@ __global__ void k_rescale(float4* film, long long n, float s)
 }
 
 // primary-ray normal renderer (config 1): pixel-centre rays (renderer_raycast.cpp:77-83), |sn| shading
-__global__ void k_normal_raygen(DevScene S, float4* rays)
+__global__ void k_normal_raygen(DevScene S, float4* rays, int pix0, int npix)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S.width * S.height) return;
-    const int x = i % S.width, y = i / S.width;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // ray i of this call = pixel pix0 + i
+    if (i >= npix) return;
+    const int x = (pix0 + i) % S.width, y = (pix0 + i) / S.width;
     // thin lens: the lens centre (lens sample (.5,.5)), i.e. the in-focus pinhole image
     const f3 cp = camera_point(S, 0.5f, 0.5f);
     const f3 wo = camera_wo(S, ((float)x + 0.5f) / (float)S.width, ((float)y + 0.5f) / (float)S.height, cp);
     rays[2 * i] = make_float4(cp.x, cp.y, cp.z, LMB_EPS_ISECT);
     rays[2 * i + 1] = make_float4(wo.x, wo.y, wo.z, LMB_FLT_MAX);
 }
-__global__ void k_normal_shade(DevScene S, const float4* hits, float4* film)
+__global__ void k_normal_shade(DevScene S, const float4* hits, float4* film, int pix0, int npix)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S.width * S.height) return;
+    if (i >= npix) return;
     const float4 h = hits[i];
     const uint32_t tri = __float_as_uint(h.w);
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -838,7 +839,7 @@ __global__ void k_normal_shade(DevScene S, const float4* hits, float4* film)
         tri_geom(S, tri, h.y, h.z, F3(0, 0, 0), g);
         c = make_float4(fabsf(g.sn.x), fabsf(g.sn.y), fabsf(g.sn.z), 0.f);
     }
-    film[i] = c;
+    film[pix0 + i] = c;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -855,7 +856,9 @@ struct Scene {
     Pool pool{};
     uint32_t pool_size = 0;
     std::vector<void*> pool_allocs;
-    void* h_pinned = nullptr;   // 8 x u64 readback
+    void* h_pinned = nullptr;   // 8 x u64 readback + 4 x u64 upload
+    void* film = nullptr;       // device film of the host-buffer call lmb200_render (reused across calls)
+    int64_t film_cap = 0;
     int num_sms = 148;
     // k_shadow runs on its own stream beside k_bsdf / k_extend of the same iteration (tail filling)
     cudaStream_t shadow_stream = nullptr;
@@ -867,6 +870,7 @@ struct Scene {
         for (void* p : pool_allocs) cudaFree(p);
         for (void* p : allocs) cudaFree(p);
         if (d_counter) cudaFree(d_counter);
+        if (film) cudaFree(film);
         if (h_pinned) cudaFreeHost(h_pinned);
         if (shadow_stream) cudaStreamDestroy(shadow_stream);
         if (ev_nee) cudaEventDestroy(ev_nee);
@@ -927,27 +931,29 @@ static int ensure_pool(Scene* s, uint32_t n)
     return LMB200_OK;
 }
 
-static int render_normal(Scene* s, float4* film, cudaStream_t st)
+// Pixels [pix0, pix0 + npx) of the primary-ray image (the whole image on one GPU; lmb200_render_multi gives each GPU a
+// contiguous share of the pixels and leaves the rest of its film zero, so that the film sum is the image).
+static int render_normal(Scene* s, float4* film, cudaStream_t st, int pix0, int npx)
 {
-    const int npx = s->dev.width * s->dev.height;
-    int rc = ensure_pool(s, (uint32_t)std::max(npx, 1));
-    if (rc) return rc;
-    // rays live in ray_o/ray_d-sized scratch: reuse sq_o (2*npx float4 needed) -> allocate temp
+    if (npx <= 0) return LMB200_OK;
     float4* rays = nullptr; float4* hits = nullptr;
     cudaError_t e;
     if ((e = cudaMalloc(&rays, sizeof(float4) * 2 * (size_t)npx)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(rays)");
     if ((e = cudaMalloc(&hits, sizeof(float4) * (size_t)npx)) != cudaSuccess) { cudaFree(rays); return cuda_fail(e, "cudaMalloc(hits)"); }
-    k_normal_raygen<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, rays); g_launch_count++;
-    rc = trace_closest_dev(s->accel, rays, hits, (uint64_t)npx, nullptr, st, 0);
-    if (!rc) { k_normal_shade<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, hits, film); g_launch_count++; }
-    e = cudaStreamSynchronize(st);
+    k_normal_raygen<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, rays, pix0, npx); g_launch_count++;
+    int rc = trace_closest_dev(s->accel, rays, hits, (uint64_t)npx, nullptr, st, s->accel->ring_slot());
+    if (!rc) { k_normal_shade<<<(npx + 255) / 256, 256, 0, st>>>(s->dev, hits, film, pix0, npx); g_launch_count++; }
+    e = cudaGetLastError();
+    const cudaError_t e2 = cudaStreamSynchronize(st);
     cudaFree(rays); cudaFree(hits);
     if (rc) return rc;
-    if (e != cudaSuccess) return cuda_fail(e, "render_normal");
+    if (e != cudaSuccess) return cuda_fail(e, "render_normal launch");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "render_normal");
     return LMB200_OK;
 }
 
-static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, cudaStream_t st, lmb200_render_stats* stats)
+// pix0 / npix: MODE_NORMAL only, the pixel range this call renders (npix < 0: the whole image)
+static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, cudaStream_t st, lmb200_render_stats* stats, int pix0 = 0, int npix = -1)
 {
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
@@ -955,10 +961,11 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     const uint64_t launches0 = g_launch_count.load();
     if (p->mode == LMB200_MODE_NORMAL) {
         const auto t0 = std::chrono::steady_clock::now();
-        const int rc = render_normal(s, film, st);
+        if (npix < 0) { pix0 = 0; npix = s->dev.width * s->dev.height; }
+        const int rc = render_normal(s, film, st, pix0, npix);
         if (stats) {
             memset(stats, 0, sizeof(*stats));
-            stats->samples = (int64_t)s->dev.width * s->dev.height;
+            stats->samples = (int64_t)npix;
             stats->extend_rays = stats->samples;
             stats->iterations = 1;
             stats->launches = g_launch_count.load() - launches0;
@@ -979,12 +986,12 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     int rc = ensure_pool(s, pool);
     if (rc) return rc;
     Pool& P = s->pool;
-    if (!s->h_pinned && (e = cudaHostAlloc(&s->h_pinned, 8 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    if (!s->h_pinned && (e = cudaHostAlloc(&s->h_pinned, 12 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
     volatile unsigned long long* hp = reinterpret_cast<volatile unsigned long long*>(s->h_pinned);
     if (!s->shadow_stream) {
         if ((e = cudaStreamCreateWithFlags(&s->shadow_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-        cudaEventCreateWithFlags(&s->ev_nee, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s->ev_shadow, cudaEventDisableTiming);
+        if ((e = cudaEventCreateWithFlags(&s->ev_nee, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        if ((e = cudaEventCreateWithFlags(&s->ev_shadow, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
     }
 
     RenderCfg cfg;
@@ -998,48 +1005,58 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
         cfg.tile_sx = p->tile[2] - p->tile[0]; cfg.tile_sy = p->tile[3] - p->tile[1];
     }
 
-    cudaMemsetAsync(P.nverts, 0, sizeof(int) * pool, st);
-    cudaMemsetAsync(P.traced, 0, pool, st);
-    unsigned long long init[4] = {(unsigned long long)p->sample_begin, 0ull, 0ull, 0ull};
-    cudaMemcpyAsync(P.next_sample, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    // every runtime call of the loop is checked: a failed memset / copy / event must not turn into a silently wrong image
+    struct Events {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+#define LMB_CK(call, what) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
+    LMB_CK(cudaMemsetAsync(P.nverts, 0, sizeof(int) * pool, st), "cudaMemsetAsync(nverts)");
+    LMB_CK(cudaMemsetAsync(P.traced, 0, pool, st), "cudaMemsetAsync(traced)");
+    unsigned long long* h_init = reinterpret_cast<unsigned long long*>(s->h_pinned) + 8;     // pinned: the async copy really is async
+    h_init[0] = (unsigned long long)p->sample_begin; h_init[1] = h_init[2] = h_init[3] = 0ull;
+    LMB_CK(cudaMemcpyAsync(P.next_sample, h_init, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(next_sample)");
 
-    cudaEvent_t ev0, ev1;
-    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
-    cudaEventRecord(ev0, st);
+    LMB_CK(cudaEventCreate(&ev.a), "cudaEventCreate");
+    LMB_CK(cudaEventCreate(&ev.b), "cudaEventCreate");
+    LMB_CK(cudaEventRecord(ev.a, st), "cudaEventRecord");
     const int logic_blocks = s->num_sms * 8;
     const int trace_blocks = s->accel->num_sms * s->accel->trace_blocks_per_sm;
+    const float4* d_nodes = reinterpret_cast<const float4*>(s->accel->d_nodes);
+    const float4* d_tris = reinterpret_cast<const float4*>(s->accel->d_tris);
     int64_t iters = 0;
     for (;;) {
-        cudaMemsetAsync(P.qcount, 0, 4 * sizeof(uint32_t), st);
-        cudaMemsetAsync(s->d_counter, 0, 2 * sizeof(unsigned long long), st);
+        LMB_CK(cudaMemsetAsync(P.qcount, 0, 4 * sizeof(uint32_t), st), "cudaMemsetAsync(qcount)");
+        LMB_CK(cudaMemsetAsync(s->d_counter, 0, 2 * sizeof(unsigned long long), st), "cudaMemsetAsync(work counters)");
         k_logic<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg, film);
         if (nee) {
             // the shadow rays of this iteration are traced on a second stream while the main stream goes on with
             // k_bsdf and k_extend: the two persistent traversal kernels fill each other's tails
             k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
-            cudaEventRecord(s->ev_nee, st);
-            cudaStreamWaitEvent(s->shadow_stream, s->ev_nee, 0);
-            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(reinterpret_cast<const float4*>(s->accel->d_nodes), reinterpret_cast<const float4*>(s->accel->d_tris), P, s->d_counter + 1, film);
-            cudaEventRecord(s->ev_shadow, s->shadow_stream);
+            LMB_CK(cudaEventRecord(s->ev_nee, st), "cudaEventRecord(nee)");
+            LMB_CK(cudaStreamWaitEvent(s->shadow_stream, s->ev_nee, 0), "cudaStreamWaitEvent(nee)");
+            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(d_nodes, d_tris, P, s->d_counter + 1, film);
+            LMB_CK(cudaEventRecord(s->ev_shadow, s->shadow_stream), "cudaEventRecord(shadow)");
         }
         k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
-        k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(reinterpret_cast<const float4*>(s->accel->d_nodes), reinterpret_cast<const float4*>(s->accel->d_tris), P, s->d_counter);
-        if (nee) cudaStreamWaitEvent(st, s->ev_shadow, 0);
+        k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(d_nodes, d_tris, P, s->d_counter);
+        if (nee) LMB_CK(cudaStreamWaitEvent(st, s->ev_shadow, 0), "cudaStreamWaitEvent(shadow)");
         k_stats<<<1, 1, 0, st>>>(P);
+        LMB_CK(cudaGetLastError(), "wavefront kernel launch");
         g_launch_count += nee ? 6 : 4;
-        cudaMemcpyAsync(s->h_pinned, P.qcount, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(s->h_pinned) + 4, P.next_sample, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return cuda_fail(e, "wavefront iteration"); }
+        LMB_CK(cudaMemcpyAsync(s->h_pinned, P.qcount, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(qcount)");
+        LMB_CK(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(s->h_pinned) + 4, P.next_sample, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(sample counter)");
+        LMB_CK(cudaStreamSynchronize(st), "wavefront iteration");
         iters++;
         const uint32_t live = reinterpret_cast<volatile uint32_t*>(s->h_pinned)[0];
         if (live == 0 && hp[4] >= cfg.sample_end) break;     // no live vertex and the sample counter is exhausted
     }
-    cudaEventRecord(ev1, st);
-    cudaMemcpyAsync(s->h_pinned, P.next_sample, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return cuda_fail(e, "wavefront end"); }
+    LMB_CK(cudaEventRecord(ev.b, st), "cudaEventRecord");
+    LMB_CK(cudaMemcpyAsync(s->h_pinned, P.next_sample, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
+    LMB_CK(cudaStreamSynchronize(st), "wavefront end");
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    LMB_CK(cudaEventElapsedTime(&ms, ev.a, ev.b), "cudaEventElapsedTime");
+#undef LMB_CK
     if (stats) {
         stats->samples = todo;
         stats->extend_rays = (int64_t)hp[1];
@@ -1047,6 +1064,7 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
         stats->iterations = iters;
         stats->launches = g_launch_count.load() - launches0;
         stats->seconds = ms * 1e-3;
+        stats->reduce_seconds = 0;
     }
     return LMB200_OK;
 }
@@ -1218,13 +1236,17 @@ int lmb200_render(lmb200_scene* h, const lmb200_render_params* p, float* film_ho
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     const int64_t npx = (int64_t)s->dev.width * s->dev.height;
-    void* film = nullptr;
-    if ((e = cudaMalloc(&film, sizeof(float4) * (size_t)npx)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(film)");
-    cudaMemset(film, 0, sizeof(float4) * (size_t)npx);
+    // the device film lives as long as the scene (a renderer calls this once per frame / progress image)
+    if (s->film_cap < npx) {
+        if (s->film) { cudaFree(s->film); s->film = nullptr; s->film_cap = 0; }
+        if ((e = cudaMalloc(&s->film, sizeof(float4) * (size_t)npx)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(film)");
+        s->film_cap = npx;
+    }
+    void* film = s->film;
+    if ((e = cudaMemsetAsync(film, 0, sizeof(float4) * (size_t)npx, 0)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(film)");
     int rc = render_dev(s, p, film, 0, stats);
     if (!rc && p->mode != LMB200_MODE_NORMAL) rc = lmb200_film_rescale_dev(film, npx, (float)npx / (float)p->num_samples, 0);
     if (!rc && (e = cudaMemcpy(film_host, film, sizeof(float4) * (size_t)npx, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy(film)");
-    cudaFree(film);
     return rc;
 }
 
@@ -1235,23 +1257,89 @@ int lmb200_render(lmb200_scene* h, const lmb200_render_params* p, float* film_ho
 // (scheduler.cpp:280-285), followed by the W*H/processed rescale (scheduler.cpp:288).
 namespace {
 
-typedef int (*fn_init_all)(void**, int, const int*);
-typedef int (*fn_void)(void);
-typedef int (*fn_reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
-typedef int (*fn_destroy)(void*);
+typedef ncclResult_t (*fn_init_all)(ncclComm_t*, int, const int*);
+typedef ncclResult_t (*fn_void)(void);
+typedef ncclResult_t (*fn_reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*fn_destroy)(ncclComm_t);
+typedef ncclResult_t (*fn_version)(int*);
+typedef const char* (*fn_errstr)(ncclResult_t);
+
+// restores the calling thread's current device when a multi-GPU call returns (per-ray Accel3::Intersect and the
+// caller's own CUDA code must not find another device current afterwards)
+struct DeviceGuard {
+    int dev = -1;
+    DeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; } }
+    ~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+};
 
 struct Session {
     std::vector<Scene*> sc;
     std::vector<int> devs;
     std::vector<void*> films;
     std::vector<cudaStream_t> streams;
-    std::vector<void*> comms;
+    std::vector<ncclComm_t> comms;
     void* scratch = nullptr;       // on device 0: reduced + rescaled copy that goes to the host
     int64_t npx = 0;
     fn_void gs = nullptr, ge = nullptr;
     fn_reduce reduce = nullptr;
     fn_destroy destroy = nullptr;
+    fn_errstr errstr = nullptr;
+    int nccl_version = 0;
+    double reduce_seconds = 0;     // device time of the film reductions so far (events on device 0's stream)
     lmb200_render_stats total{};
+
+    int nccl_fail(ncclResult_t r, const char* what) { return set_error(LMB200_E_NCCL, std::string(what) + ": " + (errstr ? errstr(r) : "NCCL error")); }
+
+    // sum over the GPUs of `src[g]` (count floats each) into `dst` on device 0, on the per-GPU streams
+    int reduce_all(const std::vector<void*>& src, void* dst, size_t count)
+    {
+        const int n = (int)sc.size();
+        ncclResult_t r = gs();
+        if (r != ncclSuccess) return nccl_fail(r, "ncclGroupStart");
+        ncclResult_t bad = ncclSuccess;
+        for (int g = 0; g < n; g++) {
+            cudaSetDevice(devs[g]);
+            r = reduce(src[g], g == 0 ? dst : src[g], count, ncclFloat32, ncclSum, 0, comms[g], streams[g]);
+            if (r != ncclSuccess) bad = r;
+        }
+        r = ge();
+        if (bad != ncclSuccess) return nccl_fail(bad, "ncclReduce");
+        if (r != ncclSuccess) return nccl_fail(r, "ncclGroupEnd");
+        return LMB200_OK;
+    }
+
+    // Known-answer reduce right after the communicators are created: GPU g contributes (g + 1) * (i % 7 + 1); small
+    // integers, so the sum is exact in fp32 whatever the reduction order. Catches a libnccl whose datatype / operator
+    // numbering or calling convention differs from the header this file was compiled against.
+    int self_test()
+    {
+        const int n = (int)sc.size();
+        const size_t cnt = 1024;
+        std::vector<void*> buf(n, nullptr);
+        std::vector<float> h(cnt);
+        int rc = LMB200_OK;
+        for (int g = 0; g < n && !rc; g++) {
+            for (size_t i = 0; i < cnt; i++) h[i] = (float)((g + 1) * (int)(i % 7 + 1));
+            cudaError_t e = cudaSetDevice(devs[g]);
+            if (e == cudaSuccess) e = cudaMalloc(&buf[g], (g == 0 ? 2 : 1) * cnt * sizeof(float));
+            if (e == cudaSuccess) e = cudaMemcpyAsync(buf[g], h.data(), cnt * sizeof(float), cudaMemcpyHostToDevice, streams[g]);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(streams[g]);
+            if (e != cudaSuccess) rc = cuda_fail(e, "nccl self-test setup");
+        }
+        if (!rc) rc = reduce_all(buf, reinterpret_cast<float*>(buf[0]) + cnt, cnt);
+        if (!rc) {
+            for (int g = 0; g < n; g++) { cudaSetDevice(devs[g]); cudaStreamSynchronize(streams[g]); }
+            cudaSetDevice(devs[0]);
+            const cudaError_t e = cudaMemcpy(h.data(), reinterpret_cast<float*>(buf[0]) + cnt, cnt * sizeof(float), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = cuda_fail(e, "nccl self-test readback");
+            const int tri = n * (n + 1) / 2;
+            for (size_t i = 0; i < cnt && !rc; i++)
+                if (h[i] != (float)(tri * (int)(i % 7 + 1)))
+                    rc = set_error(LMB200_E_NCCL, "ncclReduce self-test returned a wrong sum (libnccl " + std::to_string(nccl_version) + " is not ABI-compatible with the NCCL 2 header)");
+        }
+        for (int g = 0; g < n; g++) if (buf[g]) { cudaSetDevice(devs[g]); cudaFree(buf[g]); }
+        return rc;
+    }
 
     int open(lmb200_scene** scenes, int n)
     {
@@ -1280,8 +1368,17 @@ struct Session {
             gs = (fn_void)dlsym(lib, "ncclGroupStart"); ge = (fn_void)dlsym(lib, "ncclGroupEnd");
             reduce = (fn_reduce)dlsym(lib, "ncclReduce");
             destroy = (fn_destroy)dlsym(lib, "ncclCommDestroy");
-            if (!init || !gs || !ge || !reduce || !destroy) return set_error(LMB200_E_NCCL, "libnccl lacks required symbols");
-            if (init(comms.data(), n, devs.data()) != 0) return set_error(LMB200_E_NCCL, "ncclCommInitAll failed");
+            errstr = (fn_errstr)dlsym(lib, "ncclGetErrorString");
+            fn_version version = (fn_version)dlsym(lib, "ncclGetVersion");
+            if (!init || !gs || !ge || !reduce || !destroy || !version) return set_error(LMB200_E_NCCL, "libnccl lacks required symbols");
+            // the enum values passed to ncclReduce come from the NCCL 2 header: refuse any other major version
+            if (version(&nccl_version) != ncclSuccess || nccl_version < 20000 || nccl_version >= 30000)
+                return set_error(LMB200_E_NCCL, "unsupported libnccl version " + std::to_string(nccl_version) + " (need 2.x, built against " + std::to_string(NCCL_VERSION_CODE) + ")");
+            for (int g = 0; g < n; g++) for (int h = 0; h < g; h++)
+                if (devs[g] == devs[h]) return set_error(LMB200_E_INVALID, "lmb200_render_multi: two scenes live on the same device");
+            const ncclResult_t r = init(comms.data(), n, devs.data());
+            if (r != ncclSuccess) return nccl_fail(r, "ncclCommInitAll");
+            if (const int rc = self_test()) return rc;
         }
         memset(&total, 0, sizeof(total));
         return LMB200_OK;
@@ -1308,7 +1405,13 @@ struct Session {
                 q.tile[1] = y0 + (y1 - y0) * (float)g / (float)n;
                 q.tile[3] = g + 1 == n ? y1 : y0 + (y1 - y0) * (float)(g + 1) / (float)n;
             }
-            rcs[g] = render_dev(sc[g], &q, films[g], streams[g], &st[g]);
+            if (p->mode == LMB200_MODE_NORMAL) {
+                // primary-ray image: GPU g renders pixels [npx g/n, npx (g+1)/n) and leaves the rest of its film zero
+                const int pix0 = (int)(npx * g / n), pix1 = (int)(npx * (g + 1) / n);
+                rcs[g] = render_dev(sc[g], &q, films[g], streams[g], &st[g], pix0, pix1 - pix0);
+            } else {
+                rcs[g] = render_dev(sc[g], &q, films[g], streams[g], &st[g]);
+            }
             if (rcs[g]) errs[g] = g_last_error;
         };
         std::vector<std::thread> th;
@@ -1331,16 +1434,21 @@ struct Session {
     {
         const int n = (int)sc.size();
         if (n > 1) {
-            gs();
-            int bad = 0;
-            for (int g = 0; g < n; g++) {
-                cudaSetDevice(devs[g]);
-                if (reduce(films[g], g == 0 ? scratch : films[g], (size_t)npx * 4, 7 /*ncclFloat32*/, 0 /*ncclSum*/, 0, comms[g], streams[g]) != 0) bad = 1;
-            }
-            ge();
-            if (bad) return set_error(LMB200_E_NCCL, "ncclReduce failed");
-            for (int g = 1; g < n; g++) { cudaSetDevice(devs[g]); cudaStreamSynchronize(streams[g]); }
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
             cudaSetDevice(devs[0]);
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0, streams[0]);
+            const int rrc = reduce_all(films, scratch, (size_t)npx * 4);
+            cudaSetDevice(devs[0]);
+            cudaEventRecord(e1, streams[0]);
+            cudaError_t se = cudaSuccess;
+            for (int g = 0; g < n; g++) { cudaSetDevice(devs[g]); const cudaError_t x = cudaStreamSynchronize(streams[g]); if (x != cudaSuccess) se = x; }
+            cudaSetDevice(devs[0]);
+            float ms = 0.f;
+            if (!rrc && se == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) reduce_seconds += ms * 1e-3;
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            if (rrc) return rrc;
+            if (se != cudaSuccess) return cuda_fail(se, "film reduce");
         } else {
             cudaSetDevice(devs[0]);
             cudaMemcpyAsync(scratch, films[0], sizeof(float4) * (size_t)npx, cudaMemcpyDeviceToDevice, streams[0]);
@@ -1370,11 +1478,12 @@ struct Session {
 int lmb200_render_multi(lmb200_scene** scenes, int num_gpus, const lmb200_render_params* p, float* film_host, lmb200_render_stats* stats)
 {
     if (!scenes || num_gpus < 1 || !p || !film_host) return set_error(LMB200_E_INVALID, "null argument");
+    DeviceGuard guard;
     Session S;
     int rc = S.open(scenes, num_gpus);
     if (!rc) rc = S.pass(p, p->sample_begin, p->sample_end);
     if (!rc) rc = S.gather(p->mode == LMB200_MODE_NORMAL ? 1.0f : (float)S.npx / (float)p->num_samples, film_host);
-    if (!rc && stats) *stats = S.total;
+    if (!rc && stats) { *stats = S.total; stats->reduce_seconds = S.reduce_seconds; }
     return rc;
 }
 
@@ -1390,6 +1499,7 @@ int lmb200_render_timed(lmb200_scene** scenes, int num_gpus, const lmb200_render
     if (!scenes || num_gpus < 1 || !p || !film_host) return set_error(LMB200_E_INVALID, "null argument");
     if (p->mode == LMB200_MODE_NORMAL) return lmb200_render_multi(scenes, num_gpus, p, film_host, stats);
     if (pass_samples <= 0) pass_samples = 10000000;
+    DeviceGuard guard;
     Session S;
     int rc = S.open(scenes, num_gpus);
     const auto t0 = std::chrono::steady_clock::now();
@@ -1414,7 +1524,7 @@ int lmb200_render_timed(lmb200_scene** scenes, int num_gpus, const lmb200_render
         if (render_time > 0 && std::chrono::duration<double>(now - t0).count() > render_time) break;
     }
     if (!rc) rc = S.gather(done > 0 ? (float)S.npx / (float)done : 1.0f, film_host);
-    if (!rc && stats) { *stats = S.total; stats->samples = done; }
+    if (!rc && stats) { *stats = S.total; stats->samples = done; stats->reduce_seconds = S.reduce_seconds; }
     return rc;
 }
 

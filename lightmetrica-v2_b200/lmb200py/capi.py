@@ -65,14 +65,14 @@ class RenderParams(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("samples", C.c_int64), ("extend_rays", C.c_int64), ("shadow_rays", C.c_int64), ("iterations", C.c_int64),
-                ("launches", C.c_uint64), ("seconds", C.c_double)]
+                ("launches", C.c_uint64), ("seconds", C.c_double), ("reduce_seconds", C.c_double)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int64)
 
 EXPORTS = [
     "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build", "lmb200_accel_build_ex",
-    "lmb200_accel_get_stats", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
+    "lmb200_accel_get_stats", "lmb200_accel_device", "lmb200_accel_replicate", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
     "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_arrays", "lmb200_accel_create_host_only",
     "lmb200_scene_create", "lmb200_scene_create_ex", "lmb200_scene_create_shared", "lmb200_registry_put", "lmb200_registry_get", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
     "lmb200_render", "lmb200_render_multi", "lmb200_render_timed",
@@ -97,6 +97,9 @@ def lib():
     L.lmb200_accel_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.lmb200_accel_build_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     L.lmb200_accel_get_stats.argtypes = [C.c_void_p, C.POINTER(AccelStats)]
+    L.lmb200_accel_device.argtypes = [C.c_void_p]
+    L.lmb200_accel_replicate.restype = C.c_void_p
+    L.lmb200_accel_replicate.argtypes = [C.c_void_p, C.c_int]
     L.lmb200_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.lmb200_trace_closest_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.lmb200_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]

@@ -284,25 +284,45 @@ public:
 
         // ---- render ----
         // If the YAML selected accel::lmb200 too, its device BVH (same triangle list, same order) is reused
-        // on its device; other GPUs build their own replica.
+        // on the GPU it lives on (if that is one of ours); the BVH is built ONCE (by accel::lmb200 or by scene 0) and
+        // replicated device to device onto the other GPUs.
         lmb200_accel* sharedAccel = lmb200_registry_get(scene->GetAccel());
-        std::vector<lmb200_scene*> scenes;
+        const int sharedDev = sharedAccel ? lmb200_accel_device(sharedAccel) : -1;
+        std::vector<lmb200_scene*> scenes(numGpus_, nullptr);
+        std::vector<lmb200_accel*> replicas;
+        auto cleanup = [&]() {
+            for (auto* t : scenes) if (t) lmb200_scene_destroy(t);
+            for (auto* r : replicas) lmb200_accel_destroy(r);
+        };
+        auto fail = [&]() {
+            LM_LOG_ERROR(std::string("renderer::lmb200pt: ") + lmb200_last_error());
+            cleanup();
+        };
+        lmb200_accel* source = nullptr;     // a built device BVH to replicate from
+        if (sharedAccel && sharedDev >= device_ && sharedDev < device_ + numGpus_)
+        {
+            scenes[sharedDev - device_] = lmb200_scene_create_shared(&d, sharedAccel);
+            if (!scenes[sharedDev - device_]) { fail(); return; }
+            LM_LOG_INFO("renderer::lmb200pt: reusing the BVH of accel::lmb200 on device " + std::to_string(sharedDev));
+            source = sharedAccel;
+        }
+        else if (sharedAccel) source = sharedAccel;      // lives on a GPU outside [device, device + num_gpus): replicate from it
         for (int g = 0; g < numGpus_; g++)
         {
-            lmb200_scene* s = nullptr;
-            if (g == 0 && sharedAccel)
+            if (scenes[g]) continue;
+            if (source)
             {
-                s = lmb200_scene_create_shared(&d, sharedAccel);
-                if (s) LM_LOG_INFO("renderer::lmb200pt: reusing the BVH of accel::lmb200");
+                lmb200_accel* r = lmb200_accel_replicate(source, device_ + g);
+                if (!r) { fail(); return; }
+                replicas.push_back(r);
+                scenes[g] = lmb200_scene_create_shared(&d, r);
             }
-            if (!s) s = lmb200_scene_create_ex(device_ + g, &d, builder_);
-            if (!s)
+            else
             {
-                LM_LOG_ERROR(std::string("renderer::lmb200pt: ") + lmb200_last_error());
-                for (auto* t : scenes) lmb200_scene_destroy(t);
-                return;
+                scenes[g] = lmb200_scene_create_ex(device_ + g, &d, builder_);
+                if (scenes[g]) source = lmb200_scene_accel(scenes[g]);
             }
-            scenes.push_back(s);
+            if (!scenes[g]) { fail(); return; }
         }
         lmb200_render_params p;
         memset(&p, 0, sizeof(p));
@@ -334,7 +354,7 @@ public:
             rc = numGpus_ > 1 ? lmb200_render_multi(scenes.data(), numGpus_, &p, rgba.data(), &st)
                               : lmb200_render(scenes[0], &p, rgba.data(), &st);
         }
-        for (auto* s : scenes) lmb200_scene_destroy(s);
+        cleanup();
         if (rc != LMB200_OK)
         {
             LM_LOG_ERROR(std::string("renderer::lmb200pt: ") + lmb200_last_error());

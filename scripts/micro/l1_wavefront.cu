@@ -53,6 +53,47 @@ __global__ void kC(const float4* __restrict__ tab, const uint32_t* __restrict__ 
     }
     out[tid] = acc;
 }
+// D/E: 64-byte records aligned to 64 bytes (two 32-byte sectors, never straddling a line): four 16-byte / two 32-byte loads
+__global__ void kD(const float4* __restrict__ tab, const uint32_t* __restrict__ idx, int n, int iters, float* out)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    for (int it = 0; it < iters; it++) {
+        const uint32_t r = idx[(tid + it * 7919) % n];
+        const float4* p = tab + (size_t)r * 4;
+        const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+        acc += a.x + b.y + c.z + d.w;
+    }
+    out[tid] = acc;
+}
+__global__ void kE(const float4* __restrict__ tab, const uint32_t* __restrict__ idx, int n, int iters, float* out)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    for (int it = 0; it < iters; it++) {
+        const uint32_t r = idx[(tid + it * 7919) % n];
+        const char* b = reinterpret_cast<const char*>(tab + (size_t)r * 4);
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[8*k]), "=f"(v[8*k+1]), "=f"(v[8*k+2]), "=f"(v[8*k+3]), "=f"(v[8*k+4]), "=f"(v[8*k+5]), "=f"(v[8*k+6]), "=f"(v[8*k+7]) : "l"(b + 32 * k));
+        acc += v[0] + v[5] + v[10] + v[15];
+    }
+    out[tid] = acc;
+}
+// F: 48-byte records (triangle records), three 16-byte loads
+__global__ void kF(const float4* __restrict__ tab, const uint32_t* __restrict__ idx, int n, int iters, float* out)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    for (int it = 0; it < iters; it++) {
+        const uint32_t r = idx[(tid + it * 7919) % n];
+        const float4* p = tab + (size_t)r * 3;
+        const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        acc += a.x + b.y + c.z;
+    }
+    out[tid] = acc;
+}
 int main()
 {
     const int nrec = 1 << 20;                 // 80 MB of records: L2-resident on B200 (126 MB)
@@ -66,18 +107,23 @@ int main()
     const int blocks = 148 * 9, threads = 128, iters = 64;
     cudaMalloc(&out, blocks * threads * 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int which = 0; which < 3; which++) {
+    for (int which = 0; which < 6; which++) {
         float best = 1e9f;
         for (int rep = 0; rep < 4; rep++) {
             cudaEventRecord(e0);
             if (which == 0) kA<<<blocks, threads>>>(tab, idx, n, iters, out);
             if (which == 1) kB<<<blocks, threads>>>(tab, idx, n, iters, out);
             if (which == 2) kC<<<blocks, threads>>>(tab, idx, n, iters, out);
+            if (which == 3) kD<<<blocks, threads>>>(tab, idx, n, iters, out);
+            if (which == 4) kE<<<blocks, threads>>>(tab, idx, n, iters, out);
+            if (which == 5) kF<<<blocks, threads>>>(tab, idx, n, iters, out);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
         }
         const double recs = (double)blocks * threads * iters;
-        printf("%s: %.3f ms  %.1f G records/s  %.0f GB/s useful\n", which == 0 ? "A own record, 5 x 16 B" : which == 1 ? "B pieces dealt across lanes" : "C own record, 3 x 32 B", best, recs / best / 1e6, recs * 80 / best / 1e6);
+        static const char* names[6] = {"A own 80 B record, 5 x 16 B", "B 80 B pieces dealt across lanes", "C own 80 B record, 3 x 32 B", "D own 64 B aligned record, 4 x 16 B", "E own 64 B aligned record, 2 x 32 B", "F own 48 B record, 3 x 16 B"};
+        static const int bytes[6] = {80, 80, 80, 64, 64, 48};
+        printf("%s: %.3f ms  %.1f G records/s  %.0f GB/s useful\n", names[which], best, recs / best / 1e6, recs * bytes[which] / best / 1e6);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

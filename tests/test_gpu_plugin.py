@@ -194,3 +194,25 @@ def test_renderer_plugin_textured_bsdfs():
     floor = trimmed(ra, rb)
     assert trimmed(ours, ra) < 1.25 * floor, (trimmed(ours, ra), floor)
     assert np.allclose(ours.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.03)
+
+
+def test_renderer_plugin_two_gpus():
+    """`num_gpus: 2` in the YAML: the plugin builds the BVH once, replicates it device to device, renders through
+    lmb200_render_multi (per-GPU films + one ncclReduce, replacing contexts.combine_each(film->Accumulate),
+    scheduler.cpp:280-288) and must reproduce the 1-GPU image of the same seed."""
+    from lmb200py import capi
+    if capi.lib().lmb200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = scenedesc.cornell_box(32, 32, glossy_block=True)
+    N = 32 * 32 * 256
+    for accel in ("qbvh", "lmb200"):       # with accel::lmb200 the renderer shares its device BVH on GPU 0
+        R = ob.RefScene(sc, accel=accel)
+        one, _ = R.render("lmb200pt", N, seed=1, extra={"mode": "ptdirect"}, in_tree=True)
+        two, _ = R.render("lmb200pt", N, seed=1, extra={"mode": "ptdirect", "num_gpus": 2}, in_tree=True)
+        assert np.allclose(one, two, rtol=2e-4, atol=1e-5)
+    # time-budgeted + progressive on 2 GPUs
+    R = ob.RefScene(sc, accel="qbvh")
+    img, _ = R.render("lmb200pt", 1000, seed=1, in_tree=True,
+                      extra={"mode": "ptdirect", "num_gpus": 2, "render_time": 0.4, "progress_image_update_interval": 0.1, "grain_size": 200})
+    ref, _ = R.render("ptdirect", 32 * 32 * 1024, seed=1, threads=os.cpu_count() or 1)
+    assert abs(img.mean() - ref.mean()) / ref.mean() < 0.05

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import bindings as ob
-from lmb200py import capi, scenedesc
+from lmb200py import capi, scenedesc, scenes
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -315,3 +315,90 @@ def test_render_multi_tile_partitioning():
     assert st.samples == N
     assert rel_rmse(film[..., :3], one) < 1.25 * rel_rmse(two, one)
     assert np.allclose(film[..., :3].mean(axis=(0, 1)), one.mean(axis=(0, 1)), rtol=0.02)
+
+
+def _two_scenes(sc):
+    L = capi.lib()
+    if L.lmb200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    scenes_ = [capi.Scene(sc, device=g) for g in range(2)]
+    return L, scenes_, (C.c_void_p * 2)(*[s.h_ for s in scenes_])
+
+
+def test_render_multi_normal_mode_equals_single_gpu():
+    """MODE_NORMAL through lmb200_render_multi: every GPU renders its share of the pixels, the film sum is the image
+    (round 1 summed N full images: N times too bright)."""
+    sc = scenedesc.cornell_box(64, 40, glossy_block=True)
+    L, scenes_, arr = _two_scenes(sc)
+    one, _ = scenes_[0].render(capi.MODE_NORMAL, 64 * 40)
+    p = scenes_[0].params(capi.MODE_NORMAL, 64 * 40)
+    film = np.zeros((40, 64, 4), np.float32)
+    st = capi.RenderStats()
+    capi.check(L.lmb200_render_multi(arr, 2, C.byref(p), film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    assert st.samples == 64 * 40 and st.extend_rays == 64 * 40
+    assert np.array_equal(film[..., :3], one)
+    # the time-budget entry point forwards MODE_NORMAL to the same path
+    film[:] = 0
+    capi.check(L.lmb200_render_timed(arr, 2, C.byref(p), -1.0, 0, -1.0, capi.PROGRESS_FN(0), None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    assert np.array_equal(film[..., :3], one)
+
+
+def test_render_timed_two_gpus_progress_and_exact_range():
+    """lmb200_render_timed on 2 GPUs: progress images come from a periodic NCCL reduce of the per-GPU films
+    (scheduler.cpp:221-255, 280-288); without a time budget the call renders exactly the sample range and equals the
+    1-GPU image; stats report the reduce time."""
+    sc = scenedesc.cornell_box(32, 32)
+    L, scenes_, arr = _two_scenes(sc)
+    film = np.zeros((32, 32, 4), np.float32)
+    st = capi.RenderStats()
+    ticks = []
+
+    def on_progress(user, rgba, done, tick):
+        img = np.ctypeslib.as_array(rgba, shape=(32, 32, 4))
+        ticks.append((int(done), int(tick), float(img[..., :3].mean())))
+        return 0
+    cb = capi.PROGRESS_FN(on_progress)
+    p = scenes_[0].params(capi.MODE_PTDIRECT, 1, seed=9)
+    capi.check(L.lmb200_render_timed(arr, 2, C.byref(p), 0.6, 200000, 0.1, cb, None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    assert st.samples >= 200000 and st.samples % 200000 == 0
+    assert len(ticks) >= 2 and [t[1] for t in ticks] == list(range(1, len(ticks) + 1))
+    assert st.reduce_seconds > 0
+    ref, _ = scenes_[0].render(capi.MODE_PTDIRECT, 32 * 32 * 2048, seed=1)
+    assert abs(film[..., :3].mean() - ref.mean()) / ref.mean() < 0.05
+    assert all(abs(t[2] - ref.mean()) / ref.mean() < 0.25 for t in ticks)
+    N = 32 * 32 * 16
+    p = scenes_[0].params(capi.MODE_PTDIRECT, N, seed=3)
+    capi.check(L.lmb200_render_timed(arr, 2, C.byref(p), -1.0, 5000, -1.0, capi.PROGRESS_FN(0), None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
+    one, _ = scenes_[0].render(capi.MODE_PTDIRECT, N, seed=3)
+    assert st.samples == N and np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
+
+
+def test_render_multi_rejects_two_scenes_on_one_device():
+    sc = scenedesc.cornell_box(16, 16)
+    L = capi.lib()
+    scenes_ = [capi.Scene(sc, device=0) for _ in range(2)]
+    arr = (C.c_void_p * 2)(*[s.h_ for s in scenes_])
+    p = scenes_[0].params(capi.MODE_PTDIRECT, 1000)
+    film = np.zeros((16, 16, 4), np.float32)
+    with pytest.raises(capi.LmbError, match="same device"):
+        capi.check(L.lmb200_render_multi(arr, 2, C.byref(p), film.ctypes.data_as(C.c_void_p), None))
+
+
+def test_accel_replicate_on_second_gpu():
+    """lmb200_accel_replicate: device-to-device copy of the BVH; the replica traces the same hits and a scene sharing
+    it renders the same image."""
+    L = capi.lib()
+    if L.lmb200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    verts = scenes.soup(50000, seed=3, extent=10.0, edge=0.2)
+    lo, hi = scenes.bounds(verts)
+    rays = scenes.random_rays(100000, lo, hi, seed=5)
+    a = capi.Accel(0)
+    a.build(verts)
+    h0 = a.trace_closest(rays)
+    r = L.lmb200_accel_replicate(a.h, 1)
+    assert r and L.lmb200_accel_device(r) == 1 and L.lmb200_accel_device(a.h) == 0
+    h1 = np.zeros(len(rays), dtype=capi.HIT_DTYPE)
+    capi.check(L.lmb200_trace_closest(r, rays.ctypes.data_as(C.c_void_p), h1.ctypes.data_as(C.c_void_p), len(rays)))
+    assert np.array_equal(h0.view(np.uint32), h1.view(np.uint32))
+    L.lmb200_accel_destroy(r)
