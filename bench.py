@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--pt-tris", type=int, default=1_000_000)
     ap.add_argument("--pt-spp", type=int, default=1024)
     ap.add_argument("--pt-pool", type=int, default=0, help="wavefront pool size (0 = library default)")
+    ap.add_argument("--pt-cpu-spp", type=int, default=2, help="bounded CPU sample of the path-tracing workload (samples per pixel)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[4] leg (10M triangles, 4K film, NCCL film reduce)")
+    ap.add_argument("--c4-spp", type=int, default=64)
     return ap.parse_args()
 
 
@@ -209,6 +212,12 @@ def run_reference(a):
             "data": "synthetic", "config": cfg,
             "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}, **others),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not a.no_pt:
+        # the other half of the metric on the reference's side: renderer::ptdirect on the configs[2] scene, bounded sample
+        from lmb200py import scenedesc
+        pt = pt_cpu_baseline(scenedesc.config2_scene(a.pt_tris, 1920, 1080), 1920, 1080, a.pt_cpu_spp)
+        line["path_tracing"] = dict({"metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene"}, **pt)
+        line["pt_msamples_s"] = pt["value"]
     emit(line)
 
 
@@ -320,13 +329,21 @@ def main():
     mean_kernel_s = float(np.mean(kernel_ms)) * 1e-3
     achieved = b_ray * a.rays / mean_kernel_s / 1e9
     peak, peak_src = hbm_peak()
-    traffic = None
+    # DRAM traffic per launch comes from one kept ncu capture (profiles/traffic.json); it is only reported while the
+    # traversal sources still hash to what it was captured on
+    traffic, traffic_note = None, "no profiles/traffic.json"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_ray") * a.rays   # per launch, like `achieved`
+            tj = json.load(open(tpath))
+            if tj.get("source_hash") == source_hash():
+                traffic = tj.get("dram_bytes_per_ray") * a.rays   # per launch, like `achieved`
+                traffic_note = "ncu dram__bytes_read.sum + dram__bytes_write.sum per ray x rays per launch, captured on source hash " + tj["source_hash"]
+            else:
+                traffic_note = "stale: profiles/traffic.json was captured on source hash %s, the kernel now hashes to %s" % (tj.get("source_hash"), source_hash())
         except Exception:
             traffic = None
+    ceiling = pcie_ceiling(torch, dist, world, dev, h_rays, d_rays, h_hits, d_hits)
 
     # ---- parity spot check + CPU baseline (rank 0, N=1) ----
     cpu = None
@@ -349,6 +366,11 @@ def main():
     pt = None
     if not a.no_pt:
         pt = bench_pt(a, torch, dist, capi, world, rank, local, dev)
+    c4 = None
+    if not a.no_c4:
+        del d_rays, d_hits, h_rays, h_hits
+        torch.cuda.empty_cache()
+        c4 = bench_config4(a, torch, dist, capi, world, rank, local, dev)
 
     launches = int(L.lmb200_launch_count() - launches0)
     if rank == 0:
@@ -356,9 +378,12 @@ def main():
                 "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(a),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.rays * 32, "d2h_bytes_per_step": a.rays * 16,
-                        "api": "lmb200_trace_closest(host pinned rays -> host pinned hits)", "host_affinity": numa},
+                        "api": "lmb200_trace_closest(host pinned rays -> host pinned hits)", "host_affinity": numa,
+                        "gbs": e2e_value * 1e6 * 48 / 1e9, "pcie_ceiling_gbs": ceiling, "frac_of_pcie_ceiling": e2e_value * 1e6 * 48 / 1e9 / ceiling,
+                        "pcie_ceiling_how": "concurrent pinned H2D (32 B/ray) + D2H (16 B/ray) torch copies of the same buffers, all ranks at once"},
                 "gpu_launches": launches, "clocks": clock_info,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+                             "frac_dram_actual": (traffic / mean_kernel_s / 1e9 / peak) if traffic else None,
                              "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": npr.value, "tris_per_ray": tpr.value,
                              "kernel": "lmb200::trace_kernel<false,false>", "kernel_ms": mean_kernel_s * 1e3,
                              # second ceiling, informational: node fetches/s against the rate at which a fetch-only kernel reads random
@@ -367,7 +392,13 @@ def main():
                              "frac_of_fetch_ceiling": npr.value * a.rays / mean_kernel_s / 81.4e9},
                 "cpu_baseline": cpu, "parity": parity,
                 "bvh": {"nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
-                "path_tracing": pt}
+                "path_tracing": pt, "config4": c4,
+                # the two secondary figures once more as flat keys (nested objects may be dropped by a summariser)
+                "pt_msamples_s": pt["value"] if pt else None, "pt_e2e_msamples_s": pt["e2e"]["value"] if pt else None,
+                "pt_roofline_frac": pt["roofline"]["frac"] if pt else None,
+                "pt_cpu_msamples_s": pt["cpu_baseline"]["value"] if pt and pt.get("cpu_baseline") else None,
+                "incoherent_1m_mesh_mrays_s": pt["incoherent_1m_tri_mesh"]["value"] if pt else None,
+                "config4_msamples_s": c4["value"] if c4 else None, "film_reduce_ms": c4["film_reduce_ms"] if c4 else None}
         emit(line)
     if world > 1:
         dist.barrier()
@@ -436,36 +467,100 @@ def incoherent_on_scene(a, torch, dist, capi, S, verts, world, dev, stream):
             "target": ">= 1000 Mrays/s per GPU"}
 
 
-def bench_pt(a, torch, dist, capi, world, rank, local, dev):
-    """ptdirect on the 1M-triangle mesh scene (BASELINE configs[2] geometry/materials/lights) at pt_spp samples per pixel (1024 = the config),
-    sample range sharded contiguously over ranks, films summed with one NCCL reduce, then rescaled."""
-    from lmb200py import scenedesc, distributed
-    sc = scenedesc.config2_scene(a.pt_tris, 1920, 1080)
-    S = capi.Scene(sc, device=local)
-    _k = S.keep
-    W, H = 1920, 1080
-    N = W * H * a.pt_spp
-    film = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+S_STATE_BYTES = 113      # per-slot path state a vertex step reads and writes back (render.cu Pool: sample 8, nverts 4, thr 16,
+                         # ray_o 16, ray_d 16, hit 16, traced 1, vtx_p 16, vtx_wi 16, vtx_v 4), ptdirect
+
+
+def pt_roofline(st, samples, seconds, world):
+    """B_sample = sum over extend rays of B_ray + sum over shadow rays of B_ray(any-hit) + V (2 S_state) + splats 16,
+    with nodes / records per ray counted by the instrumented kernels over the actual extend and shadow queues."""
+    er, sr = max(st.extend_rays, 1), max(st.shadow_rays, 1)
+    b_ext = 32 + 16 + 80.0 * st.extend_nodes / er + 48.0 * st.extend_tris / er
+    b_sh = 32 + 16 + 80.0 * st.shadow_nodes / sr + 48.0 * st.shadow_tris / sr      # ray + (contribution, pixel)
+    n = max(st.samples, 1)
+    b_sample = st.extend_rays / n * b_ext + st.shadow_rays / n * b_sh + st.vertices / n * 2 * S_STATE_BYTES + st.shadow_rays / n * 16
+    peak, src = hbm_peak()
+    achieved = b_sample * samples / seconds / 1e9 / world        # per GPU
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": src,
+            "bytes_per_sample": b_sample, "vertices_per_sample": st.vertices / n, "extend_rays_per_sample": st.extend_rays / n,
+            "shadow_rays_per_sample": st.shadow_rays / n, "extend": {"nodes_per_ray": st.extend_nodes / er, "tris_per_ray": st.extend_tris / er, "bytes_per_ray": b_ext},
+            "shadow": {"nodes_per_ray": st.shadow_nodes / sr, "tris_per_ray": st.shadow_tris / sr, "bytes_per_ray": b_sh},
+            "state_bytes_per_vertex": 2 * S_STATE_BYTES, "kernel": "lmb200::k_extend (dominant, ~60 % of the frame) + k_shadow + shading kernels",
+            "counted_on": "a %d-sample instrumented run of the same scene (count_work)" % st.samples}
+
+
+def pt_cpu_baseline(sc, W, H, spp):
+    """The reference's own renderer::ptdirect (oracle/_ref: real Scene3 + accel::qbvh + Scheduler shim on all host threads) on a
+    bounded sample of the same scene; the C port when the compiled reference is not present."""
+    from oracle import bindings as ob
+    cores = os.cpu_count() or 1
+    N = W * H * spp
+    if ob.have_ref():
+        t0 = time.perf_counter()
+        R = ob.RefScene(sc, accel="qbvh")
+        build_s = time.perf_counter() - t0
+        img, sec = R.render("ptdirect", N, seed=1, threads=cores)
+        return {"value": N / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                "sample": f"{spp} spp of the same {W}x{H} scene ({N} samples, {sec:.1f} s), renderer::ptdirect + accel::qbvh from oracle/_ref, scene build {build_s:.0f} s not timed",
+                "mean_rgb": [float(x) for x in img.mean(axis=(0, 1))]}
+    P = ob.PortPT(sc)
+    N = W * H // 4
+    t0 = time.perf_counter()
+    img, _ = P.render(1, N, seed=1)
+    sec = time.perf_counter() - t0
+    return {"value": N / sec / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+            "sample": f"{N} samples of the same scene, oracle/lm_oracle_pt.c (scalar), {sec:.1f} s"}
+
+
+def render_sharded(torch, dist, capi, S, film, W, H, N, rank, world, stream, pool=0, count=False, time_reduce=False):
+    """One frame through the multi-process path: every rank renders its share of the sample range into its own unscaled film,
+    one NCCL reduce to rank 0 (replaces contexts.combine_each(film->Accumulate), scheduler.cpp:280-285), rescale by W H / N."""
+    from lmb200py import distributed
     L = capi.lib()
     b, e = distributed.shard_range(N, rank, world)
     st = capi.RenderStats()
+    film.zero_()
+    p = S.params(capi.MODE_PTDIRECT, N, seed=1, begin=b, end=e, pool=pool)
+    p.count_work = 1 if count else 0
+    capi.check(L.lmb200_render_dev(S.h_, C.byref(p), film.data_ptr(), stream, C.byref(st)))
+    r0 = r1 = None
+    if time_reduce and world > 1:
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+    distributed.reduce_film(film, dist if world > 1 else None)
+    if r0 is not None:
+        r1.record()
+    capi.check(L.lmb200_film_rescale_dev(film.data_ptr(), W * H, distributed.film_scale(W, H, N), stream))
+    return st, (r0, r1)
+
+
+def bench_pt(a, torch, dist, capi, world, rank, local, dev):
+    """ptdirect on the 1M-triangle mesh scene (BASELINE configs[2] geometry/materials/lights) at pt_spp samples per pixel (1024 = the config),
+    sample range sharded contiguously over ranks, films summed with one NCCL reduce, then rescaled."""
+    from lmb200py import scenedesc
+    W, H = 1920, 1080
+    sc = scenedesc.config2_scene(a.pt_tris, W, H)
+    S = capi.Scene(sc, device=local)
+    _k = S.keep
+    N = W * H * a.pt_spp
+    film = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    h_film = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+    L = capi.lib()
     stream = torch.cuda.current_stream().cuda_stream
 
-    def once():
-        film.zero_()
-        p = S.params(capi.MODE_PTDIRECT, N, seed=1, begin=b, end=e, pool=a.pt_pool)
-        capi.check(L.lmb200_render_dev(S.h_, C.byref(p), film.data_ptr(), stream, C.byref(st)))
-        distributed.reduce_film(film, dist if world > 1 else None)
-        capi.check(L.lmb200_film_rescale_dev(film.data_ptr(), W * H, distributed.film_scale(W, H, N), stream))
-    once()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st, _ = render_sharded(torch, dist, capi, S, film, W, H, N, rank, world, stream, a.pt_pool)      # warm-up frame
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     reps = 2
     for _ in range(reps):
-        once()
+        st, _ = render_sharded(torch, dist, capi, S, film, W, H, N, rank, world, stream, a.pt_pool)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
@@ -473,13 +568,122 @@ def bench_pt(a, torch, dist, capi, world, rank, local, dev):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    sec = float(ms.item()) * 1e-3
+    mean_rgb = [float(x) for x in film[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None
+
+    # ---- end to end through the public call: host film out. N = 1: lmb200_render (the call renderer::lmb200pt makes);
+    # N > 1: per-rank lmb200_render_dev + NCCL reduce + rank 0 copies the film to pinned host memory. Wall clock.
+    sync_all()
+    t0 = time.perf_counter()
+    if world == 1:
+        p = S.params(capi.MODE_PTDIRECT, N, seed=1, pool=a.pt_pool)
+        st1 = capi.RenderStats()
+        capi.check(L.lmb200_render(S.h_, C.byref(p), h_film.data_ptr(), C.byref(st1)))
+    else:
+        render_sharded(torch, dist, capi, S, film, W, H, N, rank, world, stream, a.pt_pool)
+        if rank == 0:
+            h_film.copy_(film, non_blocking=True)
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = {"value": N / float(e2e_s.item()) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(capi.RenderParams),
+           "d2h_bytes_per_step": W * H * 16,
+           "api": "lmb200_render(params -> host film)" if world == 1 else "lmb200_render_dev per rank + NCCL film reduce + rank-0 film to pinned host memory"}
+
+    # ---- roofline: algorithmic bytes per sample from an instrumented (untimed) run at 16 spp
+    Nc = W * H * min(16, a.pt_spp)
+    stc, _ = render_sharded(torch, dist, capi, S, film, W, H, Nc, 0, 1, stream, a.pt_pool, count=True)
+    torch.cuda.synchronize()
+    roof = pt_roofline(stc, N, sec, world)
+
     target = incoherent_on_scene(a, torch, dist, capi, S, _k["verts"], world, dev, stream)
     S.close()
+    cpu = None
+    if rank == 0 and world == 1:
+        cpu = pt_cpu_baseline(sc, W, H, a.pt_cpu_spp)
     return {"incoherent_1m_tri_mesh": target,
-            "metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene", "value": N / (float(ms.item()) * 1e-3) / 1e6,
+            "metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene", "value": N / sec / 1e6,
             "unit": "Msamples/s", "spp": a.pt_spp, "samples": N, "ms": float(ms.item()), "rays_per_sample": float(rays.item()) / N,
-            "mrays_per_s": float(rays.item()) / (float(ms.item()) * 1e-3) / 1e6, "film_reduce": "torch.distributed NCCL reduce" if world > 1 else "none (1 GPU)", "scaling": "strong (fixed image and spp, sample range sharded over ranks)",
-            "mean_rgb": [float(x) for x in film[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None}
+            "mrays_per_s": float(rays.item()) / sec / 1e6, "film_reduce": "torch.distributed NCCL reduce" if world > 1 else "none (1 GPU)", "scaling": "strong (fixed image and spp, sample range sharded over ranks)",
+            "mean_rgb": mean_rgb, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+
+
+def bench_config4(a, torch, dist, capi, world, rank, local, dev):
+    """BASELINE configs[4]: 10M-triangle instanced scene, 3840x2160 film, ptdirect at c4_spp samples per pixel (the config names 4096;
+    throughput is per sample), sample range sharded over ranks, the 133 MB film summed with ONE NCCL reduce timed on its own."""
+    from lmb200py import scenedesc
+    W, H = 3840, 2160
+    sc, verts = scenedesc.config4_scene(W, H)
+    t0 = time.perf_counter()
+    S = capi.Scene(sc, device=local, builder=capi.BUILD_GPU_LBVH)
+    create_s = time.perf_counter() - t0
+    ast = capi.AccelStats()
+    L = capi.lib()
+    capi.check(L.lmb200_accel_get_stats(L.lmb200_scene_accel(S.h_), C.byref(ast)))
+    N = W * H * a.c4_spp
+    film = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    render_sharded(torch, dist, capi, S, film, W, H, N // 8, rank, world, stream)      # warm-up (also warms the NCCL reduce)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st, (r0, r1) = render_sharded(torch, dist, capi, S, film, W, H, N, rank, world, stream, time_reduce=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), r0.elapsed_time(r1) if r0 is not None else 0.0, st.seconds * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, red_ms, render_ms = [float(x) for x in t.tolist()]
+    ok = bool(torch.isfinite(film).all().item()) if rank == 0 else None
+    mean_rgb = [float(x) for x in film[..., :3].mean(dim=(0, 1)).tolist()] if rank == 0 else None
+    S.close()
+    return {"metric": "Msamples/s ptdirect, 10M-tri instanced scene, 3840x2160", "value": N / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
+            "triangles": int(len(verts)) + 2, "spp": a.c4_spp, "samples": N, "ms": ms, "render_ms": render_ms,
+            "film_reduce_ms": red_ms if world > 1 else None, "film_bytes": W * H * 16,
+            "film_reduce_gbs": (W * H * 16 / (red_ms * 1e-3) / 1e9) if (world > 1 and red_ms > 0) else None,
+            "note": "film_reduce_ms is the max over ranks of the device time of the one NCCL reduce; it includes waiting for the slowest rank's render",
+            "bvh": {"builder": "device LBVH", "nodes": ast.num_nodes, "node_bytes": ast.node_bytes, "tri_bytes": ast.tri_bytes,
+                    "build_s": ast.build_seconds, "scene_create_s": create_s},
+            "scaling": "strong", "finite": ok, "mean_rgb": mean_rgb}
+
+
+def pcie_ceiling(torch, dist, world, dev, h_rays, d_rays, h_hits, d_hits):
+    """What the box's host<->device path can move at all: the e2e leg's own pinned buffers copied with plain torch copies,
+    H2D (rays) and D2H (hits) concurrently on two streams, all ranks at once. GB/s summed over ranks."""
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    n = min(h_rays.shape[0], 1 << 25)
+
+    def once():
+        with torch.cuda.stream(s1):
+            d_rays[:n].copy_(h_rays[:n], non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_hits[:n].copy_(d_hits[:n], non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return 3 * n * 48 * world / float(dt.item()) / 1e9
+
+
+def source_hash():
+    """Identifies the traversal kernel a kept ncu figure (profiles/traffic.json) was captured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("traverse.cuh", "accel.cu", "bvh.h", "triaccel.h", "bvh_build.cpp"):
+        h.update(open(os.path.join(ROOT, "lightmetrica-v2_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 if __name__ == "__main__":

@@ -240,6 +240,8 @@ typedef struct lmb200_render_params {
      * image as whole-image sampling (stratified over tiles: a different sampling pattern, statistically identical);
      * splats of camera-vertex light sampling still land anywhere, so films are summed as usual. */
     float    tile[4];
+    int32_t  count_work;         /* 1 = run the instrumented traversal kernels and fill lmb200_render_stats::extend_nodes ...
+                                    shadow_tris (for the roofline's algorithmic bytes per sample); such a run is never timed */
     int32_t  tile_partition;     /* lmb200_render_multi / _timed only: 1 = GPU g of n draws its raster positions in the
                                     horizontal strip [g/n, (g+1)/n) of the image (default 0: every GPU samples the whole image) */
 } lmb200_render_params;
@@ -251,6 +253,9 @@ typedef struct lmb200_render_stats {
     uint64_t launches;
     double   seconds;            /* device time of the wavefront loop (CUDA events) */
     double   reduce_seconds;     /* lmb200_render_multi / _timed: device time of the NCCL film reductions; else 0 */
+    int64_t  vertices;           /* path vertices processed (camera vertices included): one k_logic/k_nee/k_bsdf pass each */
+    int64_t  extend_nodes, extend_tris;   /* count_work only: 80-byte nodes / 48-byte triangle records fetched by the extend rays */
+    int64_t  shadow_nodes, shadow_tris;   /* ... and by the shadow rays */
 } lmb200_render_stats;
 
 /* Builds the accel (device) and uploads shading data. */

@@ -329,7 +329,7 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     if (a->d_nodes) { cudaFree(a->d_nodes); a->d_nodes = nullptr; }
     if (a->d_tris) { cudaFree(a->d_tris); a->d_tris = nullptr; }
-    if (!a->d_counter && (e = cudaMalloc(&a->d_counter, 4 * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
+    if (!a->d_counter && (e = cudaMalloc(&a->d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
     const uint32_t n = (uint32_t)ntris;
     DevBuf D;
     float* d_verts = D.alloc<float>(9 * (size_t)n);

@@ -81,7 +81,8 @@ struct Pool {
     float4* sq_c;                 // contribution rgb, w = pixel (int bits)
     // counters: [0] vq size, [1] eq size, [2] sq size, [3] unused
     uint32_t* qcount;
-    unsigned long long* next_sample;   // [0] next sample index to hand out, [1] extend rays, [2] shadow rays, [3] samples started
+    unsigned long long* next_sample;   // [0] next sample index to hand out, [1] extend rays, [2] shadow rays, [3] path vertices,
+                                       // [4],[5] nodes / triangle records fetched by extend rays, [6],[7] by shadow rays (count_work runs only)
 };
 
 struct RenderCfg {
@@ -771,13 +772,22 @@ struct ExtendIo {
         P.hit[P.eq[qi]] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
     }
 };
+// COUNT variants (instrumented, never timed): nodes / triangle records fetched, summed into P.next_sample[4..7]
+__device__ __forceinline__ void add_work(unsigned long long* dst, const TravCounters& cnt)
+{
+    unsigned long long a = cnt.nodes, b = cnt.tris;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31u) == 0) { atomicAdd(dst, a); atomicAdd(dst + 1, b); }
+}
+template <bool COUNT>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
 k_extend(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter)
 {
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ExtendIo io{P, P.qcount[1]};
-    TravCounters cnt;
-    persistent_trace<false, false, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+    TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+    if (COUNT) add_work(P.next_sample + 4, cnt);
 }
 
 // shadow: any hit over the shadow queue, unoccluded contributions are splatted (film_hdr.cpp:218-223)
@@ -793,13 +803,15 @@ struct ShadowIo {
         }
     }
 };
+template <bool COUNT>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
 k_shadow(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter, float4* film)
 {
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ShadowIo io{P, P.qcount[2], film};
-    TravCounters cnt;
-    persistent_trace<true, false, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+    TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+    if (COUNT) add_work(P.next_sample + 6, cnt);
 }
 
 __global__ void k_stats(Pool P)
@@ -807,6 +819,7 @@ __global__ void k_stats(Pool P)
     // fold the queue sizes of this iteration into the running ray counters
     P.next_sample[1] += P.qcount[1];
     P.next_sample[2] += P.qcount[2];
+    P.next_sample[3] += P.qcount[0];
 }
 
 __global__ void k_rescale(float4* film, long long n, float s)
@@ -926,7 +939,7 @@ static int ensure_pool(Scene* s, uint32_t n)
     if ((rc = pool_alloc(s, &P.sq_d, n))) return rc;
     if ((rc = pool_alloc(s, &P.sq_c, n))) return rc;
     if ((rc = pool_alloc(s, &P.qcount, 4))) return rc;
-    if ((rc = pool_alloc(s, &P.next_sample, 4))) return rc;
+    if ((rc = pool_alloc(s, &P.next_sample, 8))) return rc;
     s->pool_size = n;
     return LMB200_OK;
 }
@@ -986,7 +999,7 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     int rc = ensure_pool(s, pool);
     if (rc) return rc;
     Pool& P = s->pool;
-    if (!s->h_pinned && (e = cudaHostAlloc(&s->h_pinned, 12 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    if (!s->h_pinned && (e = cudaHostAlloc(&s->h_pinned, 16 * sizeof(unsigned long long), cudaHostAllocDefault)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
     volatile unsigned long long* hp = reinterpret_cast<volatile unsigned long long*>(s->h_pinned);
     if (!s->shadow_stream) {
         if ((e = cudaStreamCreateWithFlags(&s->shadow_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
@@ -1013,9 +1026,10 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
 #define LMB_CK(call, what) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
     LMB_CK(cudaMemsetAsync(P.nverts, 0, sizeof(int) * pool, st), "cudaMemsetAsync(nverts)");
     LMB_CK(cudaMemsetAsync(P.traced, 0, pool, st), "cudaMemsetAsync(traced)");
-    unsigned long long* h_init = reinterpret_cast<unsigned long long*>(s->h_pinned) + 8;     // pinned: the async copy really is async
-    h_init[0] = (unsigned long long)p->sample_begin; h_init[1] = h_init[2] = h_init[3] = 0ull;
-    LMB_CK(cudaMemcpyAsync(P.next_sample, h_init, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(next_sample)");
+    unsigned long long* h_init = reinterpret_cast<unsigned long long*>(s->h_pinned) + 8;     // [8..16)     // pinned: the async copy really is async
+    h_init[0] = (unsigned long long)p->sample_begin;
+    for (int k = 1; k < 8; k++) h_init[k] = 0ull;
+    LMB_CK(cudaMemcpyAsync(P.next_sample, h_init, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(next_sample)");
 
     LMB_CK(cudaEventCreate(&ev.a), "cudaEventCreate");
     LMB_CK(cudaEventCreate(&ev.b), "cudaEventCreate");
@@ -1024,6 +1038,7 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     const int trace_blocks = s->accel->num_sms * s->accel->trace_blocks_per_sm;
     const float4* d_nodes = reinterpret_cast<const float4*>(s->accel->d_nodes);
     const float4* d_tris = reinterpret_cast<const float4*>(s->accel->d_tris);
+    const bool count = p->count_work != 0;
     int64_t iters = 0;
     for (;;) {
         LMB_CK(cudaMemsetAsync(P.qcount, 0, 4 * sizeof(uint32_t), st), "cudaMemsetAsync(qcount)");
@@ -1035,11 +1050,13 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
             k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
             LMB_CK(cudaEventRecord(s->ev_nee, st), "cudaEventRecord(nee)");
             LMB_CK(cudaStreamWaitEvent(s->shadow_stream, s->ev_nee, 0), "cudaStreamWaitEvent(nee)");
-            k_shadow<<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(d_nodes, d_tris, P, s->d_counter + 1, film);
+            if (count) k_shadow<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(d_nodes, d_tris, P, s->d_counter + 1, film);
+            else k_shadow<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(d_nodes, d_tris, P, s->d_counter + 1, film);
             LMB_CK(cudaEventRecord(s->ev_shadow, s->shadow_stream), "cudaEventRecord(shadow)");
         }
         k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
-        k_extend<<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(d_nodes, d_tris, P, s->d_counter);
+        if (count) k_extend<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(d_nodes, d_tris, P, s->d_counter);
+        else k_extend<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(d_nodes, d_tris, P, s->d_counter);
         if (nee) LMB_CK(cudaStreamWaitEvent(st, s->ev_shadow, 0), "cudaStreamWaitEvent(shadow)");
         k_stats<<<1, 1, 0, st>>>(P);
         LMB_CK(cudaGetLastError(), "wavefront kernel launch");
@@ -1052,7 +1069,7 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
         if (live == 0 && hp[4] >= cfg.sample_end) break;     // no live vertex and the sample counter is exhausted
     }
     LMB_CK(cudaEventRecord(ev.b, st), "cudaEventRecord");
-    LMB_CK(cudaMemcpyAsync(s->h_pinned, P.next_sample, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
+    LMB_CK(cudaMemcpyAsync(s->h_pinned, P.next_sample, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(counters)");
     LMB_CK(cudaStreamSynchronize(st), "wavefront end");
     float ms = 0.f;
     LMB_CK(cudaEventElapsedTime(&ms, ev.a, ev.b), "cudaEventElapsedTime");
@@ -1065,6 +1082,9 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
         stats->launches = g_launch_count.load() - launches0;
         stats->seconds = ms * 1e-3;
         stats->reduce_seconds = 0;
+        stats->vertices = (int64_t)hp[3];
+        stats->extend_nodes = (int64_t)hp[4]; stats->extend_tris = (int64_t)hp[5];
+        stats->shadow_nodes = (int64_t)hp[6]; stats->shadow_tris = (int64_t)hp[7];
     }
     return LMB200_OK;
 }
@@ -1361,8 +1381,15 @@ struct Session {
         cudaError_t e = cudaMalloc(&scratch, sizeof(float4) * (size_t)npx);
         if (e != cudaSuccess) return cuda_fail(e, "session scratch");
         if (n > 1) {
-            void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            // Which libnccl: (1) $LMB200_NCCL_LIB if set (lmb200py points it at the copy bundled with PyTorch, so that a
+            // process that also imports torch ends up with ONE libnccl.so.2 — the dynamic linker shares objects by soname,
+            // and torch's libtorch_cuda.so needs symbols newer than an older system copy has); (2) a libnccl.so.2 that is
+            // already loaded in the process; (3) the system library. Never RTLD_GLOBAL: nobody else should bind to it.
+            void* lib = nullptr;
+            if (const char* path = getenv("LMB200_NCCL_LIB")) if (*path) lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+            if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+            if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+            if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
             if (!lib) return set_error(LMB200_E_NCCL, std::string("cannot load libnccl: ") + dlerror());
             fn_init_all init = (fn_init_all)dlsym(lib, "ncclCommInitAll");
             gs = (fn_void)dlsym(lib, "ncclGroupStart"); ge = (fn_void)dlsym(lib, "ncclGroupEnd");
@@ -1422,7 +1449,9 @@ struct Session {
         for (int g = 0; g < n; g++) {
             if (rcs[g]) return set_error(rcs[g], errs[g]);
             total.samples += st[g].samples; total.extend_rays += st[g].extend_rays; total.shadow_rays += st[g].shadow_rays;
-            total.launches += st[g].launches;
+            total.launches += st[g].launches; total.vertices += st[g].vertices;
+            total.extend_nodes += st[g].extend_nodes; total.extend_tris += st[g].extend_tris;
+            total.shadow_nodes += st[g].shadow_nodes; total.shadow_tris += st[g].shadow_tris;
             secs = std::max(secs, st[g].seconds); iters = std::max(iters, st[g].iterations);
         }
         total.seconds += secs; total.iterations += iters;

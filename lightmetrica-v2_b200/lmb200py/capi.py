@@ -60,12 +60,13 @@ class SceneDesc(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("num_samples", C.c_int64), ("sample_begin", C.c_int64), ("sample_end", C.c_int64),
                 ("max_num_vertices", C.c_int32), ("min_num_vertices", C.c_int32), ("seed", C.c_uint64), ("pool_size", C.c_int32),
-                ("tile", C.c_float * 4), ("tile_partition", C.c_int32)]
+                ("tile", C.c_float * 4), ("count_work", C.c_int32), ("tile_partition", C.c_int32)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("samples", C.c_int64), ("extend_rays", C.c_int64), ("shadow_rays", C.c_int64), ("iterations", C.c_int64),
-                ("launches", C.c_uint64), ("seconds", C.c_double), ("reduce_seconds", C.c_double)]
+                ("launches", C.c_uint64), ("seconds", C.c_double), ("reduce_seconds", C.c_double), ("vertices", C.c_int64),
+                ("extend_nodes", C.c_int64), ("extend_tris", C.c_int64), ("shadow_nodes", C.c_int64), ("shadow_tris", C.c_int64)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int64)
@@ -81,6 +82,24 @@ EXPORTS = [
 _lib = None
 
 
+def _point_at_torch_nccl():
+    """lmb200_render_multi dlopens libnccl lazily. In a Python process that may also import torch, both must end up with the
+    same libnccl.so.2 (objects are shared by soname; torch's libtorch_cuda.so needs the newer copy it ships with), so the
+    library is told to use the wheel's copy when there is one."""
+    if os.environ.get("LMB200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["LMB200_NCCL_LIB"] = cand
+                return
+    except Exception:      # noqa: BLE001
+        pass
+
+
 def lib():
     """Loads liblmb200.so; raises (loudly) if it has not been built — there is no CPU fallback."""
     global _lib
@@ -88,6 +107,7 @@ def lib():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} not found: run ./build.sh (or __graft_entry__.build()). lmb200 has no CPU fallback.")
+    _point_at_torch_nccl()
     L = C.CDLL(LIB_PATH)
     L.lmb200_last_error.restype = C.c_char_p
     L.lmb200_accel_create.restype = C.c_void_p

@@ -335,6 +335,26 @@ def config2_scene(target_tris=1_000_000, w=1920, h=1080, seed=42, half=50.0, n_o
     return s
 
 
+def config4_scene(w=3840, h=2160, instances=100, asset_tris=100_000):
+    """BASELINE.json configs[4]: a 10M-triangle "instanced" scene — `instances` copies of one `asset_tris`-triangle asset on a
+    10 x 10 grid, flattened to world-space triangles exactly as the reference's accels do (accel_qbvh.cpp:161-194) — under one
+    area light, 4K film."""
+    base, _ = scenes.mesh_scene(asset_tris, seed=7, half=5.0, n_objects=20)
+    side = int(np.ceil(np.sqrt(instances)))
+    inst = []
+    for k in range(instances):
+        off = np.array([(k % side - (side - 1) / 2) * 10.0, 0.0, (k // side - (side - 1) / 2) * 10.0], np.float32)
+        inst.append((base.reshape(-1, 3) + off).reshape(-1, 9))
+    verts = np.ascontiguousarray(np.concatenate(inst), np.float32)
+    sc = Scene()
+    sc.add_bsdf("w", "diffuse", (0.6, 0.6, 0.6))
+    sc.add_light("lamp", (40.0, 40.0, 40.0))
+    sc.add_mesh_tris(verts, "w")
+    sc.add_quad((-20, 30, -20), (20, 30, -20), (20, 30, 20), (-20, 30, 20), "w", "lamp")
+    sc.set_camera((0.0, 25.0, 70.0), (0.0, 0.0, 0.0), (0, 1, 0), 45.0, w, h)
+    return sc, verts
+
+
 def specular_box(w=64, h=64, point_light=True):
     """Cornell-style box with a glass sphere (bsdf::flesnel), a mirror block (bsdf::reflect_all), a refract_all slab
     and, optionally, a light::point besides the ceiling area light: exercises the delta BSDFs and the delta light."""

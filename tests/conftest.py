@@ -27,6 +27,10 @@ def _ensure_built():
 
 _ensure_built()
 
+# one libnccl.so.2 per process: the multi-GPU entry points must pick the copy torch will load later (see lmb200py/capi.py)
+from lmb200py import capi as _capi      # noqa: E402
+_capi._point_at_torch_nccl()
+
 
 @pytest.fixture(scope="session")
 def have_gpu():

@@ -12,7 +12,7 @@ def run(extra_env=None):
     env = dict(os.environ)
     env.update(extra_env or {})
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--tris", "3000", "--steps", "1", "--warmup", "1",
-                        "--cpu-rays", "40000"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+                        "--cpu-rays", "40000", "--pt-tris", "20000", "--pt-cpu-spp", "1"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     return p.stdout
 
@@ -29,6 +29,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("configs[3]") and d["vs_baseline"] is None
+    # the path-tracing half of the metric on the reference's side
+    pt = d["path_tracing"]
+    assert pt["unit"] == "Msamples/s" and pt["value"] > 0 and pt["kind"] in ("reference", "port") and d["pt_msamples_s"] == pt["value"]
 
 
 def test_reference_arm_non_zero_rank_is_silent():
@@ -42,7 +45,7 @@ import pytest  # noqa: E402
 def test_lmb200_arm_json_contract_small():
     """The product arm on a reduced workload: one JSON line with every key of the bench contract, parity spot check clean."""
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "2", "--warmup", "3", "--rays", "2097152",
-                        "--tris", "200000", "--cpu-rays", "50000", "--pt-tris", "50000", "--pt-spp", "2"],
+                        "--tris", "200000", "--cpu-rays", "50000", "--pt-tris", "50000", "--pt-spp", "2", "--pt-cpu-spp", "1", "--c4-spp", "1"],
                        capture_output=True, text=True, cwd=ROOT, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
@@ -59,3 +62,11 @@ def test_lmb200_arm_json_contract_small():
     assert d["gpu_launches"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["parity"]["index_mismatches"] == 0 and d["parity"]["tuv_bit_mismatches"] == 0
     assert d["path_tracing"]["value"] > 0 and d["path_tracing"]["incoherent_1m_tri_mesh"]["value"] > 0
+    pt = d["path_tracing"]
+    assert 0 < pt["e2e"]["value"] <= pt["value"] * 1.05 and pt["e2e"]["d2h_bytes_per_step"] == 1920 * 1080 * 16
+    assert pt["roofline"]["bound"] == "hbm" and 0 < pt["roofline"]["frac"] < 1.5 and pt["roofline"]["vertices_per_sample"] > 1
+    assert pt["cpu_baseline"]["value"] > 0 and pt["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["pcie_ceiling_gbs"] > 0 and 0 < d["e2e"]["frac_of_pcie_ceiling"] < 1.3
+    c4 = d["config4"]
+    assert c4["value"] > 0 and c4["triangles"] > 9_500_000 and c4["film_bytes"] == 3840 * 2160 * 16 and c4["finite"] is True
+    assert d["pt_msamples_s"] == pt["value"] and d["config4_msamples_s"] == c4["value"]

@@ -88,20 +88,8 @@ def test_config4_10m_instanced_triangles_hbm_sizing():
     """configs[4]: 10M-triangle "instanced" scene (flattened to world space like the reference, accel_qbvh.cpp:161-194),
     4K film. Checks the HBM-resident sizing: device build of 10M triangles, 3840x2160 film, a short ptdirect run, and
     closest-hit parity with the oracle on a ray sample."""
-    base, _ = scenes.mesh_scene(100_000, seed=7, half=5.0, n_objects=20)
-    g = np.random.Generator(np.random.Philox(11))
-    inst = []
-    for k in range(100):                       # 100 instances of a 100k-triangle asset
-        off = np.array([(k % 10 - 4.5) * 10.0, 0.0, (k // 10 - 4.5) * 10.0], np.float32)
-        inst.append((base.reshape(-1, 3) + off).reshape(-1, 9))
-    verts = np.ascontiguousarray(np.concatenate(inst), np.float32)
+    sc, verts = scenedesc.config4_scene()
     assert 9_500_000 < len(verts) < 10_500_000
-    sc = scenedesc.Scene()
-    sc.add_bsdf("w", "diffuse", (0.6, 0.6, 0.6))
-    sc.add_light("lamp", (40.0, 40.0, 40.0))
-    sc.add_mesh_tris(verts, "w")
-    sc.add_quad((-20, 30, -20), (20, 30, -20), (20, 30, 20), (-20, 30, 20), "w", "lamp")
-    sc.set_camera((0.0, 25.0, 70.0), (0.0, 0.0, 0.0), (0, 1, 0), 45.0, 3840, 2160)
     S = capi.Scene(sc, builder=capi.BUILD_GPU_LBVH)
     st = capi.AccelStats()
     capi.check(capi.lib().lmb200_accel_get_stats(capi.lib().lmb200_scene_accel(S.h_), st))

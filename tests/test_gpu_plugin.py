@@ -29,6 +29,12 @@ def rel_rmse(a, b):
     return float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
 
 
+def same_image(a, b):
+    """Same samples, different fp32 summation order (atomic splats, per-GPU partial films): equal up to rounding of the
+    accumulation, which scales with the brightest pixels (two runs on ONE GPU differ by ~1e-5 of the image maximum)."""
+    return np.allclose(a, b, rtol=2e-4, atol=2e-5 * max(float(np.max(b)), 1.0))
+
+
 SIMPLE_YAML_MESH = """
     mesh1:
       interface: trianglemesh
@@ -209,7 +215,7 @@ def test_renderer_plugin_two_gpus():
         R = ob.RefScene(sc, accel=accel)
         one, _ = R.render("lmb200pt", N, seed=1, extra={"mode": "ptdirect"}, in_tree=True)
         two, _ = R.render("lmb200pt", N, seed=1, extra={"mode": "ptdirect", "num_gpus": 2}, in_tree=True)
-        assert np.allclose(one, two, rtol=2e-4, atol=1e-5)
+        assert same_image(one, two)
     # time-budgeted + progressive on 2 GPUs
     R = ob.RefScene(sc, accel="qbvh")
     img, _ = R.render("lmb200pt", 1000, seed=1, in_tree=True,

@@ -17,6 +17,12 @@ def rel_rmse(a, b):
     return float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
 
 
+def same_image(a, b):
+    """Same samples, different fp32 summation order (atomic splats, per-GPU partial films): equal up to rounding of the
+    accumulation, which scales with the brightest pixels (two runs on ONE GPU differ by ~1e-5 of the image maximum)."""
+    return np.allclose(a, b, rtol=2e-4, atol=2e-5 * max(float(np.max(b)), 1.0))
+
+
 @pytest.mark.parametrize("mode", [capi.MODE_PTDIRECT, capi.MODE_PT, capi.MODE_PTMIS])
 @pytest.mark.parametrize("scene_name", ["cornell", "config2", "specular"])
 def test_same_samples_as_oracle(mode, scene_name):
@@ -131,7 +137,7 @@ def test_render_multi_nccl_reduce():
     st = capi.RenderStats()
     capi.check(L.lmb200_render_multi(arr, 2, C.byref(p), film.ctypes.data_as(C.c_void_p), C.byref(st)))
     assert st.samples == N
-    assert np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
+    assert same_image(film[..., :3], one)
 
 
 def test_time_budget_and_progress():
@@ -163,7 +169,7 @@ def test_time_budget_and_progress():
     p = S.params(capi.MODE_PTDIRECT, N, seed=3)
     capi.check(L.lmb200_render_timed(arr, 1, C.byref(p), -1.0, 5000, -1.0, capi.PROGRESS_FN(0), None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
     one, _ = S.render(capi.MODE_PTDIRECT, N, seed=3)
-    assert st.samples == N and np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
+    assert st.samples == N and same_image(film[..., :3], one)
 
 
 def test_gpu_built_scene_renders_the_same_image():
@@ -370,7 +376,7 @@ def test_render_timed_two_gpus_progress_and_exact_range():
     p = scenes_[0].params(capi.MODE_PTDIRECT, N, seed=3)
     capi.check(L.lmb200_render_timed(arr, 2, C.byref(p), -1.0, 5000, -1.0, capi.PROGRESS_FN(0), None, film.ctypes.data_as(C.c_void_p), C.byref(st)))
     one, _ = scenes_[0].render(capi.MODE_PTDIRECT, N, seed=3)
-    assert st.samples == N and np.allclose(film[..., :3], one, rtol=2e-4, atol=1e-5)
+    assert st.samples == N and same_image(film[..., :3], one)
 
 
 def test_render_multi_rejects_two_scenes_on_one_device():
