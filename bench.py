@@ -7,7 +7,7 @@ no data-path collective). One "step" = one pass of lmb200_trace_closest over the
 
   value     Mrays/s, device-resident rays/hits, CUDA events on the launching stream, max over ranks
   e2e       Mrays/s through the host-buffer C-ABI call (pinned host rays in, hits out, copies inside)
-  roofline  algorithmic bytes per ray (48 + nodes/ray*80 + tris/ray*48, counted by the instrumented
+  roofline  algorithmic bytes per ray (48 + nodes/ray*64 + tris/ray*48, counted by the instrumented
             kernel) * rays / kernel time, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the CPU oracle on a bounded ray sample of the same scene (rank 0, N=1 only)
   path_tracing  secondary figure: wavefront ptdirect Msamples/s on configs[2] at full size (1 M-triangle
@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "lightmetrica-v2_b200"))
 
+NODE_BYTES = 64.0     # csrc/bvh.h Node64 (round 1: 80); a triangle record is 48 algorithmic bytes (stored in a 64-byte unit)
 METRIC = "Mrays/s incoherent closest-hit (64Mi random rays vs 4M-tri synthetic BVH, per-GPU batch)"
 UNIT = "Mrays/s"
 
@@ -325,7 +326,7 @@ def main():
     npr, tpr = C.c_double(), C.c_double()
     ncount = min(a.rays, 1 << 22)
     capi.check(L.lmb200_trace_count_dev(accel.h, d_rays.data_ptr(), ncount, C.byref(npr), C.byref(tpr)))
-    b_ray = 48.0 + npr.value * 80.0 + tpr.value * 48.0
+    b_ray = 48.0 + npr.value * NODE_BYTES + tpr.value * 48.0
     mean_kernel_s = float(np.mean(kernel_ms)) * 1e-3
     achieved = b_ray * a.rays / mean_kernel_s / 1e9
     peak, peak_src = hbm_peak()
@@ -387,9 +388,10 @@ def main():
                              "peak_source": peak_src, "bytes_per_ray": b_ray, "nodes_per_ray": npr.value, "tris_per_ray": tpr.value,
                              "kernel": "lmb200::trace_kernel<false,false>", "kernel_ms": mean_kernel_s * 1e3,
                              # second ceiling, informational: node fetches/s against the rate at which a fetch-only kernel reads random
-                             # 80-byte records on a B200 (81.4 G/s, measured once with scripts/micro/l1_wavefront.cu, profiles/r01_sweep.md)
-                             "node_fetches_per_s": npr.value * a.rays / mean_kernel_s, "record_fetch_ceiling_per_s": 81.4e9,
-                             "frac_of_fetch_ceiling": npr.value * a.rays / mean_kernel_s / 81.4e9},
+                             # 64-byte aligned records with two 256-bit loads on a B200 (112.8 G/s, scripts/micro/l1_wavefront.cu pattern E,
+                             # profiles/r02_sweep.md; the 80-byte node of round 1: 81.4 G/s)
+                             "node_fetches_per_s": npr.value * a.rays / mean_kernel_s, "record_fetch_ceiling_per_s": 112.8e9,
+                             "frac_of_fetch_ceiling": npr.value * a.rays / mean_kernel_s / 112.8e9},
                 "cpu_baseline": cpu, "parity": parity,
                 "bvh": {"nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
                 "path_tracing": pt, "config4": c4,
@@ -458,7 +460,7 @@ def incoherent_on_scene(a, torch, dist, capi, S, verts, world, dev, stream):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     npr, tpr = C.c_double(), C.c_double()
     capi.check(L.lmb200_trace_count_dev(acc, rays.data_ptr(), 1 << 22, C.byref(npr), C.byref(tpr)))
-    bpr = 48 + 80 * npr.value + 48 * tpr.value
+    bpr = 48 + NODE_BYTES * npr.value + 48 * tpr.value
     rate = n / (float(ms.item()) * 1e-3)
     peak = hbm_peak()[0]
     return {"value": world * rate / 1e6, "unit": "Mrays/s", "per_gpu": rate / 1e6, "rays_per_gpu": n, "triangles": int(len(verts)),
@@ -475,8 +477,8 @@ def pt_roofline(st, samples, seconds, world):
     """B_sample = sum over extend rays of B_ray + sum over shadow rays of B_ray(any-hit) + V (2 S_state) + splats 16,
     with nodes / records per ray counted by the instrumented kernels over the actual extend and shadow queues."""
     er, sr = max(st.extend_rays, 1), max(st.shadow_rays, 1)
-    b_ext = 32 + 16 + 80.0 * st.extend_nodes / er + 48.0 * st.extend_tris / er
-    b_sh = 32 + 16 + 80.0 * st.shadow_nodes / sr + 48.0 * st.shadow_tris / sr      # ray + (contribution, pixel)
+    b_ext = 32 + 16 + NODE_BYTES * st.extend_nodes / er + 48.0 * st.extend_tris / er
+    b_sh = 32 + 16 + NODE_BYTES * st.shadow_nodes / sr + 48.0 * st.shadow_tris / sr      # ray + (contribution, pixel)
     n = max(st.samples, 1)
     b_sample = st.extend_rays / n * b_ext + st.shadow_rays / n * b_sh + st.vertices / n * 2 * S_STATE_BYTES + st.shadow_rays / n * 16
     peak, src = hbm_peak()

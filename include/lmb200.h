@@ -53,8 +53,8 @@ typedef struct lmb200_accel lmb200_accel;
 typedef struct lmb200_accel_stats {
     uint64_t num_triangles;       /* triangles given to build */
     uint64_t num_valid_triangles; /* non-degenerate (TriAccel k != 3, triaccel.h:73-77) */
-    uint64_t num_nodes;           /* 80-byte wide nodes */
-    uint64_t node_bytes, tri_bytes;
+    uint64_t num_nodes;           /* 64-byte wide nodes */
+    uint64_t node_bytes, tri_bytes; /* 64 bytes per node, 64 per triangle unit (48-byte record + pad) */
     double   build_seconds;       /* host build */
     double   upload_seconds;
     float    sah_cost;
@@ -109,16 +109,23 @@ int lmb200_trace_any(lmb200_accel* a, const lmb200_ray* rays, uint8_t* occluded,
 int lmb200_trace_any_dev(lmb200_accel* a, const void* rays_dev, void* occluded_dev, uint64_t n, void* stream);
 
 /* Traversal work counters for the roofline's algorithmic-byte figure: mean
- * 80-byte nodes and 48-byte triangle records fetched per ray over the given DEVICE ray batch
+ * 64-byte nodes and 48-byte triangle records fetched per ray over the given DEVICE ray batch
  * (instrumented copy of the closest-hit kernel, not timed). */
 int lmb200_trace_count_dev(lmb200_accel* a, const void* rays_dev, uint64_t n, double* nodes_per_ray, double* tris_per_ray);
 
 /* Number of kernels this library has launched so far in this process (bench.py gpu_launches). */
 uint64_t lmb200_launch_count(void);
 
-/* Host copies of the flattened structure, for tests (host logic is checked without a GPU). */
-int lmb200_accel_host_arrays(const lmb200_accel* a, const void** nodes80, uint64_t* num_nodes,
-                             const void** tris48, const uint32_t** tri_index, uint64_t* num_tris);
+/* Host view of the flattened structure, for tests (host logic is checked without a GPU): ONE array of 64-byte units,
+ * unit 0 = the root node (csrc/bvh.h: Node64 | 48-byte TriAccel record + 16 bytes of padding). A node's children are
+ * contiguous from Node64::base: its internal children in slot order, then the triangles of its leaf slots. Node origins
+ * are 16-bit coordinates on the scene grid: origin[a] = grid_lo[a] + k[a] * grid_step[a]. */
+typedef struct lmb200_bvh_layout {
+    const void* units;
+    uint64_t num_units, num_nodes, num_triangles;
+    float grid_lo[3], grid_step[3];
+} lmb200_bvh_layout;
+int lmb200_accel_host_layout(const lmb200_accel* a, lmb200_bvh_layout* out);
 /* Build on the host only (no device needed); such an accel cannot trace. For tests. */
 lmb200_accel* lmb200_accel_create_host_only(void);
 
@@ -254,7 +261,7 @@ typedef struct lmb200_render_stats {
     double   seconds;            /* device time of the wavefront loop (CUDA events) */
     double   reduce_seconds;     /* lmb200_render_multi / _timed: device time of the NCCL film reductions; else 0 */
     int64_t  vertices;           /* path vertices processed (camera vertices included): one k_logic/k_nee/k_bsdf pass each */
-    int64_t  extend_nodes, extend_tris;   /* count_work only: 80-byte nodes / 48-byte triangle records fetched by the extend rays */
+    int64_t  extend_nodes, extend_tris;   /* count_work only: 64-byte nodes / 48-byte triangle records fetched by the extend rays */
     int64_t  shadow_nodes, shadow_tris;   /* ... and by the shadow rays */
 } lmb200_render_stats;
 

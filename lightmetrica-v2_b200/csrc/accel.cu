@@ -43,7 +43,7 @@ struct BatchIoAny {
 
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
-trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+trace_kernel(const BvhDev bvh,
              const float4* __restrict__ rays, void* __restrict__ out,
              const uint64_t n_host, const uint32_t* __restrict__ n_dev,
              unsigned long long* __restrict__ counter, unsigned long long* __restrict__ work_counters)
@@ -53,10 +53,10 @@ trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     if (ANY) {
         BatchIoAny io{rays, reinterpret_cast<uint8_t*>(out), n};
-        persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+        persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
     } else {
         BatchIoClosest io{rays, reinterpret_cast<float4*>(out), n};
-        persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+        persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
     }
     if (COUNT) {
         const unsigned lane = threadIdx.x & 31u;
@@ -67,13 +67,13 @@ trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
 }
 
 // one ray, one warp: the per-ray Accel3::Intersect path (mailbox in mapped pinned host memory)
-__global__ void trace_one_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* ray, float4* out)
+__global__ void trace_one_kernel(const BvhDev bvh, const float4* ray, float4* out)
 {
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(32)];
     if (threadIdx.x != 0) return;
     Trav T;
     TravCounters cnt;
-    const bool hit = lmb_traverse<false, false, 32>(nodes, tris, ray[0], ray[1], T, smem, cnt);
+    const bool hit = lmb_traverse<false, false, 32>(bvh, ray[0], ray[1], T, LMB_SM_BASE(smem), cnt);
     out[0] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
 }
 
@@ -85,11 +85,19 @@ struct Mailbox {
     ~Mailbox() { if (host) { cudaSetDevice(device); cudaFreeHost(host); cudaStreamDestroy(stream); } }
 };
 
+BvhDev bvh_dev(const Accel* a)
+{
+    BvhDev b;
+    b.units = reinterpret_cast<const float4*>(a->d_units);
+    for (int k = 0; k < 3; k++) { b.gstep[k] = a->bvh.grid.step[k]; b.glo2[k] = a->bvh.grid.lo[k] - 8388608.0f * a->bvh.grid.step[k]; }
+    return b;
+}
+
 template <bool ANY, bool COUNT>
 static int launch_trace(Accel* a, const void* rays, void* out, uint64_t n, const uint32_t* n_dev, cudaStream_t st, unsigned long long* work, int slot)
 {
     unsigned long long* counter = a->d_counter + slot;
-    if (!a->d_nodes) return set_error(LMB200_E_STATE, "accel not built on a device");
+    if (!a->d_units) return set_error(LMB200_E_STATE, "accel not built on a device");
     if (n == 0 && !n_dev) return LMB200_OK;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counter)");
@@ -99,8 +107,7 @@ static int launch_trace(Accel* a, const void* rays, void* out, uint64_t n, const
     if (n_dev || blocks > persistent) blocks = persistent;
     if (blocks == 0) blocks = 1;
     trace_kernel<ANY, COUNT><<<(unsigned)blocks, LMB_TRACE_BLOCK, 0, st>>>(
-        reinterpret_cast<const float4*>(a->d_nodes), reinterpret_cast<const float4*>(a->d_tris),
-        reinterpret_cast<const float4*>(rays), out, n, n_dev, counter, work);
+        bvh_dev(a), reinterpret_cast<const float4*>(rays), out, n, n_dev, counter, work);
     g_launch_count++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "trace_kernel launch");
@@ -122,8 +129,7 @@ int trace_any_dev(Accel* a, const void* rays, void* occ, uint64_t n, const uint3
 void Accel::free_device()
 {
     if (device >= 0) cudaSetDevice(device);
-    if (d_nodes) cudaFree(d_nodes);
-    if (d_tris) cudaFree(d_tris);
+    if (d_units) cudaFree(d_units);
     if (d_counter) cudaFree(d_counter);
     for (int i = 0; i < LMB_NBUF; i++) {
         if (stage_rays[i]) cudaFree(stage_rays[i]);
@@ -133,7 +139,7 @@ void Accel::free_device()
     for (int i = 0; i < 4; i++) { if (streams[i]) cudaStreamDestroy(streams[i]); streams[i] = nullptr; }
     for (int i = 0; i < 3 * LMB_NBUF; i++) { if (events[i]) cudaEventDestroy(events[i]); events[i] = nullptr; }
     stage_cap = 0;
-    d_nodes = d_tris = nullptr; d_counter = nullptr;
+    d_units = nullptr; num_units = 0; d_counter = nullptr;
 }
 
 Accel::~Accel() { free_device(); }
@@ -151,16 +157,23 @@ static int check_depth(int max_depth)
 
 int mirror_to_host(Accel* a)
 {
-    if (!a->gpu_built || !a->bvh.nodes.empty()) return LMB200_OK;
+    if (!a->gpu_built || !a->bvh.units.empty()) return LMB200_OK;
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    const size_t nn = a->bvh.stats.num_nodes, nt = a->bvh.stats.num_valid;
-    a->bvh.nodes.resize(nn);
-    a->bvh.tris.resize(nt);
-    if ((e = cudaMemcpy(a->bvh.nodes.data(), a->d_nodes, nn * sizeof(Node80), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "D2H nodes");
-    if (nt && (e = cudaMemcpy(a->bvh.tris.data(), a->d_tris, nt * sizeof(TriRecord), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "D2H tris");
-    a->bvh.tri_index.resize(nt);
-    for (size_t i = 0; i < nt; i++) a->bvh.tri_index[i] = a->bvh.tris[i].tri;
+    a->bvh.units.resize(a->num_units);
+    if ((e = cudaMemcpy(a->bvh.units.data(), a->d_units, a->num_units * sizeof(Unit64), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "D2H units");
+    return LMB200_OK;
+}
+
+int Accel::finish_device_setup()
+{
+    cudaDeviceProp prop;
+    const cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false, false>, LMB_TRACE_BLOCK, 0);
+    trace_blocks_per_sm = occ > 0 ? occ : 4;
     return LMB200_OK;
 }
 
@@ -169,21 +182,13 @@ int Accel::upload()
     const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    if (d_nodes) { cudaFree(d_nodes); d_nodes = nullptr; }
-    if (d_tris) { cudaFree(d_tris); d_tris = nullptr; }
-    const size_t nb = bvh.nodes.size() * sizeof(Node80);
-    const size_t tb = std::max<size_t>(bvh.tris.size(), 1) * sizeof(TriRecord);
-    if ((e = cudaMalloc(&d_nodes, nb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(nodes)");
-    if ((e = cudaMalloc(&d_tris, tb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tris)");
+    if (d_units) { cudaFree(d_units); d_units = nullptr; }
+    num_units = bvh.units.size();
+    const size_t nb = num_units * sizeof(Unit64);
+    if ((e = cudaMalloc(&d_units, nb)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(units)");
     if (!d_counter && (e = cudaMalloc(&d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
-    if ((e = cudaMemcpy(d_nodes, bvh.nodes.data(), nb, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(nodes)");
-    if (!bvh.tris.empty() && (e = cudaMemcpy(d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tris)");
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
-    num_sms = prop.multiProcessorCount;
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false, false>, LMB_TRACE_BLOCK, 0);
-    trace_blocks_per_sm = occ > 0 ? occ : 4;
+    if ((e = cudaMemcpy(d_units, bvh.units.data(), nb, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(units)");
+    if (const int rc = finish_device_setup()) return rc;
     upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return LMB200_OK;
 }
@@ -199,7 +204,7 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
 {
     if (!a || (!rays && n) || (!out && n)) return set_error(LMB200_E_INVALID, "null argument");
     if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
-    if (!a->d_nodes) return set_error(LMB200_E_STATE, "accel not built");
+    if (!a->d_units) return set_error(LMB200_E_STATE, "accel not built");
     if (n == 0) return LMB200_OK;
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
@@ -322,15 +327,8 @@ int lmb200_accel_build_ex(lmb200_accel* h, const float* verts, uint64_t ntris, i
     if (!rc) rc = check_depth(a->bvh.stats.max_depth);
     if (rc) return rc;
     a->built = true;
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, a->device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
-    a->num_sms = prop.multiProcessorCount;
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false, false>, LMB_TRACE_BLOCK, 0);
-    a->trace_blocks_per_sm = occ > 0 ? occ : 4;
     a->upload_seconds = 0;
-    return LMB200_OK;
+    return a->finish_device_setup();
 }
 
 int lmb200_accel_device(const lmb200_accel* h)
@@ -344,30 +342,23 @@ int lmb200_accel_device(const lmb200_accel* h)
 lmb200_accel* lmb200_accel_replicate(const lmb200_accel* h, int device)
 {
     const Accel* src = reinterpret_cast<const Accel*>(h);
-    if (!src || !src->built || src->host_only || !src->d_nodes) { set_error(LMB200_E_STATE, "replicate: source accel is not built on a device"); return nullptr; }
+    if (!src || !src->built || src->host_only || !src->d_units) { set_error(LMB200_E_STATE, "replicate: source accel is not built on a device"); return nullptr; }
     Accel* a = reinterpret_cast<Accel*>(lmb200_accel_create(device));
     if (!a) return nullptr;
-    const size_t nn = src->gpu_built ? (size_t)src->bvh.stats.num_nodes : src->bvh.nodes.size();
-    const size_t nt = src->gpu_built ? (size_t)src->bvh.stats.num_valid : src->bvh.tris.size();
-    const size_t nb = nn * sizeof(Node80), tb = std::max<size_t>(nt, 1) * sizeof(TriRecord);
+    const size_t nb = src->num_units * sizeof(Unit64);
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaMalloc(&a->d_nodes, nb);
-    if (e == cudaSuccess) e = cudaMalloc(&a->d_tris, tb);
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_units, nb);
     if (e == cudaSuccess) e = cudaMalloc(&a->d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemcpyPeer(a->d_nodes, device, src->d_nodes, src->device, nb);
-    if (e == cudaSuccess && nt) e = cudaMemcpyPeer(a->d_tris, device, src->d_tris, src->device, nt * sizeof(TriRecord));
+    if (e == cudaSuccess) e = cudaMemcpyPeer(a->d_units, device, src->d_units, src->device, nb);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cuda_fail(e, "lmb200_accel_replicate"); delete a; return nullptr; }
+    a->num_units = src->num_units;
     a->bvh.stats = src->bvh.stats;
+    a->bvh.grid = src->bvh.grid;
     for (int k = 0; k < 3; k++) { a->bvh.scene_lo[k] = src->bvh.scene_lo[k]; a->bvh.scene_hi[k] = src->bvh.scene_hi[k]; }
-    a->gpu_built = true;          // host mirror is filled on demand from the device arrays
+    a->gpu_built = true;          // host mirror is filled on demand from the device array
     a->built = true;
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { cuda_fail(e, "cudaGetDeviceProperties"); delete a; return nullptr; }
-    a->num_sms = prop.multiProcessorCount;
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_kernel<false, false>, LMB_TRACE_BLOCK, 0);
-    a->trace_blocks_per_sm = occ > 0 ? occ : 4;
+    if (a->finish_device_setup()) { delete a; return nullptr; }
     return reinterpret_cast<lmb200_accel*>(a);
 }
 
@@ -378,9 +369,9 @@ int lmb200_accel_get_stats(const lmb200_accel* h, lmb200_accel_stats* out)
     if (!a->built) return set_error(LMB200_E_STATE, "accel not built");
     out->num_triangles = a->bvh.stats.num_triangles;
     out->num_valid_triangles = a->bvh.stats.num_valid;
-    out->num_nodes = a->gpu_built ? a->bvh.stats.num_nodes : a->bvh.nodes.size();
-    out->node_bytes = out->num_nodes * sizeof(Node80);
-    out->tri_bytes = (a->gpu_built ? a->bvh.stats.num_valid : a->bvh.tris.size()) * sizeof(TriRecord);
+    out->num_nodes = a->bvh.stats.num_nodes;
+    out->node_bytes = out->num_nodes * sizeof(Node64);
+    out->tri_bytes = a->bvh.stats.num_valid * sizeof(TriUnit);
     out->build_seconds = a->bvh.stats.build_seconds;
     out->upload_seconds = a->upload_seconds;
     out->sah_cost = a->bvh.stats.sah_cost;
@@ -388,18 +379,17 @@ int lmb200_accel_get_stats(const lmb200_accel* h, lmb200_accel_stats* out)
     return LMB200_OK;
 }
 
-int lmb200_accel_host_arrays(const lmb200_accel* h, const void** nodes80, uint64_t* num_nodes,
-                             const void** tris48, const uint32_t** tri_index, uint64_t* num_tris)
+int lmb200_accel_host_layout(const lmb200_accel* h, lmb200_bvh_layout* out)
 {
     Accel* a = const_cast<Accel*>(reinterpret_cast<const Accel*>(h));
-    if (!a) return set_error(LMB200_E_INVALID, "null argument");
+    if (!a || !out) return set_error(LMB200_E_INVALID, "null argument");
     if (!a->built) return set_error(LMB200_E_STATE, "accel not built");
     if (const int rc = mirror_to_host(a)) return rc;
-    if (nodes80) *nodes80 = a->bvh.nodes.data();
-    if (num_nodes) *num_nodes = a->bvh.nodes.size();
-    if (tris48) *tris48 = a->bvh.tris.data();
-    if (tri_index) *tri_index = a->bvh.tri_index.data();
-    if (num_tris) *num_tris = a->bvh.tris.size();
+    out->units = a->bvh.units.data();
+    out->num_units = a->bvh.units.size();
+    out->num_nodes = a->bvh.stats.num_nodes;
+    out->num_triangles = a->bvh.stats.num_valid;
+    for (int k = 0; k < 3; k++) { out->grid_lo[k] = a->bvh.grid.lo[k]; out->grid_step[k] = a->bvh.grid.step[k]; }
     return LMB200_OK;
 }
 
@@ -417,7 +407,7 @@ int lmb200_trace_closest_one(lmb200_accel* h, const lmb200_ray* ray, lmb200_hit*
 {
     Accel* a = reinterpret_cast<Accel*>(h);
     if (!a || !ray || !hit) return set_error(LMB200_E_INVALID, "null argument");
-    if (a->host_only || !a->d_nodes) return set_error(LMB200_E_STATE, "accel not built on a device");
+    if (a->host_only || !a->d_units) return set_error(LMB200_E_STATE, "accel not built on a device");
     static thread_local Mailbox mb;
     cudaError_t e;
     if (mb.device != a->device) {
@@ -429,7 +419,7 @@ int lmb200_trace_closest_one(lmb200_accel* h, const lmb200_ray* ray, lmb200_hit*
         mb.device = a->device;
     }
     memcpy(mb.host, ray, sizeof(lmb200_ray));
-    trace_one_kernel<<<1, 32, 0, mb.stream>>>(reinterpret_cast<const float4*>(a->d_nodes), reinterpret_cast<const float4*>(a->d_tris), mb.dev, mb.dev + 2);
+    trace_one_kernel<<<1, 32, 0, mb.stream>>>(bvh_dev(a), mb.dev, mb.dev + 2);
     g_launch_count++;
     if ((e = cudaStreamSynchronize(mb.stream)) != cudaSuccess) return cuda_fail(e, "trace_one");
     memcpy(hit, mb.host + 2, sizeof(lmb200_hit));
@@ -460,7 +450,7 @@ int lmb200_trace_count_dev(lmb200_accel* h, const void* rays_dev, uint64_t n, do
 {
     Accel* a = reinterpret_cast<Accel*>(h);
     if (!a || !rays_dev || !n) return set_error(LMB200_E_INVALID, "null argument");
-    if (a->host_only || !a->d_nodes) return set_error(LMB200_E_STATE, "accel not built on a device");
+    if (a->host_only || !a->d_units) return set_error(LMB200_E_STATE, "accel not built on a device");
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     void* scratch = nullptr;

@@ -1,5 +1,5 @@
-// Host BVH builder: binned-SAH binary tree (multi-threaded) -> greedy collapse to 8-wide ->
-// octant-ordered, quantised 80-byte nodes + leaf-ordered 48-byte TriAccel records.
+// Host BVH builder: binned-SAH binary tree (multi-threaded) -> SAH-optimal collapse to 8-wide ->
+// octant-ordered, quantised 64-byte nodes and 64-byte triangle units (48-byte TriAccel record + pad) in one array.
 // Replaces Accel_QBVH::Build (/root/reference/src/liblightmetrica/accel/accel_qbvh.cpp:152-396).
 // What is kept from the reference: triangles are world-space, every triangle's box is padded
 // by Math::Eps() = 1e-4 (accel_qbvh.cpp:189-190) so node culling is never tighter than the
@@ -47,7 +47,7 @@ struct BinNode {
 };
 
 constexpr int kBins = 16;
-constexpr int kMaxLeaf = 3;           // triangles per leaf slot (3 unary bits in Node80::meta)
+constexpr int kMaxLeaf = 3;           // triangles per leaf slot (2 bits per slot in Node64::counts)
 constexpr float kCostNode = 1.0f;     // binary build SAH: one split step
 constexpr float kCostTri = 1.0f;      // binary build SAH: one triangle test
 // wide-node SAH used by the collapse (Ylitie et al. 2017, sec. 4.1): one 8-wide node visit vs one triangle test
@@ -210,13 +210,21 @@ struct Emitter {
 
     struct Pending { uint32_t bin; uint32_t wide; int depth; };
 
+    uint64_t num_nodes = 0;
+
     void emit_all() {
-        out.nodes.clear(); out.tris.clear(); out.tri_index.clear();
-        out.nodes.emplace_back();
-        memset(&out.nodes[0], 0, sizeof(Node80));
+        out.units.clear();
+        out.units.emplace_back();
+        memset(&out.units[0], 0, sizeof(Unit64));
+        num_nodes = 1;
         const uint32_t nrefs = (uint32_t)B.refs.size();
-        if (nrefs == 0) { out.nodes[0].e[0] = out.nodes[0].e[1] = out.nodes[0].e[2] = 127; return; }
-        out.tris.reserve(nrefs); out.tri_index.reserve(nrefs);
+        if (nrefs == 0) {       // empty scene: a root whose eight slots are empty
+            Node64& r = out.units[0].node;
+            r.e[0] = r.e[1] = r.e[2] = 127;
+            for (int s = 0; s < 8; s++) for (int a = 0; a < 3; a++) { r.qlo[a][s] = 255; r.qhi[a][s] = 0; }
+            return;
+        }
+        out.units.reserve((size_t)nrefs + nrefs / 2);
         plan();
         std::vector<Pending> st;
         st.push_back({0, 0, 1});
@@ -294,14 +302,17 @@ struct Emitter {
             collect(root.left, k, ch, is_leaf, n);
             collect(root.left + 1, 8 - k, ch, is_leaf, n);
         }
-        // 2. node box + quantisation grid
+        // 2. node box + quantisation grid. The origin is the node minimum snapped DOWN to the scene grid (16 bits per
+        //    axis); child planes are quantised against the decoded origin, so the snap costs range, not tightness.
         Box nb; nb.reset();
         for (int i = 0; i < n; i++) nb.grow(B.nodes[ch[i]].box);
-        Node80 node; memset(&node, 0, sizeof(node));
+        Node64 node; memset(&node, 0, sizeof(node));
         double scale[3];
+        float origin[3];
         for (int a = 0; a < 3; a++) {
-            node.p[a] = nb.lo[a];
-            const double ext = (double)nb.hi[a] - (double)nb.lo[a];
+            node.k[a] = grid_floor(out.grid, a, nb.lo[a]);
+            origin[a] = grid_origin(out.grid, a, node.k[a]);
+            const double ext = std::max(0.0, (double)nb.hi[a] - (double)origin[a]);
             // the traversal evaluates q*step + base as fma(1 + q*2^-15, step*2^15, base - step*2^15): child
             // boxes are widened by kQSlack grid steps to cover that rounding, and e+15 must stay a valid exponent
             int e = ext > 0 ? (int)std::ceil(std::log2(ext / 254.0)) : -126;
@@ -333,42 +344,44 @@ struct Emitter {
         int child_in_slot[8];
         for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
         for (int i = 0; i < n; i++) child_in_slot[slot_of[i]] = i;
-        // 4. allocate children and triangles in slot order
-        node.child_base = (uint32_t)out.nodes.size();
-        node.tri_base = (uint32_t)out.tris.size();
-        uint32_t n_internal = 0, tri_off = 0;
+        // 4. allocate the children in the unit array: internal children first (slot order), then the triangles of the
+        //    leaf slots (slot order)
+        uint32_t n_internal = 0, n_tris = 0;
+        for (int i = 0; i < n; i++) { if (is_leaf[i]) n_tris += B.nodes[ch[i]].total; else n_internal++; }
+        const uint32_t base = (uint32_t)out.units.size();
+        out.units.resize(out.units.size() + n_internal + n_tris);
+        node.base = base;
+        uint32_t tri_off = 0;
         const float inv_root = 1.0f / root_area;
         for (int s = 0; s < 8; s++) {
             const int i = child_in_slot[s];
-            if (i < 0) { node.meta[s] = 0; for (int a = 0; a < 3; a++) { node.qlo[a][s] = 255; node.qhi[a][s] = 0; } continue; }
+            if (i < 0) { for (int a = 0; a < 3; a++) { node.qlo[a][s] = 255; node.qhi[a][s] = 0; } continue; }
             const BinNode& c = B.nodes[ch[i]];
             for (int a = 0; a < 3; a++) {
-                double ql = std::floor(((double)c.box.lo[a] - (double)node.p[a]) / scale[a] - kQSlack);
-                double qh = std::ceil(((double)c.box.hi[a] - (double)node.p[a]) / scale[a] + kQSlack);
+                double ql = std::floor(((double)c.box.lo[a] - (double)origin[a]) / scale[a] - kQSlack);
+                double qh = std::ceil(((double)c.box.hi[a] - (double)origin[a]) / scale[a] + kQSlack);
                 ql = std::max(0.0, std::min(255.0, ql));
                 qh = std::max(0.0, std::min(255.0, qh));
                 node.qlo[a][s] = (uint8_t)ql; node.qhi[a][s] = (uint8_t)qh;
             }
             if (is_leaf[i]) {
-                node.meta[s] = (uint8_t)((((1u << c.total) - 1u) << 5) | tri_off);
+                node.counts |= (uint16_t)(c.total << (2 * s));
                 for (uint32_t k = 0; k < c.total; k++) {
                     const uint32_t id = B.refs[c.first + k].id;
-                    out.tris.push_back(recs[id]);
-                    out.tri_index.push_back(id);
+                    TriUnit& tu = out.units[base + n_internal + tri_off + k].tri;
+                    tu.rec = recs[id];
+                    tu.pad[0] = tu.pad[1] = tu.pad[2] = tu.pad[3] = 0;
                 }
                 tri_off += c.total;
                 sah += LMB_WIDE_COST_TRI * c.total * c.box.half_area() * inv_root;
             } else {
                 node.imask |= (uint8_t)(1u << s);
-                node.meta[s] = (uint8_t)(0x20u | (24u + s));
-                n_internal++;
             }
         }
         sah += LMB_WIDE_COST_NODE * nb.half_area() * inv_root;
-        out.nodes[p.wide] = node;
-        // 5. reserve the internal children (contiguous, slot order) and schedule them
-        const uint32_t base = node.child_base;
-        out.nodes.resize(out.nodes.size() + n_internal);
+        out.units[p.wide].node = node;
+        num_nodes += n_internal;
+        // 5. schedule the internal children (contiguous, slot order)
         uint32_t rel = 0;
         for (int s = 0; s < 8; s++) {
             const int i = child_in_slot[s];
@@ -380,6 +393,33 @@ struct Emitter {
 };
 
 }  // namespace
+
+void make_scene_grid(const float lo[3], const float hi[3], SceneGrid& g)
+{
+    for (int a = 0; a < 3; a++) {
+        const double l = std::isfinite(lo[a]) ? lo[a] : 0.0, h = std::isfinite(hi[a]) && hi[a] >= lo[a] ? hi[a] : l;
+        int e = (int)std::ceil(std::log2(std::max(h - l, 1e-30) / 65535.0));
+        e = std::max(-100, std::min(100, e));
+        for (;; e++) {
+            const double step = std::ldexp(1.0, e);
+            const double gl = std::floor(l / step) * step;
+            // 65535 steps must reach the top, and lo + k step must be exact in fp32 for every k (|value| / step < 2^23)
+            if (gl + 65535.0 * step >= h && std::fabs(gl) / step < 4194304.0 && (std::fabs(gl) + 65535.0 * step) / step < 8388608.0) {
+                g.lo[a] = (float)gl; g.step[a] = (float)step;
+                break;
+            }
+        }
+    }
+}
+
+uint16_t grid_floor(const SceneGrid& g, int axis, float x)
+{
+    double k = std::floor(((double)x - (double)g.lo[axis]) / (double)g.step[axis]);
+    k = std::max(0.0, std::min(65535.0, k));
+    uint32_t ki = (uint32_t)k;
+    while (ki > 0 && grid_origin(g, axis, ki) > x) ki--;
+    return (uint16_t)ki;
+}
 
 void build_bvh(const float* verts, uint64_t ntris, HostBVH& out, int num_threads)
 {
@@ -434,13 +474,18 @@ void build_bvh(const float* verts, uint64_t ntris, HostBVH& out, int num_threads
     }
     B.run(num_threads);
 
+    {
+        float glo[3], ghi[3];
+        for (int a = 0; a < 3; a++) { glo[a] = nvalid ? scene.lo[a] - pad : 0.f; ghi[a] = nvalid ? scene.hi[a] + pad : 0.f; }
+        make_scene_grid(glo, ghi, out.grid);
+    }
     Emitter E{B, recs, out};
     E.emit_all();
 
     for (int a = 0; a < 3; a++) { out.scene_lo[a] = scene.lo[a]; out.scene_hi[a] = scene.hi[a]; }
     out.stats.num_triangles = ntris;
     out.stats.num_valid = nvalid;
-    out.stats.num_nodes = out.nodes.size();
+    out.stats.num_nodes = E.num_nodes;
     out.stats.sah_cost = (float)E.sah;
     out.stats.max_depth = E.max_depth;
     out.stats.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -1,4 +1,4 @@
-// GPU builder for the same flattened structure as bvh_build.cpp (Node80 + leaf-ordered TriRecords):
+// GPU builder for the same flattened structure as bvh_build.cpp (one array of 64-byte units, bvh.h):
 // Morton-ordered binary radix tree (Karras 2012) -> bottom-up box fit -> level-by-level collapse to
 // 8-wide nodes with <=3-triangle leaves -> octant slot assignment + quantisation, all on the device.
 // Replaces the serial recursive build of the reference (/root/reference/src/liblightmetrica/accel/
@@ -215,7 +215,7 @@ struct WorkItem { uint32_t bin; uint32_t wide; };
 __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkItem* out, uint32_t* out_count,
                            RadixTree T, const Box6* __restrict__ leaf_box, const Box6* __restrict__ node_box,
                            const uint32_t* __restrict__ idx, const TriRecord* __restrict__ recs,
-                           Node80* nodes, uint32_t* node_count, TriRecord* tris_out, uint32_t* tri_count, int n_prims)
+                           Unit64* units, uint32_t* node_count, uint32_t* unit_count, SceneGrid grid, int n_prims)
 {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_in) return;
@@ -243,12 +243,19 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
         cb[i] = box_of(ch[i]);
         for (int a = 0; a < 3; a++) { nb.lo[a] = fminf(nb.lo[a], cb[i].lo[a]); nb.hi[a] = fmaxf(nb.hi[a], cb[i].hi[a]); }
     }
-    Node80 node;
+    Node64 node;
     memset(&node, 0, sizeof(node));
     double scale[3];
+    float origin[3];
     for (int a = 0; a < 3; a++) {
-        node.p[a] = nb.lo[a];
-        const double ext = (double)nb.hi[a] - (double)nb.lo[a];
+        // node origin = the box minimum snapped down to the 16-bit scene grid (bvh.h); decoded exactly as the traversal does
+        double kd = floor(((double)nb.lo[a] - (double)grid.lo[a]) / (double)grid.step[a]);
+        kd = fmax(0.0, fmin(65535.0, kd));
+        uint32_t ki = (uint32_t)kd;
+        while (ki > 0 && fmaf((float)ki, grid.step[a], grid.lo[a]) > nb.lo[a]) ki--;
+        node.k[a] = (uint16_t)ki;
+        origin[a] = fmaf((float)ki, grid.step[a], grid.lo[a]);
+        const double ext = fmax(0.0, (double)nb.hi[a] - (double)origin[a]);
         int e = ext > 0 ? (int)ceil(log2(ext / 254.0)) : -126;
         e = max(-126, min(110, e));
         while (e < 110 && ceil(ext / ldexp(1.0, e) + 2 * kQSlackDev) > 255.0) e++;
@@ -281,18 +288,18 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
         const bool leaf = (ch[i] & 0x80000000u) || count_of(ch[i]) <= LMB_GPU_LEAF;
         if (leaf) n_tris += count_of(ch[i]); else n_internal++;
     }
-    const uint32_t cbase = n_internal ? atomicAdd(node_count, n_internal) : 0u;
-    const uint32_t tbase = n_tris ? atomicAdd(tri_count, n_tris) : 0u;
+    // children: internal nodes first (slot order), then the triangles of the leaf slots (slot order), one allocation
+    const uint32_t base = atomicAdd(unit_count, n_internal + n_tris);
+    if (n_internal) atomicAdd(node_count, n_internal);
     const uint32_t qbase = n_internal ? atomicAdd(out_count, n_internal) : 0u;
-    node.child_base = cbase;
-    node.tri_base = tbase;
+    node.base = base;
     uint32_t rel = 0, toff = 0;
     for (int s = 0; s < 8; s++) {
         const int i = child_in_slot[s];
-        if (i < 0) { node.meta[s] = 0; for (int a = 0; a < 3; a++) { node.qlo[a][s] = 255; node.qhi[a][s] = 0; } continue; }
+        if (i < 0) { for (int a = 0; a < 3; a++) { node.qlo[a][s] = 255; node.qhi[a][s] = 0; } continue; }
         for (int a = 0; a < 3; a++) {
-            double ql = floor(((double)cb[i].lo[a] - (double)node.p[a]) / scale[a] - kQSlackDev);
-            double qh = ceil(((double)cb[i].hi[a] - (double)node.p[a]) / scale[a] + kQSlackDev);
+            double ql = floor(((double)cb[i].lo[a] - (double)origin[a]) / scale[a] - kQSlackDev);
+            double qh = ceil(((double)cb[i].hi[a] - (double)origin[a]) / scale[a] + kQSlackDev);
             ql = fmax(0.0, fmin(255.0, ql)); qh = fmax(0.0, fmin(255.0, qh));
             node.qlo[a][s] = (uint8_t)ql; node.qhi[a][s] = (uint8_t)qh;
         }
@@ -300,17 +307,21 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
         if (leaf) {
             const uint32_t cnt = count_of(ch[i]);
             const uint32_t first = (ch[i] & 0x80000000u) ? (ch[i] & 0x7fffffffu) : T.first[ch[i]];
-            node.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | toff);
-            for (uint32_t k = 0; k < cnt; k++) tris_out[tbase + toff + k] = recs[idx[first + k]];
+            node.counts |= (uint16_t)(cnt << (2 * s));
+            for (uint32_t k = 0; k < cnt; k++) {
+                TriUnit tu;
+                tu.rec = recs[idx[first + k]];
+                tu.pad[0] = tu.pad[1] = tu.pad[2] = tu.pad[3] = 0u;
+                units[base + n_internal + toff + k].tri = tu;
+            }
             toff += cnt;
         } else {
             node.imask |= (uint8_t)(1u << s);
-            node.meta[s] = (uint8_t)(0x20u | (24u + s));
-            out[qbase + rel] = WorkItem{ch[i], cbase + rel};
+            out[qbase + rel] = WorkItem{ch[i], base + rel};
             rel++;
         }
     }
-    nodes[it.wide] = node;
+    units[it.wide].node = node;
 }
 
 struct DevBuf {
@@ -321,14 +332,13 @@ struct DevBuf {
 
 }  // namespace
 
-// Builds on the accel's device from HOST vertices; fills a->d_nodes / a->d_tris and the stats.
+// Builds on the accel's device from HOST vertices; fills a->d_units and the stats.
 int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
 {
     const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    if (a->d_nodes) { cudaFree(a->d_nodes); a->d_nodes = nullptr; }
-    if (a->d_tris) { cudaFree(a->d_tris); a->d_tris = nullptr; }
+    if (a->d_units) { cudaFree(a->d_units); a->d_units = nullptr; a->num_units = 0; }
     if (!a->d_counter && (e = cudaMalloc(&a->d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
     const uint32_t n = (uint32_t)ntris;
     DevBuf D;
@@ -378,21 +388,27 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     uint32_t* counters = D.alloc<uint32_t>(4);   // [0] node count, [1] tri count, [2] out queue count
     if (!T.left || !T.right || !T.parent_internal || !T.parent_leaf || !T.first || !T.last || !leaf_box || !node_box || !flags || !q0 || !q1 || !counters)
         return set_error(LMB200_E_CUDA, "out of device memory (gpu build)");
-    const size_t node_cap = std::max<uint32_t>(nv, 1);
-    if ((e = cudaMalloc(&a->d_nodes, node_cap * sizeof(Node80))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(nodes)");
-    if ((e = cudaMalloc(&a->d_tris, std::max<size_t>(nv, 1) * sizeof(TriRecord))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(tris)");
-    uint32_t num_nodes = 1;
+    // scene grid for the 16-bit node origins (as build_bvh): the padded bounds of the valid triangles
+    {
+        float glo[3], ghi[3];
+        for (int k = 0; k < 3; k++) { glo[k] = nv ? h_scene[k] - pad : 0.f; ghi[k] = nv ? h_scene[3 + k] + pad : 0.f; }
+        make_scene_grid(glo, ghi, a->bvh.grid);
+    }
+    // every wide node has >= 2 children or is the root, so there are at most nv nodes; plus nv triangle units
+    const size_t unit_cap = 2 * (size_t)std::max<uint32_t>(nv, 1) + 1;
+    if ((e = cudaMalloc(&a->d_units, unit_cap * sizeof(Unit64))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(units)");
+    uint32_t num_nodes = 1, num_units = 1;
     int depth = 1;
     if (nv == 0) {
-        Node80 root; memset(&root, 0, sizeof(root));
-        root.e[0] = root.e[1] = root.e[2] = 127;
-        for (int s = 0; s < 8; s++) for (int ax = 0; ax < 3; ax++) { root.qlo[ax][s] = 255; root.qhi[ax][s] = 0; }
-        cudaMemcpy(a->d_nodes, &root, sizeof(root), cudaMemcpyHostToDevice);
+        Unit64 root; memset(&root, 0, sizeof(root));
+        root.node.e[0] = root.node.e[1] = root.node.e[2] = 127;
+        for (int s = 0; s < 8; s++) for (int ax = 0; ax < 3; ax++) { root.node.qlo[ax][s] = 255; root.node.qhi[ax][s] = 0; }
+        cudaMemcpy(a->d_units, &root, sizeof(root), cudaMemcpyHostToDevice);
     } else {
         cudaMemset(flags, 0, sizeof(int) * nv);
         if (nv > 1) { k_radix_tree<<<(nv - 1 + TB - 1) / TB, TB>>>(keys2, (int)nv, T); g_launch_count++; }
         k_fit<<<(nv + TB - 1) / TB, TB>>>(boxes, idx2, (int)nv, pad, T, leaf_box, node_box, flags); g_launch_count++;
-        const uint32_t hc[4] = {1u, 0u, 0u, 0u};
+        const uint32_t hc[4] = {1u, 1u, 0u, 0u};      // [0] nodes, [1] units (the root is unit 0), [2] out queue count
         cudaMemcpy(counters, hc, sizeof(hc), cudaMemcpyHostToDevice);
         const WorkItem rootw{0u, 0u};
         cudaMemcpy(q0, &rootw, sizeof(rootw), cudaMemcpyHostToDevice);
@@ -401,11 +417,12 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
         while (n_in) {
             cudaMemset(counters + 2, 0, sizeof(uint32_t));
             k_collapse<<<(n_in + 127) / 128, 128>>>(qin, n_in, qout, counters + 2, T, leaf_box, node_box, idx2, recs,
-                                                    reinterpret_cast<Node80*>(a->d_nodes), counters, reinterpret_cast<TriRecord*>(a->d_tris), counters + 1, (int)nv);
+                                                    reinterpret_cast<Unit64*>(a->d_units), counters, counters + 1, a->bvh.grid, (int)nv);
             g_launch_count++;
             uint32_t h[3];
             if ((e = cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "gpu collapse");
             num_nodes = h[0];
+            num_units = h[1];
             n_in = h[2];
             std::swap(qin, qout);
             if (n_in) depth++;
@@ -414,7 +431,8 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     }
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(e, "gpu build");
     // the host mirror (lmb200_accel_host_arrays) is filled lazily from the device arrays
-    a->bvh.nodes.clear(); a->bvh.tris.clear(); a->bvh.tri_index.clear();
+    a->bvh.units.clear();
+    a->num_units = num_units;
     a->gpu_built = true;
     a->bvh.stats.num_triangles = ntris;
     a->bvh.stats.num_valid = nv;

@@ -5,6 +5,7 @@
 #include <string>
 #include "../../include/lmb200.h"
 #include "bvh.h"
+#include "bvh_dev.h"
 
 #ifndef LMB_TRACE_BLOCK
 #define LMB_TRACE_BLOCK 128
@@ -33,8 +34,8 @@ struct Accel {
     bool built = false;
     bool gpu_built = false;     // built by build_bvh_gpu: bvh.nodes/tris mirror is filled on demand
     HostBVH bvh;
-    void* d_nodes = nullptr;
-    void* d_tris = nullptr;
+    void* d_units = nullptr;     // the flattened BVH: bvh.h Unit64 array (nodes + triangle units), root = unit 0
+    uint64_t num_units = 0;
     unsigned long long* d_counter = nullptr;   // LMB_NUM_COUNTERS work counters (see above)
     std::atomic<unsigned> ring{0};
     int ring_slot() { return 4 + (int)(ring.fetch_add(1) % LMB_COUNTER_RING); }
@@ -51,10 +52,12 @@ struct Accel {
     ~Accel();
     int upload();
     void free_device();
+    int finish_device_setup();   // occupancy / SM count of the device the units live on
 };
 
 int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris);   // bvh_build_gpu.cu
 int mirror_to_host(Accel* a);                                            // accel.cu
+BvhDev bvh_dev(const Accel* a);                                          // accel.cu
 
 // n_dev != nullptr: the ray count is read from device memory (wavefront queues).
 int trace_closest_dev(Accel* a, const void* rays, void* hits, uint64_t n, const uint32_t* n_dev, cudaStream_t st, int slot);

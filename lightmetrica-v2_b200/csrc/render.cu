@@ -781,12 +781,12 @@ __device__ __forceinline__ void add_work(unsigned long long* dst, const TravCoun
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
-k_extend(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter)
+k_extend(const BvhDev bvh, Pool P, unsigned long long* __restrict__ counter)
 {
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ExtendIo io{P, P.qcount[1]};
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
-    persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+    persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
     if (COUNT) add_work(P.next_sample + 4, cnt);
 }
 
@@ -805,12 +805,12 @@ struct ShadowIo {
 };
 template <bool COUNT>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
-k_shadow(const float4* __restrict__ nodes, const float4* __restrict__ tris, Pool P, unsigned long long* __restrict__ counter, float4* film)
+k_shadow(const BvhDev bvh, Pool P, unsigned long long* __restrict__ counter, float4* film)
 {
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     ShadowIo io{P, P.qcount[2], film};
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
-    persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(nodes, tris, io, counter, smem, cnt);
+    persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
     if (COUNT) add_work(P.next_sample + 6, cnt);
 }
 
@@ -1036,8 +1036,7 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     LMB_CK(cudaEventRecord(ev.a, st), "cudaEventRecord");
     const int logic_blocks = s->num_sms * 8;
     const int trace_blocks = s->accel->num_sms * s->accel->trace_blocks_per_sm;
-    const float4* d_nodes = reinterpret_cast<const float4*>(s->accel->d_nodes);
-    const float4* d_tris = reinterpret_cast<const float4*>(s->accel->d_tris);
+    const BvhDev bvh = bvh_dev(s->accel);
     const bool count = p->count_work != 0;
     int64_t iters = 0;
     for (;;) {
@@ -1050,13 +1049,13 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
             k_nee<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
             LMB_CK(cudaEventRecord(s->ev_nee, st), "cudaEventRecord(nee)");
             LMB_CK(cudaStreamWaitEvent(s->shadow_stream, s->ev_nee, 0), "cudaStreamWaitEvent(nee)");
-            if (count) k_shadow<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(d_nodes, d_tris, P, s->d_counter + 1, film);
-            else k_shadow<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(d_nodes, d_tris, P, s->d_counter + 1, film);
+            if (count) k_shadow<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(bvh, P, s->d_counter + 1, film);
+            else k_shadow<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, s->shadow_stream>>>(bvh, P, s->d_counter + 1, film);
             LMB_CK(cudaEventRecord(s->ev_shadow, s->shadow_stream), "cudaEventRecord(shadow)");
         }
         k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
-        if (count) k_extend<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(d_nodes, d_tris, P, s->d_counter);
-        else k_extend<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(d_nodes, d_tris, P, s->d_counter);
+        if (count) k_extend<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(bvh, P, s->d_counter);
+        else k_extend<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(bvh, P, s->d_counter);
         if (nee) LMB_CK(cudaStreamWaitEvent(st, s->ev_shadow, 0), "cudaStreamWaitEvent(shadow)");
         k_stats<<<1, 1, 0, st>>>(P);
         LMB_CK(cudaGetLastError(), "wavefront kernel launch");
@@ -1105,7 +1104,7 @@ lmb200_scene* lmb200_scene_create_shared(const lmb200_scene_desc* d, lmb200_acce
 {
     Accel* a = reinterpret_cast<Accel*>(accel);
     if (!a || !d) { set_error(LMB200_E_INVALID, "null argument"); return nullptr; }
-    if (!a->built || a->host_only || !a->d_nodes) { set_error(LMB200_E_STATE, "shared accel is not built on a device"); return nullptr; }
+    if (!a->built || a->host_only || !a->d_units) { set_error(LMB200_E_STATE, "shared accel is not built on a device"); return nullptr; }
     if (a->bvh.stats.num_triangles != d->num_tris) { set_error(LMB200_E_INVALID, "shared accel was built over a different triangle list"); return nullptr; }
     return scene_create(a->device, d, LMB200_BUILD_HOST_SAH, a);
 }

@@ -1,4 +1,4 @@
-// Device traversal of the 80-byte wide BVH (bvh.h) with the bit-exact TriAccel leaf test.
+// Device traversal of the 64-byte-unit wide BVH (bvh.h) with the bit-exact TriAccel leaf test.
 // Replaces the reference's stack(64) QBVH loop (/root/reference/src/liblightmetrica/accel/
 // accel_qbvh.cpp:398-497: unordered child push, SSE 4-box slab test) with an octant-ordered
 // 8-wide traversal written for SIMT efficiency:
@@ -7,12 +7,14 @@
 //     slowest ray of its warp is done,
 //   * one thread per ray, (node-group, triangle-group) pairs in registers and a short stack of
 //     8-byte entries in shared memory (overflow to local memory),
+//   * a node is one 64-byte-aligned unit fetched with two 256-bit loads (two sectors of one line),
 //   * triangle tests are batched across the warp (parked per lane until LMB_TRI_BATCH lanes have
 //     some), so the triangle code runs with many lanes instead of ~2.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "triaccel.h"
+#include "bvh_dev.h"
 
 namespace lmb200 {
 
@@ -28,6 +30,22 @@ namespace lmb200 {
 #endif
 
 struct TravCounters { uint32_t nodes, tris; };
+
+// 32 bytes with one 256-bit load through the read-only path (sm_100: ld.global.nc.v8)
+__device__ __forceinline__ void lmb_ld256(const float4* __restrict__ p, uint32_t (&w)[8])
+{
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
+// 16-bit grid coordinate (low or high half of `word`) -> the float 2^23 + k, exactly (bytes of k under the 0x4B exponent)
+template <int HIGH>
+__device__ __forceinline__ float lmb_k2f(uint32_t word)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(0x4B000000u), "n"(HIGH ? 0x7632 : 0x7610));
+    return __uint_as_float(r);
+}
 
 __device__ __forceinline__ float lmb_safe_inv(float d)
 {
@@ -85,25 +103,26 @@ __device__ __forceinline__ void lmb_child(const uint32_t nearx, const uint32_t n
 }
 
 // Intersects the 8 quantised child boxes of one node; bit s of the result = slot s was hit. Empty slots
-// carry an inverted box (qlo = 255 > qhi = 0) and a zero meta byte, so they never contribute.
-__device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const float4 n2, const float4 n3, const float4 n4,
+// carry an inverted box (qlo = 255 > qhi = 0), so they never contribute. px,py,pz: the node's grid origin; ew: the
+// exponent bytes; q[0..11]: the six plane rows (qlo x,y,z then qhi x,y,z), two words (slots 0-3, 4-7) each.
+__device__ __forceinline__ uint32_t lmb_intersect_node(const float px, const float py, const float pz, const uint32_t ew,
+                                                       const uint32_t* __restrict__ q,
                                                        const float ox, const float oy, const float oz,
                                                        const float idx, const float idy, const float idz,
                                                        const float tmin, const float tmax, const uint32_t one)
 {
-    const uint32_t ew = __float_as_uint(n0.w);
     // grid step * 2^15 (exponent bytes are biased; the builder keeps e + 15 <= 254)
     const float sx = __uint_as_float(((ew & 0xffu) + 15u) << 23) * idx;
     const float sy = __uint_as_float((((ew >> 8) & 0xffu) + 15u) << 23) * idy;
     const float sz = __uint_as_float((((ew >> 16) & 0xffu) + 15u) << 23) * idz;
-    const float bx = fmaf(n0.x - ox, idx, -sx);
-    const float by = fmaf(n0.y - oy, idy, -sy);
-    const float bz = fmaf(n0.z - oz, idz, -sz);
+    const float bx = fmaf(px - ox, idx, -sx);
+    const float by = fmaf(py - oy, idy, -sy);
+    const float bz = fmaf(pz - oz, idz, -sz);
     const bool negx = idx < 0.f, negy = idy < 0.f, negz = idz < 0.f;
     uint32_t hits8 = 0;
     {
-        const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
-        const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
+        const uint32_t qlox = q[0], qloy = q[2], qloz = q[4];
+        const uint32_t qhix = q[6], qhiy = q[8], qhiz = q[10];
         const uint32_t nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
         const uint32_t neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
         const uint32_t nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
@@ -113,8 +132,8 @@ __device__ __forceinline__ uint32_t lmb_intersect_node(const float4 n0, const fl
         lmb_child<3>(nearx, neary, nearz, farx, fary, farz, sx, sy, sz, bx, by, bz, tmin, tmax, one, hits8);
     }
     {
-        const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
-        const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
+        const uint32_t qlox = q[1], qloy = q[3], qloz = q[5];
+        const uint32_t qhix = q[7], qhiy = q[9], qhiz = q[11];
         const uint32_t nearx = negx ? qhix : qlox, farx = negx ? qlox : qhix;
         const uint32_t neary = negy ? qhiy : qloy, fary = negy ? qloy : qhiy;
         const uint32_t nearz = negz ? qhiz : qloz, farz = negz ? qloz : qhiz;
@@ -164,22 +183,37 @@ __device__ __forceinline__ void trav_init(Trav& T, const float4 ro, const float4
     T.sp = 0;
 }
 
-// shared-memory stack: entry e of thread t lives at smem[e * STRIDE + t] (conflict-free). `smem` is the
-// calling thread's own column (block base + threadIdx.x) and STRIDE the compile-time block size, so a
-// push/pop is one address computation instead of re-deriving the thread index every time.
+// Shared-memory stack: entry e of thread t lives at shared address sm_base + 8 * (e * STRIDE + t) (conflict-free).
+// T.sp holds the SHARED-SPACE BYTE ADDRESS of the next free entry of this thread's column instead of a level index, so
+// a push / pop is one STS / LDS on that address plus an add (the index form made the compiler re-derive the column from
+// S2R on every push and pop: registers are too tight to keep it). The level is (T.sp - sm_base) / (8 * STRIDE), as
+// 8 * thread < 8 * STRIDE; sm_base is the shared-space address of the block's stack area, a compile-time constant.
 template <int STRIDE>
-__device__ __forceinline__ void trav_push(Trav& T, uint2* __restrict__ smem, uint2* __restrict__ lstack, const uint2 v)
+__device__ __forceinline__ uint32_t trav_level(const Trav& T, const uint32_t sm_base) { return ((uint32_t)T.sp - sm_base) / (8u * STRIDE); }
+template <int STRIDE>
+__device__ __forceinline__ void trav_push(Trav& T, const uint32_t sm_base, uint2* __restrict__ lstack, const uint2 v)
 {
-    if (T.sp < LMB_SM_STACK) smem[T.sp * STRIDE] = v;
-    else lstack[T.sp - LMB_SM_STACK] = v;
-    T.sp++;
+    const uint32_t lvl = trav_level<STRIDE>(T, sm_base);
+    if (lvl < LMB_SM_STACK) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"((uint32_t)T.sp), "r"(v.x), "r"(v.y) : "memory");
+    else lstack[lvl - LMB_SM_STACK] = v;
+    T.sp += 8 * STRIDE;
 }
 template <int STRIDE>
-__device__ __forceinline__ uint2 trav_pop(Trav& T, const uint2* __restrict__ smem, const uint2* __restrict__ lstack)
+__device__ __forceinline__ uint2 trav_pop(Trav& T, const uint32_t sm_base, const uint2* __restrict__ lstack)
 {
-    T.sp--;
-    return T.sp < LMB_SM_STACK ? smem[T.sp * STRIDE] : lstack[T.sp - LMB_SM_STACK];
+    T.sp -= 8 * STRIDE;
+    const uint32_t lvl = trav_level<STRIDE>(T, sm_base);
+    uint2 v;
+    if (lvl < LMB_SM_STACK) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)T.sp) : "memory");
+    else v = lstack[lvl - LMB_SM_STACK];
+    return v;
 }
+template <int STRIDE>
+__device__ __forceinline__ bool trav_stack_empty(const Trav& T, const uint32_t sm_base) { return (uint32_t)T.sp - sm_base < 8u * STRIDE; }
+// to be called after trav_init: points T.sp at the calling thread's column
+__device__ __forceinline__ void trav_stack_reset(Trav& T, const uint32_t sm_base) { T.sp = (int)(sm_base + 8u * threadIdx.x); }
+// shared-space address of a block's stack area (call it on the __shared__ array itself so that it folds to a constant)
+#define LMB_SM_BASE(arr) ((uint32_t)__cvta_generic_to_shared(arr))
 
 // One traversal step of an active lane: open the nearest pending node, then maybe test triangles.
 // Triangle work is batched across the warp: the triangles hit by a node test are parked in a
@@ -190,8 +224,8 @@ __device__ __forceinline__ uint2 trav_pop(Trav& T, const uint2* __restrict__ sme
 // Returns true when the ray is finished. Closest hit: tie on t -> larger triangle index wins, which
 // is what a linear scan with the reference's "reject t > maxT" rule yields (accel_naive.cpp:92-124).
 template <bool ANY, bool COUNT, int STRIDE>
-__device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                          uint2* __restrict__ smem, uint2* __restrict__ lstack, TravCounters& cnt, const unsigned lanes)
+__device__ __forceinline__ bool trav_step(Trav& T, const BvhDev& bvh,
+                                          const uint32_t smem, uint2* __restrict__ lstack, TravCounters& cnt, const unsigned lanes)
 {
     // `lanes`: the lanes of this warp that execute this step together (the caller's ballot of active lanes)
     uint2 fresh = make_uint2(0u, 0u);
@@ -202,27 +236,38 @@ __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ no
         if (T.ngroup.y & 0xff000000u) trav_push<STRIDE>(T, smem, lstack, T.ngroup);
         const uint32_t slot = (bit - 24u) ^ (T.oct_inv4 & 7u);
         const uint32_t rel = __popc(hits_imask & ~(0xffffffffu << slot) & 0xffu);
-        const float4* np = nodes + (size_t)(T.ngroup.x + rel) * 5u;
-        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        const float4* np = bvh.units + (size_t)(T.ngroup.x + rel) * 4u;
+        uint32_t h[8], q[8];
+        lmb_ld256(np, h);            // header (4 words) + qlo x, y
+        lmb_ld256(np + 2, q);        // qlo z + qhi x, y, z
         if (COUNT) cnt.nodes++;
-        const uint32_t hits8 = lmb_intersect_node(n0, n2, n3, n4, T.ox, T.oy, T.oz, T.idx, T.idy, T.idz, T.tmin, T.tmax, T.one);
-        const uint32_t imask = __float_as_uint(n0.w) >> 24;
-        T.ngroup.x = __float_as_uint(n1.x);
+        uint32_t planes[12];
+        planes[0] = h[4]; planes[1] = h[5]; planes[2] = h[6]; planes[3] = h[7];
+#pragma unroll
+        for (int k = 0; k < 8; k++) planes[4 + k] = q[k];
+        const float px = fmaf(lmb_k2f<0>(h[0]), bvh.gstep[0], bvh.glo2[0]);
+        const float py = fmaf(lmb_k2f<1>(h[0]), bvh.gstep[1], bvh.glo2[1]);
+        const float pz = fmaf(lmb_k2f<0>(h[1]), bvh.gstep[2], bvh.glo2[2]);
+        const uint32_t hits8 = lmb_intersect_node(px, py, pz, h[2], planes, T.ox, T.oy, T.oz, T.idx, T.idy, T.idz, T.tmin, T.tmax, T.one);
+        const uint32_t imask = h[2] >> 24;
+        T.ngroup.x = h[3];
         T.ngroup.y = (lmb_xor_permute8(hits8 & imask, T.oct_inv4 >> 8) << 24) | imask;
-        // triangles of the hit leaf slots (rare: ~5 % of the node visits of an incoherent ray):
-        // meta byte = unary count << 5 | offset into the node's triangle block
+        // triangles of the hit leaf slots (rare: ~5 % of the node visits of an incoherent ray): two count bits per
+        // slot; the triangle units follow the node's internal children, in slot order
         uint32_t leaf = hits8 & ~imask;
-        fresh.x = __float_as_uint(n1.y);
+        const uint32_t counts = h[1] >> 16;
+        fresh.x = h[3] + __popc(imask);
         while (leaf) {
             const uint32_t sl = __ffs(leaf) - 1;
             leaf &= leaf - 1;
-            const uint32_t word = __float_as_uint(sl < 4u ? n1.z : n1.w);
-            const uint32_t mb = (word >> ((sl & 3u) * 8u)) & 0xffu;
-            fresh.y |= (mb >> 5) << (mb & 31u);
+            const uint32_t c = (counts >> (2u * sl)) & 3u;
+            const uint32_t below = counts & ~(0xffffffffu << (2u * sl));
+            const uint32_t off = __popc(below & 0x5555u) + 2u * __popc(below & 0xaaaau);
+            fresh.y |= ((1u << c) - 1u) << off;
         }
     }
     // next node group
-    if ((T.ngroup.y & 0xff000000u) == 0u && T.sp > 0) T.ngroup = trav_pop<STRIDE>(T, smem, lstack);
+    if ((T.ngroup.y & 0xff000000u) == 0u && !trav_stack_empty<STRIDE>(T, smem)) T.ngroup = trav_pop<STRIDE>(T, smem, lstack);
     const bool no_nodes = (T.ngroup.y & 0xff000000u) == 0u;
 
     // park the fresh triangles if the pending slot is free
@@ -235,7 +280,7 @@ __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ no
             while (T.pend.y) {
                 const uint32_t i = __ffs(T.pend.y) - 1;
                 T.pend.y &= T.pend.y - 1;
-                const float4* tp = tris + (size_t)(T.pend.x + i) * 3u;
+                const float4* tp = bvh.units + (size_t)(T.pend.x + i) * 4u;
                 const float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
                 if (COUNT) cnt.tris++;
                 float t, u, v;
@@ -259,10 +304,9 @@ __device__ __forceinline__ bool trav_step(Trav& T, const float4* __restrict__ no
 //   void load(uint64_t i, float4& ro, float4& rd);   ray i
 //   void store(uint64_t i, const Trav& T);           result of ray i (T.hid == 0xffffffff: miss)
 template <bool ANY, bool COUNT, int STRIDE, typename Io>
-__device__ __forceinline__ void persistent_trace(const float4* __restrict__ nodes, const float4* __restrict__ tris, Io& io,
-                                                 unsigned long long* __restrict__ counter, uint2* __restrict__ smem_block, TravCounters& cnt)
+__device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
+                                                 unsigned long long* __restrict__ counter, const uint32_t smem, TravCounters& cnt)
 {
-    uint2* const smem = smem_block + threadIdx.x;     // this thread's stack column
     const uint64_t n = io.count();
     const unsigned lane = threadIdx.x & 31u;
     uint2 lstack[LMB_LOCAL_STACK];
@@ -286,6 +330,7 @@ __device__ __forceinline__ void persistent_trace(const float4* __restrict__ node
                         float4 ro, rd;
                         io.load(i, ro, rd);
                         trav_init(T, ro, rd);
+                        trav_stack_reset(T, smem);
                         ray_index = i;
                         active = true;
                     }
@@ -299,7 +344,7 @@ __device__ __forceinline__ void persistent_trace(const float4* __restrict__ node
         unsigned live = __ballot_sync(0xffffffffu, active);
         for (;;) {
             if (active) {
-                if (trav_step<ANY, COUNT, STRIDE>(T, nodes, tris, smem, lstack, cnt, live)) {
+                if (trav_step<ANY, COUNT, STRIDE>(T, bvh, smem, lstack, cnt, live)) {
                     io.store(ray_index, T);
                     active = false;
                 }
@@ -313,13 +358,13 @@ __device__ __forceinline__ void persistent_trace(const float4* __restrict__ node
 
 // Whole-ray helper for single-ray callers (per-ray Accel3::Intersect path).
 template <bool ANY, bool COUNT, int STRIDE>
-__device__ __forceinline__ bool lmb_traverse(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                             const float4 ro, const float4 rd, Trav& T, uint2* __restrict__ smem_block, TravCounters& cnt)
+__device__ __forceinline__ bool lmb_traverse(const BvhDev& bvh,
+                                             const float4 ro, const float4 rd, Trav& T, const uint32_t smem, TravCounters& cnt)
 {
-    uint2* const smem = smem_block + threadIdx.x;
     uint2 lstack[LMB_LOCAL_STACK];
     trav_init(T, ro, rd);
-    while (!trav_step<ANY, COUNT, STRIDE>(T, nodes, tris, smem, lstack, cnt, __activemask())) {}
+    trav_stack_reset(T, smem);
+    while (!trav_step<ANY, COUNT, STRIDE>(T, bvh, smem, lstack, cnt, __activemask())) {}
     return T.hid != 0xffffffffu;
 }
 

@@ -63,6 +63,11 @@ class RenderParams(C.Structure):
                 ("tile", C.c_float * 4), ("count_work", C.c_int32), ("tile_partition", C.c_int32)]
 
 
+class BvhLayout(C.Structure):
+    _fields_ = [("units", C.c_void_p), ("num_units", C.c_uint64), ("num_nodes", C.c_uint64), ("num_triangles", C.c_uint64),
+                ("grid_lo", C.c_float * 3), ("grid_step", C.c_float * 3)]
+
+
 class RenderStats(C.Structure):
     _fields_ = [("samples", C.c_int64), ("extend_rays", C.c_int64), ("shadow_rays", C.c_int64), ("iterations", C.c_int64),
                 ("launches", C.c_uint64), ("seconds", C.c_double), ("reduce_seconds", C.c_double), ("vertices", C.c_int64),
@@ -74,7 +79,7 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int64, 
 EXPORTS = [
     "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build", "lmb200_accel_build_ex",
     "lmb200_accel_get_stats", "lmb200_accel_device", "lmb200_accel_replicate", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
-    "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_arrays", "lmb200_accel_create_host_only",
+    "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_layout", "lmb200_accel_create_host_only",
     "lmb200_scene_create", "lmb200_scene_create_ex", "lmb200_scene_create_shared", "lmb200_registry_put", "lmb200_registry_get", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
     "lmb200_render", "lmb200_render_multi", "lmb200_render_timed",
 ]
@@ -127,8 +132,7 @@ def lib():
     L.lmb200_trace_any_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     L.lmb200_trace_count_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.lmb200_launch_count.restype = C.c_uint64
-    L.lmb200_accel_host_arrays.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
-                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.lmb200_accel_host_layout.argtypes = [C.c_void_p, C.POINTER(BvhLayout)]
     if hasattr(L, "lmb200_scene_create"):
         L.lmb200_scene_create.restype = C.c_void_p
         L.lmb200_scene_create.argtypes = [C.c_int, C.POINTER(SceneDesc)]
@@ -197,18 +201,12 @@ class Accel:
         check(lib().lmb200_accel_get_stats(self.h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in AccelStats._fields_}
 
-    def host_arrays(self):
-        nodes, tris, idx = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        nn, nt = C.c_uint64(), C.c_uint64()
-        check(lib().lmb200_accel_host_arrays(self.h, C.byref(nodes), C.byref(nn), C.byref(tris), C.byref(idx), C.byref(nt)))
-        nodes_a = np.ctypeslib.as_array(C.cast(nodes, C.POINTER(C.c_uint8)), shape=(nn.value * 80,)).copy()
-        if nt.value:
-            tris_a = np.ctypeslib.as_array(C.cast(tris, C.POINTER(C.c_uint8)), shape=(nt.value * 48,)).copy()
-            idx_a = np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_uint32)), shape=(nt.value,)).copy()
-        else:
-            tris_a = np.zeros(0, np.uint8)
-            idx_a = np.zeros(0, np.uint32)
-        return nodes_a, tris_a, idx_a
+    def host_layout(self):
+        """The flattened structure as (units (N,64) uint8 copy, num_nodes, num_triangles, (grid_lo, grid_step))."""
+        lay = BvhLayout()
+        check(lib().lmb200_accel_host_layout(self.h, C.byref(lay)))
+        units = np.ctypeslib.as_array(C.cast(lay.units, C.POINTER(C.c_uint8)), shape=(lay.num_units, 64)).copy()
+        return units, int(lay.num_nodes), int(lay.num_triangles), (np.array(lay.grid_lo[:], np.float32), np.array(lay.grid_step[:], np.float32))
 
     def trace_closest(self, rays):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)

@@ -35,6 +35,7 @@ def port():
         L.orc_any.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
         L.orc_wide_closest.restype = C.c_longlong
         L.orc_wide_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+        L.orc_wide_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
         L.orc_triaccel_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_triaccel_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -104,14 +105,24 @@ class PortScene:
         return occ
 
 
-def wide_closest(nodes80, tris48, rays):
-    """Scalar walk of the product's flattened nodes (host-logic checker, no GPU)."""
+def wide_closest(units, grid, rays):
+    """Scalar walk of the product's flattened 64-byte units (host-logic checker, no GPU). grid = (lo[3], step[3])."""
     rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
     n = rays.shape[0]
     tuv = np.zeros((n, 3), np.float32)
     tri = np.zeros(n, np.int32)
-    port().orc_wide_closest(_p(nodes80), _p(tris48), _p(rays), n, _p(tuv), _p(tri))
+    g = np.ascontiguousarray(np.concatenate([grid[0], grid[1]]), np.float32)
+    port().orc_wide_closest(_p(units), _p(g), _p(rays), n, _p(tuv), _p(tri))
     return tuv, tri
+
+
+def wide_count(units, grid, rays):
+    """(nodes per ray, triangle records per ray) of an ordered CPU walk of the product's structure: tree-quality figure."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    g = np.ascontiguousarray(np.concatenate([grid[0], grid[1]]), np.float32)
+    out = np.zeros(2, np.float64)
+    port().orc_wide_count(_p(units), _p(g), _p(rays), rays.shape[0], _p(out))
+    return out[0] / rays.shape[0], out[1] / rays.shape[0]
 
 
 def mesh_scene_yaml(handle, accel="qbvh", w=16, h=16):

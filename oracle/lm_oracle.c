@@ -279,18 +279,48 @@ long long orc_any(const orc_scene* s, const float* rays, long long n, uint8_t* o
 
 /* ---------------------------------------------------------------------------------------------
  * Checker for the PRODUCT's flattened structure (lightmetrica-v2_b200/csrc/bvh.h): a scalar walk
- * of the 80-byte nodes with exact box decoding in double precision. It lets the CPU test-suite
- * verify the host builder (every triangle reachable, boxes conservative, slot order encoding)
+ * of the 64-byte units with exact box decoding in double precision. It lets the CPU test-suite
+ * verify the builders (every triangle reachable, boxes conservative, slot order encoding)
  * without a GPU. It visits ALL children whose decoded box the ray touches, in arbitrary order. */
 typedef struct {
-    float p[3]; uint8_t e[3]; uint8_t imask; uint32_t child_base, tri_base; uint8_t meta[8];
+    uint16_t k[3]; uint16_t counts; uint8_t e[3]; uint8_t imask; uint32_t base;
     uint8_t qlo[3][8]; uint8_t qhi[3][8];
-} orc_node80;
+} orc_node64;
+typedef struct { orc_tri rec; uint32_t pad[4]; } orc_triunit;
 
-long long orc_wide_closest(const void* nodes80, const void* tris48, const float* rays, long long n, float* tuv, int32_t* tri)
+static uint32_t orc_slot_tri_offset(const orc_node64* nd, int s)
 {
-    const orc_node80* nodes = (const orc_node80*)nodes80;
-    const orc_tri* tris = (const orc_tri*)tris48;   /* faceIndex slot holds the input index */
+    uint32_t off = 0; int j;
+    for (j = 0; j < s; j++) off += (nd->counts >> (2 * j)) & 3u;
+    return off;
+}
+static uint32_t orc_popc8(uint32_t x) { uint32_t c = 0; for (; x; x &= x - 1) c++; return c; }
+
+static int orc_slot_hit(const orc_node64* nd, const float* grid, int s, const float* o, const float* d, double mint, double maxt, double* tnear)
+{
+    double tn = mint, tf = maxt;
+    int a;
+    for (a = 0; a < 3; a++) {
+        const double org = (double)grid[a] + (double)grid[3 + a] * nd->k[a];
+        const double sc = ldexp(1.0, (int)nd->e[a] - 127);
+        const double lo = org + sc * nd->qlo[a][s], hi = org + sc * nd->qhi[a][s];
+        if (nd->qlo[a][s] > nd->qhi[a][s]) return 0;       /* empty slot */
+        if (d[a] == 0.0f) { if (o[a] < lo || o[a] > hi) return 0; }
+        else {
+            double t0 = (lo - o[a]) / d[a], t1 = (hi - o[a]) / d[a];
+            if (t0 > t1) { const double tt = t0; t0 = t1; t1 = tt; }
+            if (t0 > tn) tn = t0;
+            if (t1 < tf) tf = t1;
+        }
+    }
+    if (tnear) *tnear = tn;
+    return tn <= tf;
+}
+
+/* grid: lo[3], step[3] of the scene grid (lmb200_bvh_layout) */
+long long orc_wide_closest(const void* units64, const float* grid, const float* rays, long long n, float* tuv, int32_t* tri)
+{
+    const orc_node64* units = (const orc_node64*)units64;
     long long hits = 0, i;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : hits)
     for (i = 0; i < n; i++) {
@@ -299,35 +329,23 @@ long long orc_wide_closest(const void* nodes80, const void* tris48, const float*
         const float mint = r[3];
         float maxt = r[7], bu = 0, bv = 0;
         int32_t best = -1;
-        uint32_t stack[256]; int sp = 0;
+        uint32_t stack[512]; int sp = 0;
         stack[sp++] = 0;
         while (sp) {
-            const orc_node80* nd = &nodes[stack[--sp]];
-            int s, a;
+            const orc_node64* nd = &units[stack[--sp]];
+            const uint32_t nint = orc_popc8(nd->imask);
+            int s;
             uint32_t rel = 0;
             for (s = 0; s < 8; s++) {
-                const uint8_t m = nd->meta[s];
-                double tn = mint, tf = maxt;
-                int miss = 0;
                 const int internal = (nd->imask >> s) & 1;
-                if (m == 0) continue;
-                for (a = 0; a < 3; a++) {
-                    const double sc = ldexp(1.0, (int)nd->e[a] - 127);
-                    const double lo = (double)nd->p[a] + sc * nd->qlo[a][s], hi = (double)nd->p[a] + sc * nd->qhi[a][s];
-                    if (d[a] == 0.0f) { if (o[a] < lo || o[a] > hi) miss = 1; }
-                    else {
-                        double t0 = (lo - o[a]) / d[a], t1 = (hi - o[a]) / d[a];
-                        if (t0 > t1) { const double tt = t0; t0 = t1; t1 = tt; }
-                        if (t0 > tn) tn = t0;
-                        if (t1 < tf) tf = t1;
-                    }
-                }
-                if (internal) { const uint32_t child = nd->child_base + rel; rel++; if (!miss && tn <= tf) stack[sp++] = child; }
-                else if (!miss && tn <= tf) {
-                    const uint32_t off = m & 31u, cnt = (m >> 5) == 7 ? 3 : ((m >> 5) == 3 ? 2 : 1);
+                const uint32_t cnt = (nd->counts >> (2 * s)) & 3u;
+                const int hit = orc_slot_hit(nd, grid, s, o, d, mint, maxt, 0);
+                if (internal) { const uint32_t child = nd->base + rel; rel++; if (hit && sp < 512) stack[sp++] = child; }
+                else if (cnt && hit) {
+                    const uint32_t off = orc_slot_tri_offset(nd, s);
                     uint32_t k;
                     for (k = 0; k < cnt; k++) {
-                        const orc_tri* T = &tris[nd->tri_base + off + k];
+                        const orc_tri* T = &((const orc_triunit*)&units[nd->base + nint + off + k])->rec;
                         float t, u, v;
                         if (orc_triaccel_intersect(T, o, d, mint, maxt, &u, &v, &t)) {
                             const int32_t id = (int32_t)T->faceIndex;
@@ -342,4 +360,65 @@ long long orc_wide_closest(const void* nodes80, const void* tris48, const float*
         tri[i] = best;
     }
     return hits;
+}
+
+/* Work estimator for tree-quality experiments on the CPU (no GPU needed): walks the flattened structure in the
+ * PRODUCT's traversal order — children of a node in octant priority (slot ^ (7 - ray octant), highest first), the
+ * remaining siblings pushed as one stack entry, triangles tested as soon as their leaf slot is hit — and counts the
+ * 64-byte nodes and triangle records fetched. The device kernel defers triangle tests by a few steps, so its counts
+ * are slightly higher; ratios between trees carry over. out[0] = nodes, out[1] = triangle records (totals). */
+void orc_wide_count(const void* units64, const float* grid, const float* rays, long long n, double* out)
+{
+    const orc_node64* units = (const orc_node64*)units64;
+    double tn_nodes = 0, tn_tris = 0;
+    long long i;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : tn_nodes, tn_tris)
+    for (i = 0; i < n; i++) {
+        const float* r = rays + 8 * i;
+        const float* o = r; const float* d = r + 4;
+        const float mint = r[3];
+        float maxt = r[7];
+        int32_t best = -1;
+        const uint32_t oct = (d[0] < 0 ? 1u : 0u) | (d[1] < 0 ? 2u : 0u) | (d[2] < 0 ? 4u : 0u);
+        const uint32_t oi = 7u - oct;
+        /* stack entry: base unit of a sibling group, pending priority bits, imask */
+        struct { uint32_t base, pend, imask; } stack[256];
+        int sp = 0;
+        uint32_t g_base = 0, g_pend = 0x80u, g_imask = 0;       /* root: relative index 0 */
+        for (;;) {
+            if (!g_pend) { if (!sp) break; sp--; g_base = stack[sp].base; g_pend = stack[sp].pend; g_imask = stack[sp].imask; continue; }
+            {
+                uint32_t bit = 7; const orc_node64* nd; uint32_t slot, rel, nint, hits8 = 0, pr = 0; int s;
+                while (!((g_pend >> bit) & 1u)) bit--;
+                g_pend &= ~(1u << bit);
+                if (g_pend && sp < 256) { stack[sp].base = g_base; stack[sp].pend = g_pend; stack[sp].imask = g_imask; sp++; }
+                slot = bit ^ oi;
+                rel = orc_popc8(g_imask & ((1u << slot) - 1u));
+                nd = &units[g_base + rel];
+                tn_nodes += 1;
+                nint = orc_popc8(nd->imask);
+                for (s = 0; s < 8; s++) if (orc_slot_hit(nd, grid, s, o, d, mint, maxt, 0)) hits8 |= 1u << s;
+                for (s = 0; s < 8; s++) {
+                    const uint32_t cnt = (nd->counts >> (2 * s)) & 3u;
+                    if (!((hits8 >> s) & 1u) || ((nd->imask >> s) & 1u) || !cnt) continue;
+                    {
+                        const uint32_t off = orc_slot_tri_offset(nd, s);
+                        uint32_t k;
+                        for (k = 0; k < cnt; k++) {
+                            const orc_tri* T = &((const orc_triunit*)&units[nd->base + nint + off + k])->rec;
+                            float t, u, v;
+                            tn_tris += 1;
+                            if (orc_triaccel_intersect(T, o, d, mint, maxt, &u, &v, &t)) {
+                                const int32_t id = (int32_t)T->faceIndex;
+                                if (t < maxt || best < 0 || id > best) { maxt = t; best = id; }
+                            }
+                        }
+                    }
+                }
+                for (s = 0; s < 8; s++) if (((hits8 & nd->imask) >> s) & 1u) pr |= 1u << (s ^ oi);
+                g_base = nd->base; g_pend = pr; g_imask = nd->imask;
+            }
+        }
+    }
+    out[0] = tn_nodes; out[1] = tn_tris;
 }

@@ -29,6 +29,19 @@ for name, verts in [("soup4M", scenes.soup(4000000, seed=42, extent=100.0, edge=
     capi.check(L.lmb200_trace_count_dev(A.h, d_rays.data_ptr(), 1 << 22, C.byref(npr), C.byref(tpr)))
     out[name] = dict(mrays=n / ms / 1e3, nodes=npr.value, tris=tpr.value, hit=float((d_hits[:, 3].view(torch.int32) != -1).float().mean()))
     A.close()
+if os.environ.get("SWEEP_PT", "1") != "0":
+    from lmb200py import scenedesc
+    sc = scenedesc.config2_scene(1000000, 1920, 1080)
+    S = capi.Scene(sc)
+    N = 1920 * 1080 * 32
+    S.render(capi.MODE_PTDIRECT, N // 4, seed=1)
+    best = 0
+    for _ in range(2):
+        img, st = S.render(capi.MODE_PTDIRECT, N, seed=1)
+        best = max(best, N / st["seconds"] / 1e6)
+    out["ptdirect"] = dict(msamples=best, mean=float(img.mean()))
+    S.close()
+out = {k: {a: (round(b, 2) if isinstance(b, float) else b) for a, b in v.items()} for k, v in out.items()}
 print("RESULT", json.dumps(out))
 ''' % ROOT
 libs = [os.path.join(ROOT, 'lightmetrica-v2_b200', 'lib', 'liblmb200.so')] + sorted(glob.glob(os.path.join(ROOT, 'lightmetrica-v2_b200', 'lib', 'variants', '*.so')))

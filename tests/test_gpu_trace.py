@@ -198,7 +198,7 @@ def test_gpu_builder_same_hits_and_valid_structure(ntri, extent, edge):
     """The device builder (Morton radix tree + collapse on the GPU) produces another tree of the same format:
     hits must be bit-identical to the oracle's (the closest hit does not depend on the tree), every triangle must
     be referenced once, and every quantised child box must contain what is below it."""
-    from test_host import decode_nodes
+    from test_host import check_structure
     verts = scenes.soup(ntri, seed=77, extent=extent, edge=edge) if ntri else np.zeros((0, 9), np.float32)
     lo, hi = (scenes.bounds(verts) if ntri else (np.zeros(3, np.float32), np.ones(3, np.float32)))
     rays = scenes.random_rays(40000, lo - 0.3, hi + 0.3, seed=5)
@@ -208,25 +208,10 @@ def test_gpu_builder_same_hits_and_valid_structure(ntri, extent, edge):
     tuv_o, tri_o = ob.PortScene(verts).closest(rays)
     assert_bit_exact(*gpu_closest(A, rays), tuv_o, tri_o)
     assert np.array_equal(A.trace_any(rays).astype(bool), tri_o >= 0)
-    nodes, tris, idx = A.host_arrays()
-    N = decode_nodes(nodes)
+    units, num_nodes, num_tris, grid = A.host_layout()
+    assert num_tris == ntri and st["num_nodes"] == num_nodes
+    idx = check_structure(units, num_nodes, num_tris, grid, verts, ob.PortScene(verts).records() if ntri else np.zeros((0, 12), np.uint32))
     assert sorted(idx.tolist()) == list(range(ntri))
-    if ntri:
-        rec = tris.view(np.uint32).reshape(-1, 12)
-        port = ob.PortScene(verts).records()
-        assert np.array_equal(rec[:, :10], port[idx][:, :10])          # device TriAccel precompute is bit-exact
-    pad = 1e-4
-    for nd in N:
-        sc = np.ldexp(1.0, nd["e"].astype(int) - 127)
-        for s in range(8):
-            m = int(nd["meta"][s])
-            if m == 0 or (nd["imask"] >> s) & 1:
-                continue
-            lo_s = nd["p"].astype(np.float64) + sc * nd["qlo"][:, s]
-            hi_s = nd["p"].astype(np.float64) + sc * nd["qhi"][:, s]
-            for k in range({1: 1, 3: 2, 7: 3}[m >> 5]):
-                v = verts[idx[nd["tri_base"] + (m & 31) + k]].reshape(3, 3).astype(np.float64)
-                assert (v.min(axis=0) - pad >= lo_s - 1e-9).all() and (v.max(axis=0) + pad <= hi_s + 1e-9).all()
 
 
 def test_gpu_builder_large_and_degenerate():

@@ -62,11 +62,66 @@ def test_no_device_fails_loudly(have_gpu):
         capi.Accel(0)
 
 
-def decode_nodes(nodes):
-    dt = np.dtype([("p", "f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "u4"), ("tri_base", "u4"),
-                   ("meta", "u1", 8), ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])
-    assert dt.itemsize == 80
-    return nodes.view(dt)
+NODE_DT = np.dtype([("k", "<u2", 3), ("counts", "<u2"), ("e", "u1", 3), ("imask", "u1"), ("base", "<u4"),
+                    ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])
+assert NODE_DT.itemsize == 64
+
+
+def check_structure(units, num_nodes, num_tris, grid, verts, records):
+    """Walks the flattened 64-byte units from the root (csrc/bvh.h): every unit is referenced exactly once, every valid
+    triangle sits in exactly one leaf slot with its bit-exact TriAccel record, every quantised child box contains what is
+    below it (triangles padded by the reference's 1e-4; a child node's own boxes up to one step of ITS grid).
+    Returns the input indices of the triangles in unit order."""
+    N = units.view(NODE_DT).reshape(-1)
+    W = units.view(np.uint32).reshape(-1, 16)
+    glo, gstep = grid[0].astype(np.float64), grid[1].astype(np.float64)
+    seen = np.zeros(len(units), np.int32)
+    seen[0] = 1
+    tri_ids = []
+    pad = 1e-4
+    stack = [0]
+    n_nodes = 0
+
+    def boxes(nd):
+        org = glo + gstep * nd["k"].astype(np.float64)
+        sc = np.ldexp(1.0, nd["e"].astype(int) - 127)
+        return org[:, None] + sc[:, None] * nd["qlo"], org[:, None] + sc[:, None] * nd["qhi"], sc
+
+    while stack:
+        ni = stack.pop()
+        nd = N[ni]
+        n_nodes += 1
+        lo, hi, _ = boxes(nd)
+        nint = bin(int(nd["imask"])).count("1")
+        rel = toff = 0
+        for s in range(8):
+            cnt = (int(nd["counts"]) >> (2 * s)) & 3
+            if (int(nd["imask"]) >> s) & 1:
+                assert cnt == 0
+                c = int(nd["base"]) + rel
+                rel += 1
+                seen[c] += 1
+                ch = N[c]
+                clo, chi, csc = boxes(ch)
+                used = ch["qlo"][0] <= ch["qhi"][0]
+                assert used.any()
+                assert (clo[:, used].min(axis=1) >= lo[:, s] - csc - 1e-9).all() and (chi[:, used].max(axis=1) <= hi[:, s] + csc + 1e-9).all()
+                stack.append(c)
+            elif cnt:
+                for k in range(cnt):
+                    u = int(nd["base"]) + nint + toff + k
+                    seen[u] += 1
+                    tid = int(W[u, 10])
+                    tri_ids.append(tid)
+                    assert np.array_equal(W[u, :10], records[tid, :10])          # bit-exact TriAccel precompute
+                    v = verts[tid].reshape(3, 3).astype(np.float64)
+                    assert (v.min(axis=0) - pad >= lo[:, s] - 1e-9).all() and (v.max(axis=0) + pad <= hi[:, s] + 1e-9).all()
+                toff += cnt
+            else:
+                assert (nd["qlo"][:, s] == 255).all() and (nd["qhi"][:, s] == 0).all()      # empty slot: inverted box
+    assert (seen == 1).all()                      # no orphan and no shared unit
+    assert n_nodes == num_nodes and len(tri_ids) == num_tris and n_nodes + len(tri_ids) == len(units)
+    return np.array(tri_ids, np.int64)
 
 
 @pytest.mark.parametrize("n,extent,edge", [(1, 1.0, 0.3), (2, 1.0, 0.3), (7, 1.0, 0.3), (300, 2.0, 0.3), (20000, 10.0, 0.2)])
@@ -74,47 +129,29 @@ def test_builder_structure(n, extent, edge):
     verts = scenes.soup(n, seed=3, extent=extent, edge=edge)
     A = capi.Accel(host_only=True)
     st = A.build(verts)
-    nodes, tris, idx = A.host_arrays()
-    N = decode_nodes(nodes)
-    assert st["num_valid_triangles"] == n and len(idx) == n
+    units, num_nodes, num_tris, grid = A.host_layout()
+    assert st["num_valid_triangles"] == n == num_tris and st["num_nodes"] == num_nodes
+    assert st["node_bytes"] == 64 * num_nodes and st["tri_bytes"] == 64 * num_tris
+    idx = check_structure(units, num_nodes, num_tris, grid, verts, ob.PortScene(verts).records())
     assert sorted(idx.tolist()) == list(range(n))          # every triangle referenced exactly once
-    # records are the bit-exact TriAccel precompute, in leaf order
-    rec = tris.view(np.uint32).reshape(-1, 12)
-    port = ob.PortScene(verts).records()
-    assert np.array_equal(rec[:, :10], port[idx][:, :10]) and np.array_equal(rec[:, 10], idx)
-    # every child box contains its triangles (padded by the reference's 1e-4) / its child node's boxes
-    pad = 1e-4
-    seen_nodes = np.zeros(len(N), bool)
-    seen_nodes[0] = True
-    for ni, nd in enumerate(N):
-        sc = np.ldexp(1.0, nd["e"].astype(int) - 127)
-        rel = 0
-        for s in range(8):
-            m = int(nd["meta"][s])
-            if m == 0:
-                continue
-            lo = nd["p"].astype(np.float64) + sc * nd["qlo"][:, s]
-            hi = nd["p"].astype(np.float64) + sc * nd["qhi"][:, s]
-            if (nd["imask"] >> s) & 1:
-                assert m == (0x20 | (24 + s))
-                c = nd["child_base"] + rel
-                rel += 1
-                assert not seen_nodes[c]
-                seen_nodes[c] = True
-                ch = N[c]
-                csc = np.ldexp(1.0, ch["e"].astype(int) - 127)
-                used = ch["meta"] != 0
-                clo = ch["p"].astype(np.float64)[:, None] + csc[:, None] * ch["qlo"][:, used]
-                chi = ch["p"].astype(np.float64)[:, None] + csc[:, None] * ch["qhi"][:, used]
-                # the child's own grid may round outward by < 1 step of ITS grid beyond the parent's slot box
-                assert (clo.min(axis=1) >= lo - csc - 1e-9).all() and (chi.max(axis=1) <= hi + csc + 1e-9).all()
-            else:
-                cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
-                off = m & 31
-                for k in range(cnt):
-                    v = verts[idx[nd["tri_base"] + off + k]].reshape(3, 3).astype(np.float64)
-                    assert (v.min(axis=0) - pad >= lo - 1e-9).all() and (v.max(axis=0) + pad <= hi + 1e-9).all()
-    assert seen_nodes.all()
+
+
+def test_builder_far_from_origin_and_anisotropic():
+    """The 16-bit scene grid of the node origins: a scene far from the origin (coarse fp32 there) and a very flat one."""
+    for off, scale in [((5.0e4, -3.0e4, 1.0e3), (1.0, 1.0, 1.0)), ((0.0, 0.0, 0.0), (100.0, 1e-3, 10.0))]:
+        verts = scenes.soup(3000, seed=5, extent=4.0, edge=0.2).reshape(-1, 3) * np.array(scale, np.float32) + np.array(off, np.float32)
+        verts = np.ascontiguousarray(verts.reshape(-1, 9), np.float32)
+        A = capi.Accel(host_only=True)
+        A.build(verts)
+        units, num_nodes, num_tris, grid = A.host_layout()
+        check_structure(units, num_nodes, num_tris, grid, verts, ob.PortScene(verts).records())
+        lo, hi = scenes.bounds(verts)
+        rays = scenes.random_rays(20000, lo, hi, seed=7)
+        tuv_w, tri_w = ob.wide_closest(units, grid, rays)
+        # against the linear scan (accel::naive semantics): at coordinates of 5e4 the reference-style box test of the port's
+        # own BVH (1e-4 pad, fp32 slabs) is itself no longer conservative
+        tuv_p, tri_p = ob.PortScene(verts).closest(rays, use_bvh=False)
+        assert np.array_equal(tri_w, tri_p) and np.array_equal(tuv_w.view(np.uint32), tuv_p.view(np.uint32))
 
 
 def test_builder_closest_equals_oracle():
@@ -124,8 +161,8 @@ def test_builder_closest_equals_oracle():
     rays[:5000, 7] = 2.0
     A = capi.Accel(host_only=True)
     A.build(verts)
-    nodes, tris, idx = A.host_arrays()
-    tuv_w, tri_w = ob.wide_closest(nodes, tris, rays)
+    units, _, _, grid = A.host_layout()
+    tuv_w, tri_w = ob.wide_closest(units, grid, rays)
     tuv_p, tri_p = ob.PortScene(verts).closest(rays)
     assert np.array_equal(tri_w, tri_p)
     assert np.array_equal(tuv_w.view(np.uint32), tuv_p.view(np.uint32))
@@ -141,9 +178,9 @@ def test_builder_edge_cases():
     verts = np.array([t] * 40 + [[0, 0, 0, 1, 1, 1, 2, 2, 2]] + [[np.nan] * 9], np.float32)
     st = A.build(verts)
     assert st["num_valid_triangles"] == 40
-    nodes, tris, idx = A.host_arrays()
+    units, _, _, grid = A.host_layout()
     rays = np.array([[0.2, 0.2, 1, 0, 0, 0, -1, 3.4e38]], np.float32)
-    tuv, tri = ob.wide_closest(nodes, tris, rays)
+    tuv, tri = ob.wide_closest(units, grid, rays)
     assert tri[0] == 39      # tie rule: larger index wins
 
 
