@@ -363,6 +363,11 @@ def main():
         if world == 1:
             cpu = base
 
+    # ---- the per-ray drop-in: Accel3::Intersect-shaped calls from 16 host threads (persistent service kernel) ----
+    one = None
+    if rank == 0 and world == 1:
+        one = bench_intersect_one(a, capi, accel, h_rays)
+
     # ---- secondary: path-traced samples/s on configs[2] (full size by default), NCCL film reduce ----
     pt = None
     if not a.no_pt:
@@ -394,6 +399,7 @@ def main():
                              "frac_of_fetch_ceiling": npr.value * a.rays / mean_kernel_s / 112.8e9},
                 "cpu_baseline": cpu, "parity": parity,
                 "bvh": {"nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
+                "intersect_one": one, "intersect_one_mrays_s": one["value"] if one else None,
                 "path_tracing": pt, "config4": c4,
                 # the two secondary figures once more as flat keys (nested objects may be dropped by a summariser)
                 "pt_msamples_s": pt["value"] if pt else None, "pt_e2e_msamples_s": pt["e2e"]["value"] if pt else None,
@@ -405,6 +411,22 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_intersect_one(a, capi, accel, h_rays, threads=16, n=200_000):
+    """lmb200_trace_closest_one from `threads` host threads (each a loop of synchronous single-ray calls: how Scheduler_::Process
+    drives Accel3::Intersect, scheduler.cpp:146-175) on the bench scene; the CPU figure beside it is the C port of accel::qbvh's
+    traversal on the same rays and thread count (the reference's own accel::qbvh is timed by --impl reference)."""
+    L = capi.lib()
+    rays = np.ascontiguousarray(h_rays.numpy()[:n])
+    hits = np.zeros(n, capi.HIT_DTYPE)
+    sec = C.c_double()
+    capi.check(L.lmb200_trace_closest_one_mt(accel.h, rays.ctypes.data, hits.ctypes.data, min(n, 20000), threads, C.byref(sec)))   # warm-up, starts the service
+    capi.check(L.lmb200_trace_closest_one_mt(accel.h, rays.ctypes.data, hits.ctypes.data, n, threads, C.byref(sec)))
+    capi.check(L.lmb200_trace_closest_one_mt(accel.h, rays.ctypes.data, hits.ctypes.data, 2000, 1, C.byref(s1 := C.c_double())))
+    return {"value": n / sec.value / 1e6, "unit": "Mrays/s", "host_threads": threads, "rays": n,
+            "latency_us_one_thread": s1.value / 2000 * 1e6, "api": "lmb200_trace_closest_one (persistent service kernel, mapped pinned mailboxes)",
+            "scene": "the bench scene (4M-triangle soup, incoherent rays)"}
 
 
 def bind_to_gpu_numa_node(torch, index):
@@ -491,7 +513,7 @@ def pt_roofline(st, samples, seconds, world):
             "counted_on": "a %d-sample instrumented run of the same scene (count_work)" % st.samples}
 
 
-def pt_cpu_baseline(sc, W, H, spp):
+def pt_cpu_baseline(sc, W, H, spp, with_drop_in=False):
     """The reference's own renderer::ptdirect (oracle/_ref: real Scene3 + accel::qbvh + Scheduler shim on all host threads) on a
     bounded sample of the same scene; the C port when the compiled reference is not present."""
     from oracle import bindings as ob
@@ -502,9 +524,24 @@ def pt_cpu_baseline(sc, W, H, spp):
         R = ob.RefScene(sc, accel="qbvh")
         build_s = time.perf_counter() - t0
         img, sec = R.render("ptdirect", N, seed=1, threads=cores)
-        return {"value": N / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                "sample": f"{spp} spp of the same {W}x{H} scene ({N} samples, {sec:.1f} s), renderer::ptdirect + accel::qbvh from oracle/_ref, scene build {build_s:.0f} s not timed",
-                "mean_rgb": [float(x) for x in img.mean(axis=(0, 1))]}
+        out = {"value": N / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+               "sample": f"{spp} spp of the same {W}x{H} scene ({N} samples, {sec:.1f} s), renderer::ptdirect + accel::qbvh from oracle/_ref, scene build {build_s:.0f} s not timed",
+               "mean_rgb": [float(x) for x in img.mean(axis=(0, 1))]}
+        del R
+        if with_drop_in:
+            # the accel drop-in alone: the reference's OWN renderer::ptdirect (its CPU threads) with every Accel3::Intersect
+            # answered by accel::lmb200's per-ray service on the GPU
+            try:
+                plug = os.path.join(ROOT, "lightmetrica-v2_b200", "plugin", "accel_lmb200")
+                if os.path.exists(plug + ".so") and ob.ref().ref_load_plugin(plug.encode()) == 1:
+                    R2 = ob.RefScene(sc, accel="lmb200")
+                    img2, sec2 = R2.render("ptdirect", N, seed=1, threads=cores)
+                    out["reference_renderer_on_accel_lmb200"] = {"value": N / sec2 / 1e6, "unit": "Msamples/s", "threads": cores,
+                                                                  "what": "renderer::ptdirect (reference, CPU threads) + accel::lmb200 (per-ray GPU service), same samples",
+                                                                  "mean_rgb": [float(x) for x in img2.mean(axis=(0, 1))]}
+            except Exception as e:      # noqa: BLE001
+                out["reference_renderer_on_accel_lmb200"] = {"unavailable": str(e)[:200]}
+        return out
     P = ob.PortPT(sc)
     N = W * H // 4
     t0 = time.perf_counter()
@@ -603,7 +640,7 @@ def bench_pt(a, torch, dist, capi, world, rank, local, dev):
     S.close()
     cpu = None
     if rank == 0 and world == 1:
-        cpu = pt_cpu_baseline(sc, W, H, a.pt_cpu_spp)
+        cpu = pt_cpu_baseline(sc, W, H, a.pt_cpu_spp, with_drop_in=True)
     return {"incoherent_1m_tri_mesh": target,
             "metric": "Msamples/s ptdirect (NEE), 1920x1080, 1M-tri synthetic scene", "value": N / sec / 1e6,
             "unit": "Msamples/s", "spp": a.pt_spp, "samples": N, "ms": float(ms.item()), "rays_per_sample": float(rays.item()) / N,

@@ -9,7 +9,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 HOSTCXX=/usr/bin/g++
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 NVFLAGS="-O3 -std=c++17 -lineinfo $ARCH -ccbin $HOSTCXX -Xcompiler -fPIC,-O2,-ffp-contract=off,-Wall -Xptxas -v --fmad=false"
-for f in accel render bvh_build_gpu; do
+for f in accel render bvh_build_gpu service; do
   if [ -f "$SRC/$f.cu" ]; then
     if [ ! -f "$OUT/obj/$f.o" ] || [ -n "$(find "$SRC" "$ROOT/include" -newer "$OUT/obj/$f.o" -type f | head -1)" ]; then
       $NVCC $NVFLAGS -c "$SRC/$f.cu" -o "$OUT/obj/$f.o" 2> "$OUT/obj/$f.ptxas.log" || { cat "$OUT/obj/$f.ptxas.log"; exit 1; }
@@ -23,5 +23,6 @@ fi
 OBJS="$OUT/obj/accel.o $OUT/obj/bvh_build.o"
 [ -f "$OUT/obj/render.o" ] && OBJS="$OBJS $OUT/obj/render.o"
 [ -f "$OUT/obj/bvh_build_gpu.o" ] && OBJS="$OBJS $OUT/obj/bvh_build_gpu.o"
+[ -f "$OUT/obj/service.o" ] && OBJS="$OBJS $OUT/obj/service.o"
 $NVCC $ARCH -shared -ccbin $HOSTCXX -o "$OUT/liblmb200.so" $OBJS -Xlinker -soname=liblmb200.so -lpthread -ldl
 echo "build: $OUT/liblmb200.so"

@@ -97,11 +97,17 @@ int lmb200_accel_build_ex(lmb200_accel* a, const float* verts, uint64_t ntris, i
 int lmb200_trace_closest(lmb200_accel* a, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n);
 int lmb200_trace_closest_dev(lmb200_accel* a, const void* rays_dev, void* hits_dev, uint64_t n, void* stream);
 
-/* One ray, synchronously, on the GPU — the exact shape of Accel3::Intersect (accel3.h:68). Safe to
- * call concurrently from many host threads (the reference's renderers do, scheduler.cpp:146-175):
- * each thread owns a stream and a pinned mailbox. Correct but latency-bound (one launch per ray);
- * batches should use lmb200_trace_closest*. */
+/* One ray, synchronously, on the GPU — the exact shape of Accel3::Intersect (accel3.h:68). Safe to call concurrently
+ * from many host threads (the reference's renderers do, scheduler.cpp:146-175). No kernel launch per ray: the first call
+ * starts a persistent service kernel (one block) that polls per-thread mailboxes in mapped pinned host memory, traverses
+ * with the same code as the batch kernels (bit-identical hits) and writes the hit back into the mailbox the caller spins
+ * on. The kernel leaves by itself after 2 ms without a request (so it never blocks a device-wide synchronisation for
+ * longer) and is restarted on demand. Latency is one PCIe round trip plus one single-lane traversal; batches should
+ * still use lmb200_trace_closest*. */
 int lmb200_trace_closest_one(lmb200_accel* a, const lmb200_ray* ray, lmb200_hit* hit);
+/* The same for n rays from `threads` host threads at once, each calling the per-ray entry point in a loop over its
+ * share (how Scheduler_::Process drives Accel3::Intersect); *seconds receives the wall time. For measurements. */
+int lmb200_trace_closest_one_mt(lmb200_accel* a, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n, int threads, double* seconds);
 
 /* Replaces Scene3::Visible's query (scene3.h:107-116): occluded[i] = 1 iff ANY triangle is hit
  * within [tmin, tmax] (same boolean as the reference's closest-hit query, early exit). */

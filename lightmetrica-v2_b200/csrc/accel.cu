@@ -66,25 +66,6 @@ trace_kernel(const BvhDev bvh,
     }
 }
 
-// one ray, one warp: the per-ray Accel3::Intersect path (mailbox in mapped pinned host memory)
-__global__ void trace_one_kernel(const BvhDev bvh, const float4* ray, float4* out)
-{
-    __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(32)];
-    if (threadIdx.x != 0) return;
-    Trav T;
-    TravCounters cnt;
-    const bool hit = lmb_traverse<false, false, 32>(bvh, ray[0], ray[1], T, LMB_SM_BASE(smem), cnt);
-    out[0] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
-}
-
-struct Mailbox {
-    int device = -1;
-    cudaStream_t stream = nullptr;
-    float4* host = nullptr;   // [0..1] ray, [2] hit
-    float4* dev = nullptr;
-    ~Mailbox() { if (host) { cudaSetDevice(device); cudaFreeHost(host); cudaStreamDestroy(stream); } }
-};
-
 BvhDev bvh_dev(const Accel* a)
 {
     BvhDev b;
@@ -128,6 +109,7 @@ int trace_any_dev(Accel* a, const void* rays, void* occ, uint64_t n, const uint3
 
 void Accel::free_device()
 {
+    service_destroy(this);       // the service kernel reads d_units: it must be gone first
     if (device >= 0) cudaSetDevice(device);
     if (d_units) cudaFree(d_units);
     if (d_counter) cudaFree(d_counter);
@@ -182,6 +164,7 @@ int Accel::upload()
     const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    service_destroy(this);       // a rebuild invalidates what a running service kernel traverses
     if (d_units) { cudaFree(d_units); d_units = nullptr; }
     num_units = bvh.units.size();
     const size_t nb = num_units * sizeof(Unit64);
@@ -408,22 +391,7 @@ int lmb200_trace_closest_one(lmb200_accel* h, const lmb200_ray* ray, lmb200_hit*
     Accel* a = reinterpret_cast<Accel*>(h);
     if (!a || !ray || !hit) return set_error(LMB200_E_INVALID, "null argument");
     if (a->host_only || !a->d_units) return set_error(LMB200_E_STATE, "accel not built on a device");
-    static thread_local Mailbox mb;
-    cudaError_t e;
-    if (mb.device != a->device) {
-        if ((e = cudaSetDevice(a->device)) != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-        if (mb.host) { cudaFreeHost(mb.host); cudaStreamDestroy(mb.stream); mb.host = nullptr; }
-        if ((e = cudaHostAlloc(reinterpret_cast<void**>(&mb.host), 3 * sizeof(float4), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(mailbox)");
-        if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&mb.dev), mb.host, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
-        if ((e = cudaStreamCreateWithFlags(&mb.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-        mb.device = a->device;
-    }
-    memcpy(mb.host, ray, sizeof(lmb200_ray));
-    trace_one_kernel<<<1, 32, 0, mb.stream>>>(bvh_dev(a), mb.dev, mb.dev + 2);
-    g_launch_count++;
-    if ((e = cudaStreamSynchronize(mb.stream)) != cudaSuccess) return cuda_fail(e, "trace_one");
-    memcpy(hit, mb.host + 2, sizeof(lmb200_hit));
-    return LMB200_OK;
+    return service_trace_one(a, ray, hit);
 }
 
 int lmb200_trace_closest_dev(lmb200_accel* h, const void* rays_dev, void* hits_dev, uint64_t n, void* stream)

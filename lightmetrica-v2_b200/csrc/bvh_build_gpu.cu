@@ -338,6 +338,7 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    service_destroy(a);
     if (a->d_units) { cudaFree(a->d_units); a->d_units = nullptr; a->num_units = 0; }
     if (!a->d_counter && (e = cudaMalloc(&a->d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
     const uint32_t n = (uint32_t)ntris;

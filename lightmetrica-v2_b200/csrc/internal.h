@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include "../../include/lmb200.h"
 #include "bvh.h"
@@ -28,6 +29,8 @@ extern std::atomic<uint64_t> g_launch_count;
 int set_error(int code, const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 
+struct Service;      // service.cu: the persistent per-ray kernel and its mailboxes
+
 struct Accel {
     int device = -1;
     bool host_only = false;
@@ -49,6 +52,9 @@ struct Accel {
     cudaEvent_t events[3 * LMB_NBUF] = {};
     uint64_t stage_cap = 0;
 
+    Service* service = nullptr;   // per-ray Accel3::Intersect service, created on first use
+    std::mutex service_mu;
+
     ~Accel();
     int upload();
     void free_device();
@@ -58,6 +64,8 @@ struct Accel {
 int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris);   // bvh_build_gpu.cu
 int mirror_to_host(Accel* a);                                            // accel.cu
 BvhDev bvh_dev(const Accel* a);                                          // accel.cu
+int service_trace_one(Accel* a, const lmb200_ray* ray, lmb200_hit* hit);  // service.cu
+void service_destroy(Accel* a);                                          // service.cu: stops the kernel, frees the mailboxes
 
 // n_dev != nullptr: the ray count is read from device memory (wavefront queues).
 int trace_closest_dev(Accel* a, const void* rays, void* hits, uint64_t n, const uint32_t* n_dev, cudaStream_t st, int slot);
