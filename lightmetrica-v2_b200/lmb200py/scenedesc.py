@@ -87,10 +87,36 @@ class Scene:
                            lens_radius=None if lens_radius is None else float(lens_radius), focal_distance=float(focal_distance))
 
     # ---- consumers ----
-    def to_yaml(self, mesh_handles, accel="qbvh", renderer="ptdirect", renderer_params=None):
+    def write_obj(self, directory):
+        """One Wavefront OBJ file per mesh (a single shape each: trianglemesh::obj concatenates the shapes of a file in
+        reverse, trianglemesh_obj.cpp:80-91), positions / normals printed with 9 significant digits. Returns the paths."""
+        import os
+        os.makedirs(directory, exist_ok=True)
+        paths = []
+        for i, m in enumerate(self.meshes):
+            lines = [f"# mesh {i} of a lmb200py.scenedesc scene", f"o mesh{i}"]
+            lines += ["v %.9g %.9g %.9g" % tuple(float(x) for x in v) for v in np.asarray(m["verts"], np.float32).reshape(-1, 3)]
+            has_n = m["normals"] is not None
+            if has_n:
+                lines += ["vn %.9g %.9g %.9g" % tuple(float(x) for x in v) for v in np.asarray(m["normals"], np.float32).reshape(-1, 3)]
+            for f in np.asarray(m["faces"], np.int64).reshape(-1, 3) + 1:
+                lines.append(("f %d//%d %d//%d %d//%d" % (f[0], f[0], f[1], f[1], f[2], f[2])) if has_n else ("f %d %d %d" % tuple(f)))
+            path = os.path.join(directory, f"mesh{i}.obj")
+            with open(path, "w") as fh:
+                fh.write("\n".join(lines) + "\n")
+            paths.append(path)
+        return paths
+
+    def to_yaml(self, mesh_handles, accel="qbvh", renderer="ptdirect", renderer_params=None, obj_paths=None):
+        """mesh_handles: handles of meshes registered with the oracle host (type `mem`); obj_paths: instead, one OBJ file
+        per mesh, loaded by the reference's own trianglemesh::obj (tinyobjloader)."""
         def v3(x):
             return " ".join(repr(float(t)) for t in x)
         out = ["lightmetrica:", "  version: 1.1.0", "  assets:"]
+        if obj_paths is not None:
+            for i, path in enumerate(obj_paths):
+                out += [f"    mesh{i}:", "      interface: trianglemesh", "      type: obj", "      params:", f"        path: {path}"]
+            mesh_handles = []
         for i, h in enumerate(mesh_handles):
             out += [f"    mesh{i}:", "      interface: trianglemesh", "      type: mem", "      params:", f"        handle: {h}"]
         for name, t in self.textures.items():

@@ -293,14 +293,17 @@ class PortPT:
 class RefScene:
     """The reference itself (oracle/_ref) on a scenedesc.Scene: real scene3 + assets + renderers."""
 
-    def __init__(self, scene, accel="qbvh", plugins=()):
+    def __init__(self, scene, accel="qbvh", plugins=(), obj_paths=None):
+        """obj_paths: load the meshes from these Wavefront OBJ files through the reference's trianglemesh::obj instead of
+        registering the in-memory arrays with the host shim."""
         L = ref()
         for p in plugins:
             if not L.ref_load_plugin(p.encode()):
                 raise RuntimeError(f"failed to load plugin {p}")
         handles = []
         self._keep = []
-        for m in scene.meshes:
+        self.obj_paths = obj_paths
+        for m in (scene.meshes if obj_paths is None else []):
             ps = np.ascontiguousarray(m["verts"], np.float32)
             fs = np.ascontiguousarray(m["faces"], np.uint32)
             ns = None if m["normals"] is None else np.ascontiguousarray(m["normals"], np.float32)
@@ -311,7 +314,7 @@ class RefScene:
         self.scene = scene
         self.handles = handles
         self.accel = accel
-        self.yaml = scene.to_yaml(handles, accel=accel)
+        self.yaml = scene.to_yaml(handles, accel=accel, obj_paths=obj_paths)
         self.s = L.ref_session_create(self.yaml.encode(), accel.encode())
         if not self.s:
             raise RuntimeError(L.ref_last_error().decode())
@@ -330,7 +333,7 @@ class RefScene:
         pd.update(extra or {})
         ow, oh, sec = C.c_int(), C.c_int(), C.c_double()
         if in_tree:
-            y = self.scene.to_yaml(self.handles, accel=self.accel, renderer=renderer, renderer_params=pd)
+            y = self.scene.to_yaml(self.handles, accel=self.accel, renderer=renderer, renderer_params=pd, obj_paths=self.obj_paths)
             s = ref().ref_session_create(y.encode(), self.accel.encode())
             if not s:
                 raise RuntimeError(ref().ref_last_error().decode())

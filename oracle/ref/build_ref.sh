@@ -39,6 +39,7 @@ src/liblightmetrica/asset/light/light_env.cpp
 src/liblightmetrica/asset/sensor/sensor_pinhole.cpp
 src/liblightmetrica/asset/sensor/sensor_thinlens.cpp
 src/liblightmetrica/asset/trianglemesh/trianglemesh_raw.cpp
+src/liblightmetrica/asset/trianglemesh/trianglemesh_obj.cpp
 src/liblightmetrica/random.cpp
 plugin/texture_checker/texture_checker.cpp
 "

@@ -26,3 +26,22 @@
 #include <vector>
 #include <map>
 #include <lightmetrica/macros.h>
+
+// trianglemesh_obj.cpp:48-50 joins the property tree's base path and the `path` parameter with boost::filesystem::path
+// and turns the result back into a string: the only Boost use in the translation units compiled here.
+namespace boost { namespace filesystem {
+class path {
+public:
+    path() {}
+    path(const std::string& s) : s_(s) {}
+    path(const char* s) : s_(s) {}
+    path operator/(const path& rhs) const
+    {
+        if (s_.empty() || (!rhs.s_.empty() && rhs.s_[0] == '/')) return rhs;
+        return path(s_.back() == '/' ? s_ + rhs.s_ : s_ + "/" + rhs.s_);
+    }
+    const std::string& string() const { return s_; }
+private:
+    std::string s_;
+};
+} }

@@ -17,6 +17,15 @@ from oracle import bindings as ob  # noqa: E402
 from lmb200py import scenes  # noqa: E402
 
 
+def cornell_obj():
+    """configs[0] says "Cornell box (tinyobjloader)": the Cornell box of scenedesc.cornell_box as Wavefront OBJ files, one
+    per mesh, for the reference's own trianglemesh::obj loader (tests/test_gpu_plugin.py::test_config0_through_the_obj_loader)."""
+    from lmb200py import scenedesc
+    sc = scenedesc.cornell_box(512, 512, glossy_block=True)
+    paths = sc.write_obj(os.path.join(HERE, "cornell_obj"))
+    print("cornell_obj:", len(paths), "files,", sum(os.path.getsize(p) for p in paths), "bytes")
+
+
 def accel_golden():
     # (1) random soup, the StubTriangleMesh_Random recipe (test_accel3.cpp:191-224)
     verts = scenes.soup(3000, seed=11, extent=4.0, edge=0.25)
@@ -104,6 +113,7 @@ def outdoor_golden():
 
 
 if __name__ == "__main__":
+    cornell_obj()
     which = sys.argv[1:] or ["accel", "pt"]
     if "accel" in which:
         accel_golden()

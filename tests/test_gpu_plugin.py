@@ -222,3 +222,31 @@ def test_renderer_plugin_two_gpus():
                       extra={"mode": "ptdirect", "num_gpus": 2, "render_time": 0.4, "progress_image_update_interval": 0.1, "grain_size": 200})
     ref, _ = R.render("ptdirect", 32 * 32 * 1024, seed=1, threads=os.cpu_count() or 1)
     assert abs(img.mean() - ref.mean()) / ref.mean() < 0.05
+
+
+def test_config0_through_the_obj_loader():
+    """BASELINE configs[0] as it is written: the Cornell box loaded by the reference's own trianglemesh::obj (tinyobjloader,
+    trianglemesh_obj.cpp:46-94) from the committed tests/golden/cornell_obj/*.obj, 512 x 512 at 64 spp, selected from the
+    scene YAML: `renderer: lmb200pt` (+ `accel: lmb200`) against the reference's renderer::pt on accel::qbvh at equal spp.
+    Bar: 8x8 block-mean relRMSE <= 1.25x the reference's own two-seed floor; mean radiance within 2 %."""
+    obj_dir = os.path.join(ROOT, "tests", "golden", "cornell_obj")
+    sc = scenedesc.cornell_box(512, 512, glossy_block=True)
+    paths = [os.path.join(obj_dir, f"mesh{i}.obj") for i in range(len(sc.meshes))]
+    assert all(os.path.exists(p) for p in paths)
+    N = 512 * 512 * 64
+    cores = os.cpu_count() or 1
+
+    def bm(img, b=8):
+        h, w, c = img.shape
+        return img.reshape(h // b, b, w // b, b, c).mean(axis=(1, 3))
+    Rq = ob.RefScene(sc, accel="qbvh", obj_paths=paths)
+    ra, _ = Rq.render("pt", N, seed=1, threads=cores)
+    rb, _ = Rq.render("pt", N, seed=2, threads=cores)
+    floor = rel_rmse(bm(ra), bm(rb))
+    Ro = ob.RefScene(sc, accel="lmb200", obj_paths=paths)
+    ours, _ = Ro.render("lmb200pt", N, seed=3, extra={"mode": "pt"}, in_tree=True)
+    assert rel_rmse(bm(ours), bm(ra)) < 1.25 * floor, (rel_rmse(bm(ours), bm(ra)), floor)
+    assert np.allclose(ours.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.02)
+    # the OBJ route and the in-memory route describe the same box: same samples => same image from our renderer
+    mem, _ = ob.RefScene(sc, accel="lmb200").render("lmb200pt", N, seed=3, extra={"mode": "pt"}, in_tree=True)
+    assert same_image(ours, mem)

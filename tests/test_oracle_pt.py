@@ -162,3 +162,18 @@ def test_tile_partitioning_port_is_statistically_the_whole_image():
     # a strip's own camera rays stay inside it: with pt (no light sampling from the camera vertex) nothing lands outside
     top, _ = P.render(0, N, seed=3, begin=0, end=N // 4, tile=(0, 0, 1, 0.25))
     assert top[8:].max() == 0 and top[:8].max() > 0
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="needs oracle/_ref")
+def test_reference_obj_loader_route_equals_in_memory_meshes():
+    """configs[0] route: the committed Cornell OBJ files through the reference's trianglemesh::obj (tinyobjloader) give the
+    reference renderer exactly the scene the in-memory meshes give it (same seed, one thread => bit-identical image)."""
+    obj_dir = os.path.join(os.path.dirname(__file__), "golden", "cornell_obj")
+    big = scenedesc.cornell_box(512, 512, glossy_block=True)          # what the fixtures were written from
+    sc = scenedesc.cornell_box(24, 24, glossy_block=True)
+    assert len(sc.meshes) == len(big.meshes) and all(np.array_equal(a["verts"], b["verts"]) for a, b in zip(sc.meshes, big.meshes))
+    paths = [os.path.join(obj_dir, f"mesh{i}.obj") for i in range(len(sc.meshes))]
+    N = 24 * 24 * 32
+    a, _ = ob.RefScene(sc, accel="qbvh", obj_paths=paths).render("ptdirect", N, seed=4, threads=1)
+    b, _ = ob.RefScene(sc, accel="qbvh").render("ptdirect", N, seed=4, threads=1)
+    assert np.array_equal(a, b) and a.mean() > 0
