@@ -398,7 +398,7 @@ def main():
                              "node_fetches_per_s": npr.value * a.rays / mean_kernel_s, "record_fetch_ceiling_per_s": 112.8e9,
                              "frac_of_fetch_ceiling": npr.value * a.rays / mean_kernel_s / 112.8e9},
                 "cpu_baseline": cpu, "parity": parity,
-                "bvh": {"nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
+                "bvh": {"builder": "device LBVH (library default)", "nodes": bst["num_nodes"], "node_bytes": bst["node_bytes"], "tri_bytes": bst["tri_bytes"], "build_s": bst["build_seconds"]},
                 "intersect_one": one, "intersect_one_mrays_s": one["value"] if one else None,
                 "path_tracing": pt, "config4": c4,
                 # the two secondary figures once more as flat keys (nested objects may be dropped by a summariser)

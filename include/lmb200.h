@@ -80,14 +80,20 @@ int lmb200_accel_device(const lmb200_accel* a);
  * the replica and destroys it with lmb200_accel_destroy. */
 lmb200_accel* lmb200_accel_replicate(const lmb200_accel* a, int device);
 
-/* Same, with a choice of builder. Both produce the same node/record format and therefore the same
- * hits (the closest hit does not depend on the tree); they differ in build time and tree quality.
- *   LMB200_BUILD_HOST_SAH  multi-threaded binned-SAH build on the host + SAH-optimal 8-wide collapse
- *                          (what lmb200_accel_build does)
- *   LMB200_BUILD_GPU_LBVH  Morton-order radix tree + collapse entirely on the device: milliseconds
- *                          instead of seconds, lower tree quality */
+/* Same, with a choice of builder. All produce the same unit format and therefore the same hits (the closest hit does not
+ * depend on the tree); they differ in build time and tree quality (B200, 4 M-triangle soup / 1 M-triangle mesh scene,
+ * incoherent rays, profiles/r02_sweep.md):
+ *   LMB200_BUILD_HOST_SAH      multi-threaded binned-SAH build on the host + SAH-optimal 8-wide collapse: 3.5 s / 0.6 s,
+ *                              the quality reference (100 % / 100 %). What a host-only accel uses.
+ *   LMB200_BUILD_GPU_LBVH      Morton-order radix tree + greedy collapse on the device: 25 ms / 7 ms, 101 % / 99 % of the
+ *                              SAH tree's traversal rate. THE DEFAULT of lmb200_accel_build / lmb200_scene_create.
+ *   LMB200_BUILD_GPU_LBVH_SAH  the same tree with the SAH-optimal collapse: 103 % / 95 %
+ *   LMB200_BUILD_GPU_PLOC      parallel locally-ordered clustering + SAH-optimal collapse: 90 % / 95 % */
 #define LMB200_BUILD_HOST_SAH 0
 #define LMB200_BUILD_GPU_LBVH 1
+#define LMB200_BUILD_GPU_PLOC 2
+#define LMB200_BUILD_GPU_LBVH_SAH 3
+#define LMB200_BUILD_DEFAULT LMB200_BUILD_GPU_LBVH
 int lmb200_accel_build_ex(lmb200_accel* a, const float* verts, uint64_t ntris, int builder);
 
 /* Replaces Accel3::Intersect (accel3.h:68; accel_qbvh.cpp:398-497) for a batch of n rays.

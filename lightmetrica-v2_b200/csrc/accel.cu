@@ -283,11 +283,8 @@ lmb200_accel* lmb200_accel_create_host_only(void)
 
 void lmb200_accel_destroy(lmb200_accel* a) { delete reinterpret_cast<Accel*>(a); }
 
-int lmb200_accel_build(lmb200_accel* h, const float* verts, uint64_t ntris)
+static int build_host_sah(Accel* a, const float* verts, uint64_t ntris)
 {
-    Accel* a = reinterpret_cast<Accel*>(h);
-    if (!a || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
-    if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27, as the reference's leaf encoding accel_qbvh.cpp:62-72)");
     build_bvh(verts, ntris, a->bvh, 0);
     a->built = false;
     a->gpu_built = false;
@@ -297,16 +294,31 @@ int lmb200_accel_build(lmb200_accel* h, const float* verts, uint64_t ntris)
     return a->upload();
 }
 
+int lmb200_accel_build(lmb200_accel* h, const float* verts, uint64_t ntris)
+{
+    Accel* a = reinterpret_cast<Accel*>(h);
+    if (!a || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
+    if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27, as the reference's leaf encoding accel_qbvh.cpp:62-72)");
+    // the default builder of a device accel is the device builder (milliseconds instead of seconds, 99-101 % of the SAH
+    // tree's traversal rate); a host-only accel can only be built on the host
+    return lmb200_accel_build_ex(h, verts, ntris, a->host_only ? LMB200_BUILD_HOST_SAH : LMB200_BUILD_DEFAULT);
+}
+
 int lmb200_accel_build_ex(lmb200_accel* h, const float* verts, uint64_t ntris, int builder)
 {
-    if (builder == LMB200_BUILD_HOST_SAH) return lmb200_accel_build(h, verts, ntris);
-    if (builder != LMB200_BUILD_GPU_LBVH) return set_error(LMB200_E_INVALID, "unknown builder");
+    if (builder == LMB200_BUILD_HOST_SAH) {
+        Accel* a0 = reinterpret_cast<Accel*>(h);
+        if (!a0 || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
+        if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27, as the reference's leaf encoding accel_qbvh.cpp:62-72)");
+        return build_host_sah(a0, verts, ntris);
+    }
+    if (builder != LMB200_BUILD_GPU_LBVH && builder != LMB200_BUILD_GPU_PLOC && builder != LMB200_BUILD_GPU_LBVH_SAH) return set_error(LMB200_E_INVALID, "unknown builder");
     Accel* a = reinterpret_cast<Accel*>(h);
     if (!a || (!verts && ntris)) return set_error(LMB200_E_INVALID, "null argument");
     if (a->host_only) return set_error(LMB200_E_STATE, "the GPU builder needs a device accel");
     if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27)");
     a->built = false;
-    int rc = build_bvh_gpu(a, verts, ntris);
+    int rc = build_bvh_gpu(a, verts, ntris, builder);
     if (!rc) rc = check_depth(a->bvh.stats.max_depth);
     if (rc) return rc;
     a->built = true;

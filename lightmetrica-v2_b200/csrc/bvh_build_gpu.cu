@@ -1,6 +1,9 @@
-// GPU builder for the same flattened structure as bvh_build.cpp (one array of 64-byte units, bvh.h):
-// Morton-ordered binary radix tree (Karras 2012) -> bottom-up box fit -> level-by-level collapse to
-// 8-wide nodes with <=3-triangle leaves -> octant slot assignment + quantisation, all on the device.
+// GPU builders for the same flattened structure as bvh_build.cpp (one array of 64-byte units, bvh.h), all on the device:
+//   LMB200_BUILD_GPU_LBVH      Morton-ordered binary radix tree (Karras 2012) -> bottom-up box fit -> level-by-level greedy
+//                              collapse to 8-wide nodes (open the largest child first, single-triangle leaves)
+//   LMB200_BUILD_GPU_LBVH_SAH  the same tree with the host builder's SAH-optimal collapse (dynamic programme)
+//   LMB200_BUILD_GPU_PLOC      parallel locally-ordered clustering instead of the radix tree, SAH-optimal collapse
+// followed by octant slot assignment + quantisation.
 // Replaces the serial recursive build of the reference (/root/reference/src/liblightmetrica/accel/
 // accel_qbvh.cpp:202-383: ~2 s per 100 k triangles) when time-to-first-ray matters more than tree
 // quality: LBVH trees are not SAH-optimised, so traversal is slower than on the host-built tree
@@ -10,6 +13,8 @@
 
 #include <cub/cub.cuh>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cfloat>
 
 namespace lmb200 {
@@ -324,18 +329,353 @@ __global__ void k_collapse(const WorkItem* __restrict__ in, uint32_t n_in, WorkI
     units[it.wide].node = node;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// PLOC builder (parallel locally-ordered clustering, Meister & Bittner 2018) + SAH-optimal wide collapse on the device.
+// The Morton-ordered radix tree above splits by key bits only; PLOC builds the binary tree bottom-up by repeatedly
+// merging mutual nearest neighbours (smallest merged surface area within +-LMB_PLOC_RADIUS positions of the Morton-ordered
+// cluster array), which gives trees close to a top-down SAH build. The same dynamic programme as the host builder
+// (bvh_build.cpp Emitter::plan, Ylitie et al. 2017 sec. 4.1) then chooses the 8-wide nodes: its tables are filled for
+// every new binary node right when the node is created (children are always older than their parent).
+#ifndef LMB_PLOC_RADIUS
+#define LMB_PLOC_RADIUS 12
+#endif
+#ifndef LMB_WIDE_COST_NODE
+#define LMB_WIDE_COST_NODE 1.0f
+#endif
+#ifndef LMB_GPU_MAX_LEAF
+#define LMB_GPU_MAX_LEAF 3      // triangles per leaf slot the collapse may choose (<= 3: two count bits per slot)
+#endif
+#ifndef LMB_GPU_COST_TRI
+#define LMB_GPU_COST_TRI 1.2f
+#endif
+#undef LMB_WIDE_COST_TRI
+#define LMB_WIDE_COST_TRI LMB_GPU_COST_TRI
+
+struct PlocTree {
+    uint32_t* left; uint32_t* right;      // children of internal node k (refs: bit 31 set = leaf, sorted position)
+    uint32_t* count;                      // triangles below internal node k
+    Box6* box;                            // box of internal node k
+    float* cost;                          // 7 per internal node: cheapest representation with <= i+1 slots
+    unsigned long long* choice;           // per internal node: take[7] (2 bits each) | dist_k[7] (3 bits each, at bit 14) | int_k (3 bits, at bit 35)
+};
+
+__device__ __forceinline__ Box6 box_union(const Box6& a, const Box6& b)
+{
+    Box6 m;
+    for (int k = 0; k < 3; k++) { m.lo[k] = fminf(a.lo[k], b.lo[k]); m.hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+    return m;
+}
+
+// nearest neighbour of every cluster within the search radius (ties: the lower position)
+__global__ void k_ploc_nn(const Box6* __restrict__ cb, uint32_t n, uint32_t* __restrict__ nn)
+{
+    constexpr int R = LMB_PLOC_RADIUS, TB = 256;
+    __shared__ Box6 tile[TB + 2 * R];
+    const int base = (int)(blockIdx.x * TB) - R;
+    for (int t = threadIdx.x; t < TB + 2 * R; t += TB) {
+        const int g = base + t;
+        if (g >= 0 && g < (int)n) tile[t] = cb[g];
+    }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * TB + threadIdx.x;
+    if (i >= n) return;
+    const Box6 me = tile[threadIdx.x + R];
+    float best = FLT_MAX; uint32_t bj = i;
+    for (int d = -R; d <= R; d++) {
+        const int j = (int)i + d;
+        if (d == 0 || j < 0 || j >= (int)n) continue;
+        const float a = half_area(box_union(me, tile[threadIdx.x + R + d]));
+        if (a < best) { best = a; bj = (uint32_t)j; }
+    }
+    nn[i] = bj;
+}
+
+// flags for the scan: low word = the cluster survives (1) or is absorbed by its partner (0); high word = it creates a node
+__global__ void k_ploc_flags(const uint32_t* __restrict__ nn, uint32_t n, int force_pairs, unsigned long long* __restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t j = nn[i];
+    bool mutual = j != i && nn[j] == i;
+    if (force_pairs) { j = i ^ 1u; mutual = j < n; }      // guaranteed progress: neighbours (2k, 2k+1) merge
+    unsigned long long f = 1ull;
+    if (mutual) f = i < j ? (1ull | (1ull << 32)) : 0ull;
+    flags[i] = f;
+}
+
+__device__ __forceinline__ void dp_children(const PlocTree& T, const Box6* __restrict__ leaf_box, uint32_t ref, float* c /*[7]*/, uint32_t& total)
+{
+    if (ref & 0x80000000u) {
+        const float v = half_area(leaf_box[ref & 0x7fffffffu]) * LMB_WIDE_COST_TRI;
+        for (int i = 0; i < 7; i++) c[i] = v;
+        total = 1;
+    } else {
+        // L2 loads: in the radix-tree pass these were written by another SM earlier in the same launch
+        for (int i = 0; i < 7; i++) c[i] = __ldcg(T.cost + (size_t)ref * 7 + i);
+        total = __ldcg(T.count + ref);
+    }
+}
+
+// Collapse tables of the new binary node k with children L, R and box b (bvh_build.cpp Emitter::plan for one node): cost[i-1] =
+// cheapest way to represent the subtree with at most i wide-node slots; take / dist_k / int_k remember how.
+__device__ __forceinline__ void dp_node(const PlocTree& T, const Box6* __restrict__ leaf_box, uint32_t k, uint32_t L, uint32_t R, const Box6& b)
+{
+    float cl7[7], cr7[7];
+    uint32_t tl, tr;
+    dp_children(T, leaf_box, L, cl7, tl);
+    dp_children(T, leaf_box, R, cr7, tr);
+    const uint32_t total = tl + tr;
+    const float area = half_area(b);
+    const float leaf = total <= (uint32_t)LMB_GPU_MAX_LEAF ? area * (float)total * LMB_WIDE_COST_TRI : FLT_MAX;
+    unsigned long long ch = 0;
+    float c[7];
+    // LMB_GPU_DP_FULL: a subtree that has at least i triangles must use exactly i slots (the budget is only left unused when
+    // there are not enough triangles), i.e. the collapse picks the SAH-best cut among the FULLEST wide nodes; without it the
+    // classic "at most i slots" programme of the host builder.
+    auto distribute = [&](int jn, uint32_t& kbest) {
+        float best = FLT_MAX; kbest = 1;
+        for (int kk = 1; kk < jn; kk++) {
+            if (kk > 7 || jn - kk > 7) continue;
+#ifdef LMB_GPU_DP_FULL
+            if ((uint32_t)kk > tl || (uint32_t)(jn - kk) > tr) continue;
+#endif
+            const float v = cl7[kk - 1] + cr7[jn - kk - 1];
+            if (v < best) { best = v; kbest = (uint32_t)kk; }
+        }
+        return best;
+    };
+    uint32_t ik;
+#ifdef LMB_GPU_DP_FULL
+    const float internal = distribute((int)min(total, 8u), ik) + area * LMB_WIDE_COST_NODE;
+#else
+    const float internal = distribute(8, ik) + area * LMB_WIDE_COST_NODE;
+#endif
+    ch |= (unsigned long long)ik << 35;
+    if (leaf <= internal) c[0] = leaf; else { c[0] = internal; ch |= 1ull; }
+    for (int i2 = 2; i2 <= 7; i2++) {
+        uint32_t dk = 1;
+#ifdef LMB_GPU_DP_FULL
+        const float d = (uint32_t)i2 <= total ? distribute(i2, dk) : FLT_MAX;
+        ch |= (unsigned long long)dk << (14 + 3 * (i2 - 1));
+        if (d < FLT_MAX) { c[i2 - 1] = d; ch |= 2ull << (2 * (i2 - 1)); } else { c[i2 - 1] = c[i2 - 2]; ch |= 3ull << (2 * (i2 - 1)); }
+#else
+        const float d = distribute(i2, dk);
+        ch |= (unsigned long long)dk << (14 + 3 * (i2 - 1));
+        if (d < c[i2 - 2]) { c[i2 - 1] = d; ch |= 2ull << (2 * (i2 - 1)); } else { c[i2 - 1] = c[i2 - 2]; ch |= 3ull << (2 * (i2 - 1)); }
+#endif
+    }
+    T.left[k] = L; T.right[k] = R; T.count[k] = total; T.box[k] = b; T.choice[k] = ch;
+    for (int i2 = 0; i2 < 7; i2++) T.cost[(size_t)k * 7 + i2] = c[i2];
+}
+
+// applies the merges of one round: new internal nodes (with their collapse tables) and the compacted cluster array
+__global__ void k_ploc_apply(const uint32_t* __restrict__ cl, const Box6* __restrict__ cb, const uint32_t* __restrict__ nn, uint32_t n, int force_pairs,
+                             const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ scan, uint32_t node_base,
+                             uint32_t* __restrict__ cl_out, Box6* __restrict__ cb_out, PlocTree T, const Box6* __restrict__ leaf_box)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long f = flags[i];
+    if (!(f & 1ull)) return;                               // absorbed
+    const uint32_t pos = (uint32_t)(scan[i] & 0xffffffffull);
+    if (!(f >> 32)) { cl_out[pos] = cl[i]; cb_out[pos] = cb[i]; return; }
+    const uint32_t j = force_pairs ? (i ^ 1u) : nn[i];
+    const uint32_t k = node_base + (uint32_t)(scan[i] >> 32);
+    const uint32_t L = cl[i], R = cl[j];
+    const Box6 b = box_union(cb[i], cb[j]);
+    dp_node(T, leaf_box, k, L, R, b);
+    cl_out[pos] = k; cb_out[pos] = b;
+}
+
+// Collapse tables for the Morton radix tree: a second bottom-up pass in the pattern of k_fit (the second thread to reach a
+// node handles it), after the boxes are known.
+__global__ void k_dp_radix(int n, RadixTree R, PlocTree T, const Box6* __restrict__ leaf_box, int* flags)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || n == 1) return;
+    uint32_t p = R.parent_leaf[k];
+    for (;;) {
+        __threadfence();
+        if (atomicAdd(&flags[p], 1) == 0) return;
+        __threadfence();
+        dp_node(T, leaf_box, p, R.left[p], R.right[p], load_box_cg(&T.box[p]));
+        if (p == 0) return;
+        p = R.parent_internal[p];
+    }
+}
+
+__global__ void k_ploc_init(uint32_t n, const Box6* __restrict__ leaf_box, uint32_t* cl, Box6* cb)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cl[i] = 0x80000000u | i; cb[i] = leaf_box[i];
+}
+
+__global__ void k_leaf_boxes(const Box6* __restrict__ boxes, const uint32_t* __restrict__ idx, uint32_t n, float pad, Box6* leaf_box)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Box6 b = boxes[idx[k]];
+    for (int a = 0; a < 3; a++) { b.lo[a] -= pad; b.hi[a] += pad; }
+    leaf_box[k] = b;
+}
+
+// One thread per wide node: its slots are what the collapse tables planned (bvh_build.cpp Emitter::collect), then octant
+// slot assignment, quantisation and allocation exactly as k_collapse / Emitter::emit_node.
+__global__ void k_emit_dp(const WorkItem* __restrict__ in, uint32_t n_in, WorkItem* out, uint32_t* out_count,
+                          PlocTree T, const Box6* __restrict__ leaf_box, const uint32_t* __restrict__ idx, const TriRecord* __restrict__ recs,
+                          Unit64* units, uint32_t* node_count, uint32_t* unit_count, SceneGrid grid, int n_prims)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_in) return;
+    const WorkItem it = in[w];
+    uint32_t ch[8]; bool is_leaf[8]; int n = 0;
+    auto box_of = [&](uint32_t ref) -> Box6 { return (ref & 0x80000000u) ? leaf_box[ref & 0x7fffffffu] : T.box[ref]; };
+    auto count_of = [&](uint32_t ref) -> uint32_t { return (ref & 0x80000000u) ? 1u : T.count[ref]; };
+    if (n_prims == 1 || (it.bin & 0x80000000u)) { ch[n] = n_prims == 1 ? 0x80000000u : it.bin; is_leaf[n++] = true; }
+    else if (it.wide == 0 && T.count[it.bin] <= 3u && !(T.choice[it.bin] & 3ull)) { ch[n] = it.bin; is_leaf[n++] = true; }   // the whole tree is one leaf slot
+    else {
+        // collect(left, int_k) + collect(right, 8 - int_k), iteratively
+        uint32_t sref[16]; int sbud[16]; int sp = 0;
+        const int ik = (int)((T.choice[it.bin] >> 35) & 7ull);
+        sref[sp] = T.right[it.bin]; sbud[sp++] = 8 - ik;
+        sref[sp] = T.left[it.bin]; sbud[sp++] = ik;
+        while (sp) {
+            uint32_t ref = sref[--sp]; int bud = sbud[sp];
+            if (ref & 0x80000000u) { ch[n] = ref; is_leaf[n++] = true; continue; }
+            const unsigned long long c = T.choice[ref];
+            int take = (int)((c >> (2 * (bud - 1))) & 3ull);
+            while (take == 3) { bud--; take = (int)((c >> (2 * (bud - 1))) & 3ull); }
+            if (take == 0) { ch[n] = ref; is_leaf[n++] = true; }
+            else if (take == 1) { ch[n] = ref; is_leaf[n++] = false; }
+            else {
+                const int k = (int)((c >> (14 + 3 * (bud - 1))) & 7ull);
+                sref[sp] = T.right[ref]; sbud[sp++] = bud - k;
+                sref[sp] = T.left[ref]; sbud[sp++] = k;
+            }
+        }
+    }
+    Box6 cb[8];
+    Box6 nb; for (int a = 0; a < 3; a++) { nb.lo[a] = FLT_MAX; nb.hi[a] = -FLT_MAX; }
+    for (int i = 0; i < n; i++) { cb[i] = box_of(ch[i]); nb = box_union(nb, cb[i]); }
+    Node64 node;
+    memset(&node, 0, sizeof(node));
+    double scale[3];
+    float origin[3];
+    for (int a = 0; a < 3; a++) {
+        double kd = floor(((double)nb.lo[a] - (double)grid.lo[a]) / (double)grid.step[a]);
+        kd = fmax(0.0, fmin(65535.0, kd));
+        uint32_t ki = (uint32_t)kd;
+        while (ki > 0 && fmaf((float)ki, grid.step[a], grid.lo[a]) > nb.lo[a]) ki--;
+        node.k[a] = (uint16_t)ki;
+        origin[a] = fmaf((float)ki, grid.step[a], grid.lo[a]);
+        const double ext = fmax(0.0, (double)nb.hi[a] - (double)origin[a]);
+        int e = ext > 0 ? (int)ceil(log2(ext / 254.0)) : -126;
+        e = max(-126, min(110, e));
+        while (e < 110 && ceil(ext / ldexp(1.0, e) + 2 * kQSlackDev) > 255.0) e++;
+        node.e[a] = (uint8_t)(e + 127);
+        scale[a] = ldexp(1.0, e);
+    }
+    int slot_of[8]; bool slot_used[8], child_done[8];
+    for (int i = 0; i < 8; i++) { slot_used[i] = false; child_done[i] = false; slot_of[i] = -1; }
+    for (int round = 0; round < n; round++) {
+        int bc = -1, bs = -1; float bscore = -FLT_MAX;
+        for (int i = 0; i < n; i++) {
+            if (child_done[i]) continue;
+            float cen[3];
+            for (int a = 0; a < 3; a++) cen[a] = 0.5f * (cb[i].lo[a] + cb[i].hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
+            for (int s = 0; s < 8; s++) {
+                if (slot_used[s]) continue;
+                const float score = ((s & 1) ? cen[0] : -cen[0]) + ((s & 2) ? cen[1] : -cen[1]) + ((s & 4) ? cen[2] : -cen[2]);
+                if (score > bscore) { bscore = score; bc = i; bs = s; }
+            }
+        }
+        slot_of[bc] = bs; slot_used[bs] = true; child_done[bc] = true;
+    }
+    int child_in_slot[8];
+    for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
+    for (int i = 0; i < n; i++) child_in_slot[slot_of[i]] = i;
+    uint32_t n_internal = 0, n_tris = 0;
+    for (int i = 0; i < n; i++) { if (is_leaf[i]) n_tris += count_of(ch[i]); else n_internal++; }
+    const uint32_t base = atomicAdd(unit_count, n_internal + n_tris);
+    if (n_internal) atomicAdd(node_count, n_internal);
+    const uint32_t qbase = n_internal ? atomicAdd(out_count, n_internal) : 0u;
+    node.base = base;
+    uint32_t rel = 0, toff = 0;
+    for (int s = 0; s < 8; s++) {
+        const int i = child_in_slot[s];
+        if (i < 0) { for (int a = 0; a < 3; a++) { node.qlo[a][s] = 255; node.qhi[a][s] = 0; } continue; }
+        for (int a = 0; a < 3; a++) {
+            double ql = floor(((double)cb[i].lo[a] - (double)origin[a]) / scale[a] - kQSlackDev);
+            double qh = ceil(((double)cb[i].hi[a] - (double)origin[a]) / scale[a] + kQSlackDev);
+            ql = fmax(0.0, fmin(255.0, ql)); qh = fmax(0.0, fmin(255.0, qh));
+            node.qlo[a][s] = (uint8_t)ql; node.qhi[a][s] = (uint8_t)qh;
+        }
+        if (is_leaf[i]) {
+            // the (<= 3) triangles below this binary subtree
+            uint32_t st[4]; int sp = 0; uint32_t cnt = 0;
+            st[sp++] = ch[i];
+            while (sp) {
+                const uint32_t ref = st[--sp];
+                if (ref & 0x80000000u) {
+                    TriUnit tu;
+                    tu.rec = recs[idx[ref & 0x7fffffffu]];
+                    tu.pad[0] = tu.pad[1] = tu.pad[2] = tu.pad[3] = 0u;
+                    units[base + n_internal + toff + cnt].tri = tu;
+                    cnt++;
+                } else { st[sp++] = T.right[ref]; st[sp++] = T.left[ref]; }
+            }
+            node.counts |= (uint16_t)(cnt << (2 * s));
+            toff += cnt;
+        } else {
+            node.imask |= (uint8_t)(1u << s);
+            out[qbase + rel] = WorkItem{ch[i], base + rel};
+            rel++;
+        }
+    }
+    units[it.wide].node = node;
+}
+
+// Scratch memory of one build: ONE device allocation carved up by a bump pointer (a cudaMalloc / cudaFree pair per
+// temporary array - about 25 of them - cost more than all the kernels of the build together), with a plain cudaMalloc
+// as the fallback should the estimate ever be too small.
 struct DevBuf {
-    std::vector<void*> ptrs;
-    template <typename T> T* alloc(size_t n) { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr; ptrs.push_back(p); return reinterpret_cast<T*>(p); }
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+    uint8_t* arena = nullptr;
+    size_t cap = 0, used = 0;
+    std::vector<void*> extra;
+    bool reserve(size_t bytes)
+    {
+        if (cudaMalloc(reinterpret_cast<void**>(&arena), bytes) != cudaSuccess) { cudaGetLastError(); arena = nullptr; return false; }
+        cap = bytes; used = 0;
+        return true;
+    }
+    template <typename T> T* alloc(size_t n)
+    {
+        const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (arena && used + bytes <= cap) { T* p = reinterpret_cast<T*>(arena + used); used += bytes; return p; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        extra.push_back(p);
+        return reinterpret_cast<T*>(p);
+    }
+    ~DevBuf() { if (arena) cudaFree(arena); for (void* p : extra) cudaFree(p); }
 };
 
 }  // namespace
 
 // Builds on the accel's device from HOST vertices; fills a->d_units and the stats.
-int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
+int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris, int builder)
 {
+    const bool ploc = builder == LMB200_BUILD_GPU_PLOC;
+    const bool greedy = builder == LMB200_BUILD_GPU_LBVH;      // radix tree + greedy collapse; LMB200_BUILD_GPU_LBVH_SAH: + collapse tables
     const auto t0 = std::chrono::steady_clock::now();
+    const bool timing = getenv("LMB200_BUILD_TIMING") != nullptr;
+    auto tick = [&](const char* what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[lmb200 gpu build] %-28s %8.3f ms\n", what, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     service_destroy(a);
@@ -343,6 +683,9 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     if (!a->d_counter && (e = cudaMalloc(&a->d_counter, LMB_NUM_COUNTERS * sizeof(unsigned long long))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(counter)");
     const uint32_t n = (uint32_t)ntris;
     DevBuf D;
+    // per triangle: vertices 36, record 48, box 24, keys 2 x 8, indices 2 x 4, validity 1, radix tree 24, leaf / node boxes 48, flags 4,
+    // work queues 16, collapse tables 40, sort scratch ~20; the clustering builder adds cluster arrays, neighbours and scan buffers (~110)
+    D.reserve((size_t)std::max<uint32_t>(n, 1024) * (ploc ? 420 : 300) + (64u << 20));
     float* d_verts = D.alloc<float>(9 * (size_t)n);
     TriRecord* recs = D.alloc<TriRecord>(n);
     Box6* boxes = D.alloc<Box6>(n);
@@ -353,7 +696,9 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     uint32_t* idx = D.alloc<uint32_t>(n);
     uint32_t* idx2 = D.alloc<uint32_t>(n);
     if (!d_verts || !recs || !boxes || !valid || !scene || !keys || !keys2 || !idx || !idx2) return set_error(LMB200_E_CUDA, "out of device memory (gpu build)");
+    tick("alloc 1");
     if (n && (e = cudaMemcpy(d_verts, verts_host, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "H2D verts");
+    tick("H2D verts");
     const float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
     cudaMemcpy(scene, init, sizeof(init), cudaMemcpyHostToDevice);
     const int TB = 256;
@@ -369,6 +714,7 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     void* tmp = D.alloc<uint8_t>(tmp_bytes);
     if (!tmp) return set_error(LMB200_E_CUDA, "out of device memory (sort)");
     if (n) { cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, (int)n); g_launch_count += 8; }
+    tick("prep + morton + sort");
     std::vector<uint8_t> h_valid(n);
     if (n) cudaMemcpy(h_valid.data(), valid, n, cudaMemcpyDeviceToHost);
     uint32_t nv = 0;
@@ -377,6 +723,7 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
     if (nv) for (int k = 0; k < 6; k++) extent = std::max(extent, std::fabs(h_scene[k]));
     const float pad = 1e-4f + 4e-6f * extent;     // as bvh_build.cpp
 
+    tick("count valid");
     // tree
     RadixTree T;
     T.left = D.alloc<uint32_t>(nv); T.right = D.alloc<uint32_t>(nv); T.parent_internal = D.alloc<uint32_t>(nv); T.parent_leaf = D.alloc<uint32_t>(nv);
@@ -395,6 +742,7 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
         for (int k = 0; k < 3; k++) { glo[k] = nv ? h_scene[k] - pad : 0.f; ghi[k] = nv ? h_scene[3 + k] + pad : 0.f; }
         make_scene_grid(glo, ghi, a->bvh.grid);
     }
+    tick("alloc 2");
     // every wide node has >= 2 children or is the root, so there are at most nv nodes; plus nv triangle units
     const size_t unit_cap = 2 * (size_t)std::max<uint32_t>(nv, 1) + 1;
     if ((e = cudaMalloc(&a->d_units, unit_cap * sizeof(Unit64))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(units)");
@@ -405,10 +753,81 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
         root.node.e[0] = root.node.e[1] = root.node.e[2] = 127;
         for (int s = 0; s < 8; s++) for (int ax = 0; ax < 3; ax++) { root.node.qlo[ax][s] = 255; root.node.qhi[ax][s] = 0; }
         cudaMemcpy(a->d_units, &root, sizeof(root), cudaMemcpyHostToDevice);
+    } else if (ploc) {
+        // ---- PLOC: bottom-up clustering of the Morton-ordered triangles, collapse tables filled on the way ----
+        PlocTree P;
+        P.left = D.alloc<uint32_t>(nv); P.right = D.alloc<uint32_t>(nv); P.count = D.alloc<uint32_t>(nv);
+        P.box = node_box; P.cost = D.alloc<float>(7 * (size_t)nv); P.choice = D.alloc<unsigned long long>(nv);
+        uint32_t* cl[2] = {D.alloc<uint32_t>(nv), D.alloc<uint32_t>(nv)};
+        Box6* cbx[2] = {D.alloc<Box6>(nv), D.alloc<Box6>(nv)};
+        uint32_t* nn = D.alloc<uint32_t>(nv);
+        unsigned long long* fl = D.alloc<unsigned long long>(nv + 1);
+        unsigned long long* sc = D.alloc<unsigned long long>(nv + 1);
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, fl, sc, (int)nv + 1);
+        void* scan_tmp = D.alloc<uint8_t>(scan_bytes);
+        if (!P.left || !P.right || !P.count || !P.cost || !P.choice || !cl[0] || !cl[1] || !cbx[0] || !cbx[1] || !nn || !fl || !sc || !scan_tmp)
+            return set_error(LMB200_E_CUDA, "out of device memory (gpu build, clustering)");
+        k_leaf_boxes<<<(nv + TB - 1) / TB, TB>>>(boxes, idx2, nv, pad, leaf_box); g_launch_count++;
+        k_ploc_init<<<(nv + TB - 1) / TB, TB>>>(nv, leaf_box, cl[0], cbx[0]); g_launch_count++;
+        uint32_t nc = nv, node_base = 0;
+        int cur = 0, rounds = 0;
+        while (nc > 1) {
+            int force = 0;
+            for (;;) {
+                k_ploc_nn<<<(nc + 255) / 256, 256>>>(cbx[cur], nc, nn);
+                k_ploc_flags<<<(nc + TB - 1) / TB, TB>>>(nn, nc, force, fl);
+                cudaMemsetAsync(fl + nc, 0, sizeof(unsigned long long));
+                cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, fl, sc, (int)nc + 1);
+                g_launch_count += 4;
+                unsigned long long tot = 0;
+                if ((e = cudaMemcpy(&tot, sc + nc, sizeof(tot), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "gpu clustering");
+                const uint32_t merges = (uint32_t)(tot >> 32), survivors = (uint32_t)(tot & 0xffffffffull);
+                // mutual nearest neighbours normally pair up a third or more of the clusters; if a round pairs fewer than
+                // 1/16, neighbours (2k, 2k+1) are merged instead so that the number of rounds stays logarithmic
+                if (!force && merges < std::max<uint32_t>(1u, nc / 16u)) { force = 1; continue; }
+                k_ploc_apply<<<(nc + TB - 1) / TB, TB>>>(cl[cur], cbx[cur], nn, nc, force, fl, sc, node_base, cl[cur ^ 1], cbx[cur ^ 1], P, leaf_box);
+                g_launch_count++;
+                node_base += merges; nc = survivors; cur ^= 1;
+                break;
+            }
+            if (++rounds > 4096) return set_error(LMB200_E_STATE, "gpu build: clustering did not converge");
+        }
+        uint32_t root_ref = 0;
+        if ((e = cudaMemcpy(&root_ref, cl[cur], sizeof(root_ref), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "gpu clustering");
+        const uint32_t hc[4] = {1u, 1u, 0u, 0u};
+        cudaMemcpy(counters, hc, sizeof(hc), cudaMemcpyHostToDevice);
+        const WorkItem rootw{root_ref, 0u};
+        cudaMemcpy(q0, &rootw, sizeof(rootw), cudaMemcpyHostToDevice);
+        uint32_t n_in = 1;
+        WorkItem* qin = q0; WorkItem* qout = q1;
+        while (n_in) {
+            cudaMemset(counters + 2, 0, sizeof(uint32_t));
+            k_emit_dp<<<(n_in + 127) / 128, 128>>>(qin, n_in, qout, counters + 2, P, leaf_box, idx2, recs,
+                                                   reinterpret_cast<Unit64*>(a->d_units), counters, counters + 1, a->bvh.grid, (int)nv);
+            g_launch_count++;
+            uint32_t h[3];
+            if ((e = cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "gpu collapse");
+            num_nodes = h[0]; num_units = h[1]; n_in = h[2];
+            std::swap(qin, qout);
+            if (n_in) depth++;
+            if (depth > 64) return set_error(LMB200_E_STATE, "gpu build: tree too deep");
+        }
     } else {
+        // ---- Morton radix tree (Karras 2012), boxes and collapse tables bottom-up, SAH-optimal collapse top-down ----
+        PlocTree P;
+        P.left = T.left; P.right = T.right; P.box = node_box; P.count = nullptr; P.cost = nullptr; P.choice = nullptr;
+        if (!greedy) {
+            P.count = D.alloc<uint32_t>(nv); P.cost = D.alloc<float>(7 * (size_t)nv); P.choice = D.alloc<unsigned long long>(nv);
+            if (!P.count || !P.cost || !P.choice) return set_error(LMB200_E_CUDA, "out of device memory (gpu build, collapse tables)");
+        }
         cudaMemset(flags, 0, sizeof(int) * nv);
         if (nv > 1) { k_radix_tree<<<(nv - 1 + TB - 1) / TB, TB>>>(keys2, (int)nv, T); g_launch_count++; }
         k_fit<<<(nv + TB - 1) / TB, TB>>>(boxes, idx2, (int)nv, pad, T, leaf_box, node_box, flags); g_launch_count++;
+        if (!greedy) {
+            cudaMemset(flags, 0, sizeof(int) * nv);
+            k_dp_radix<<<(nv + TB - 1) / TB, TB>>>((int)nv, T, P, leaf_box, flags); g_launch_count++;
+        }
         const uint32_t hc[4] = {1u, 1u, 0u, 0u};      // [0] nodes, [1] units (the root is unit 0), [2] out queue count
         cudaMemcpy(counters, hc, sizeof(hc), cudaMemcpyHostToDevice);
         const WorkItem rootw{0u, 0u};
@@ -417,8 +836,12 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
         WorkItem* qin = q0; WorkItem* qout = q1;
         while (n_in) {
             cudaMemset(counters + 2, 0, sizeof(uint32_t));
-            k_collapse<<<(n_in + 127) / 128, 128>>>(qin, n_in, qout, counters + 2, T, leaf_box, node_box, idx2, recs,
-                                                    reinterpret_cast<Unit64*>(a->d_units), counters, counters + 1, a->bvh.grid, (int)nv);
+            if (greedy)      // open the largest child first, single-triangle leaves
+                k_collapse<<<(n_in + 127) / 128, 128>>>(qin, n_in, qout, counters + 2, T, leaf_box, node_box, idx2, recs,
+                                                        reinterpret_cast<Unit64*>(a->d_units), counters, counters + 1, a->bvh.grid, (int)nv);
+            else
+            k_emit_dp<<<(n_in + 127) / 128, 128>>>(qin, n_in, qout, counters + 2, P, leaf_box, idx2, recs,
+                                                   reinterpret_cast<Unit64*>(a->d_units), counters, counters + 1, a->bvh.grid, (int)nv);
             g_launch_count++;
             uint32_t h[3];
             if ((e = cudaMemcpy(h, counters, sizeof(h), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuda_fail(e, "gpu collapse");
@@ -431,6 +854,7 @@ int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris)
         }
     }
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(e, "gpu build");
+    tick("tree + collapse");
     // the host mirror (lmb200_accel_host_arrays) is filled lazily from the device arrays
     a->bvh.units.clear();
     a->num_units = num_units;

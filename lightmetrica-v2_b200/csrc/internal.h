@@ -61,7 +61,7 @@ struct Accel {
     int finish_device_setup();   // occupancy / SM count of the device the units live on
 };
 
-int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris);   // bvh_build_gpu.cu
+int build_bvh_gpu(Accel* a, const float* verts_host, uint64_t ntris, int builder);   // bvh_build_gpu.cu
 int mirror_to_host(Accel* a);                                            // accel.cu
 BvhDev bvh_dev(const Accel* a);                                          // accel.cu
 int service_trace_one(Accel* a, const lmb200_ray* ray, lmb200_hit* hit);  // service.cu

@@ -1096,7 +1096,7 @@ extern "C" {
 
 static lmb200_scene* scene_create(int device, const lmb200_scene_desc* d, int builder, Accel* shared);
 
-lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d) { return scene_create(device, d, LMB200_BUILD_HOST_SAH, nullptr); }
+lmb200_scene* lmb200_scene_create(int device, const lmb200_scene_desc* d) { return scene_create(device, d, LMB200_BUILD_DEFAULT, nullptr); }
 
 lmb200_scene* lmb200_scene_create_ex(int device, const lmb200_scene_desc* d, int builder) { return scene_create(device, d, builder, nullptr); }
 
@@ -1111,7 +1111,7 @@ lmb200_scene* lmb200_scene_create_shared(const lmb200_scene_desc* d, lmb200_acce
 
 static lmb200_scene* scene_create(int device, const lmb200_scene_desc* d, int builder, Accel* shared)
 {
-    if (builder != LMB200_BUILD_HOST_SAH && builder != LMB200_BUILD_GPU_LBVH) { set_error(LMB200_E_INVALID, "unknown builder"); return nullptr; }
+    if (builder < LMB200_BUILD_HOST_SAH || builder > LMB200_BUILD_GPU_LBVH_SAH) { set_error(LMB200_E_INVALID, "unknown builder"); return nullptr; }
     if (!d || (d->num_tris && (!d->verts || !d->tri_prim)) || !d->prims || !d->bsdfs) { set_error(LMB200_E_INVALID, "null scene field"); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error(LMB200_E_CUDA, "no CUDA device available (lmb200 has no CPU fallback)"); return nullptr; }

@@ -11,7 +11,8 @@ MODE_PT, MODE_PTDIRECT, MODE_NORMAL, MODE_PTMIS = 0, 1, 2, 3
 BSDF_NULL, BSDF_DIFFUSE, BSDF_COOKTORRANCE, BSDF_REFLECT_ALL, BSDF_REFRACT_ALL, BSDF_FLESNEL = 0, 1, 2, 3, 4, 5
 LIGHT_AREA, LIGHT_POINT, LIGHT_DIRECTIONAL, LIGHT_ENV = 0, 1, 2, 3
 CAMERA_PINHOLE, CAMERA_THINLENS = 0, 1
-BUILD_HOST_SAH, BUILD_GPU_LBVH = 0, 1
+BUILD_HOST_SAH, BUILD_GPU_LBVH, BUILD_GPU_PLOC, BUILD_GPU_LBVH_SAH = 0, 1, 2, 3
+BUILD_DEFAULT = BUILD_GPU_LBVH        # what lmb200_accel_build / lmb200_scene_create use on a device accel
 
 RAY_DTYPE = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"),
                       ("dx", "f4"), ("dy", "f4"), ("dz", "f4"), ("tmax", "f4")])
@@ -191,10 +192,14 @@ class Accel:
         except Exception:
             pass
 
-    def build(self, verts, builder=BUILD_HOST_SAH):
+    def build(self, verts, builder=None):
+        """builder=None: the library default (device builder on a device accel, host SAH on a host-only one)."""
         verts = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 9)
         self._verts = verts
-        check(lib().lmb200_accel_build_ex(self.h, _ptr(verts), verts.shape[0], builder))
+        if builder is None:
+            check(lib().lmb200_accel_build(self.h, _ptr(verts), verts.shape[0]))
+        else:
+            check(lib().lmb200_accel_build_ex(self.h, _ptr(verts), verts.shape[0], builder))
         return self.stats()
 
     def stats(self):
@@ -225,7 +230,7 @@ class Accel:
 class Scene:
     """Mirror of the reference's Renderer interface (Initialize/Render, renderer.h:68-81) over a flattened scene."""
 
-    def __init__(self, scene, device=0, builder=BUILD_HOST_SAH):
+    def __init__(self, scene, device=0, builder=BUILD_DEFAULT):
         self.desc, self.keep = scene.flatten()
         self.w, self.h = scene.camera["w"], scene.camera["h"]
         self.h_ = lib().lmb200_scene_create_ex(device, C.byref(self.desc), builder)

@@ -2,7 +2,7 @@
 // (/root/reference/src/liblightmetrica/accel/accel_qbvh.cpp et al.) through the reference's own
 // component mechanism: built as plugin/accel_lmb200.so, registered at dlopen time with
 // LM_COMPONENT_REGISTER_IMPL (component.h:660-667), selected from the scene YAML with
-//     accel: {type: lmb200, params: {device: 0, builder: host}}
+//     accel: {type: lmb200, params: {device: 0, builder: gpu}}
 // All compute happens in liblmb200.so (CUDA, include/lmb200.h); this file only flattens the
 // scene the way the reference accels do and fills the Intersection the way they do.
 #include <lightmetrica/lightmetrica.h>
@@ -33,13 +33,17 @@ public:
     LM_IMPL_F(Initialize) = [this](const PropertyNode* prop) -> bool
     {
         device_ = (prop && prop->Child("device")) ? prop->ChildAs<int>("device", 0) : 0;
-        // builder: host (binned SAH on the host, default) | gpu (Morton radix tree on the device, ~100x faster to build)
-        builder_ = LMB200_BUILD_HOST_SAH;
+        // builder: gpu (Morton radix tree on the device, milliseconds, default) | host (binned SAH on the host, seconds) |
+        //          gpu_sah (radix tree + SAH-optimal collapse) | ploc (clustering + SAH-optimal collapse)
+        builder_ = LMB200_BUILD_DEFAULT;
         if (prop && prop->Child("builder"))
         {
-            const auto b = prop->ChildAs<std::string>("builder", "host");
+            const auto b = prop->ChildAs<std::string>("builder", "gpu");
             if (b == "gpu") builder_ = LMB200_BUILD_GPU_LBVH;
-            else if (b != "host") { LM_LOG_ERROR("accel::lmb200: unknown builder '" + b + "' (host | gpu)"); return false; }
+            else if (b == "host") builder_ = LMB200_BUILD_HOST_SAH;
+            else if (b == "gpu_sah") builder_ = LMB200_BUILD_GPU_LBVH_SAH;
+            else if (b == "ploc") builder_ = LMB200_BUILD_GPU_PLOC;
+            else { LM_LOG_ERROR("accel::lmb200: unknown builder '" + b + "' (gpu | host | gpu_sah | ploc)"); return false; }
         }
         if (accel_) { lmb200_accel_destroy(accel_); accel_ = nullptr; }
         accel_ = lmb200_accel_create(device_);
@@ -98,7 +102,7 @@ public:
 private:
 
     int device_ = 0;
-    int builder_ = LMB200_BUILD_HOST_SAH;
+    int builder_ = LMB200_BUILD_DEFAULT;
     lmb200_accel* accel_ = nullptr;
     std::vector<uint32_t> primOfTri_;
     std::vector<uint32_t> faceOfTri_;

@@ -4,7 +4,7 @@
 // Selected from the scene YAML with
 //     renderer: {type: lmb200pt, params: {mode: ptdirect, num_samples: ..., max_num_vertices: -1,
 //                                         min_num_vertices: 0, num_gpus: 1, device: 0, pool_size: 0,
-//                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000, builder: host,
+//                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000, builder: gpu,
 //                                         texture_resolution: 1024, tile_partitioning: 0}}
 // It reads the scene through the reference's interfaces (Scene3::PrimitiveAt, TriangleMesh::*,
 // BSDF::Reflectance/Glossiness, Light::Emittance, Sensor::GetFilm/GetProjectionMatrix), flattens
@@ -55,9 +55,12 @@ public:
             if (prop->Child("tile_partitioning")) tilePartitioning_ = prop->ChildAs<int>("tile_partitioning", 0) != 0;
             if (prop->Child("builder"))
             {
-                const auto b = prop->ChildAs<std::string>("builder", "host");
+                const auto b = prop->ChildAs<std::string>("builder", "gpu");
                 if (b == "gpu") builder_ = LMB200_BUILD_GPU_LBVH;
-                else if (b != "host") { LM_LOG_ERROR("renderer::lmb200pt: unknown builder '" + b + "' (host | gpu)"); return false; }
+                else if (b == "host") builder_ = LMB200_BUILD_HOST_SAH;
+                else if (b == "gpu_sah") builder_ = LMB200_BUILD_GPU_LBVH_SAH;
+                else if (b == "ploc") builder_ = LMB200_BUILD_GPU_PLOC;
+                else { LM_LOG_ERROR("renderer::lmb200pt: unknown builder '" + b + "' (gpu | host | gpu_sah | ploc)"); return false; }
             }
         }
         if (mode == "pt") mode_ = LMB200_MODE_PT;
@@ -514,7 +517,7 @@ private:
     std::vector<lmb200_texture> textures_;                 // baked TexR textures of the scene being rendered
     std::vector<std::vector<float>> textureData_;
     std::map<const Texture*, int> textureIndex_;           // texture -> index + 1
-    int builder_ = LMB200_BUILD_HOST_SAH;
+    int builder_ = LMB200_BUILD_DEFAULT;
     double renderTime_ = -1.0;
     double progressImageInterval_ = -1.0;
     long long grainSize_ = 10000;

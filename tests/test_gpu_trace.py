@@ -54,15 +54,16 @@ def test_golden_vectors_from_reference():
     assert np.array_equal(A.trace_any(g["rays"]).astype(bool), g["face"] >= 0)
 
 
+@pytest.mark.parametrize("builder", [None, capi.BUILD_HOST_SAH])       # the default (device builder) and the host SAH builder
 @pytest.mark.parametrize("ntri,extent,edge,nray", [(1, 1.0, 0.4, 2000), (9, 1.0, 0.4, 5000), (2000, 3.0, 0.3, 50000), (200000, 30.0, 0.2, 400000)])
-def test_random_soup_vs_oracle(ntri, extent, edge, nray):
+def test_random_soup_vs_oracle(ntri, extent, edge, nray, builder):
     verts = scenes.soup(ntri, seed=100 + ntri, extent=extent, edge=edge)
     lo, hi = scenes.bounds(verts)
     rays = scenes.random_rays(nray, lo - 0.5, hi + 0.5, seed=3)
     rays[: nray // 4, 7] = extent * 0.3          # bounded ranges
     rays[nray // 4: nray // 3, 3] = 0.0          # tmin = 0 as in the reference tests
     A = capi.Accel(0)
-    A.build(verts)
+    A.build(verts, builder=builder)
     P = ob.PortScene(verts)
     tuv_o, tri_o = P.closest(rays)
     assert_bit_exact(*gpu_closest(A, rays), tuv_o, tri_o)
@@ -75,10 +76,11 @@ def test_mesh_scene_vs_oracle():
     rays = scenes.random_rays(300000, lo, hi, seed=11)
     cam = scenes.camera_rays((0, 9, 21), (0, 2, 0), (0, 1, 0), 45.0, 320, 180)    # coherent primary rays too
     rays = np.concatenate([rays, cam])
-    A = capi.Accel(0)
-    A.build(verts)
     tuv_o, tri_o = ob.PortScene(verts).closest(rays)
-    assert_bit_exact(*gpu_closest(A, rays), tuv_o, tri_o)
+    for builder in (None, capi.BUILD_HOST_SAH):
+        A = capi.Accel(0)
+        A.build(verts, builder=builder)
+        assert_bit_exact(*gpu_closest(A, rays), tuv_o, tri_o)
 
 
 def test_edge_cases():
@@ -238,9 +240,10 @@ def test_full_size_properties():
     assert np.array_equal(np.stack([hits["t"], hits["u"], hits["v"]], axis=1)[:100000].view(np.uint32), tuv_o.view(np.uint32))
 
 
-@pytest.mark.parametrize("ntri,extent,edge", [(0, 1.0, 0.3), (1, 1.0, 0.3), (2, 1.0, 0.3), (3, 1.0, 0.3), (5, 1.0, 0.3), (300, 2.0, 0.3), (50000, 12.0, 0.2)])
-def test_gpu_builder_same_hits_and_valid_structure(ntri, extent, edge):
-    """The device builder (Morton radix tree + collapse on the GPU) produces another tree of the same format:
+@pytest.mark.parametrize("builder", [capi.BUILD_GPU_LBVH, capi.BUILD_GPU_LBVH_SAH, capi.BUILD_GPU_PLOC])
+@pytest.mark.parametrize("ntri,extent,edge", [(0, 1.0, 0.3), (1, 1.0, 0.3), (2, 1.0, 0.3), (3, 1.0, 0.3), (4, 1.0, 0.3), (5, 1.0, 0.3), (9, 1.0, 0.3), (300, 2.0, 0.3), (50000, 12.0, 0.2)])
+def test_gpu_builder_same_hits_and_valid_structure(ntri, extent, edge, builder):
+    """The device builders (Morton radix tree, or PLOC clustering with the SAH-optimal collapse) produce other trees of the same format:
     hits must be bit-identical to the oracle's (the closest hit does not depend on the tree), every triangle must
     be referenced once, and every quantised child box must contain what is below it."""
     from test_host import check_structure
@@ -248,7 +251,7 @@ def test_gpu_builder_same_hits_and_valid_structure(ntri, extent, edge):
     lo, hi = (scenes.bounds(verts) if ntri else (np.zeros(3, np.float32), np.ones(3, np.float32)))
     rays = scenes.random_rays(40000, lo - 0.3, hi + 0.3, seed=5)
     A = capi.Accel(0)
-    st = A.build(verts, builder=capi.BUILD_GPU_LBVH)
+    st = A.build(verts, builder=builder)
     assert st["num_valid_triangles"] == ntri
     tuv_o, tri_o = ob.PortScene(verts).closest(rays)
     assert_bit_exact(*gpu_closest(A, rays), tuv_o, tri_o)
@@ -265,10 +268,11 @@ def test_gpu_builder_large_and_degenerate():
     verts = np.concatenate([verts, verts[:1000], np.zeros((10, 9), np.float32), np.full((3, 9), np.nan, np.float32)])
     lo, hi = scenes.bounds(verts[:-3])
     rays = scenes.random_rays(1 << 20, lo, hi, seed=3)
-    A, B = capi.Accel(0), capi.Accel(0)
+    A, B, P = capi.Accel(0), capi.Accel(0), capi.Accel(0)
     sa = A.build(verts, builder=capi.BUILD_HOST_SAH)
     sb = B.build(verts, builder=capi.BUILD_GPU_LBVH)
-    assert sa["num_valid_triangles"] == sb["num_valid_triangles"] == len(verts) - 13
-    ha, hb = A.trace_closest(rays), B.trace_closest(rays)
-    assert np.array_equal(ha.view(np.uint32), hb.view(np.uint32))
-    assert sb["build_seconds"] < sa["build_seconds"]
+    sp = P.build(verts, builder=capi.BUILD_GPU_PLOC)
+    assert sa["num_valid_triangles"] == sb["num_valid_triangles"] == sp["num_valid_triangles"] == len(verts) - 13
+    ha, hb, hp = A.trace_closest(rays), B.trace_closest(rays), P.trace_closest(rays)
+    assert np.array_equal(ha.view(np.uint32), hb.view(np.uint32)) and np.array_equal(ha.view(np.uint32), hp.view(np.uint32))
+    assert sb["build_seconds"] < sa["build_seconds"] and sp["build_seconds"] < sa["build_seconds"]
