@@ -103,6 +103,13 @@ int lmb200_accel_build_ex(lmb200_accel* a, const float* verts, uint64_t ntris, i
 int lmb200_trace_closest(lmb200_accel* a, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n);
 int lmb200_trace_closest_dev(lmb200_accel* a, const void* rays_dev, void* hits_dev, uint64_t n, void* stream);
 
+/* Compact wire form of the host-buffer calls: 24 bytes per ray (o.xyz, d.xyz as 6 floats) and ONE [tmin, tmax] for the
+ * whole batch - the shape of Accel3::Intersect's own arguments (a Ray of origin + direction, minT and maxT passed
+ * separately, accel3.h:68; Scene3::Intersect always passes (Eps, Inf), scene3.cpp:461). Same hits as the 32-byte form;
+ * a quarter less host-to-device traffic, which is what bounds these calls once several GPUs share a host memory path. */
+int lmb200_trace_closest_compact(lmb200_accel* a, const float* rays24, float tmin, float tmax, lmb200_hit* hits, uint64_t n);
+int lmb200_trace_any_compact(lmb200_accel* a, const float* rays24, float tmin, float tmax, uint8_t* occluded, uint64_t n);
+
 /* One ray, synchronously, on the GPU — the exact shape of Accel3::Intersect (accel3.h:68). Safe to call concurrently
  * from many host threads (the reference's renderers do, scheduler.cpp:146-175). No kernel launch per ray: the first call
  * starts a persistent service kernel (one block) that polls per-thread mailboxes in mapped pinned host memory, traverses

@@ -41,17 +41,45 @@ struct BatchIoAny {
     __device__ __forceinline__ void store(uint64_t i, const Trav& T) const { out[i] = T.hid != LMB200_MISS ? 1 : 0; }
 };
 
-template <bool ANY, bool COUNT>
+// compact wire form: 24 bytes per ray (origin, direction), one [tmin, tmax] for the whole batch (lmb200_trace_*_compact)
+template <typename Out>
+struct BatchIoCompact {
+    const float2* __restrict__ rays; Out* __restrict__ out; uint64_t n; float tmin, tmax;
+    __device__ __forceinline__ uint64_t count() const { return n; }
+    __device__ __forceinline__ void load(uint64_t i, float4& ro, float4& rd) const
+    {
+        const float2 a = __ldg(rays + 3 * i), b = __ldg(rays + 3 * i + 1), c = __ldg(rays + 3 * i + 2);
+        ro = make_float4(a.x, a.y, b.x, tmin); rd = make_float4(b.y, c.x, c.y, tmax);
+    }
+    __device__ __forceinline__ void store(uint64_t i, const Trav& T) const;
+};
+template <> __device__ __forceinline__ void BatchIoCompact<float4>::store(uint64_t i, const Trav& T) const
+{
+    const bool hit = T.hid != LMB200_MISS;
+    out[i] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
+}
+template <> __device__ __forceinline__ void BatchIoCompact<uint8_t>::store(uint64_t i, const Trav& T) const { out[i] = T.hid != LMB200_MISS ? 1 : 0; }
+
+// COMPACT: `rays` holds 24-byte rays and (tmin, tmax) apply to all of them
+template <bool ANY, bool COUNT, bool COMPACT = false>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
 trace_kernel(const BvhDev bvh,
              const float4* __restrict__ rays, void* __restrict__ out,
              const uint64_t n_host, const uint32_t* __restrict__ n_dev,
-             unsigned long long* __restrict__ counter, unsigned long long* __restrict__ work_counters)
+             unsigned long long* __restrict__ counter, unsigned long long* __restrict__ work_counters, const float tmin = 0.f, const float tmax = 0.f)
 {
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
     const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
-    if (ANY) {
+    if (COMPACT) {
+        if (ANY) {
+            BatchIoCompact<uint8_t> io{reinterpret_cast<const float2*>(rays), reinterpret_cast<uint8_t*>(out), n, tmin, tmax};
+            persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
+        } else {
+            BatchIoCompact<float4> io{reinterpret_cast<const float2*>(rays), reinterpret_cast<float4*>(out), n, tmin, tmax};
+            persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
+        }
+    } else if (ANY) {
         BatchIoAny io{rays, reinterpret_cast<uint8_t*>(out), n};
         persistent_trace<true, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
     } else {
@@ -74,8 +102,9 @@ BvhDev bvh_dev(const Accel* a)
     return b;
 }
 
-template <bool ANY, bool COUNT>
-static int launch_trace(Accel* a, const void* rays, void* out, uint64_t n, const uint32_t* n_dev, cudaStream_t st, unsigned long long* work, int slot)
+template <bool ANY, bool COUNT, bool COMPACT = false>
+static int launch_trace(Accel* a, const void* rays, void* out, uint64_t n, const uint32_t* n_dev, cudaStream_t st, unsigned long long* work, int slot,
+                        float tmin = 0.f, float tmax = 0.f)
 {
     unsigned long long* counter = a->d_counter + slot;
     if (!a->d_units) return set_error(LMB200_E_STATE, "accel not built on a device");
@@ -87,8 +116,8 @@ static int launch_trace(Accel* a, const void* rays, void* out, uint64_t n, const
     const uint64_t persistent = (uint64_t)a->num_sms * a->trace_blocks_per_sm;
     if (n_dev || blocks > persistent) blocks = persistent;
     if (blocks == 0) blocks = 1;
-    trace_kernel<ANY, COUNT><<<(unsigned)blocks, LMB_TRACE_BLOCK, 0, st>>>(
-        bvh_dev(a), reinterpret_cast<const float4*>(rays), out, n, n_dev, counter, work);
+    trace_kernel<ANY, COUNT, COMPACT><<<(unsigned)blocks, LMB_TRACE_BLOCK, 0, st>>>(
+        bvh_dev(a), reinterpret_cast<const float4*>(rays), out, n, n_dev, counter, work, tmin, tmax);
     g_launch_count++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "trace_kernel launch");
@@ -182,9 +211,12 @@ int Accel::upload()
 #endif
 // LMB_NBUF staging buffers, so that with pinned host memory the PCIe traffic of chunk k+1 and k-1
 // overlaps the kernel of chunk k.
-template <bool ANY>
-static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
+// COMPACT: rays = 24 bytes each (o.xyz, d.xyz), tmin / tmax shared by the batch
+template <bool ANY, bool COMPACT = false>
+static int trace_host(Accel* a, const void* rays_v, void* out, uint64_t n, float tmin = 0.f, float tmax = 0.f)
 {
+    const size_t ray_elem = COMPACT ? 24 : sizeof(lmb200_ray);
+    const uint8_t* rays = reinterpret_cast<const uint8_t*>(rays_v);
     if (!a || (!rays && n) || (!out && n)) return set_error(LMB200_E_INVALID, "null argument");
     if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
     if (!a->d_units) return set_error(LMB200_E_STATE, "accel not built");
@@ -222,13 +254,12 @@ static int trace_host(Accel* a, const lmb200_ray* rays, void* out, uint64_t n)
         cudaEvent_t ev_in = a->events[3 * b], ev_k = a->events[3 * b + 1], ev_out = a->events[3 * b + 2];
         const uint64_t m = std::min(chunk, n - off);
         if (c >= LMB_NBUF && (e = cudaStreamWaitEvent(s_in, ev_out, 0)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamWaitEvent"); break; }   // buffer b is free again
-        if ((e = cudaMemcpyAsync(a->stage_rays[b], rays + off, m * sizeof(lmb200_ray), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { rc = cuda_fail(e, "H2D rays"); break; }
+        if ((e = cudaMemcpyAsync(a->stage_rays[b], rays + off * ray_elem, m * ray_elem, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) { rc = cuda_fail(e, "H2D rays"); break; }
         if ((e = cudaEventRecord(ev_in, s_in)) != cudaSuccess) { rc = cuda_fail(e, "cudaEventRecord"); break; }
         cudaStream_t s_k = a->streams[(c & 1) ? 3 : 1];
         const int slot = (c & 1) ? 3 : 2;
         if ((e = cudaStreamWaitEvent(s_k, ev_in, 0)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamWaitEvent"); break; }
-        rc = ANY ? trace_any_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot)
-                 : trace_closest_dev(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, slot);
+        rc = launch_trace<ANY, false, COMPACT>(a, a->stage_rays[b], a->stage_out[b], m, nullptr, s_k, nullptr, slot, tmin, tmax);
         if (rc) break;
         if ((e = cudaEventRecord(ev_k, s_k)) != cudaSuccess) { rc = cuda_fail(e, "cudaEventRecord"); break; }
         if ((e = cudaStreamWaitEvent(s_out, ev_k, 0)) != cudaSuccess) { rc = cuda_fail(e, "cudaStreamWaitEvent"); break; }
@@ -396,6 +427,16 @@ int lmb200_trace_closest(lmb200_accel* h, const lmb200_ray* rays, lmb200_hit* hi
 int lmb200_trace_any(lmb200_accel* h, const lmb200_ray* rays, uint8_t* occluded, uint64_t n)
 {
     return trace_host<true>(reinterpret_cast<Accel*>(h), rays, occluded, n);
+}
+
+int lmb200_trace_closest_compact(lmb200_accel* h, const float* rays24, float tmin, float tmax, lmb200_hit* hits, uint64_t n)
+{
+    return trace_host<false, true>(reinterpret_cast<Accel*>(h), rays24, hits, n, tmin, tmax);
+}
+
+int lmb200_trace_any_compact(lmb200_accel* h, const float* rays24, float tmin, float tmax, uint8_t* occluded, uint64_t n)
+{
+    return trace_host<true, true>(reinterpret_cast<Accel*>(h), rays24, occluded, n, tmin, tmax);
 }
 
 int lmb200_trace_closest_one(lmb200_accel* h, const lmb200_ray* ray, lmb200_hit* hit)

@@ -79,7 +79,7 @@ PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_int64, 
 
 EXPORTS = [
     "lmb200_last_error", "lmb200_device_count", "lmb200_accel_create", "lmb200_accel_destroy", "lmb200_accel_build", "lmb200_accel_build_ex",
-    "lmb200_accel_get_stats", "lmb200_accel_device", "lmb200_accel_replicate", "lmb200_trace_closest", "lmb200_trace_closest_one", "lmb200_trace_closest_one_mt", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
+    "lmb200_accel_get_stats", "lmb200_accel_device", "lmb200_accel_replicate", "lmb200_trace_closest", "lmb200_trace_closest_compact", "lmb200_trace_any_compact", "lmb200_trace_closest_one", "lmb200_trace_closest_one_mt", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
     "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_layout", "lmb200_accel_create_host_only",
     "lmb200_scene_create", "lmb200_scene_create_ex", "lmb200_scene_create_shared", "lmb200_registry_put", "lmb200_registry_get", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
     "lmb200_render", "lmb200_render_multi", "lmb200_render_timed",
@@ -127,6 +127,8 @@ def lib():
     L.lmb200_accel_replicate.restype = C.c_void_p
     L.lmb200_accel_replicate.argtypes = [C.c_void_p, C.c_int]
     L.lmb200_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.lmb200_trace_closest_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_uint64]
+    L.lmb200_trace_any_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_uint64]
     L.lmb200_trace_closest_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.lmb200_trace_closest_one_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
     L.lmb200_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]

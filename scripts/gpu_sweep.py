@@ -13,7 +13,7 @@ L = capi.lib()
 out = {}
 for name, verts in [("soup4M", scenes.soup(4000000, seed=42, extent=100.0, edge=0.2)), ("mesh1M", scenes.mesh_scene(1000000, seed=42)[0])]:
     lo, hi = scenes.bounds(verts)
-    A = capi.Accel(0); A.build(verts)
+    B = os.environ.get('SWEEP_BUILDER'); A = capi.Accel(0); A.build(verts, builder=int(B) if B else None)
     n = 1 << 24
     d_rays = bench.gen_rays_device(torch, n, lo.tolist(), hi.tolist(), 7, torch.device('cuda'))
     d_hits = torch.empty((n, 4), dtype=torch.float32, device='cuda')
@@ -32,7 +32,7 @@ for name, verts in [("soup4M", scenes.soup(4000000, seed=42, extent=100.0, edge=
 if os.environ.get("SWEEP_PT", "1") != "0":
     from lmb200py import scenedesc
     sc = scenedesc.config2_scene(1000000, 1920, 1080)
-    S = capi.Scene(sc)
+    S = capi.Scene(sc, builder=int(os.environ.get('SWEEP_BUILDER', capi.BUILD_DEFAULT)))
     N = 1920 * 1080 * 32
     S.render(capi.MODE_PTDIRECT, N // 4, seed=1)
     best = 0

@@ -56,7 +56,8 @@ def test_lmb200_arm_json_contract_small():
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["dtype"] == "f32"
     assert d["value"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.05
-    assert d["e2e"]["h2d_bytes_per_step"] == 2097152 * 32 and d["e2e"]["d2h_bytes_per_step"] == 2097152 * 16
+    assert d["e2e"]["h2d_bytes_per_step"] == 2097152 * 24 and d["e2e"]["d2h_bytes_per_step"] == 2097152 * 16
+    assert d["e2e"]["full_ray_form"]["h2d_bytes_per_step"] == 2097152 * 32 and d["e2e"]["full_ray_form"]["value"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert d["gpu_launches"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1

@@ -149,6 +149,29 @@ def test_device_pointer_api_and_single_ray():
         assert one.view(np.uint32).tolist() == host[i:i + 1].view(np.uint32).tolist()
 
 
+def test_compact_wire_form_equals_full_form():
+    """lmb200_trace_closest_compact / lmb200_trace_any_compact: 24-byte rays + one [tmin, tmax] for the batch give exactly the
+    hits of the 32-byte form (Accel3::Intersect's own argument shape: Ray + minT + maxT, accel3.h:68)."""
+    L = capi.lib()
+    verts = scenes.soup(40000, seed=12, extent=9.0, edge=0.3)
+    lo, hi = scenes.bounds(verts)
+    rays = scenes.random_rays(70001, lo, hi, seed=6)
+    A = capi.Accel(0)
+    A.build(verts)
+    for tmin, tmax in ((1e-4, 3.4028234663852886e38), (0.0, 2.5)):
+        rays[:, 3] = tmin
+        rays[:, 7] = tmax
+        full, occ = A.trace_closest(rays), A.trace_any(rays)
+        r24 = np.ascontiguousarray(rays[:, [0, 1, 2, 4, 5, 6]])
+        hits = np.zeros(len(rays), capi.HIT_DTYPE)
+        capi.check(L.lmb200_trace_closest_compact(A.h, r24.ctypes.data, tmin, tmax, hits.ctypes.data, len(rays)))
+        assert np.array_equal(hits.view(np.uint32), full.view(np.uint32))
+        o2 = np.zeros(len(rays), np.uint8)
+        capi.check(L.lmb200_trace_any_compact(A.h, r24.ctypes.data, tmin, tmax, o2.ctypes.data, len(rays)))
+        assert np.array_equal(o2, occ)
+    assert L.lmb200_trace_closest_compact(A.h, None, 0.0, 1.0, None, 5) == -1
+
+
 def test_per_ray_service_many_threads_and_restart():
     """The per-ray Accel3::Intersect path (persistent service kernel + mailboxes): 16 host threads posting rays
     concurrently get bit-identical hits to the batch call; the service survives going idle (it exits after 2 ms without
