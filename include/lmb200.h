@@ -266,11 +266,21 @@ typedef struct lmb200_render_params {
      * image as whole-image sampling (stratified over tiles: a different sampling pattern, statistically identical);
      * splats of camera-vertex light sampling still land anywhere, so films are summed as usual. */
     float    tile[4];
+    int32_t  primary_tile;       /* coherent camera samples: the 32 samples of a group (sample index / 32) share one tile of
+                                    primary_tile x primary_tile pixels and are uniform inside it; consecutive groups visit all tiles
+                                    in a keyed pseudo-random order before any tile repeats. Every sample's raster position stays
+                                    marginally uniform over the image (the estimator of renderer_pt.cpp:84 in expectation, for any
+                                    sample count and sharding; complete rounds are stratified over the tiles), while the primary
+                                    rays a warp traces together are coherent. 0 = automatic (lmb200_default_primary_tile), < 0 = off (independent) */
     int32_t  count_work;         /* 1 = run the instrumented traversal kernels and fill lmb200_render_stats::extend_nodes ...
                                     shadow_tris (for the roofline's algorithmic bytes per sample); such a run is never timed */
     int32_t  tile_partition;     /* lmb200_render_multi / _timed only: 1 = GPU g of n draws its raster positions in the
                                     horizontal strip [g/n, (g+1)/n) of the image (default 0: every GPU samples the whole image) */
 } lmb200_render_params;
+
+/* The tile edge primary_tile = 0 resolves to for a job of num_samples samples on a width x height film: the smallest of
+ * 2, 4, ... 64 pixels whose rounds fit at least four times into the job; -1 (independent samples) for tiny jobs. */
+int lmb200_default_primary_tile(int width, int height, int64_t num_samples);
 
 typedef struct lmb200_render_stats {
     int64_t  samples;

@@ -26,6 +26,8 @@
 #include <dlfcn.h>
 #include <nccl.h>      // types and enum values only: libnccl is dlopen'ed at run time, the library has no link-time dependency on it
 
+extern "C" int lmb200_default_primary_tile(int width, int height, int64_t num_samples);
+
 namespace lmb200 {
 
 #define LMB_PI 3.14159265358979323846f
@@ -91,6 +93,7 @@ struct RenderCfg {
     unsigned long long sample_end;
     uint32_t pool;
     float tile_x0, tile_y0, tile_sx, tile_sy;   // raster sample u -> (x0 + u.x sx, y0 + u.y sy); whole image = (0, 0, 1, 1)
+    int gt_nx, gt_ny;                           // coherent camera samples: tiles per axis (0 = off), see camera_raster
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -233,6 +236,51 @@ __device__ __forceinline__ f3 camera_wo(const DevScene& S, float u0, float u1, f
     return normalize(Pf - p);
 }
 #define LMB_LENS_BLOCK 0xffffffffu   // Philox block of the lens sample (the second Next2D of renderer_pt.cpp:86)
+// Raster position of camera sample `sidx` from its two uniforms (block 0). The reference draws it uniformly over the whole
+// image, independently per sample (renderer_pt.cpp:84) - 32 neighbouring lanes then trace 32 unrelated primary rays. Here
+// the 32 samples of a group (sidx / 32) share one tile of the image and are uniform inside it, and consecutive groups walk
+// through ALL tiles in a pseudo-random order before any tile is visited again (round r = group / #tiles uses its own
+// permutation of the tiles, a keyed 4-round Feistel network with cycle walking: integer arithmetic only, so the oracle
+// port computes the same tiles). Every sample's raster position is still marginally uniform over the image, for any sample
+// count and any split of the sample range (same expected image as the reference's estimator); complete rounds are
+// stratified over the tiles (less noise than independent positions, never more); and the primary rays a warp generates and
+// traces together are coherent.
+__host__ __device__ __forceinline__ uint32_t lmb_hash32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+__host__ __device__ __forceinline__ uint32_t lmb_permute_tiles(uint32_t x, uint32_t n, uint32_t key)
+{
+    uint32_t hb = 1;
+    while ((1u << (2u * hb)) < n) hb++;
+    const uint32_t mask = (1u << hb) - 1u;
+    do {
+        uint32_t L = x >> hb, R = x & mask;
+        for (uint32_t r = 0; r < 4u; r++) {
+            const uint32_t F = lmb_hash32(R ^ key ^ (r * 0x9e3779b9u)) & mask;
+            const uint32_t t = L ^ F; L = R; R = t;
+        }
+        x = (L << hb) | R;
+    } while (x >= n);
+    return x;
+}
+__device__ __forceinline__ void camera_raster(const RenderCfg& cfg, unsigned long long sidx, float ux, float uy, float& X, float& Y)
+{
+    float rx = ux, ry = uy;
+    if (cfg.gt_nx > 0) {
+        const uint32_t T = (uint32_t)cfg.gt_nx * (uint32_t)cfg.gt_ny;
+        const unsigned long long g = sidx >> 5, round = g / T;
+        const uint32_t key = lmb_hash32((uint32_t)cfg.seed ^ lmb_hash32((uint32_t)(cfg.seed >> 32) ^ lmb_hash32((uint32_t)round ^ lmb_hash32((uint32_t)(round >> 32)))));
+        const uint32_t t = lmb_permute_tiles((uint32_t)(g - round * T), T, key);
+        const uint32_t tx = t % (uint32_t)cfg.gt_nx, ty = t / (uint32_t)cfg.gt_nx;
+        rx = ((float)tx + ux) / (float)cfg.gt_nx;
+        ry = ((float)ty + uy) / (float)cfg.gt_ny;
+    }
+    X = cfg.tile_x0 + rx * cfg.tile_sx;
+    Y = cfg.tile_y0 + ry * cfg.tile_sy;
+}
+
 __device__ __forceinline__ int pixel_index(const DevScene& S, float rx, float ry)   // film_hdr.cpp:218-223
 {
     int px = (int)(rx * (float)S.width), py = (int)(ry * (float)S.height);
@@ -599,7 +647,9 @@ __global__ void __launch_bounds__(256) k_logic(DevScene S, Pool P, RenderCfg cfg
                     // renderer::pt / ptmis compute the raster position up front and drop the sample if it fails (renderer_pt.cpp:94-99)
                     const float4 u = rng_block(cfg.seed, sidx, 0u);
                     float rx, ry;
-                    ok = raster_position(S, cp, camera_wo(S, cfg.tile_x0 + u.y * cfg.tile_sx, cfg.tile_y0 + u.z * cfg.tile_sy, cp), rx, ry);
+                    float sx, sy;
+                    camera_raster(cfg, sidx, u.y, u.z, sx, sy);
+                    ok = raster_position(S, cp, camera_wo(S, sx, sy, cp), rx, ry);
                     if (ok) pixel = pixel_index(S, rx, ry);
                 }
                 if (ok && !(cfg.max_verts != -1 && 1 >= cfg.max_verts)) {
@@ -705,7 +755,7 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
     const uint32_t rounds = (nq + stride - 1) / stride;
     for (uint32_t r = 0; r < rounds; r++) {
         const uint32_t qi = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        bool emit = false;
+        bool emit = false, is_primary = false;
         uint32_t i = 0;
         if (qi < nq) {
             i = P.vq[qi];
@@ -713,6 +763,7 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
             const float4 vp = P.vtx_p[i];
             const uint32_t tri = __float_as_uint(vp.w);
             const bool is_sensor = tri == LMB200_MISS;
+            is_primary = is_sensor;
             const f3 p = F3(vp.x, vp.y, vp.z);
             float4 thr = P.thr[i];
             f3 wo = F3(0, 0, 0), fs, sn_here = F3(0, 0, 0);
@@ -720,7 +771,9 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
             bool ok = true, specular_here = false;
             if (is_sensor) {
                 const float4 u = rng_block(cfg.seed, P.sample[i], 0u);
-                wo = camera_wo(S, cfg.tile_x0 + u.y * cfg.tile_sx, cfg.tile_y0 + u.z * cfg.tile_sy, p);
+                float sx, sy;
+                camera_raster(cfg, P.sample[i], u.y, u.z, sx, sy);
+                wo = camera_wo(S, sx, sy, p);
                 float rx = 0.f, ry = 0.f;
                 bool inside;
                 const float im = importance_raster(S, p, wo, rx, ry, inside);
@@ -756,20 +809,26 @@ __global__ void __launch_bounds__(256) k_bsdf(DevScene S, Pool P, RenderCfg cfg)
                 P.nverts[i] = 0;                                               // path ends; slot is refilled by k_logic
             }
         }
-        const uint32_t q = queue_slot(P.qcount + 1, emit);
-        if (emit) P.eq[q] = i;
+        // two-ended extend queue: primary rays (coherent in generation order, see camera_raster) from the front, all other
+        // rays from the back, so that the warps of k_extend get runs of primary rays instead of a mix
+        const bool prim = emit && is_primary;
+        const uint32_t qp = queue_slot(P.qcount + 1, prim);
+        const uint32_t qs = queue_slot(P.qcount + 3, emit && !prim);
+        if (prim) P.eq[qp] = i;
+        else if (emit) P.eq[cfg.pool - 1u - qs] = i;
     }
 }
 
 // extend: closest hit over the extend queue (slot indirection), persistent warps with lane refill
 struct ExtendIo {
-    Pool P; uint32_t n;
+    Pool P; uint32_t n_primary, n, last;      // ray qi: eq[qi] for qi < n_primary (front of the queue), else eq[last - (qi - n_primary)] (back)
     __device__ __forceinline__ uint64_t count() const { return n; }
-    __device__ __forceinline__ void load(uint64_t qi, float4& ro, float4& rd) const { const uint32_t i = P.eq[qi]; ro = P.ray_o[i]; rd = P.ray_d[i]; }
+    __device__ __forceinline__ uint32_t slot(uint64_t qi) const { return P.eq[qi < n_primary ? (uint32_t)qi : last - ((uint32_t)qi - n_primary)]; }
+    __device__ __forceinline__ void load(uint64_t qi, float4& ro, float4& rd) const { const uint32_t i = slot(qi); ro = P.ray_o[i]; rd = P.ray_d[i]; }
     __device__ __forceinline__ void store(uint64_t qi, const Trav& T) const
     {
         const bool hit = T.hid != LMB200_MISS;
-        P.hit[P.eq[qi]] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
+        P.hit[slot(qi)] = make_float4(hit ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
     }
 };
 // COUNT variants (instrumented, never timed): nodes / triangle records fetched, summed into P.next_sample[4..7]
@@ -781,10 +840,10 @@ __device__ __forceinline__ void add_work(unsigned long long* dst, const TravCoun
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
-k_extend(const BvhDev bvh, Pool P, unsigned long long* __restrict__ counter)
+k_extend(const BvhDev bvh, Pool P, unsigned long long* __restrict__ counter, const uint32_t pool)
 {
     __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
-    ExtendIo io{P, P.qcount[1]};
+    ExtendIo io{P, P.qcount[1], P.qcount[1] + P.qcount[3], pool - 1u};
     TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     persistent_trace<false, COUNT, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt);
     if (COUNT) add_work(P.next_sample + 4, cnt);
@@ -817,7 +876,7 @@ k_shadow(const BvhDev bvh, Pool P, unsigned long long* __restrict__ counter, flo
 __global__ void k_stats(Pool P)
 {
     // fold the queue sizes of this iteration into the running ray counters
-    P.next_sample[1] += P.qcount[1];
+    P.next_sample[1] += P.qcount[1] + P.qcount[3];
     P.next_sample[2] += P.qcount[2];
     P.next_sample[3] += P.qcount[0];
 }
@@ -993,7 +1052,7 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
                                            "primitive when a ray escapes to the env emitter shape, scene3.cpp:463-475 + renderer_pt.cpp:183)");
     if (p->sample_end < p->sample_begin) return set_error(LMB200_E_INVALID, "sample_end < sample_begin");
     const int64_t todo = p->sample_end - p->sample_begin;
-    uint32_t pool = p->pool_size > 0 ? (uint32_t)p->pool_size : (1u << 22);   // 4 Mi slots: best on B200 (profiles/r01_sweep.md)
+    uint32_t pool = p->pool_size > 0 ? (uint32_t)p->pool_size : (1u << 23);   // 8 Mi slots: best on B200 (profiles/r02_sweep.md; 4 Mi in round 1)
     if ((int64_t)pool > todo) pool = (uint32_t)std::max<int64_t>(todo, 1);
     pool = (pool + 31u) & ~31u;
     int rc = ensure_pool(s, pool);
@@ -1011,6 +1070,12 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
     cfg.mode = p->mode; cfg.max_verts = p->max_num_vertices; cfg.min_verts = p->min_num_vertices;
     cfg.seed = p->seed; cfg.sample_end = (unsigned long long)p->sample_end; cfg.pool = pool;
     cfg.tile_x0 = 0.f; cfg.tile_y0 = 0.f; cfg.tile_sx = 1.f; cfg.tile_sy = 1.f;
+    {
+        // coherent camera sample groups (camera_raster): tiles of primary_tile x primary_tile pixels; 0 = automatic, < 0 = off
+        const int tp = p->primary_tile == 0 ? lmb200_default_primary_tile(s->dev.width, s->dev.height, p->num_samples) : p->primary_tile;
+        cfg.gt_nx = tp > 0 ? (s->dev.width + tp - 1) / tp : 0;
+        cfg.gt_ny = tp > 0 ? (s->dev.height + tp - 1) / tp : 0;
+    }
     if (p->tile[0] != 0.f || p->tile[1] != 0.f || p->tile[2] != 0.f || p->tile[3] != 0.f) {
         if (!(p->tile[0] >= 0.f && p->tile[1] >= 0.f && p->tile[2] <= 1.f && p->tile[3] <= 1.f && p->tile[2] > p->tile[0] && p->tile[3] > p->tile[1]))
             return set_error(LMB200_E_INVALID, "tile must satisfy 0 <= x0 < x1 <= 1 and 0 <= y0 < y1 <= 1");
@@ -1054,8 +1119,8 @@ static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, c
             LMB_CK(cudaEventRecord(s->ev_shadow, s->shadow_stream), "cudaEventRecord(shadow)");
         }
         k_bsdf<<<logic_blocks, 256, 0, st>>>(s->dev, P, cfg);
-        if (count) k_extend<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(bvh, P, s->d_counter);
-        else k_extend<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(bvh, P, s->d_counter);
+        if (count) k_extend<true><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(bvh, P, s->d_counter, pool);
+        else k_extend<false><<<trace_blocks, LMB_TRACE_BLOCK, 0, st>>>(bvh, P, s->d_counter, pool);
         if (nee) LMB_CK(cudaStreamWaitEvent(st, s->ev_shadow, 0), "cudaStreamWaitEvent(shadow)");
         k_stats<<<1, 1, 0, st>>>(P);
         LMB_CK(cudaGetLastError(), "wavefront kernel launch");
@@ -1231,6 +1296,18 @@ lmb200_accel* lmb200_registry_get(const void* owner)
     std::lock_guard<std::mutex> lock(g_reg_mu);
     auto it = g_registry.find(owner);
     return it == g_registry.end() ? nullptr : it->second;
+}
+
+int lmb200_default_primary_tile(int width, int height, int64_t num_samples)
+{
+    // the smallest tile whose rounds (every tile visited once: 32 * #tiles samples) fit at least four times into the job, so
+    // that even a partial last round leaves no visible coverage pattern; small tiles make the primary rays of a group
+    // more coherent (ptdirect on configs[2]: 986 Msamples/s ungrouped, 1046 / 1072 / 1093 / 1113 with 16 / 8 / 4 / 2 pixels)
+    for (int tp = 2; tp <= 64; tp *= 2) {
+        const int64_t tiles = (int64_t)((width + tp - 1) / tp) * ((height + tp - 1) / tp);
+        if (num_samples >= 4 * 32 * tiles) return tp;
+    }
+    return -1;
 }
 
 int lmb200_render_dev(lmb200_scene* h, const lmb200_render_params* p, void* film_dev, void* stream, lmb200_render_stats* stats)
@@ -1534,12 +1611,20 @@ int lmb200_render_timed(lmb200_scene** scenes, int num_gpus, const lmb200_render
     auto last_tick = t0;
     int64_t done = 0, cursor = p->sample_begin;
     int64_t ticks = 0;
+    // the camera-sample tiling (lmb200_render_params::primary_tile) is resolved ONCE for the job, not per pass: without a time
+    // budget from the job's sample count (the passes then reproduce lmb200_render exactly), with one from the pass size
+    int job_tile = p->primary_tile;
+    if (job_tile == 0 && num_gpus >= 1 && scenes[0]) {
+        const Scene* s0 = reinterpret_cast<const Scene*>(scenes[0]);
+        job_tile = lmb200_default_primary_tile(s0->dev.width, s0->dev.height, render_time <= 0 ? p->num_samples : pass_samples);
+    }
     while (!rc) {
         int64_t n = pass_samples;
         if (render_time <= 0) n = std::min<int64_t>(n, p->sample_end - cursor);
         if (n <= 0) break;
         lmb200_render_params q = *p;
         q.num_samples = n;
+        q.primary_tile = job_tile;
         rc = S.pass(&q, cursor, cursor + n);
         if (rc) break;
         cursor += n; done += n;

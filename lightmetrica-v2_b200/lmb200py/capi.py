@@ -61,7 +61,7 @@ class SceneDesc(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("num_samples", C.c_int64), ("sample_begin", C.c_int64), ("sample_end", C.c_int64),
                 ("max_num_vertices", C.c_int32), ("min_num_vertices", C.c_int32), ("seed", C.c_uint64), ("pool_size", C.c_int32),
-                ("tile", C.c_float * 4), ("count_work", C.c_int32), ("tile_partition", C.c_int32)]
+                ("tile", C.c_float * 4), ("primary_tile", C.c_int32), ("count_work", C.c_int32), ("tile_partition", C.c_int32)]
 
 
 class BvhLayout(C.Structure):
@@ -82,7 +82,7 @@ EXPORTS = [
     "lmb200_accel_get_stats", "lmb200_accel_device", "lmb200_accel_replicate", "lmb200_trace_closest", "lmb200_trace_closest_compact", "lmb200_trace_any_compact", "lmb200_trace_closest_one", "lmb200_trace_closest_one_mt", "lmb200_trace_closest_dev", "lmb200_trace_any", "lmb200_trace_any_dev",
     "lmb200_trace_count_dev", "lmb200_launch_count", "lmb200_accel_host_layout", "lmb200_accel_create_host_only",
     "lmb200_scene_create", "lmb200_scene_create_ex", "lmb200_scene_create_shared", "lmb200_registry_put", "lmb200_registry_get", "lmb200_scene_destroy", "lmb200_scene_accel", "lmb200_render_dev", "lmb200_film_rescale_dev",
-    "lmb200_render", "lmb200_render_multi", "lmb200_render_timed",
+    "lmb200_render", "lmb200_render_multi", "lmb200_render_timed", "lmb200_default_primary_tile",
 ]
 
 _lib = None
@@ -153,6 +153,7 @@ def lib():
         L.lmb200_render_dev.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
         L.lmb200_film_rescale_dev.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
         L.lmb200_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(RenderStats)]
+        L.lmb200_default_primary_tile.argtypes = [C.c_int, C.c_int, C.c_int64]
         L.lmb200_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RenderParams), C.c_void_p, C.POINTER(RenderStats)]
         L.lmb200_render_timed.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RenderParams), C.c_double, C.c_int64, C.c_double,
                                           PROGRESS_FN, C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
@@ -250,8 +251,9 @@ class Scene:
         except Exception:
             pass
 
-    def params(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None, pool=0, tile=None, tile_partition=False):
+    def params(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None, pool=0, tile=None, tile_partition=False, primary_tile=0):
         p = RenderParams()
+        p.primary_tile = primary_tile
         if tile is not None:
             p.tile = (C.c_float * 4)(*tile)
         p.tile_partition = 1 if tile_partition else 0

@@ -252,6 +252,7 @@ def _port_pt():
         L.orc_pt_scene_destroy.argtypes = [C.c_void_p]
         L.orc_pt_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_pt_render_tile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_pt_render_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_render_normal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L._pt_ready = True
     return L
@@ -270,17 +271,20 @@ class PortPT:
             _port_pt().orc_pt_scene_destroy(self.s)
             self.s = None
 
-    def render(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None, tile=None):
+    def render(self, mode, num_samples, seed=1, max_verts=-1, min_verts=0, begin=0, end=None, tile=None, primary_tile=0):
         """Returns (film (H,W,3) scaled by W*H/num_samples, counts [extend, shadow]). tile = (x0, y0, x1, y1): camera samples
-        drawn inside that raster rectangle (tile partitioning, include/lmb200.h)."""
+        drawn inside that raster rectangle (tile partitioning, include/lmb200.h). primary_tile: lmb200_render_params::primary_tile
+        (0 = the library's automatic choice, asked from lmb200_default_primary_tile; -1 = independent samples)."""
         end = num_samples if end is None else end
         film = np.zeros((self.h, self.w, 4), np.float32)
         counts = np.zeros(2, np.int64)
-        if tile is None:
-            _port_pt().orc_pt_render(self.s, mode, max_verts, min_verts, seed, begin, end, _p(film), _p(counts))
-        else:
-            t = np.asarray(tile, np.float32)
-            _port_pt().orc_pt_render_tile(self.s, mode, max_verts, min_verts, seed, begin, end, _p(t), _p(film), _p(counts))
+        t = np.asarray((0.0, 0.0, 1.0, 1.0) if tile is None else tile, np.float32)
+        if primary_tile == 0:
+            # the product's own rule for "automatic" (a function of the job size): asked from the C ABI so that port and
+            # device draw the same camera samples
+            from lmb200py import capi
+            primary_tile = capi.lib().lmb200_default_primary_tile(self.w, self.h, int(num_samples))
+        _port_pt().orc_pt_render_ex(self.s, mode, max_verts, min_verts, seed, begin, end, _p(t), int(primary_tile), _p(film), _p(counts))
         return film[..., :3] * np.float32(self.w * self.h / num_samples), counts
 
     def render_normal(self):

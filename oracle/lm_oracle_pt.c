@@ -492,12 +492,34 @@ static float geometry_term(const geom_t* g1, const geom_t* g2)
     return t / d2;
 }
 
+/* keyed bijection of [0, n): 4-round Feistel network on 2 hb bits with cycle walking (render.cu lmb_permute_tiles) */
+static uint32_t hash32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+static uint32_t permute_tiles(uint32_t x, uint32_t n, uint32_t key)
+{
+    uint32_t hb = 1, mask;
+    while ((1u << (2u * hb)) < n) hb++;
+    mask = (1u << hb) - 1u;
+    do {
+        uint32_t L = x >> hb, R = x & mask, r;
+        for (r = 0; r < 4u; r++) {
+            const uint32_t F = hash32(R ^ key ^ (r * 0x9e3779b9u)) & mask;
+            const uint32_t t = L ^ F; L = R; R = t;
+        }
+        x = (L << hb) | R;
+    } while (x >= n);
+    return x;
+}
+
 /* One sample of renderer::pt (mode 0, renderer_pt.cpp:68-231), renderer::ptdirect (mode 1,
  * renderer_ptdirect.cpp:76-282) or renderer::ptmis (mode 3, renderer_ptmis.cpp:79-290). RNG blocks: 0 = camera (x1,x2 = raster sample); iteration `it`
  * (= numVertices at loop top) uses block 2it-1 = (light pick, light u0, light u1, RR) and block
  * 2it = (bsdf u0, bsdf u1, component, -). */
 static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed, uint64_t sample,
-                        const float* tile, float* film, int64_t* n_extend, int64_t* n_shadow)
+                        const float* tile, int gt_nx, int gt_ny, float* film, int64_t* n_extend, int64_t* n_shadow)
 {
     float u[4], rx = 0.0f, ry = 0.0f;
     v3 init_wo, thr = V(1, 1, 1), wi = V(0, 0, 0);
@@ -509,6 +531,17 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
     if (S->d.camera.kind == 1) rng_block(seed, sample, 0xffffffffu, ul);   /* lens sample (the second Next2D of renderer_pt.cpp:86) */
     memset(&geom, 0, sizeof(geom));
     geom.degenerated = 1;
+    /* coherent camera sample groups (render.cu camera_raster): the 32 samples of group sample / 32 share one of the
+     * gt_nx x gt_ny tiles; consecutive groups walk through all tiles in a keyed pseudo-random order per round */
+    if (gt_nx > 0) {
+        const uint32_t T = (uint32_t)gt_nx * (uint32_t)gt_ny;
+        const uint64_t g = sample >> 5, round = g / T;
+        const uint32_t key = hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) ^ hash32((uint32_t)round ^ hash32((uint32_t)(round >> 32)))));
+        const uint32_t t = permute_tiles((uint32_t)(g - round * T), T, key);
+        const uint32_t tx = t % (uint32_t)gt_nx, ty = t / (uint32_t)gt_nx;
+        u[1] = ((float)tx + u[1]) / (float)gt_nx;
+        u[2] = ((float)ty + u[2]) / (float)gt_ny;
+    }
     /* optional tile partitioning: the raster sample is drawn inside tile = {x0, y0, x1, y1} (whole image: 0,0,1,1) */
     init_wo = camera_sample(S, tile[0] + u[1] * (tile[2] - tile[0]), tile[1] + u[2] * (tile[3] - tile[1]), ul[0], ul[1], &geom.p);
     if (mode != 1 && !raster_position(S, geom.p, init_wo, &rx, &ry)) return;      /* renderer_pt.cpp:94-99, renderer_ptmis.cpp:100-105 */
@@ -649,19 +682,27 @@ void orc_pt_scene_destroy(orc_pt_scene* S)
 /* Renders global sample indices [begin,end) of a num_samples job into film (W*H*4 floats, zeroed by
  * the caller), UNSCALED; threads accumulate into private films that are summed at the end, as
  * Scheduler_::Process does (scheduler.cpp:157-164, 280-285). counts[0]=extend rays, [1]=shadow rays. */
-void orc_pt_render_tile(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
-                        int64_t begin, int64_t end, const float* tile, float* film, int64_t* counts);
+void orc_pt_render_ex(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
+                      int64_t begin, int64_t end, const float* tile, int primary_tile, float* film, int64_t* counts);
 void orc_pt_render(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
                    int64_t begin, int64_t end, float* film, int64_t* counts)
 {
     const float whole[4] = {0.0f, 0.0f, 1.0f, 1.0f};
-    orc_pt_render_tile(S, mode, max_verts, min_verts, seed, begin, end, whole, film, counts);
+    orc_pt_render_ex(S, mode, max_verts, min_verts, seed, begin, end, whole, 0, film, counts);
 }
 /* Same with the camera samples drawn inside the raster rectangle tile = {x0, y0, x1, y1} (include/lmb200.h, tile partitioning). */
 void orc_pt_render_tile(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
                         int64_t begin, int64_t end, const float* tile, float* film, int64_t* counts)
 {
+    orc_pt_render_ex(S, mode, max_verts, min_verts, seed, begin, end, tile, 0, film, counts);
+}
+/* primary_tile: the RESOLVED lmb200_render_params::primary_tile (tile edge in pixels; <= 0 = off; 0 is resolved by the caller) */
+void orc_pt_render_ex(const orc_pt_scene* S, int mode, int max_verts, int min_verts, uint64_t seed,
+                      int64_t begin, int64_t end, const float* tile, int primary_tile, float* film, int64_t* counts)
+{
     const size_t npx = (size_t)S->d.camera.width * S->d.camera.height;
+    const int tp = primary_tile;
+    const int gt_nx = tp > 0 ? (S->d.camera.width + tp - 1) / tp : 0, gt_ny = tp > 0 ? (S->d.camera.height + tp - 1) / tp : 0;
     int64_t ne = 0, ns = 0;
 #pragma omp parallel reduction(+ : ne, ns)
     {
@@ -669,7 +710,7 @@ void orc_pt_render_tile(const orc_pt_scene* S, int mode, int max_verts, int min_
         int64_t i;
         size_t k;
 #pragma omp for schedule(dynamic, 4096)
-        for (i = begin; i < end; i++) sample_path(S, mode, max_verts, min_verts, seed, (uint64_t)i, tile, local, &ne, &ns);
+        for (i = begin; i < end; i++) sample_path(S, mode, max_verts, min_verts, seed, (uint64_t)i, tile, gt_nx, gt_ny, local, &ne, &ns);
 #pragma omp critical
         for (k = 0; k < npx * 4; k++) film[k] += local[k];
         free(local);

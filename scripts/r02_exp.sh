@@ -1,2 +1,2 @@
 #!/bin/bash
-SWEEP_BUILDER=0 python scripts/gpu_sweep.py hgreedy 2>&1 | cut -c1-420
+python -m pytest tests/test_gpu_plugin.py -q -rf 2>&1 | tail -5

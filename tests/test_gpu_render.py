@@ -48,6 +48,25 @@ def test_same_samples_as_oracle(mode, scene_name):
     assert st["samples"] == N
 
 
+@pytest.mark.parametrize("primary_tile", [-1, 4, 16])
+def test_coherent_camera_sample_groups(primary_tile):
+    """lmb200_render_params::primary_tile: groups of 32 samples share a random tile of the image (coherent primary rays). Same
+    samples as the oracle for every setting (off, 4 and 16 pixels; the default of 8 is what every other test runs), and the
+    setting does not change the expected image: a grouped render agrees with an ungrouped one of another seed within the
+    ungrouped two-seed noise."""
+    sc = scenedesc.cornell_box(48, 40, glossy_block=True)
+    N = 48 * 40 * 64
+    S = capi.Scene(sc)
+    port, counts = ob.PortPT(sc).render(capi.MODE_PTDIRECT, N, seed=7, primary_tile=primary_tile)
+    gpu, st = S.render(capi.MODE_PTDIRECT, N, seed=7, primary_tile=primary_tile)
+    assert rel_rmse(gpu, port) < 1e-3 and st["extend_rays"] == counts[0] and st["shadow_rays"] == counts[1]
+    a, _ = S.render(capi.MODE_PTDIRECT, 4 * N, seed=1, primary_tile=-1)
+    b, _ = S.render(capi.MODE_PTDIRECT, 4 * N, seed=2, primary_tile=-1)
+    g, _ = S.render(capi.MODE_PTDIRECT, 4 * N, seed=3, primary_tile=primary_tile)
+    assert rel_rmse(g, a) < 1.25 * rel_rmse(b, a)
+    assert np.allclose(g.mean(axis=(0, 1)), a.mean(axis=(0, 1)), rtol=0.02)
+
+
 def test_pool_size_and_sharding_invariance():
     """The image depends only on (seed, sample index): any pool size and any split of the sample range
     (= any GPU count) gives the same film up to fp32 summation order."""
