@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--pt-spp", type=int, default=1024)
     ap.add_argument("--pt-pool", type=int, default=0, help="wavefront pool size (0 = library default)")
     ap.add_argument("--pt-cpu-spp", type=int, default=2, help="bounded CPU sample of the path-tracing workload (samples per pixel)")
+    ap.add_argument("--no-one", action="store_true", help="skip the per-ray Accel3::Intersect figure (its persistent service kernel distorts an ncu launch list)")
     ap.add_argument("--no-c4", action="store_true", help="skip the configs[4] leg (10M triangles, 4K film, NCCL film reduce)")
     ap.add_argument("--c4-spp", type=int, default=64)
     return ap.parse_args()
@@ -373,7 +374,7 @@ def main():
 
     # ---- the per-ray drop-in: Accel3::Intersect-shaped calls from 16 host threads (persistent service kernel) ----
     one = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not a.no_one:
         one = bench_intersect_one(a, capi, accel, h_rays)
 
     # ---- secondary: path-traced samples/s on configs[2] (full size by default), NCCL film reduce ----

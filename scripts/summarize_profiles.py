@@ -20,7 +20,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__warps_eligible.avg.per_cycle_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__cycles_elapsed.avg", "smsp__sass_average_data_bytes_per_sector_mem_local_op_ld.ratio",
-        "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "smsp__cycles_active.avg"]
+        "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "smsp__cycles_active.avg",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum",
+        "lts__t_sectors_srcunit_tex_op_read.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]
 
 
 def launches(fname="launches.csv", suffix="launches", cmd="python bench.py --rays 16777216 --steps 2 --warmup 3 --cpu-rays 100000 --pt-spp 32"):
@@ -66,10 +68,11 @@ def full(rep, name):
 
 
 os.makedirs(OUT, exist_ok=True)
-launches()
-launches("launches_default.csv", "launches_default_cmd", "python bench.py --steps 2 --warmup 1   (first 600 launches)")
-t = full("prof_trace.ncu-rep", "trace_kernel")
-full("prof_extend.ncu-rep", "k_extend")
+launches((sys.argv[2] if len(sys.argv) > 2 else "") + "launches.csv")
+launches((sys.argv[2] if len(sys.argv) > 2 else "") + "launches_default.csv", "launches_default_cmd", "python bench.py --steps 2 --warmup 1   (first 600 launches)")
+PREFIX = sys.argv[2] if len(sys.argv) > 2 else ""
+t = full(PREFIX + "prof_trace.ncu-rep", "trace_kernel")
+full(PREFIX + "prof_extend.ncu-rep", "k_extend")
 if t:
     def num(k):
         u, v = t[k]
@@ -77,8 +80,11 @@ if t:
         mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         return v * mult
     traffic = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    sys.path.insert(0, ROOT)
+    import bench
     json.dump({"tag": tag, "trace_kernel_dram_bytes_per_launch": traffic, "rays_per_launch": 16777216,
-               "dram_bytes_per_ray": traffic / 16777216,
+               "dram_bytes_per_ray": traffic / 16777216, "source_hash": bench.source_hash(),
+               "source_hash_of": "sha256 of csrc/{traverse.cuh,accel.cu,bvh.h,triaccel.h,bvh_build.cpp} at capture time (bench.py source_hash())",
                "note": "ncu --set full capture of lmb200::trace_kernel<false,false> at 16 Mi rays / 4 M triangles; bench.py scales it per ray"},
               open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print("profiles written for", tag)
