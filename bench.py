@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--pt-cpu-spp", type=int, default=2, help="bounded CPU sample of the path-tracing workload (samples per pixel)")
     ap.add_argument("--no-one", action="store_true", help="skip the per-ray Accel3::Intersect figure (its persistent service kernel distorts an ncu launch list)")
     ap.add_argument("--no-c4", action="store_true", help="skip the configs[4] leg (10M triangles, 4K film, NCCL film reduce)")
-    ap.add_argument("--c4-spp", type=int, default=64)
+    ap.add_argument("--c4-spp", type=int, default=256, help="samples per pixel of the configs[4] leg (the config names 4096; throughput is per sample)")
     return ap.parse_args()
 
 

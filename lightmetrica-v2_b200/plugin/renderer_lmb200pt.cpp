@@ -5,7 +5,7 @@
 //     renderer: {type: lmb200pt, params: {mode: ptdirect, num_samples: ..., max_num_vertices: -1,
 //                                         min_num_vertices: 0, num_gpus: 1, device: 0, pool_size: 0,
 //                                         render_time: -1, progress_image_update_interval: -1, grain_size: 10000, builder: gpu,
-//                                         texture_resolution: 1024, tile_partitioning: 0}}
+//                                         texture_resolution: 1024, tile_partitioning: 0, primary_tile: 0}}
 // It reads the scene through the reference's interfaces (Scene3::PrimitiveAt, TriangleMesh::*,
 // BSDF::Reflectance/Glossiness, Light::Emittance, Sensor::GetFilm/GetProjectionMatrix), flattens
 // it into the POD arrays of include/lmb200.h and calls liblmb200.so; the film comes back through
@@ -53,6 +53,7 @@ public:
             if (prop->Child("pool_size")) poolSize_ = prop->ChildAs<int>("pool_size", 0);
             if (prop->Child("texture_resolution")) textureResolution_ = prop->ChildAs<int>("texture_resolution", 1024);
             if (prop->Child("tile_partitioning")) tilePartitioning_ = prop->ChildAs<int>("tile_partitioning", 0) != 0;
+            if (prop->Child("primary_tile")) primaryTile_ = prop->ChildAs<int>("primary_tile", 0);
             if (prop->Child("builder"))
             {
                 const auto b = prop->ChildAs<std::string>("builder", "gpu");
@@ -339,6 +340,7 @@ public:
         p.seed = (uint64_t)initRng->NextUInt();
         p.pool_size = poolSize_;
         p.tile_partition = tilePartitioning_ ? 1 : 0;
+        p.primary_tile = primaryTile_;
         const int W = film->Width(), H = film->Height();
         std::vector<float> rgba((size_t)W * H * 4, 0.f);
         lmb200_render_stats st;
@@ -513,6 +515,7 @@ private:
     int poolSize_ = 0;
     int textureResolution_ = 1024;
     bool tilePartitioning_ = false;                       // num_gpus > 1: each GPU samples its own horizontal strip of the raster
+    int primaryTile_ = 0;                                 // lmb200_render_params::primary_tile: 0 = automatic, < 0 = independent raster positions
     const Scene3* curScene_ = nullptr;                    // valid during Render
     std::vector<lmb200_texture> textures_;                 // baked TexR textures of the scene being rendered
     std::vector<std::vector<float>> textureData_;
