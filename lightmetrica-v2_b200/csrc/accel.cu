@@ -156,14 +156,21 @@ void Accel::free_device()
 
 Accel::~Accel() { free_device(); }
 
-// The traversal stack holds one entry per level of the wide tree (the not yet visited siblings of the node a ray
-// descended into): LMB_SM_STACK entries in shared memory + LMB_LOCAL_STACK in local memory, pushed without a bounds
-// check. A tree deeper than that is refused here instead of corrupting a thread's state on the device.
+// The traversal stack holds one entry per level of the wide tree below the root (the not yet visited siblings of the node a
+// ray descended into): LMB_SM_STACK - 1 entries in shared memory, pushed without a bounds check. A deeper tree is refused
+// here instead of corrupting a neighbouring thread's stack on the device.
+static int depth_limit()
+{
+    // LMB200_DEPTH_LIMIT lowers the limit (tests exercise the refusal / fallback paths with ordinary scenes)
+    static const int limit = [] { const char* e = getenv("LMB200_DEPTH_LIMIT"); const int v = e ? atoi(e) : 0; return v >= 1 && v < LMB_SM_STACK ? v : LMB_SM_STACK; }();
+    return limit;
+}
+static bool depth_fits(int max_depth) { return max_depth <= depth_limit(); }
 static int check_depth(int max_depth)
 {
-    if (max_depth > LMB_SM_STACK + LMB_LOCAL_STACK)
+    if (!depth_fits(max_depth))
         return set_error(LMB200_E_STATE, "BVH depth " + std::to_string(max_depth) + " exceeds the traversal stack capacity of " +
-                                             std::to_string(LMB_SM_STACK + LMB_LOCAL_STACK) + " levels");
+                                             std::to_string(depth_limit()) + " levels");
     return LMB200_OK;
 }
 
@@ -364,8 +371,10 @@ int lmb200_accel_build_ex(lmb200_accel* h, const float* verts, uint64_t ntris, i
     if (ntris >= (1ull << 27)) return set_error(LMB200_E_INVALID, "too many triangles (limit 2^27)");
     a->built = false;
     int rc = build_bvh_gpu(a, verts, ntris, builder);
-    if (!rc) rc = check_depth(a->bvh.stats.max_depth);
     if (rc) return rc;
+    // a Morton / clustering tree over adversarial input (long chains) can be deeper than the traversal stack: the binned SAH
+    // builder, which falls back to median splits, takes over in that case
+    if (!depth_fits(a->bvh.stats.max_depth)) return build_host_sah(a, verts, ntris);
     a->built = true;
     a->upload_seconds = 0;
     return a->finish_device_setup();

@@ -207,6 +207,7 @@ service_kernel(const BvhDev bvh, ServiceShared* S, ServiceCtl* ctl, const unsign
     const unsigned slot0 = blockIdx.x * LMB_SERVICE_BSLOTS;      // this block's mailboxes: [slot0, slot0 + BSLOTS)
     if (threadIdx.x < LMB_SERVICE_BSLOTS) s_req[threadIdx.x] = S->slot[slot0 + threadIdx.x].done;     // nothing pending below this stamp
     if (threadIdx.x == 0) s_exit = 0;
+    trav_lut_init<LMB_SERVICE_BSLOTS>(LMB_SM_BASE(s_stack));
     __syncthreads();
 
     if (warp == 0) {
@@ -266,7 +267,8 @@ service_kernel(const BvhDev bvh, ServiceShared* S, ServiceCtl* ctl, const unsign
                 TravCounters cnt;
                 uint2 lstack[LMB_LOCAL_STACK];
                 trav_init(T, s_ray[ls][0], s_ray[ls][1]);
-                T.sp = (int)(sm_base + 8u * ls);
+                trav_stack_reset_t<LMB_SERVICE_BSLOTS>(T, sm_base, ls);
+                trav_set_lut<LMB_SERVICE_BSLOTS>(T, sm_base);
                 while (!trav_step<false, false, LMB_SERVICE_BSLOTS>(T, bvh, sm_base, lstack, cnt, 1u)) {}
                 res = make_float4(T.hid != LMB200_MISS ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid));
             }

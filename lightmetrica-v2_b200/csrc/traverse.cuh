@@ -19,9 +19,9 @@
 namespace lmb200 {
 
 #ifndef LMB_SM_STACK
-#define LMB_SM_STACK 8          // entries per thread in shared memory
+#define LMB_SM_STACK 16         // entries per thread in shared memory (one of them the sentinel): trees up to 15 levels
 #endif
-#define LMB_LOCAL_STACK 24      // overflow entries in local memory
+#define LMB_LOCAL_STACK 1       // (no overflow area any more; the array argument is kept for the call sites)
 #ifndef LMB_REFILL_BELOW
 #define LMB_REFILL_BELOW 26     // refill the warp when fewer lanes than this are active
 #endif
@@ -145,25 +145,29 @@ __device__ __forceinline__ uint32_t lmb_intersect_node(const float px, const flo
     return hits8;
 }
 
-// Moves bit s of an 8-bit mask to bit s ^ o (o = 7 - ray octant) with three masked delta swaps, turning
-// the slot-order hit mask into traversal-priority order (highest bit = nearest child). `pm` holds the
-// three swap masks of the ray: byte 0 = 0x55 if o&1, byte 1 = 0x33 if o&2, byte 2 = 0x0f if o&4 (else 0).
-__device__ __forceinline__ uint32_t lmb_xor_permute8(uint32_t x, uint32_t pm)
+// Traversal-priority order of a slot-order hit mask: bit s moves to bit s ^ o (o = 7 - ray octant; highest bit = nearest child).
+// From a table in shared memory: row o of 256 bytes, entry x = bits of x moved from s to s ^ o. One LDS per node step (round 1
+// permuted with three masked delta swaps, ~15 ALU-pipe operations). The table lives behind the block's stack area.
+#define LMB_LUT_UINT2 256
+template <int STRIDE>
+__device__ __forceinline__ void trav_lut_init(const uint32_t sm_base)      // all threads of the block, then __syncthreads()
 {
-    uint32_t t;
-    t = ((x >> 1) ^ x) & (pm & 0xffu);          x ^= t ^ (t << 1);
-    t = ((x >> 2) ^ x) & ((pm >> 8) & 0xffu);   x ^= t ^ (t << 2);
-    t = ((x >> 4) ^ x) & ((pm >> 16) & 0xffu);  x ^= t ^ (t << 4);
-    return x;
+    const uint32_t lut = sm_base + 8u * LMB_SM_STACK * STRIDE;
+    for (uint32_t i = threadIdx.x; i < 2048u; i += blockDim.x) {
+        const uint32_t o = i >> 8, x = i & 255u;
+        uint32_t r = 0;
+        for (uint32_t b = 0; b < 8u; b++) if ((x >> b) & 1u) r |= 1u << (b ^ o);
+        asm volatile("st.shared.u8 [%0], %1;" :: "r"(lut + i), "r"(r) : "memory");
+    }
 }
 
 // Per-lane traversal state. hid == 0xffffffff <=> no hit yet (triangle ids are < 2^27).
 struct Trav {
     float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tmax, hu, hv;
-    uint32_t hid, oct_inv4;   // oct_inv4: bits 2..0 = 7 - octant, bits 31..8 = the three swap masks of lmb_xor_permute8
+    uint32_t hid, oct_inv4;   // oct_inv4: bits 2..0 = 7 - octant, bits 31..8 = shared address of the ray's row of the permutation table (trav_set_lut)
     uint32_t one;      // lmb_one_bits()
     uint2 ngroup;      // x: child_base; y: bits 31..24 pending internal children (priority order) | imask
-    uint2 pend;        // parked triangle group: x = first triangle, y = 24-bit mask
+    uint2 pend;        // parked leaf slots of one node: x = its first triangle unit, y = hit leaf-slot mask | 2-bit counts << 8 (0 = none)
     int sp;
 };
 
@@ -176,42 +180,49 @@ __device__ __forceinline__ void trav_init(Trav& T, const float4 ro, const float4
     // signs taken from the clamped reciprocal so that -0.0 picks the same near/far planes it scales
     const uint32_t oct = (T.idx < 0.f ? 1u : 0u) | (T.idy < 0.f ? 2u : 0u) | (T.idz < 0.f ? 4u : 0u);
     const uint32_t oi = 7u - oct;
-    T.oct_inv4 = oi | ((oi & 1u) ? 0x5500u : 0u) | ((oi & 2u) ? 0x330000u : 0u) | ((oi & 4u) ? 0x0f000000u : 0u);
+    T.oct_inv4 = oi;      // the table row is attached by trav_set_lut
     T.hu = 0.f; T.hv = 0.f; T.hid = 0xffffffffu;
     T.ngroup = make_uint2(0u, 0x80000000u);   // root: node 0 (imask 0 resolves to relative index 0)
     T.pend = make_uint2(0u, 0u);
     T.sp = 0;
 }
 
-// Shared-memory stack: entry e of thread t lives at shared address sm_base + 8 * (e * STRIDE + t) (conflict-free).
-// T.sp holds the SHARED-SPACE BYTE ADDRESS of the next free entry of this thread's column instead of a level index, so
-// a push / pop is one STS / LDS on that address plus an add (the index form made the compiler re-derive the column from
-// S2R on every push and pop: registers are too tight to keep it). The level is (T.sp - sm_base) / (8 * STRIDE), as
-// 8 * thread < 8 * STRIDE; sm_base is the shared-space address of the block's stack area, a compile-time constant.
+// Shared-memory stack: entry e of thread t lives at shared address sm_base + 8 * (e * STRIDE + t) (conflict-free), LMB_SM_STACK
+// levels, no overflow area (builds deeper than LMB_SM_STACK - 1 are refused by the host). T.sp holds the SHARED-SPACE BYTE
+// ADDRESS of the next free entry of the thread's column, and a sentinel entry ("no pending child") sits at the bottom of
+// every column: a pop of an empty stack returns the sentinel and leaves it in place. A push is one STS and an add, a pop one
+// LDS, a test and an add - neither needs the level or the column base (round 1 kept a level index, re-derived the column
+// from S2R on every push and pop and spilled levels >= 8 to local memory: ~16 more instructions per node step).
 template <int STRIDE>
-__device__ __forceinline__ uint32_t trav_level(const Trav& T, const uint32_t sm_base) { return ((uint32_t)T.sp - sm_base) / (8u * STRIDE); }
-template <int STRIDE>
-__device__ __forceinline__ void trav_push(Trav& T, const uint32_t sm_base, uint2* __restrict__ lstack, const uint2 v)
+__device__ __forceinline__ void trav_push(Trav& T, const uint32_t, uint2* __restrict__, const uint2 v)
 {
-    const uint32_t lvl = trav_level<STRIDE>(T, sm_base);
-    if (lvl < LMB_SM_STACK) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"((uint32_t)T.sp), "r"(v.x), "r"(v.y) : "memory");
-    else lstack[lvl - LMB_SM_STACK] = v;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"((uint32_t)T.sp), "r"(v.x), "r"(v.y) : "memory");
     T.sp += 8 * STRIDE;
 }
 template <int STRIDE>
-__device__ __forceinline__ uint2 trav_pop(Trav& T, const uint32_t sm_base, const uint2* __restrict__ lstack)
+__device__ __forceinline__ uint2 trav_pop(Trav& T, const uint32_t, const uint2* __restrict__)
 {
-    T.sp -= 8 * STRIDE;
-    const uint32_t lvl = trav_level<STRIDE>(T, sm_base);
     uint2 v;
-    if (lvl < LMB_SM_STACK) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)T.sp) : "memory");
-    else v = lstack[lvl - LMB_SM_STACK];
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)T.sp - 8u * STRIDE) : "memory");
+    if (v.y & 0xff000000u) T.sp -= 8 * STRIDE;
     return v;
 }
 template <int STRIDE>
-__device__ __forceinline__ bool trav_stack_empty(const Trav& T, const uint32_t sm_base) { return (uint32_t)T.sp - sm_base < 8u * STRIDE; }
-// to be called after trav_init: points T.sp at the calling thread's column
-__device__ __forceinline__ void trav_stack_reset(Trav& T, const uint32_t sm_base) { T.sp = (int)(sm_base + 8u * threadIdx.x); }
+__device__ __forceinline__ bool trav_stack_empty(const Trav&, const uint32_t) { return false; }      // a pop is always safe
+template <int STRIDE>
+__device__ __forceinline__ void trav_stack_reset_t(Trav& T, const uint32_t sm_base, const uint32_t column)
+{
+    const uint32_t a = sm_base + 8u * column;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %1};" :: "r"(a), "r"(0u) : "memory");
+    T.sp = (int)(a + 8u * STRIDE);
+}
+
+template <int STRIDE>
+__device__ __forceinline__ void trav_set_lut(Trav& T, const uint32_t sm_base)
+{
+    const uint32_t oi = T.oct_inv4 & 7u;
+    T.oct_inv4 = oi | ((sm_base + 8u * LMB_SM_STACK * STRIDE + (oi << 8)) << 8);
+}
 // shared-space address of a block's stack area (call it on the __shared__ array itself so that it folds to a constant)
 #define LMB_SM_BASE(arr) ((uint32_t)__cvta_generic_to_shared(arr))
 
@@ -251,20 +262,14 @@ __device__ __forceinline__ bool trav_step(Trav& T, const BvhDev& bvh,
         const uint32_t hits8 = lmb_intersect_node(px, py, pz, h[2], planes, T.ox, T.oy, T.oz, T.idx, T.idy, T.idz, T.tmin, T.tmax, T.one);
         const uint32_t imask = h[2] >> 24;
         T.ngroup.x = h[3];
-        T.ngroup.y = (lmb_xor_permute8(hits8 & imask, T.oct_inv4 >> 8) << 24) | imask;
-        // triangles of the hit leaf slots (rare: ~5 % of the node visits of an incoherent ray): two count bits per
-        // slot; the triangle units follow the node's internal children, in slot order
-        uint32_t leaf = hits8 & ~imask;
-        const uint32_t counts = h[1] >> 16;
+        uint32_t pr;      // hit internal children in traversal-priority order: one table lookup (trav_lut_init)
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pr) : "r"((T.oct_inv4 >> 8) + (hits8 & imask)));
+        T.ngroup.y = (pr << 24) | imask;
+        // hit leaf slots are parked as (first triangle unit of the node, slot mask | 2-bit counts << 8): the expansion into
+        // triangle offsets is left to the flush, which runs once per parked group instead of once per node step
+        const uint32_t leaf = hits8 & ~imask;
         fresh.x = h[3] + __popc(imask);
-        while (leaf) {
-            const uint32_t sl = __ffs(leaf) - 1;
-            leaf &= leaf - 1;
-            const uint32_t c = (counts >> (2u * sl)) & 3u;
-            const uint32_t below = counts & ~(0xffffffffu << (2u * sl));
-            const uint32_t off = __popc(below & 0x5555u) + 2u * __popc(below & 0xaaaau);
-            fresh.y |= ((1u << c) - 1u) << off;
-        }
+        fresh.y = leaf ? (leaf | (h[1] >> 16 << 8)) : 0u;
     }
     // next node group
     if ((T.ngroup.y & 0xff000000u) == 0u && !trav_stack_empty<STRIDE>(T, smem)) T.ngroup = trav_pop<STRIDE>(T, smem, lstack);
@@ -277,9 +282,22 @@ __device__ __forceinline__ bool trav_step(Trav& T, const BvhDev& bvh,
         const unsigned want = __ballot_sync(lanes, T.pend.y != 0u);
         const unsigned must = __ballot_sync(lanes, collide || (no_nodes && T.pend.y != 0u));
         if (must != 0u || __popc(want) >= LMB_TRI_BATCH) {
-            while (T.pend.y) {
-                const uint32_t i = __ffs(T.pend.y) - 1;
-                T.pend.y &= T.pend.y - 1;
+            // expand the parked slots into a mask of triangle offsets (the triangle units follow the node's internal
+            // children in slot order; two count bits per slot), then test them
+            uint32_t tmask = 0;
+            {
+                const uint32_t counts = T.pend.y >> 8;
+                for (uint32_t leaf = T.pend.y & 0xffu; leaf; leaf &= leaf - 1) {
+                    const uint32_t sl = __ffs(leaf) - 1;
+                    const uint32_t c = (counts >> (2u * sl)) & 3u;
+                    const uint32_t below = counts & ~(0xffffffffu << (2u * sl));
+                    tmask |= ((1u << c) - 1u) << (__popc(below & 0x5555u) + 2u * __popc(below & 0xaaaau));
+                }
+            }
+            T.pend.y = 0u;
+            while (tmask) {
+                const uint32_t i = __ffs(tmask) - 1;
+                tmask &= tmask - 1;
                 const float4* tp = bvh.units + (size_t)(T.pend.x + i) * 4u;
                 const float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
                 if (COUNT) cnt.tris++;
@@ -297,7 +315,7 @@ __device__ __forceinline__ bool trav_step(Trav& T, const BvhDev& bvh,
 }
 
 // Shared memory a block needs (uint2 entries): the per-thread short stacks.
-#define LMB_TRAV_SMEM_UINT2(block) (LMB_SM_STACK * (block))
+#define LMB_TRAV_SMEM_UINT2(block) (LMB_SM_STACK * (block) + LMB_LUT_UINT2)
 
 // Persistent-warp driver. `Io` supplies rays and consumes results:
 //   uint64_t count() const;                          number of rays
@@ -307,6 +325,8 @@ template <bool ANY, bool COUNT, int STRIDE, typename Io>
 __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
                                                  unsigned long long* __restrict__ counter, const uint32_t smem, TravCounters& cnt)
 {
+    trav_lut_init<STRIDE>(smem);
+    __syncthreads();
     const uint64_t n = io.count();
     const unsigned lane = threadIdx.x & 31u;
     uint2 lstack[LMB_LOCAL_STACK];
@@ -330,7 +350,8 @@ __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
                         float4 ro, rd;
                         io.load(i, ro, rd);
                         trav_init(T, ro, rd);
-                        trav_stack_reset(T, smem);
+                        trav_stack_reset_t<STRIDE>(T, smem, threadIdx.x);
+                        trav_set_lut<STRIDE>(T, smem);
                         ray_index = i;
                         active = true;
                     }
@@ -363,7 +384,8 @@ __device__ __forceinline__ bool lmb_traverse(const BvhDev& bvh,
 {
     uint2 lstack[LMB_LOCAL_STACK];
     trav_init(T, ro, rd);
-    trav_stack_reset(T, smem);
+    trav_stack_reset_t<STRIDE>(T, smem, threadIdx.x);
+    trav_set_lut<STRIDE>(T, smem);
     while (!trav_step<ANY, COUNT, STRIDE>(T, bvh, smem, lstack, cnt, __activemask())) {}
     return T.hid != 0xffffffffu;
 }

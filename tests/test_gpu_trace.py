@@ -11,6 +11,7 @@ from lmb200py import capi, scenes
 
 from test_oracle import SIMPLE_PS, SIMPLE_FS, SIMPLE2_PS, SIMPLE2_FS, TS, tri_verts, simple_rays, simple2_rays, interp
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 FLT_MAX = np.float32(3.4028234663852886e38)
@@ -283,6 +284,58 @@ def test_gpu_builder_same_hits_and_valid_structure(ntri, extent, edge, builder):
     assert num_tris == ntri and st["num_nodes"] == num_nodes
     idx = check_structure(units, num_nodes, num_tris, grid, verts, ob.PortScene(verts).records() if ntri else np.zeros((0, 12), np.uint32))
     assert sorted(idx.tolist()) == list(range(ntri))
+
+
+def _spiral_scene():
+    parts = []
+    for i in range(21):
+        c = np.float32(100.0 * 2.0 ** -i)
+        base = scenes.soup(24, seed=50 + i, extent=float(c) * 0.2, edge=float(c) * 0.05).reshape(-1, 3) + c
+        parts.append(base.reshape(-1, 9))
+    return np.ascontiguousarray(np.concatenate(parts), np.float32)
+
+
+def test_deep_device_tree_falls_back_to_the_host_builder():
+    """The traversal stack holds 16 levels; a device-built tree deeper than that is handed to the binned SAH builder (which
+    falls back to median splits), and a tree that is still too deep is refused - never walked. Exercised with
+    LMB200_DEPTH_LIMIT in a child process: clusters on an exponential spiral give a 9-level radix tree and an 8-level SAH tree."""
+    import subprocess
+    import sys
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from lmb200py import capi, scenes
+from oracle import bindings as ob
+from test_gpu_trace import _spiral_scene, gpu_closest, assert_bit_exact
+verts = _spiral_scene()
+A, G, H = capi.Accel(0), capi.Accel(0), capi.Accel(host_only=True)
+try:
+    sh = H.build(verts)
+except capi.LmbError:
+    sh = {'num_nodes': -1}
+try:
+    G.build(verts, builder=capi.BUILD_HOST_SAH); print('HOST', 'ok')
+except capi.LmbError as e:
+    print('HOST', 'refused' if 'exceeds the traversal stack' in str(e) else e)
+try:
+    st = A.build(verts)
+    print('DEFAULT', st['max_depth'], st['num_nodes'] == sh['num_nodes'])
+    lo, hi = scenes.bounds(verts)
+    rays = scenes.random_rays(20000, lo, hi, seed=3)
+    assert_bit_exact(*gpu_closest(A, rays), *ob.PortScene(verts).closest(rays, use_bvh=False))
+    print('HITS ok')
+except capi.LmbError as e:
+    print('DEFAULT', 'refused' if 'exceeds the traversal stack' in str(e) else e)
+""" % (ROOT, os.path.join(ROOT, "tests"))
+    out = {}
+    for limit in ("16", "8", "7"):
+        env = dict(os.environ, LMB200_DEPTH_LIMIT=limit, PYTHONPATH=os.path.join(ROOT, "lightmetrica-v2_b200"))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
+        out[limit] = r.stdout
+    assert "DEFAULT 9 False" in out["16"] and "HITS ok" in out["16"]              # the device tree itself (9 levels)
+    assert "DEFAULT 8 True" in out["8"] and "HITS ok" in out["8"] and "HOST ok" in out["8"]      # fell back to the host tree
+    assert "DEFAULT refused" in out["7"] and "HOST refused" in out["7"]            # nothing fits: an error, not a walk
 
 
 def test_gpu_builder_large_and_degenerate():
