@@ -6,9 +6,9 @@
 //     (warp-level fetch: one atomicAdd per refill for all idle lanes) instead of idling until the
 //     slowest ray of its warp is done,
 //   * one thread per ray, (node-group, triangle-group) pairs in registers and a short stack of
-//     8-byte entries in shared memory (overflow to local memory),
+//     8-byte entries in shared memory (16 levels, a sentinel at the bottom; deeper trees are refused by the host),
 //   * a node is one 64-byte-aligned unit fetched with two 256-bit loads (two sectors of one line),
-//   * triangle tests are batched across the warp (parked per lane until LMB_TRI_BATCH lanes have
+//   * triangle tests are batched across the warp (parked per lane until some lane has to flush: then all lanes that have
 //     some), so the triangle code runs with many lanes instead of ~2.
 #pragma once
 #include <cuda_runtime.h>
@@ -24,9 +24,6 @@ namespace lmb200 {
 #define LMB_LOCAL_STACK 1       // (no overflow area any more; the array argument is kept for the call sites)
 #ifndef LMB_REFILL_BELOW
 #define LMB_REFILL_BELOW 26     // refill the warp when fewer lanes than this are active
-#endif
-#ifndef LMB_TRI_BATCH
-#define LMB_TRI_BATCH 12         // test parked triangles once this many lanes have some
 #endif
 
 struct TravCounters { uint32_t nodes, tris; };
@@ -226,10 +223,13 @@ __device__ __forceinline__ void trav_set_lut(Trav& T, const uint32_t sm_base)
 // shared-space address of a block's stack area (call it on the __shared__ array itself so that it folds to a constant)
 #define LMB_SM_BASE(arr) ((uint32_t)__cvta_generic_to_shared(arr))
 
-// One traversal step of an active lane: open the nearest pending node, then maybe test triangles.
-// Triangle work is batched across the warp: the triangles hit by a node test are parked in a
-// per-lane pending group (two registers) and tested only when at least LMB_TRI_BATCH lanes have
-// parked work, or when some lane must (it hit a second group, or it has nothing else left to do).
+// One traversal step: open the nearest pending node, then maybe test triangles. Every lane of the warp takes every step
+// (`lanes` = the full mask; a lane without a ray is in the finished state and its step does nothing), the per-ray service
+// calls it from a single lane.
+// Triangle work is batched across the warp: the leaf slots hit by a node test are parked in a per-lane pending group
+// (two registers) and tested only when some lane must (it hit a second group, or it has nothing else left to do) - then
+// by every lane that has parked work. (A second trigger, "at least N lanes have parked work", made no difference for N
+// between 8 and 24 and was dropped.)
 // Incoherent rays reach a leaf on ~5 % of their node visits, so testing at once would run the
 // triangle code on ~80 % of the warp's steps with ~2 of 32 lanes active (ncu, profiles/).
 // Returns true when the ray is finished. Closest hit: tie on t -> larger triangle index wins, which
@@ -279,9 +279,8 @@ __device__ __forceinline__ bool trav_step(Trav& T, const BvhDev& bvh,
     const bool collide = T.pend.y != 0u && fresh.y != 0u;
     if (T.pend.y == 0u) { T.pend = fresh; fresh.y = 0u; }
     {
-        const unsigned want = __ballot_sync(lanes, T.pend.y != 0u);
         const unsigned must = __ballot_sync(lanes, collide || (no_nodes && T.pend.y != 0u));
-        if (must != 0u || __popc(want) >= LMB_TRI_BATCH) {
+        if (must != 0u) {
             // expand the parked slots into a mask of triangle offsets (the triangle units follow the node's internal
             // children in slot order; two count bits per slot), then test them
             uint32_t tmask = 0;
@@ -334,6 +333,12 @@ __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
     bool active = false;
     bool exhausted = false;      // warp-uniform: the work counter has run past n
     uint64_t ray_index = 0;
+    // every lane takes every step (a lane without a ray is in the "finished" state: nothing pending, empty stack, nothing
+    // parked - its step does nothing), so the warp votes of a step use the full mask
+    T.ngroup = make_uint2(0u, 0u); T.pend = make_uint2(0u, 0u); T.oct_inv4 = 0u; T.hid = 0xffffffffu;
+    T.ox = T.oy = T.oz = T.dx = T.dy = T.dz = T.idx = T.idy = T.idz = T.tmin = T.tmax = T.hu = T.hv = 0.f; T.one = lmb_one_bits();
+    trav_stack_reset_t<STRIDE>(T, smem, threadIdx.x);
+    trav_set_lut<STRIDE>(T, smem);
 
     for (;;) {
         // ---- refill idle lanes (all 32 lanes converge here) ----
@@ -364,11 +369,11 @@ __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
         // ---- traverse until enough lanes have finished to make a refill worthwhile ----
         unsigned live = __ballot_sync(0xffffffffu, active);
         for (;;) {
-            if (active) {
-                if (trav_step<ANY, COUNT, STRIDE>(T, bvh, smem, lstack, cnt, live)) {
-                    io.store(ray_index, T);
-                    active = false;
-                }
+            if (trav_step<ANY, COUNT, STRIDE>(T, bvh, smem, lstack, cnt, 0xffffffffu) && active) {
+                io.store(ray_index, T);
+                active = false;
+                T.ngroup.y = 0u; T.pend.y = 0u;      // (an any-hit ray leaves early: put the lane into the finished state)
+                trav_stack_reset_t<STRIDE>(T, smem, threadIdx.x);
             }
             live = __ballot_sync(0xffffffffu, active);
             if (live == 0u) break;

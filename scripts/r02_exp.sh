@@ -1,2 +1,3 @@
 #!/bin/bash
-python -m pytest tests/test_gpu_trace.py -q -x -k "deep_device" 2>&1 | tail -30
+python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+python scripts/gpu_sweep.py 2>&1 | cut -c1-330
