@@ -3,4 +3,5 @@
 mkdir -p gpurun_out
 ( timeout 900 compute-sanitizer --tool memcheck --target-processes all python -m pytest tests/test_gpu_trace.py tests/test_gpu_render.py -q -x -k "not full_size and not large_and_degenerate and not 200000 and not config" 2>&1 | grep -v "^$" | tail -8 ) > gpurun_out/r02_sanitizer.txt 2>&1
 ( timeout 600 compute-sanitizer --tool racecheck --target-processes all python -m pytest tests/test_gpu_render.py -q -x -k "same_samples_as_oracle and cornell or coherent_camera" 2>&1 | grep -v "^$" | tail -6 ) >> gpurun_out/r02_sanitizer.txt 2>&1
+( timeout 600 compute-sanitizer --tool racecheck --target-processes all python -m pytest tests/test_gpu_trace.py -q -x -k "known_answers or golden_vectors or edge_cases or axis_aligned or compact_wire" 2>&1 | grep -v "^$" | tail -6 ) >> gpurun_out/r02_sanitizer.txt 2>&1
 cat gpurun_out/r02_sanitizer.txt

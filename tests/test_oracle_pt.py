@@ -177,3 +177,18 @@ def test_reference_obj_loader_route_equals_in_memory_meshes():
     a, _ = ob.RefScene(sc, accel="qbvh", obj_paths=paths).render("ptdirect", N, seed=4, threads=1)
     b, _ = ob.RefScene(sc, accel="qbvh").render("ptdirect", N, seed=4, threads=1)
     assert np.array_equal(a, b) and a.mean() > 0
+
+
+def test_port_matches_the_reference_on_the_config2_scene():
+    """configs[2] (1M triangles, diffuse + glossy, area-light NEE) at 480x270, 64 spp: the C port against the reference's
+    renderer::ptdirect + accel::qbvh golden (tests/golden/make_golden.py config2). Statistic: 6x6 block means of the image
+    with pixels clamped at 2 (the raw means are firefly-dominated); bar: 1.25x the reference's own two-seed floor, global
+    mean within 2 %."""
+    from lmb200py import capi
+    g = np.load(os.path.join(GOLD, "config2_480x270_blockmeans.npz"))
+    ra, rb = g["ptdirect_clamped_a"], g["ptdirect_clamped_b"]
+    floor = float(np.sqrt(np.mean((ra - rb) ** 2)) / np.mean(rb))
+    img, _ = ob.PortPT(scenedesc.config2_scene(1_000_000, 480, 270)).render(capi.MODE_PTDIRECT, 480 * 270 * 64, seed=9)
+    bm = np.minimum(img, 2.0).reshape(45, 6, 80, 6, 3).mean(axis=(1, 3))
+    assert float(np.sqrt(np.mean((bm - ra) ** 2)) / np.mean(ra)) < 1.25 * floor
+    assert np.allclose(bm.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.02)
