@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/r02_gpus8.txt
 python -m pytest tests -q -m gpu -rfs 2>&1 | tail -8 > gpurun_out/r02_pytest_gpu8.log
 tail -4 gpurun_out/r02_pytest_gpu8.log
-for n in 8 2; do
+for n in ${R02_NS:-8 2}; do
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/r02_bench$n.json 2> gpurun_out/r02_bench$n.err
 python - <<PY
 import json
