@@ -36,6 +36,8 @@ def port():
         L.orc_wide_closest.restype = C.c_longlong
         L.orc_wide_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         L.orc_wide_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        L.orc_wide_count_sorted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        L.orc_wide_count_cull.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
         L.orc_triaccel_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_triaccel_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -123,6 +125,26 @@ def wide_count(units, grid, rays):
     out = np.zeros(2, np.float64)
     port().orc_wide_count(_p(units), _p(g), _p(rays), rays.shape[0], _p(out))
     return out[0] / rays.shape[0], out[1] / rays.shape[0]
+
+
+def wide_count_sorted(units, grid, rays):
+    """(nodes, triangle records, entries dropped at pop time) per ray of an EXACT front-to-back walk with entry-distance cull:
+    what an ideally ordered traversal of the same tree would fetch (analysis only)."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    g = np.ascontiguousarray(np.concatenate([grid[0], grid[1]]), np.float32)
+    out = np.zeros(3, np.float64)
+    port().orc_wide_count_sorted(_p(units), _p(g), _p(rays), rays.shape[0], _p(out))
+    return tuple(out / rays.shape[0])
+
+
+def wide_count_cull(units, grid, rays, mode):
+    """orc_wide_count's octant-ordered walk with an entry-distance cull (mode 1: one bound per stacked sibling group, mode 2: per
+    child): (nodes, triangle records, children dropped unfetched) per ray. Analysis only."""
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    g = np.ascontiguousarray(np.concatenate([grid[0], grid[1]]), np.float32)
+    out = np.zeros(3, np.float64)
+    port().orc_wide_count_cull(_p(units), _p(g), _p(rays), rays.shape[0], int(mode), _p(out))
+    return tuple(out / rays.shape[0])
 
 
 def mesh_scene_yaml(handle, accel="qbvh", w=16, h=16):

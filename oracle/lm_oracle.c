@@ -422,3 +422,134 @@ void orc_wide_count(const void* units64, const float* grid, const float* rays, l
     }
     out[0] = tn_nodes; out[1] = tn_tris;
 }
+
+/* Analysis only (scripts/cpu_tree_quality.py): the same tree walked in EXACT front-to-back order - hit internal children
+ * pushed individually with their entry distance, farthest first, and dropped at pop time when the entry distance has
+ * fallen behind the closest hit. Counts what an ideally ordered traversal would fetch; the distance between this and
+ * orc_wide_count is what the octant slot order and the missing entry-distance cull leave on the table.
+ * out[0] = nodes, out[1] = triangle records, out[2] = entries dropped at pop time. */
+struct orc_sorted_entry { uint32_t unit; double tn; };
+void orc_wide_count_sorted(const void* units64, const float* grid, const float* rays, long long n, double* out)
+{
+    const orc_node64* units = (const orc_node64*)units64;
+    double tn_nodes = 0, tn_tris = 0, tn_drop = 0;
+    long long i;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : tn_nodes, tn_tris, tn_drop)
+    for (i = 0; i < n; i++) {
+        const float* r = rays + 8 * i;
+        const float* o = r; const float* d = r + 4;
+        const float mint = r[3];
+        float maxt = r[7];
+        int32_t best = -1;
+        struct orc_sorted_entry stack[512];
+        int sp = 0;
+        stack[sp].unit = 0; stack[sp].tn = mint; sp++;
+        while (sp) {
+            const orc_node64* nd;
+            uint32_t nint, rel = 0;
+            int s, first, a, b;
+            sp--;
+            if (stack[sp].tn > maxt) { tn_drop += 1; continue; }
+            nd = &units[stack[sp].unit];
+            tn_nodes += 1;
+            nint = orc_popc8(nd->imask);
+            first = sp;
+            for (s = 0; s < 8; s++) {
+                const int internal = (nd->imask >> s) & 1;
+                const uint32_t cnt = (nd->counts >> (2 * s)) & 3u;
+                double tnear = 0;
+                const int hit = orc_slot_hit(nd, grid, s, o, d, mint, maxt, &tnear);
+                if (internal) { const uint32_t child = nd->base + rel; rel++; if (hit && sp < 512) { stack[sp].unit = child; stack[sp].tn = tnear; sp++; } }
+                else if (cnt && hit) {
+                    const uint32_t off = orc_slot_tri_offset(nd, s);
+                    uint32_t k;
+                    for (k = 0; k < cnt; k++) {
+                        const orc_tri* T = &((const orc_triunit*)&units[nd->base + nint + off + k])->rec;
+                        float t, u, v;
+                        tn_tris += 1;
+                        if (orc_triaccel_intersect(T, o, d, mint, maxt, &u, &v, &t)) {
+                            const int32_t id = (int32_t)T->faceIndex;
+                            if (t < maxt || best < 0 || id > best) { maxt = t; best = id; }
+                        }
+                    }
+                }
+            }
+            /* the children just pushed: farthest at the bottom, nearest on top */
+            for (a = first + 1; a < sp; a++) {
+                const struct orc_sorted_entry key = stack[a];
+                for (b = a; b > first && stack[b - 1].tn < key.tn; b--) stack[b] = stack[b - 1];
+                stack[b] = key;
+            }
+        }
+    }
+    out[0] = tn_nodes; out[1] = tn_tris; out[2] = tn_drop;
+}
+
+/* Analysis only: orc_wide_count's octant-ordered walk with an entry-distance cull.
+ * mode 1: one lower bound per stacked sibling group = the smallest entry distance among the children still pending when the
+ *         group is pushed; the whole group is dropped at pop time when that bound lies behind the closest hit;
+ * mode 2: every pending child keeps its own entry distance and is dropped individually (the most a cull can do in this order).
+ * out[0] = nodes, out[1] = triangle records, out[2] = children dropped unfetched. */
+void orc_wide_count_cull(const void* units64, const float* grid, const float* rays, long long n, int mode, double* out)
+{
+    const orc_node64* units = (const orc_node64*)units64;
+    double tn_nodes = 0, tn_tris = 0, tn_drop = 0;
+    long long i;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : tn_nodes, tn_tris, tn_drop)
+    for (i = 0; i < n; i++) {
+        const float* r = rays + 8 * i;
+        const float* o = r; const float* d = r + 4;
+        const float mint = r[3];
+        float maxt = r[7];
+        int32_t best = -1;
+        const uint32_t oct = (d[0] < 0 ? 1u : 0u) | (d[1] < 0 ? 2u : 0u) | (d[2] < 0 ? 4u : 0u);
+        const uint32_t oi = 7u - oct;
+        struct { uint32_t base, pend, imask; double tn[8]; } stack[256], g;      /* tn indexed by priority bit */
+        int sp = 0, k;
+        g.base = 0; g.pend = 0x80u; g.imask = 0;
+        for (k = 0; k < 8; k++) g.tn[k] = mint;
+        for (;;) {
+            if (!g.pend) { if (!sp) break; g = stack[--sp]; continue; }
+            {
+                uint32_t bit = 7; const orc_node64* nd; uint32_t slot, rel, nint, hits8 = 0, pr = 0; int s;
+                double ctn[8];
+                if (mode == 1) {
+                    /* group bound: all pending children behind the hit -> drop them together */
+                    double m = 1e300; int cnt = 0;
+                    for (k = 0; k < 8; k++) if ((g.pend >> k) & 1u) { if (g.tn[k] < m) m = g.tn[k]; cnt++; }
+                    if (m > maxt) { tn_drop += cnt; g.pend = 0; continue; }
+                }
+                while (!((g.pend >> bit) & 1u)) bit--;
+                g.pend &= ~(1u << bit);
+                if (mode == 2 && g.tn[bit] > maxt) { tn_drop += 1; continue; }
+                if (g.pend && sp < 256) stack[sp++] = g;
+                slot = bit ^ oi;
+                rel = orc_popc8(g.imask & ((1u << slot) - 1u));
+                nd = &units[g.base + rel];
+                tn_nodes += 1;
+                nint = orc_popc8(nd->imask);
+                for (s = 0; s < 8; s++) { ctn[s] = 0; if (orc_slot_hit(nd, grid, s, o, d, mint, maxt, &ctn[s])) hits8 |= 1u << s; }
+                for (s = 0; s < 8; s++) {
+                    const uint32_t cnt = (nd->counts >> (2 * s)) & 3u;
+                    if (!((hits8 >> s) & 1u) || ((nd->imask >> s) & 1u) || !cnt) continue;
+                    {
+                        const uint32_t off = orc_slot_tri_offset(nd, s);
+                        uint32_t q;
+                        for (q = 0; q < cnt; q++) {
+                            const orc_tri* T = &((const orc_triunit*)&units[nd->base + nint + off + q])->rec;
+                            float t, u, v;
+                            tn_tris += 1;
+                            if (orc_triaccel_intersect(T, o, d, mint, maxt, &u, &v, &t)) {
+                                const int32_t id = (int32_t)T->faceIndex;
+                                if (t < maxt || best < 0 || id > best) { maxt = t; best = id; }
+                            }
+                        }
+                    }
+                }
+                for (s = 0; s < 8; s++) if (((hits8 & nd->imask) >> s) & 1u) { pr |= 1u << (s ^ oi); g.tn[s ^ oi] = ctn[s]; }
+                g.base = nd->base; g.pend = pr; g.imask = nd->imask;
+            }
+        }
+    }
+    out[0] = tn_nodes; out[1] = tn_tris; out[2] = tn_drop;
+}

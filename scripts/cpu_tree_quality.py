@@ -22,3 +22,8 @@ for name, verts in (("soup", scenes.soup(ns, seed=42, extent=100.0, edge=0.2) if
     npr, tpr = ob.wide_count(units, grid, rays)
     print(f"{name}: {len(verts)} tris, build {bt:.1f} s, {nn} nodes ({len(verts)/nn:.2f} tris/node), depth {st['max_depth']}, sah {st['sah_cost']:.2f}: "
           f"{npr:.2f} nodes/ray, {tpr:.2f} tris/ray, bytes/ray {48 + 64*npr + 48*tpr:.0f}")
+    sn, stt, sd = ob.wide_count_sorted(units, grid, rays)
+    for mode, what in ((1, "octant order + one entry-distance bound per stacked group"), (2, "octant order + entry distance per child")):
+        cn, ct, cd = ob.wide_count_cull(units, grid, rays, mode)
+        print(f"    {what}: {cn:.2f} nodes/ray, {ct:.2f} tris/ray, {cd:.2f} children dropped unfetched")
+    print(f"    exact front-to-back order with entry-distance cull: {sn:.2f} nodes/ray, {stt:.2f} tris/ray, {sd:.2f} entries dropped unfetched")
