@@ -99,7 +99,8 @@ int lmb200_accel_build_ex(lmb200_accel* a, const float* verts, uint64_t ntris, i
 /* Replaces Accel3::Intersect (accel3.h:68; accel_qbvh.cpp:398-497) for a batch of n rays.
  * Closest hit with the reference's acceptance rule (reject t<tmin or t>tmax, triaccel.h:137);
  * on exact ties in t the triangle with the larger index wins (= accel::naive's scan order,
- * accel_naive.cpp:92-124). */
+ * accel_naive.cpp:92-124). A ray with a NaN or infinite origin / direction component reports a miss (every comparison
+ * of the reference's triangle test fails on it) without walking the tree. */
 int lmb200_trace_closest(lmb200_accel* a, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n);
 int lmb200_trace_closest_dev(lmb200_accel* a, const void* rays_dev, void* hits_dev, uint64_t n, void* stream);
 

@@ -110,6 +110,8 @@ __device__ __forceinline__ bool wide_traverse(const BvhDev& bvh, const float4 ro
 {
     const unsigned lane = threadIdx.x & 31u;
     const float ox = ro.x, oy = ro.y, oz = ro.z, tmin = ro.w, dx = rd.x, dy = rd.y, dz = rd.z;
+    // a ray with NaN or infinite components is a miss (trav_init does the same for the lane-ordered walk)
+    if (!((ox * 0.f + oy * 0.f + oz * 0.f + dx * 0.f + dy * 0.f + dz * 0.f) == 0.f)) { result = make_float4(0.f, 0.f, 0.f, __uint_as_float(LMB200_MISS)); return true; }
     const float idx = lmb_safe_inv(dx), idy = lmb_safe_inv(dy), idz = lmb_safe_inv(dz);
     const uint32_t oct = (idx < 0.f ? 1u : 0u) | (idy < 0.f ? 2u : 0u) | (idz < 0.f ? 4u : 0u);
     const uint32_t oi = 7u - oct;

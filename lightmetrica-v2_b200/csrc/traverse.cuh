@@ -179,7 +179,11 @@ __device__ __forceinline__ void trav_init(Trav& T, const float4 ro, const float4
     const uint32_t oi = 7u - oct;
     T.oct_inv4 = oi;      // the table row is attached by trav_set_lut
     T.hu = 0.f; T.hv = 0.f; T.hid = 0xffffffffu;
-    T.ngroup = make_uint2(0u, 0x80000000u);   // root: node 0 (imask 0 resolves to relative index 0)
+    // A ray with a NaN or infinite origin / direction component never hits anything (every comparison of the triangle test
+    // fails) but its slab tests would not cull anything either - NaNs drop out of the min / max - and the walk would
+    // visit the whole tree. Such a ray starts in the finished state and reports a miss.
+    const bool finite = (ro.x * 0.f + ro.y * 0.f + ro.z * 0.f + rd.x * 0.f + rd.y * 0.f + rd.z * 0.f) == 0.f;
+    T.ngroup = make_uint2(0u, finite ? 0x80000000u : 0u);   // root: node 0 (imask 0 resolves to relative index 0)
     T.pend = make_uint2(0u, 0u);
     T.sp = 0;
 }

@@ -2,6 +2,7 @@
 closest-hit triangle index bit-exact, t/u/v bit-exact (bar: 1e-5 relative; we hold the stronger one)."""
 import ctypes as C
 import os
+import time
 
 import numpy as np
 import pytest
@@ -106,6 +107,26 @@ def test_edge_cases():
     tuv_o, tri_o = ob.PortScene(verts).closest(rays)
     assert_bit_exact(tuv, tri, tuv_o, tri_o)
     assert tri[0] == 24 and tri[1] == -1 and tri[2] == 24 and tri[3] == 24 and tri[4] == -1
+    # rays with NaN or infinite components are misses, in the batch calls and through the per-ray service, and do not walk the
+    # whole tree (NaN slab distances drop out of the min / max, so nothing would be culled): 100k of them return at once
+    bad = np.array([[np.nan, 0.2, 1, 0, 0, 0, -1, FLT_MAX], [0.2, 0.2, 1, 0, np.nan, 0, -1, FLT_MAX],
+                    [0.2, 0.2, 1, 0, 0, 0, -np.inf, FLT_MAX], [np.inf, 0.2, 1, 0, 0, 0, -1, FLT_MAX]], np.float32)
+    assert (gpu_closest(A, bad)[1] == -1).all() and (A.trace_any(bad) == 0).all()
+    assert (ob.PortScene(verts).closest(bad[:2])[1] == -1).all()
+    big = scenes.soup(200_000, seed=3, extent=10.0, edge=0.2)
+    A.build(big)
+    many = np.repeat(bad, 25_000, axis=0)
+    many[::7] = [5, 5, 5, 0, 0.3, 0.5, 0.8, FLT_MAX]
+    t0 = time.perf_counter()
+    tri_many = gpu_closest(A, many)[1]
+    assert time.perf_counter() - t0 < 5.0
+    assert (tri_many[np.arange(len(many)) % 7 != 0] == -1).all() and (tri_many[::7] == tri_many[0]).all()
+    L = capi.lib()
+    one = np.zeros(1, capi.HIT_DTYPE)
+    for k in range(8):        # both service traversals (the worker warp alternates between them while it is sampling)
+        r = np.ascontiguousarray(bad[k % 4:k % 4 + 1])
+        capi.check(L.lmb200_trace_closest_one(A.h, r.ctypes.data_as(C.c_void_p), one.ctypes.data_as(C.c_void_p)))
+        assert one["tri"][0] == capi.MISS
 
 
 def test_axis_aligned_rays_and_boxes():
