@@ -14,6 +14,10 @@
  *     (a cudaStream_t passed as void*, NULL = the legacy default stream) without synchronising.
  *     The plain entry points take HOST pointers and do the H2D/D2H copies themselves.
  *   - there is no CPU fallback: a build without a usable CUDA device fails with LMB200_E_CUDA.
+ *   - threads: lmb200_trace_closest_one may be called from any number of host threads at once (one mailbox each);
+ *     the host-buffer batch calls on one accel take turns (they share its staging buffers); *_dev calls on different
+ *     streams may overlap (each gets its own work counter); build / destroy must not run beside other calls on the
+ *     same object. A scene renders one job at a time: concurrent render calls on one scene take turns.
  */
 #ifndef LMB200_H
 #define LMB200_H

@@ -229,6 +229,7 @@ static int trace_host(Accel* a, const void* rays_v, void* out, uint64_t n, float
     if (a->host_only) return set_error(LMB200_E_STATE, "host-only accel cannot trace");
     if (!a->d_units) return set_error(LMB200_E_STATE, "accel not built");
     if (n == 0) return LMB200_OK;
+    std::lock_guard<std::mutex> lock(a->stage_mu);
     cudaError_t e = cudaSetDevice(a->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     const size_t out_elem = ANY ? 1 : sizeof(lmb200_hit);

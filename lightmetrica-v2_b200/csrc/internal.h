@@ -51,6 +51,7 @@ struct Accel {
     void* stage_out[LMB_NBUF] = {};
     cudaEvent_t events[3 * LMB_NBUF] = {};
     uint64_t stage_cap = 0;
+    std::mutex stage_mu;          // host-buffer calls on one accel take turns: they share the staging buffers and streams
 
     Service* service = nullptr;   // per-ray Accel3::Intersect service, created on first use
     std::mutex service_mu;

@@ -935,6 +935,7 @@ struct Scene {
     // k_shadow runs on its own stream beside k_bsdf / k_extend of the same iteration (tail filling)
     cudaStream_t shadow_stream = nullptr;
     cudaEvent_t ev_nee = nullptr, ev_shadow = nullptr;
+    std::recursive_mutex job_mu;      // a scene renders one job at a time (pool, film, counters and streams are per scene)
 
     ~Scene()
     {
@@ -1029,6 +1030,7 @@ static int render_normal(Scene* s, float4* film, cudaStream_t st, int pix0, int 
 // pix0 / npix: MODE_NORMAL only, the pixel range this call renders (npix < 0: the whole image)
 static int render_dev(Scene* s, const lmb200_render_params* p, void* film_dev, cudaStream_t st, lmb200_render_stats* stats, int pix0 = 0, int npix = -1)
 {
+    std::lock_guard<std::recursive_mutex> job(s->job_mu);
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     float4* film = reinterpret_cast<float4*>(film_dev);
@@ -1333,6 +1335,7 @@ int lmb200_render(lmb200_scene* h, const lmb200_render_params* p, float* film_ho
     Scene* s = reinterpret_cast<Scene*>(h);
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    std::lock_guard<std::recursive_mutex> job(s->job_mu);
     const int64_t npx = (int64_t)s->dev.width * s->dev.height;
     // the device film lives as long as the scene (a renderer calls this once per frame / progress image)
     if (s->film_cap < npx) {

@@ -82,6 +82,26 @@ def test_pool_size_and_sharding_invariance():
     assert rel_rmse(c, a) > 1e-2          # a different seed is a different sample set
 
 
+def test_render_calls_from_two_threads_on_one_scene_take_turns():
+    """A scene owns one path pool, film and set of counters: concurrent lmb200_render calls on it are serialised inside the
+    library and each returns the image of its own parameters."""
+    import threading
+    sc = scenedesc.cornell_box(48, 48, glossy_block=True)
+    S = capi.Scene(sc)
+    N = 48 * 48 * 64
+    want = [S.render(capi.MODE_PTDIRECT, N, seed=11 + k)[0] for k in range(3)]
+    got = [None] * 3
+
+    def work(k):
+        for _ in range(3):
+            got[k] = S.render(capi.MODE_PTDIRECT, N, seed=11 + k)[0]
+    th = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    for t in th: t.start()
+    for t in th: t.join()
+    for k in range(3):
+        assert same_image(got[k], want[k])
+
+
 def test_max_num_vertices_and_empty_range():
     sc = scenedesc.cornell_box(32, 32)
     S = capi.Scene(sc)

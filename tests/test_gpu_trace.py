@@ -194,6 +194,31 @@ def test_compact_wire_form_equals_full_form():
     assert L.lmb200_trace_closest_compact(A.h, None, 0.0, 1.0, None, 5) == -1
 
 
+def test_host_buffer_calls_from_several_threads_on_one_accel():
+    """The host-buffer batch calls of one accel share its staging buffers: concurrent calls from several host threads take
+    turns and every one of them gets the hits of its own rays."""
+    import threading
+    verts = scenes.soup(60000, seed=14, extent=9.0, edge=0.3)
+    lo, hi = scenes.bounds(verts)
+    A = capi.Accel(0)
+    A.build(verts)
+    batches = [scenes.random_rays(150_000 + 1000 * k, lo, hi, seed=20 + k) for k in range(6)]
+    want = [A.trace_closest(b) for b in batches]
+    got = [None] * len(batches)
+    occ = [None] * len(batches)
+
+    def work(k):
+        for _ in range(3):
+            got[k] = A.trace_closest(batches[k])
+            occ[k] = A.trace_any(batches[k])
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(batches))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for k in range(len(batches)):
+        assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32))
+        assert np.array_equal(occ[k].astype(bool), want[k]["tri"] != capi.MISS)
+
+
 def test_per_ray_service_many_threads_and_restart():
     """The per-ray Accel3::Intersect path (persistent service kernel + mailboxes): 16 host threads posting rays
     concurrently get bit-identical hits to the batch call; the service survives going idle (it exits after 2 ms without
