@@ -330,6 +330,11 @@ def main():
     full_hits = h_hits[:4096].clone()
     e2e_value = e2e_leg(lambda: capi.check(L.lmb200_trace_closest_compact(accel.h, h_rays24.data_ptr(), 1e-4, 3.4028234663852886e38, h_hits.data_ptr(), a.rays)))
     assert torch.equal(full_hits.view(torch.int32), h_hits[:4096].view(torch.int32)), "compact and full wire forms disagree"
+    # every hit of the host-buffer call against the device-resident launch of the same rays, bit for bit (d_hits holds the last timed step)
+    e2e_same = True
+    for lo_i in range(0, a.rays, 1 << 24):
+        hi_i = min(a.rays, lo_i + (1 << 24))
+        e2e_same = e2e_same and bool(torch.equal(h_hits[lo_i:hi_i].to(dev, non_blocking=False).view(torch.int32), d_hits[lo_i:hi_i].view(torch.int32)))
 
     # ---- roofline of the traversal kernel ----
     npr, tpr = C.c_double(), C.c_double()
@@ -396,6 +401,8 @@ def main():
                         "api": "lmb200_trace_closest_compact(host pinned 24-byte rays + shared [tmin, tmax] -> host pinned hits)", "host_affinity": numa,
                         "gbs": e2e_value * 1e6 * 40 / 1e9, "pcie_ceiling_gbs": ceiling, "frac_of_pcie_ceiling": e2e_value * 1e6 * 40 / 1e9 / ceiling,
                         "frac_of_device_rate": e2e_value / value,
+                        "all_hits_equal_device_launch": e2e_same,
+                        "launch": "one persistent launch per call, rays taken chunk by chunk as their uploads land (LMB200_E2E_STREAM=0: one launch per chunk)",
                         "pcie_ceiling_how": "concurrent pinned H2D + D2H torch copies (2:1 bytes) of the bench's own buffers, all ranks at once; the call is bound by min(this ceiling, the kernel rate)",
                         "full_ray_form": {"value": e2e_full, "unit": UNIT, "h2d_bytes_per_step": a.rays * 32, "d2h_bytes_per_step": a.rays * 16,
                                           "api": "lmb200_trace_closest(32-byte rays with per-ray range)", "gbs": e2e_full * 1e6 * 48 / 1e9}},

@@ -3,9 +3,11 @@
 // (/root/reference/src/liblightmetrica/accel/accel_qbvh.cpp:152-497) for ray BATCHES.
 #include "internal.h"
 #include <cstdlib>
+#include <cstdio>
 #include "traverse.cuh"
 
 #include <chrono>
+#include <immintrin.h>
 #include <cstring>
 #include <vector>
 
@@ -95,6 +97,51 @@ trace_kernel(const BvhDev bvh,
     }
 }
 
+// Streaming form (trace_host_stream): rays and results live in RINGS over the global ray index (slot = index & mask), filled
+// and emptied by the host while the kernel runs. A ring slot is reused within one launch, so the rays are read past L1 (ld.cg).
+template <typename Out, bool COMPACT>
+struct StreamIo {
+    const void* __restrict__ rays; Out* __restrict__ out; uint64_t n, mask; float tmin, tmax;
+    __device__ __forceinline__ uint64_t count() const { return n; }
+    __device__ __forceinline__ void load(uint64_t i, float4& ro, float4& rd) const
+    {
+        const uint64_t r = i & mask;
+        if (COMPACT) {
+            const float2* p = reinterpret_cast<const float2*>(rays) + 3 * r;
+            const float2 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2);
+            ro = make_float4(a.x, a.y, b.x, tmin); rd = make_float4(b.y, c.x, c.y, tmax);
+        } else {
+            const float4* p = reinterpret_cast<const float4*>(rays) + 2 * r;
+            ro = __ldcg(p); rd = __ldcg(p + 1);
+        }
+    }
+    __device__ __forceinline__ void store(uint64_t i, const Trav& T) const;
+};
+template <> __device__ __forceinline__ void StreamIo<float4, false>::store(uint64_t i, const Trav& T) const
+{ out[i & mask] = make_float4(T.hid != LMB200_MISS ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid)); }
+template <> __device__ __forceinline__ void StreamIo<float4, true>::store(uint64_t i, const Trav& T) const
+{ out[i & mask] = make_float4(T.hid != LMB200_MISS ? T.tmax : 0.f, T.hu, T.hv, __uint_as_float(T.hid)); }
+template <> __device__ __forceinline__ void StreamIo<uint8_t, false>::store(uint64_t i, const Trav& T) const { out[i & mask] = T.hid != LMB200_MISS ? 1 : 0; }
+template <> __device__ __forceinline__ void StreamIo<uint8_t, true>::store(uint64_t i, const Trav& T) const { out[i & mask] = T.hid != LMB200_MISS ? 1 : 0; }
+
+template <bool ANY, bool COMPACT>
+__global__ void __launch_bounds__(LMB_TRACE_BLOCK, LMB_TRACE_MIN_BLOCKS)
+trace_stream_kernel(const BvhDev bvh, const void* __restrict__ rays, void* __restrict__ out, const uint64_t n, const uint64_t mask,
+                    unsigned long long* __restrict__ counter, StreamGate gate, const float tmin, const float tmax)
+{
+    __shared__ uint2 smem[LMB_TRAV_SMEM_UINT2(LMB_TRACE_BLOCK)];
+    __shared__ uint32_t ws[(LMB_TRACE_BLOCK / 32) * LMB_GW_WORDS];
+    gate.ws = ws + (threadIdx.x >> 5) * LMB_GW_WORDS;
+    TravCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    if (ANY) {
+        StreamIo<uint8_t, COMPACT> io{rays, reinterpret_cast<uint8_t*>(out), n, mask, tmin, tmax};
+        persistent_trace<true, false, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt, gate);
+    } else {
+        StreamIo<float4, COMPACT> io{rays, reinterpret_cast<float4*>(out), n, mask, tmin, tmax};
+        persistent_trace<false, false, LMB_TRACE_BLOCK>(bvh, io, counter, LMB_SM_BASE(smem), cnt, gate);
+    }
+}
+
 BvhDev bvh_dev(const Accel* a)
 {
     BvhDev b;
@@ -148,6 +195,13 @@ void Accel::free_device()
         if (stage_out[i]) cudaFree(stage_out[i]);
         stage_rays[i] = stage_out[i] = nullptr;
     }
+    if (ring_rays) cudaFree(ring_rays);
+    if (ring_out) cudaFree(ring_out);
+    if (d_gate) cudaFree(d_gate);
+    if (h_gate) cudaFreeHost(h_gate);
+    for (cudaEvent_t ev : out_events) cudaEventDestroy(ev);
+    out_events.clear();
+    ring_rays = ring_out = d_gate = h_gate = nullptr; ring_cap = 0; gate_cap = 0;
     for (int i = 0; i < 4; i++) { if (streams[i]) cudaStreamDestroy(streams[i]); streams[i] = nullptr; }
     for (int i = 0; i < 3 * LMB_NBUF; i++) { if (events[i]) cudaEventDestroy(events[i]); events[i] = nullptr; }
     stage_cap = 0;
@@ -213,6 +267,137 @@ int Accel::upload()
     return LMB200_OK;
 }
 
+// Streaming host-buffer trace (the default for calls of three chunks and more): ONE persistent launch for the whole call.
+// Every boundary between the per-chunk launches of the pipeline below costs ~0.2 ms (the ending launch's warps stop refilling
+// and run on with fewer and fewer live lanes; profiles/r02_sweep.md) - 14 of them in a 64 Mi-ray call. Here the rays and the
+// results live in rings over the ray index (4 chunks deep), the kernel takes the rays of a chunk as soon as its upload has
+// landed (traverse.cuh StreamGate) and publishes each chunk's completion in mapped host memory; this thread waits for that
+// flag, starts the chunk's download and enqueues the uploads the freed ring space admits.
+#ifndef LMB_STREAM_RING_CHUNKS
+#define LMB_STREAM_RING_CHUNKS 4
+#endif
+template <bool ANY, bool COMPACT>
+static int trace_host_stream(Accel* a, const uint8_t* rays, void* out, const uint64_t n, const float tmin, const float tmax,
+                             const std::vector<uint64_t>& sched, const uint64_t chunk)
+{
+    const size_t ray_elem = COMPACT ? 24 : sizeof(lmb200_ray), out_elem = ANY ? 1 : sizeof(lmb200_hit);
+    const uint32_t C = (uint32_t)sched.size();
+    const uint64_t R = (uint64_t)LMB_STREAM_RING_CHUNKS * chunk;      // chunk is a power of two here (the call has several chunks)
+    cudaError_t e;
+    if (a->ring_cap < R) {
+        if (a->ring_rays) cudaFree(a->ring_rays);
+        if (a->ring_out) cudaFree(a->ring_out);
+        a->ring_rays = a->ring_out = nullptr; a->ring_cap = 0;
+        if ((e = cudaMalloc(&a->ring_rays, R * sizeof(lmb200_ray))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(ray ring)");
+        if ((e = cudaMalloc(&a->ring_out, R * sizeof(lmb200_hit))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(hit ring)");
+        a->ring_cap = R;
+    }
+    if (a->gate_cap < C) {
+        uint32_t cap = 64;
+        while (cap < C) cap *= 2;
+        if (a->d_gate) cudaFree(a->d_gate);
+        if (a->h_gate) cudaFreeHost(a->h_gate);
+        a->d_gate = a->h_gate = nullptr; a->gate_cap = 0;
+        if ((e = cudaMalloc(&a->d_gate, (cap + 1) * sizeof(unsigned long long) + 2 * cap * sizeof(uint32_t))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(gate)");
+        if ((e = cudaHostAlloc(&a->h_gate, (cap + 4) * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc(gate)");
+        a->gate_cap = cap;
+    }
+    while (a->out_events.size() < C) {
+        cudaEvent_t ev;
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+        a->out_events.push_back(ev);
+    }
+    const uint32_t cap = a->gate_cap;
+    unsigned long long* d_first = reinterpret_cast<unsigned long long*>(a->d_gate);
+    uint32_t* d_ready = reinterpret_cast<uint32_t*>(d_first + cap + 1);
+    uint32_t* d_done = d_ready + cap;
+    volatile uint32_t* h_done = reinterpret_cast<volatile uint32_t*>(a->h_gate);
+    volatile uint32_t* h_ctl = h_done + cap;
+    uint32_t* h_one = const_cast<uint32_t*>(h_done) + cap + 2;
+    void* dh = nullptr;
+    if ((e = cudaHostGetDevicePointer(&dh, a->h_gate, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+    std::vector<unsigned long long> first(C + 1, 0ull);
+    for (uint32_t c = 0; c < C; c++) first[c + 1] = first[c] + sched[c];
+    for (uint32_t c = 0; c < C; c++) h_done[c] = 0u;
+    h_ctl[0] = 0u; h_ctl[1] = 0u; *h_one = 1u;
+
+    cudaStream_t s_in = a->streams[0], s_k = a->streams[1], s_out = a->streams[2];
+    cudaEvent_t ev_init = a->events[0];
+    unsigned long long* counter = a->d_counter + 2;
+    int rc = LMB200_OK;
+#define LMB_ST(call, what) do { if (!rc) { const cudaError_t e_ = (call); if (e_ != cudaSuccess) rc = cuda_fail(e_, what); } } while (0)
+    LMB_ST(cudaMemcpyAsync(d_first, first.data(), (C + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, s_in), "H2D chunk table");
+    LMB_ST(cudaMemsetAsync(d_ready, 0, 2 * (size_t)cap * sizeof(uint32_t), s_in), "cudaMemsetAsync(gate flags)");
+    LMB_ST(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s_in), "cudaMemsetAsync(counter)");
+    LMB_ST(cudaEventRecord(ev_init, s_in), "cudaEventRecord");
+    LMB_ST(cudaStreamWaitEvent(s_k, ev_init, 0), "cudaStreamWaitEvent");
+    bool launched = false;
+    if (!rc) {
+        StreamGate g;
+        g.first = d_first; g.C = C; g.ready = d_ready; g.done = d_done;
+        g.h_done = reinterpret_cast<volatile uint32_t*>(dh); g.h_ctl = g.h_done + cap; g.ws = nullptr;
+        const unsigned blocks = (unsigned)((uint64_t)a->num_sms * a->trace_blocks_per_sm);
+        trace_stream_kernel<ANY, COMPACT><<<blocks, LMB_TRACE_BLOCK, 0, s_k>>>(bvh_dev(a), a->ring_rays, a->ring_out, n, R - 1, counter, g, tmin, tmax);
+        g_launch_count++;
+        LMB_ST(cudaGetLastError(), "trace_stream_kernel launch");
+        launched = !rc;
+    }
+    // copies between the caller's buffers and the rings: a chunk may wrap around the end of the ring
+    auto ring_copy = [&](const bool up, const uint32_t c, cudaStream_t st) {
+        const uint64_t g0 = first[c], m = sched[c], o = g0 & (R - 1), m0 = std::min(m, R - o);
+        for (int part = 0; part < 2 && !rc; part++) {
+            const uint64_t cnt = part == 0 ? m0 : m - m0, src = part == 0 ? g0 : g0 + m0, slot = part == 0 ? o : 0;
+            if (cnt == 0) continue;
+            if (up) LMB_ST(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(a->ring_rays) + slot * ray_elem, rays + src * ray_elem, cnt * ray_elem, cudaMemcpyHostToDevice, st), "H2D rays");
+            else LMB_ST(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out) + src * out_elem, reinterpret_cast<uint8_t*>(a->ring_out) + slot * out_elem, cnt * out_elem, cudaMemcpyDeviceToHost, st), "D2H hits");
+        }
+    };
+    uint32_t up = 0, down = 0;      // chunks whose upload / download has been enqueued
+    auto pump = [&]() {
+        // chunk `up` overwrites the ring slots of indices [first[up] - R, first[up + 1] - R): they must belong to downloaded chunks
+        while (!rc && up < C && first[up + 1] <= R + first[down]) {
+            if (down > 0) LMB_ST(cudaStreamWaitEvent(s_in, a->out_events[down - 1], 0), "cudaStreamWaitEvent");
+            ring_copy(true, up, s_in);
+            LMB_ST(cudaMemcpyAsync(d_ready + up, h_one, sizeof(uint32_t), cudaMemcpyHostToDevice, s_in), "H2D ready flag");
+            up++;
+        }
+    };
+    pump();
+    const auto t_start = std::chrono::steady_clock::now();
+    static const bool dbg = getenv("LMB200_STREAM_DEBUG") != nullptr;
+    auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() * 1e3; };
+    for (uint32_t c = 0; c < C && !rc; c++) {
+        const double t_w0 = dbg ? since() : 0;
+        // the kernel's flag: every ray of chunk c is finished and its hits are in device memory
+        for (uint64_t spins = 0; h_done[c] == 0u; spins++) {
+            if (h_ctl[0] != 0u) { rc = set_error(LMB200_E_CUDA, "streaming trace: the kernel gave up waiting for an upload"); break; }
+            if ((spins & 0xfffu) == 0xfffu) {
+                const cudaError_t q = cudaStreamQuery(s_k);
+                if (q == cudaSuccess && h_done[c] == 0u) { rc = set_error(LMB200_E_CUDA, "streaming trace: the kernel ended before all chunks were complete"); break; }
+                if (q != cudaSuccess && q != cudaErrorNotReady) { rc = cuda_fail(q, "trace_stream_kernel"); break; }
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 120.0) { rc = set_error(LMB200_E_CUDA, "streaming trace: timed out"); break; }
+            }
+            _mm_pause();
+        }
+        if (rc) break;
+        const double t_w1 = dbg ? since() : 0;
+        ring_copy(false, c, s_out);
+        LMB_ST(cudaEventRecord(a->out_events[c], s_out), "cudaEventRecord");
+        down = c + 1;
+        const double t_w2 = dbg ? since() : 0;
+        pump();
+        if (dbg) fprintf(stderr, "[stream] chunk %u (%llu rays): waited %.3f ms (from %.3f), download enqueue %.3f ms, pump %.3f ms (uploaded %u)\n", c, (unsigned long long)sched[c], t_w1 - t_w0, t_w0, t_w2 - t_w1, since() - t_w2, up);
+    }
+#undef LMB_ST
+    if (rc && launched) h_ctl[1] = 1u;      // a kernel still waiting for uploads that will not come must leave
+    for (int i = 0; i < 4; i++) {
+        e = cudaStreamSynchronize(a->streams[i]);
+        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    if (!rc && h_ctl[0] != 0u) rc = set_error(LMB200_E_CUDA, "streaming trace: the kernel reported an error");
+    return rc;
+}
+
 // Host-buffer trace: a three-stage pipeline (H2D copy | kernel | D2H copy) over three streams and
 #ifndef LMB_E2E_CHUNK_LOG2
 #define LMB_E2E_CHUNK_LOG2 23      // rays per full pipeline chunk (tuning override: env LMB200_E2E_CHUNK_LOG2); with the graded schedule below 2^21: 1050, 2^22: 1121, 2^23: 1149 Mrays/s
@@ -238,11 +423,30 @@ static int trace_host(Accel* a, const void* rays_v, void* out, uint64_t n, float
     // Chunk schedule: full-size chunks in the middle, geometrically smaller ones at both ends (1/8, 1/4, 1/2 of a chunk). The
     // pipeline's fill (first H2D copy, nothing else running) and drain (last D2H copy) then cost an eighth of what a
     // full chunk costs: with 64 Mi rays and 4 Mi-ray chunks that is ~2.5 ms of 61 ms.
+    // LMB200_E2E_STREAM=0 selects the per-chunk launches below for every call (they also serve calls of one or two chunks)
+    static const bool stream_on = [] { const char* e = getenv("LMB200_E2E_STREAM"); return !(e && atoi(e) == 0); }();
     std::vector<uint64_t> sched;
-    {
+    static const uint64_t grade_env = [] { const char* e = getenv("LMB200_E2E_GRADE"); const int v = e ? atoi(e) : 0; return (uint64_t)(v >= 1 && v <= 1024 ? v : 0); }();
+    const bool streaming = stream_on && n >= 4 * chunk && (chunk & (chunk - 1)) == 0 && chunk >= 4096;
+    if (streaming) {
+        // The streaming launch pays nothing per chunk but a few small copies. Its schedule starts with chunk / 64 and grows by
+        // 5/4 per chunk: the kernel can start a chunk only when ALL of it has been uploaded, and uploads run only ~1.3x faster
+        // than the kernel eats rays, so a chunk twice the size of everything before it (the schedule of the per-chunk launches
+        // below) makes the kernel wait for its upload (~2 ms in a 64 Mi-ray call). The tail halves down to chunk / 64: the last
+        // download is all that is not overlapped.
+        const uint64_t small = chunk / (grade_env ? grade_env : 64);
+        std::vector<uint64_t> tail;
+        uint64_t tail_sum = 0;
+        for (uint64_t c = chunk / 2; c >= std::max<uint64_t>(small, 1); c /= 2) { tail.push_back(c); tail_sum += c; }
+        uint64_t left = n - tail_sum;
+        for (uint64_t c = std::max<uint64_t>(small, 1); c < chunk && left > chunk; c = (c * 5 / 4 + 1023) & ~1023ull) { sched.push_back(c); left -= c; }
+        while (left > 0) { const uint64_t m = std::min(chunk, left); sched.push_back(m); left -= m; }
+        for (uint64_t c : tail) sched.push_back(c);
+    } else {
         uint64_t left = n;
         std::vector<uint64_t> tail;
-        for (uint64_t c = std::max<uint64_t>(chunk / 8, 1); c < chunk && left > 2 * chunk; c *= 2) {
+        const uint64_t grade = grade_env ? grade_env : 8;
+        for (uint64_t c = std::max<uint64_t>(chunk / grade, 1); c < chunk && left > 2 * chunk; c *= 2) {
             sched.push_back(c); tail.push_back(c); left -= 2 * c;
         }
         while (left > 0) { const uint64_t m = std::min(chunk, left); sched.push_back(m); left -= m; }
@@ -254,6 +458,7 @@ static int trace_host(Accel* a, const void* rays_v, void* out, uint64_t n, float
     for (int i = 0; i < 3 * LMB_NBUF; i++) {
         if (!a->events[i] && (e = cudaEventCreateWithFlags(&a->events[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
     }
+    if (streaming) return trace_host_stream<ANY, COMPACT>(a, rays, out, n, tmin, tmax, sched, chunk);
     if (a->stage_cap < chunk) {
         for (int i = 0; i < LMB_NBUF; i++) {
             if (a->stage_rays[i]) cudaFree(a->stage_rays[i]);

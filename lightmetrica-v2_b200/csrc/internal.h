@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include <string>
 #include "../../include/lmb200.h"
 #include "bvh.h"
@@ -51,6 +52,13 @@ struct Accel {
     void* stage_out[LMB_NBUF] = {};
     cudaEvent_t events[3 * LMB_NBUF] = {};
     uint64_t stage_cap = 0;
+    // streaming host-buffer path (accel.cu trace_host_stream): ring staging over the ray index space + per-chunk flags
+    void* ring_rays = nullptr; void* ring_out = nullptr;
+    uint64_t ring_cap = 0;              // rays the ring holds (a power of two)
+    void* d_gate = nullptr;             // device: first[cap + 1] (u64), ready[cap], done[cap] (u32)
+    void* h_gate = nullptr;             // mapped pinned: h_done[cap], ctl[2], one[1] (u32)
+    uint32_t gate_cap = 0;              // chunks the gate arrays hold
+    std::vector<cudaEvent_t> out_events;
     std::mutex stage_mu;          // host-buffer calls on one accel take turns: they share the staging buffers and streams
 
     Service* service = nullptr;   // per-ray Accel3::Intersect service, created on first use

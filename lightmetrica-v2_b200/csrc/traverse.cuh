@@ -320,13 +320,165 @@ __device__ __forceinline__ bool trav_step(Trav& T, const BvhDev& bvh,
 // Shared memory a block needs (uint2 entries): the per-thread short stacks.
 #define LMB_TRAV_SMEM_UINT2(block) (LMB_SM_STACK * (block) + LMB_LUT_UINT2)
 
+// ------------------------------------------------------------------------------------------------
+// Streaming gate (host-buffer calls, accel.cu trace_host_stream): ONE persistent launch serves a whole host-buffer call whose
+// rays arrive chunk by chunk while it runs. The gate lives entirely in the refill path of persistent_trace:
+//   * a warp that fetched ray indices of a chunk whose upload has not landed yet (ready[c], written by a 4-byte copy enqueued
+//     behind the chunk's upload) keeps the indices, goes on traversing the rays it has, and looks again at its next refill;
+//     only a warp with nothing else to do spins on the flag;
+//   * it counts, per warp and chunk, the rays fetched and finished, and adds a chunk's finished rays to done[c] once the warp
+//     has no ray of that chunk left in flight (one fence + one atomic per warp and chunk); the warp that completes a chunk
+//     publishes h_done[c] in mapped host memory, on which the host starts that chunk's download.
+// The per-warp bookkeeping is 16 words of shared memory; the common refill touches nothing else. NoGate compiles all of it
+// out (every other kernel).
+struct NoGate { static constexpr bool enabled = false; };
+struct StreamGate {
+    static constexpr bool enabled = true;
+    const unsigned long long* first;      // [C + 1] first global ray index of every chunk, first[C] = n
+    uint32_t C;
+    const uint32_t* ready;                // [C] device memory: chunk uploaded
+    unsigned int* done;                   // [C] device memory: finished rays per chunk
+    volatile uint32_t* h_done;            // [C] mapped host memory: chunk complete (all its hits are in device memory)
+    volatile uint32_t* h_ctl;             // mapped host memory: [0] error raised by the kernel, [1] abort requested by the host
+    uint32_t* ws;                         // shared memory, 16 words per warp (LMB_GW_*)
+};
+enum { LMB_GW_CUR = 0, LMB_GW_INFL_PREV, LMB_GW_INFL_CUR, LMB_GW_PEND_PREV, LMB_GW_PEND_CUR, LMB_GW_READY_UPTO /* chunks < this are uploaded */,
+       LMB_GW_LO_PREV = 6 /* u64 first[cur-1] */, LMB_GW_LO_CUR = 8 /* u64 first[cur] */, LMB_GW_HI_CUR = 10 /* u64 first[cur+1] */, LMB_GW_WORDS = 16 };
+#define LMB_GATE_NONE 0xffffffffffffffffull
+#ifndef LMB_GATE_TIMEOUT_CYCLES
+#define LMB_GATE_TIMEOUT_CYCLES 20000000000ll      // ~10 s at 1.9 GHz: an upload that never lands ends the kernel with an error
+#endif
+
+__device__ __forceinline__ unsigned long long gate_ws64(const StreamGate& g, const int k) { return (unsigned long long)g.ws[k] | ((unsigned long long)g.ws[k + 1] << 32); }
+__device__ __forceinline__ void gate_ws64_set(const StreamGate& g, const int k, const unsigned long long v) { g.ws[k] = (uint32_t)v; g.ws[k + 1] = (uint32_t)(v >> 32); }
+__device__ __forceinline__ void gate_init(const StreamGate& g, const unsigned lane)      // every lane of the warp
+{
+    if (lane < (unsigned)LMB_GW_WORDS) g.ws[lane] = 0u;
+    __syncwarp();
+    if (lane == 0u) gate_ws64_set(g, LMB_GW_HI_CUR, g.first[1]);      // cur = 0: [first[0] = 0, first[1])
+    __syncwarp();
+}
+__device__ __forceinline__ uint32_t gate_chunk_of(const StreamGate& g, const uint64_t i, uint32_t c)
+{
+    while (i < g.first[c]) c--;                      // first[0] = 0
+    while (i >= g.first[c + 1]) c++;                 // i < first[C]
+    return c;
+}
+// every lane of the warp calls it with the same (c, k)
+__device__ __forceinline__ void gate_add_done(const StreamGate& g, const uint32_t c, const uint32_t k, const unsigned lane)
+{
+    if (k == 0u) return;
+    __threadfence();                                 // this lane's hit stores before the count that announces them
+    __syncwarp();
+    if (lane == 0u) {
+        const unsigned old = atomicAdd(g.done + c, k);
+        if ((unsigned long long)old + k == g.first[c + 1] - g.first[c]) { __threadfence_system(); g.h_done[c] = 1u; }
+    }
+    __syncwarp();
+}
+// the finished rays of the lanes in `fin` (ray_index still holds them) are credited to their chunks
+__device__ __forceinline__ void gate_account(const StreamGate& g, const bool fin, uint64_t& ray_index, const unsigned lane)
+{
+    const unsigned m_fin = __ballot_sync(0xffffffffu, fin);
+    if (m_fin == 0u) return;
+    const uint32_t cur = g.ws[LMB_GW_CUR];
+    const bool in_cur = fin && ray_index >= gate_ws64(g, LMB_GW_LO_CUR);
+    const bool in_prev = fin && !in_cur && cur > 0u && ray_index >= gate_ws64(g, LMB_GW_LO_PREV);
+    const unsigned m_cur = __ballot_sync(0xffffffffu, in_cur), m_prev = __ballot_sync(0xffffffffu, in_prev);
+    __syncwarp();
+    if (lane == 0u) {
+        g.ws[LMB_GW_INFL_CUR] -= __popc(m_cur); g.ws[LMB_GW_PEND_CUR] += __popc(m_cur);
+        g.ws[LMB_GW_INFL_PREV] -= __popc(m_prev); g.ws[LMB_GW_PEND_PREV] += __popc(m_prev);
+    }
+    const unsigned m_other = m_fin & ~(m_cur | m_prev);
+    if (m_other) {
+        // rays of chunks the warp's two-chunk window has already left (chunks shorter than a ray lives): one by one
+        __threadfence();
+        if ((m_other >> lane) & 1u) {
+            const uint32_t c_old = gate_chunk_of(g, ray_index, cur);
+            const unsigned old = atomicAdd(g.done + c_old, 1u);
+            if ((unsigned long long)old + 1u == g.first[c_old + 1] - g.first[c_old]) { __threadfence_system(); g.h_done[c_old] = 1u; }
+        }
+    }
+    if (fin) ray_index = LMB_GATE_NONE;
+    __syncwarp();
+}
+// The lanes in `got` hold ray indices they have not loaded yet (`newly`: fetched just now, not counted yet). Moves the
+// window to the newest chunk among them, counts the new ones, and reports whether that chunk has been uploaded:
+// 0 = yes, load the rays; 1 = not yet (only if `busy`: the warp has other rays to traverse meanwhile); 2 = given up.
+__device__ __forceinline__ int gate_acquire(const StreamGate& g, const bool got, const bool newly, const uint64_t i, const bool busy, const unsigned lane)
+{
+    const unsigned m_got = __ballot_sync(0xffffffffu, got);
+    uint32_t cur = g.ws[LMB_GW_CUR];
+    int state = 0;
+    if (m_got) {
+        const uint64_t i_max = __shfl_sync(0xffffffffu, i, 31 - __clz(m_got));      // indices ascend with the lane
+        while (i_max >= gate_ws64(g, LMB_GW_HI_CUR)) {                              // move the window one chunk on
+            if (cur > 0u) gate_add_done(g, cur - 1u, g.ws[LMB_GW_PEND_PREV], lane); // what is still in flight of cur-1 finishes one by one
+            __syncwarp();
+            if (lane == 0u) {
+                g.ws[LMB_GW_INFL_PREV] = g.ws[LMB_GW_INFL_CUR]; g.ws[LMB_GW_PEND_PREV] = g.ws[LMB_GW_PEND_CUR];
+                g.ws[LMB_GW_INFL_CUR] = 0u; g.ws[LMB_GW_PEND_CUR] = 0u; g.ws[LMB_GW_CUR] = cur + 1u;
+                gate_ws64_set(g, LMB_GW_LO_PREV, gate_ws64(g, LMB_GW_LO_CUR));
+                gate_ws64_set(g, LMB_GW_LO_CUR, gate_ws64(g, LMB_GW_HI_CUR));
+                gate_ws64_set(g, LMB_GW_HI_CUR, g.first[cur + 2u]);
+            }
+            cur++;
+            __syncwarp();
+        }
+        const bool n_cur = newly && i >= gate_ws64(g, LMB_GW_LO_CUR);
+        const bool n_prev = newly && !n_cur && cur > 0u && i >= gate_ws64(g, LMB_GW_LO_PREV);
+        const unsigned f_cur = __ballot_sync(0xffffffffu, n_cur), f_prev = __ballot_sync(0xffffffffu, n_prev);
+        __syncwarp();
+        if (lane == 0u) { g.ws[LMB_GW_INFL_CUR] += __popc(f_cur); g.ws[LMB_GW_INFL_PREV] += __popc(f_prev); }
+        __syncwarp();
+        if (g.ws[LMB_GW_READY_UPTO] <= cur) {        // not known to be uploaded yet: look at the flag (uploads land in chunk order)
+            if (lane == 0u) {
+                uint32_t r;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(g.ready + cur) : "memory");
+                if (r == 0u && !busy) {
+                    // nothing else to do: poll the flag, backing off to 32 us (thousands of warps may be waiting here, all on
+                    // one address), and look at the host's abort word - a read across PCIe - only every 64th time
+                    const long long t0 = clock64();
+                    unsigned ns = 500u;
+                    for (unsigned it = 1u;; it++) {
+                        __nanosleep(ns);
+                        if (ns < 32000u) ns *= 2u;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(g.ready + cur) : "memory");
+                        if (r != 0u) break;
+                        if ((it & 63u) == 0u && (g.h_ctl[1] != 0u || clock64() - t0 > LMB_GATE_TIMEOUT_CYCLES)) { g.h_ctl[0] = 1u; state = 2; break; }
+                    }
+                }
+                if (r != 0u) g.ws[LMB_GW_READY_UPTO] = cur + 1u; else if (state == 0) state = 1;
+            }
+            state = __shfl_sync(0xffffffffu, state, 0);
+        }
+    }
+    __syncwarp();
+    if (cur > 0u && g.ws[LMB_GW_INFL_PREV] == 0u && g.ws[LMB_GW_PEND_PREV] != 0u) {        // the warp's last ray of cur-1 is done: hand the count in
+        gate_add_done(g, cur - 1u, g.ws[LMB_GW_PEND_PREV], lane);
+        if (lane == 0u) g.ws[LMB_GW_PEND_PREV] = 0u;
+        __syncwarp();
+    }
+    return state;
+}
+// at the end of the warp's life: everything it fetched is finished
+__device__ __forceinline__ void gate_finish(const StreamGate& g, uint64_t& ray_index, const unsigned lane)
+{
+    gate_account(g, ray_index != LMB_GATE_NONE, ray_index, lane);
+    const uint32_t cur = g.ws[LMB_GW_CUR];
+    if (cur > 0u) gate_add_done(g, cur - 1u, g.ws[LMB_GW_PEND_PREV], lane);
+    gate_add_done(g, cur, g.ws[LMB_GW_PEND_CUR], lane);
+}
+
 // Persistent-warp driver. `Io` supplies rays and consumes results:
 //   uint64_t count() const;                          number of rays
 //   void load(uint64_t i, float4& ro, float4& rd);   ray i
 //   void store(uint64_t i, const Trav& T);           result of ray i (T.hid == 0xffffffff: miss)
-template <bool ANY, bool COUNT, int STRIDE, typename Io>
+template <bool ANY, bool COUNT, int STRIDE, typename Io, typename Gate = NoGate>
 __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
-                                                 unsigned long long* __restrict__ counter, const uint32_t smem, TravCounters& cnt)
+                                                 unsigned long long* __restrict__ counter, const uint32_t smem, TravCounters& cnt,
+                                                 const Gate& gate = Gate())
 {
     trav_lut_init<STRIDE>(smem);
     __syncthreads();
@@ -336,7 +488,9 @@ __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
     Trav T;
     bool active = false;
     bool exhausted = false;      // warp-uniform: the work counter has run past n
-    uint64_t ray_index = 0;
+    uint64_t ray_index = Gate::enabled ? LMB_GATE_NONE : 0ull;
+    bool waiting = false, any_waiting = false;      // streaming gate only: the lane holds an index whose chunk has not been uploaded yet
+    if constexpr (Gate::enabled) gate_init(gate, lane);
     // every lane takes every step (a lane without a ray is in the "finished" state: nothing pending, empty stack, nothing
     // parked - its step does nothing), so the warp votes of a step use the full mask
     T.ngroup = make_uint2(0u, 0u); T.pend = make_uint2(0u, 0u); T.oct_inv4 = 0u; T.hid = 0xffffffffu;
@@ -346,7 +500,43 @@ __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
 
     for (;;) {
         // ---- refill idle lanes (all 32 lanes converge here) ----
-        if (!exhausted) {
+        if constexpr (Gate::enabled) {
+            if (!exhausted || any_waiting) {
+                const unsigned idle = __ballot_sync(0xffffffffu, !active);
+                if (idle) {
+                    gate_account(gate, !active && !waiting && ray_index != LMB_GATE_NONE, ray_index, lane);
+                    uint64_t i = ray_index;      // a waiting lane keeps the index it fetched earlier
+                    bool got = waiting, newly = false;
+                    if (!any_waiting && !exhausted) {
+                        unsigned long long base = 0;
+                        const int leader = __ffs(idle) - 1;
+                        if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(idle));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (!active) { i = base + __popc(idle & ((1u << lane) - 1u)); got = i < n; newly = got; }
+                        if (base + __popc(idle) >= n) exhausted = true;
+                    }
+                    const int state = gate_acquire(gate, got, newly, i, idle != 0xffffffffu, lane);
+                    if (state == 0) {
+                        if (got) {
+                            float4 ro, rd;
+                            io.load(i, ro, rd);
+                            trav_init(T, ro, rd);
+                            trav_stack_reset_t<STRIDE>(T, smem, threadIdx.x);
+                            trav_set_lut<STRIDE>(T, smem);
+                            ray_index = i;
+                            active = true;
+                        }
+                        waiting = false;
+                    } else if (state == 1) {
+                        if (got) { ray_index = i; waiting = true; }
+                    } else {
+                        if (got) ray_index = LMB_GATE_NONE;      // an upload never came: these rays are dropped, the call fails
+                        waiting = false; exhausted = true;
+                    }
+                    any_waiting = __any_sync(0xffffffffu, waiting);
+                }
+            }
+        } else if (!exhausted) {
             const unsigned idle = __ballot_sync(0xffffffffu, !active);
             if (idle) {
                 unsigned long long base = 0;
@@ -381,9 +571,10 @@ __device__ __forceinline__ void persistent_trace(const BvhDev& bvh, Io& io,
             }
             live = __ballot_sync(0xffffffffu, active);
             if (live == 0u) break;
-            if (!exhausted && __popc(live) < LMB_REFILL_BELOW) break;
+            if ((!exhausted || (Gate::enabled && any_waiting)) && __popc(live) < LMB_REFILL_BELOW) break;
         }
     }
+    if constexpr (Gate::enabled) gate_finish(gate, ray_index, lane);
 }
 
 // Whole-ray helper for single-ray callers (per-ray Accel3::Intersect path).

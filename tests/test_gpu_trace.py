@@ -219,6 +219,60 @@ def test_host_buffer_calls_from_several_threads_on_one_accel():
         assert np.array_equal(occ[k].astype(bool), want[k]["tri"] != capi.MISS)
 
 
+STREAM_CHILD = r"""
+import os, sys, threading
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'lightmetrica-v2_b200'))
+from lmb200py import capi, scenes
+L = capi.lib()
+verts = scenes.soup(120000, seed=5, extent=20.0, edge=0.3)
+lo, hi = scenes.bounds(verts)
+A = capi.Accel(0); A.build(verts)
+bad = 0
+def check(n, seed):
+    global bad
+    rays = scenes.random_rays(n, lo, hi, seed=seed)
+    rays[:, 3] = 1e-4; rays[:, 7] = 3.0e38
+    rays[::1001, 4] = np.nan          # a few rays that finish at once
+    d_rays = torch.from_numpy(rays).cuda(); d_hits = torch.empty((n, 4), dtype=torch.float32, device='cuda'); d_occ = torch.zeros(n, dtype=torch.uint8, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    capi.check(L.lmb200_trace_closest_dev(A.h, d_rays.data_ptr(), d_hits.data_ptr(), n, st))
+    capi.check(L.lmb200_trace_any_dev(A.h, d_rays.data_ptr(), d_occ.data_ptr(), n, st))
+    torch.cuda.synchronize()
+    want = d_hits.cpu().numpy().view(np.uint32); want_occ = d_occ.cpu().numpy()
+    for rep in range(2):
+        got = A.trace_closest(rays); occ = A.trace_any(rays)
+        r24 = np.ascontiguousarray(rays[:, [0, 1, 2, 4, 5, 6]])
+        h2 = np.zeros(n, capi.HIT_DTYPE); o2 = np.zeros(n, np.uint8)
+        capi.check(L.lmb200_trace_closest_compact(A.h, r24.ctypes.data, 1e-4, 3.0e38, h2.ctypes.data, n))
+        capi.check(L.lmb200_trace_any_compact(A.h, r24.ctypes.data, 1e-4, 3.0e38, o2.ctypes.data, n))
+        ok = (np.array_equal(got.view(np.uint32).reshape(-1, 4), want) and np.array_equal(occ.astype(np.uint8), want_occ)
+              and np.array_equal(h2.view(np.uint32).reshape(-1, 4), want) and np.array_equal(o2, want_occ))
+        if not ok: bad += 1
+for n, seed in ((1500001, 3), (262144, 4), (700000, 5), (65537, 6), (300000, 7)):
+    check(n, seed)
+# several host threads on one accel, each a streaming call
+th = [threading.Thread(target=check, args=(400000 + 1000 * k, 10 + k)) for k in range(3)]
+for t in th: t.start()
+for t in th: t.join()
+print("STREAM_OK" if bad == 0 else "STREAM_BAD %%d" %% bad)
+"""
+
+
+def test_streaming_host_buffer_path_with_small_chunks():
+    """The host-buffer calls of four chunks and more run as ONE persistent launch that takes the rays chunk by chunk as their
+    uploads land (accel.cu trace_host_stream, traverse.cuh StreamGate). With 64 Ki-ray chunks (LMB200_E2E_CHUNK_LOG2=16, read
+    once per process: hence the child process) a 1.5 M-ray call has ~40 chunks, wraps around the staging ring six times and
+    keeps outrunning its uploads; all four call forms must equal the device-pointer launch bit for bit. The per-chunk
+    launches (LMB200_E2E_STREAM=0) stay available and are checked the same way."""
+    import subprocess
+    import sys
+    for stream in ("1", "0"):
+        env = dict(os.environ, LMB200_E2E_CHUNK_LOG2="16", LMB200_E2E_STREAM=stream)
+        r = subprocess.run([sys.executable, "-c", STREAM_CHILD % (ROOT, ROOT)], env=env, capture_output=True, text=True, timeout=600)
+        assert "STREAM_OK" in r.stdout, (stream, r.stdout[-500:], r.stderr[-1500:])
+
+
 def test_per_ray_service_many_threads_and_restart():
     """The per-ray Accel3::Intersect path (persistent service kernel + mailboxes): 16 host threads posting rays
     concurrently get bit-identical hits to the batch call; the service survives going idle (it exits after 2 ms without
