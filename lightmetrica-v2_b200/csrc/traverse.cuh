@@ -432,7 +432,9 @@ __device__ __forceinline__ int gate_acquire(const StreamGate& g, const bool got,
         __syncwarp();
         if (lane == 0u) { g.ws[LMB_GW_INFL_CUR] += __popc(f_cur); g.ws[LMB_GW_INFL_PREV] += __popc(f_prev); }
         __syncwarp();
-        if (g.ws[LMB_GW_READY_UPTO] <= cur) {        // not known to be uploaded yet: look at the flag (uploads land in chunk order)
+        const uint32_t upto = g.ws[LMB_GW_READY_UPTO];
+        __syncwarp();                                // every lane has read it before lane 0 may update it below
+        if (upto <= cur) {                           // not known to be uploaded yet: look at the flag (uploads land in chunk order)
             if (lane == 0u) {
                 uint32_t r;
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(g.ready + cur) : "memory");
