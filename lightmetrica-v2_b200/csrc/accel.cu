@@ -427,8 +427,13 @@ static int trace_host(Accel* a, const void* rays_v, void* out, uint64_t n, float
     static const bool stream_on = [] { const char* e = getenv("LMB200_E2E_STREAM"); return !(e && atoi(e) == 0); }();
     std::vector<uint64_t> sched;
     static const uint64_t grade_env = [] { const char* e = getenv("LMB200_E2E_GRADE"); const int v = e ? atoi(e) : 0; return (uint64_t)(v >= 1 && v <= 1024 ? v : 0); }();
-    const bool streaming = stream_on && n >= 4 * chunk && (chunk & (chunk - 1)) == 0 && chunk >= 4096;
+    // mid-size calls stream too, with a chunk scaled down to a quarter of the call (a call of one or two full chunks would run
+    // upload, kernel and download one after the other)
+    uint64_t chunk_s = chunk;
+    while (chunk_s > (1u << 17) && n < 4 * chunk_s) chunk_s /= 2;      // below 512 Ki rays the plain three-step call is as fast
+    const bool streaming = stream_on && n >= 4 * chunk_s && (chunk_s & (chunk_s - 1)) == 0 && chunk_s >= 4096;
     if (streaming) {
+        const uint64_t chunk = chunk_s;      // (shadows the pipeline's chunk inside this block)
         // The streaming launch pays nothing per chunk but a few small copies. Its schedule starts with chunk / 64 and grows by
         // 5/4 per chunk: the kernel can start a chunk only when ALL of it has been uploaded, and uploads run only ~1.3x faster
         // than the kernel eats rays, so a chunk twice the size of everything before it (the schedule of the per-chunk launches
@@ -458,7 +463,7 @@ static int trace_host(Accel* a, const void* rays_v, void* out, uint64_t n, float
     for (int i = 0; i < 3 * LMB_NBUF; i++) {
         if (!a->events[i] && (e = cudaEventCreateWithFlags(&a->events[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
     }
-    if (streaming) return trace_host_stream<ANY, COMPACT>(a, rays, out, n, tmin, tmax, sched, chunk);
+    if (streaming) return trace_host_stream<ANY, COMPACT>(a, rays, out, n, tmin, tmax, sched, chunk_s);
     if (a->stage_cap < chunk) {
         for (int i = 0; i < LMB_NBUF; i++) {
             if (a->stage_rays[i]) cudaFree(a->stage_rays[i]);
