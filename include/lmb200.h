@@ -104,7 +104,10 @@ int lmb200_accel_build_ex(lmb200_accel* a, const float* verts, uint64_t ntris, i
  * Closest hit with the reference's acceptance rule (reject t<tmin or t>tmax, triaccel.h:137);
  * on exact ties in t the triangle with the larger index wins (= accel::naive's scan order,
  * accel_naive.cpp:92-124). A ray with a NaN or infinite origin / direction component reports a miss (every comparison
- * of the reference's triangle test fails on it) without walking the tree. */
+ * of the reference's triangle test fails on it) without walking the tree.
+ * Host-pointer form: the call overlaps its own uploads, traversal and downloads; from 512 Ki rays on it is ONE persistent
+ * launch that takes the rays chunk by chunk as their uploads land (pinned buffers make the copies asynchronous; pageable
+ * ones work). Environment, read once per process: LMB200_E2E_STREAM=0 (one launch per chunk), LMB200_E2E_CHUNK_LOG2. */
 int lmb200_trace_closest(lmb200_accel* a, const lmb200_ray* rays, lmb200_hit* hits, uint64_t n);
 int lmb200_trace_closest_dev(lmb200_accel* a, const void* rays_dev, void* hits_dev, uint64_t n, void* stream);
 
