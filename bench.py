@@ -22,6 +22,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -344,20 +345,10 @@ def main():
     mean_kernel_s = float(np.mean(kernel_ms)) * 1e-3
     achieved = b_ray * a.rays / mean_kernel_s / 1e9
     peak, peak_src = hbm_peak()
-    # DRAM traffic per launch comes from one kept ncu capture (profiles/traffic.json); it is only reported while the
-    # traversal sources still hash to what it was captured on
-    traffic, traffic_note = None, "no profiles/traffic.json"
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            if tj.get("source_hash") == source_hash():
-                traffic = tj.get("dram_bytes_per_ray") * a.rays   # per launch, like `achieved`
-                traffic_note = "ncu dram__bytes_read.sum + dram__bytes_write.sum per ray x rays per launch, captured on source hash " + tj["source_hash"]
-            else:
-                traffic_note = "stale: profiles/traffic.json was captured on source hash %s, the kernel now hashes to %s" % (tj.get("source_hash"), source_hash())
-        except Exception:
-            traffic = None
+    # DRAM traffic per launch comes from one kept ncu capture (profiles/traffic.json); kept_traffic_per_ray says when it
+    # still describes the shipped kernel
+    per_ray_kept, traffic_note = kept_traffic_per_ray()
+    traffic = per_ray_kept * a.rays if per_ray_kept is not None else None      # per launch, like `achieved`
     ceiling = pcie_ceiling(torch, dist, world, dev, h_rays, d_rays, h_hits, d_hits)
 
     # ---- parity spot check + CPU baseline (rank 0, N=1) ----
@@ -742,6 +733,69 @@ def source_hash():
     for f in ("traverse.cuh", "accel.cu", "bvh.h", "triaccel.h", "bvh_build.cpp"):
         h.update(open(os.path.join(ROOT, "lightmetrica-v2_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
+
+
+def layout_hash():
+    """Hash of what decides WHICH bytes the traversal kernel fetches: the unit layout and every builder."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("bvh.h", "bvh_dev.h", "triaccel.h", "bvh_build.cpp", "bvh_build_gpu.cu"):
+        h.update(open(os.path.join(ROOT, "lightmetrica-v2_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+TRACE_KERNEL_SYMBOL = "_ZN6lmb20012trace_kernelILb0ELb0ELb0EEEvNS_6BvhDevEPK6float4PvmPKjPyS8_ff"
+_MEM_OP = re.compile(r"\b(?:LDG|STG|LDS|STS|LDL|STL|ATOMG|ATOMS|ATOM|RED|LDC|LDCU|LD|ST|LDSM|MEMBAR|CCTL)(?:\.[A-Za-z0-9_]+)*")
+
+
+def mem_signature(binary=None):
+    """Hash of the ordered list of memory instructions (opcode and modifiers: width, cache operator, scope) in the shipped
+    machine code of lmb200::trace_kernel<false,false>, read with cuobjdump. Two builds with the same signature issue the same
+    loads, stores and atomics in the same order; None when cuobjdump or the library is not there."""
+    import hashlib
+    import shutil
+    import subprocess
+    binary = binary or os.path.join(ROOT, "lightmetrica-v2_b200", "lib", "liblmb200.so")
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool) or not os.path.exists(binary):
+        return None
+    try:
+        out = subprocess.run([tool, "-sass", "-fun", TRACE_KERNEL_SYMBOL, binary], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    ops = []
+    for line in out.splitlines():
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+        if m:
+            ops += _MEM_OP.findall(m.group(1))
+    if not ops:
+        return None
+    return hashlib.sha256(("\n".join(ops) + "\n").encode()).hexdigest()[:16]
+
+
+def kept_traffic_per_ray():
+    """(DRAM bytes per ray, note) from the kept ncu capture profiles/traffic.json, or (None, why not). The figure is reported
+    while the traversal sources hash to what it was captured on, or - after a change that left trace_kernel<false,false>
+    alone, like the streaming gate that is compiled out of it - while the unit layout and builders are unchanged AND the
+    kernel's machine code still issues the same memory instructions in the same order."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None, "no profiles/traffic.json"
+    try:
+        tj = json.load(open(tpath))
+        per_ray = float(tj["dram_bytes_per_ray"])
+    except Exception as ex:
+        return None, "profiles/traffic.json unreadable: %s" % ex
+    what = "ncu dram__bytes_read.sum + dram__bytes_write.sum per ray x rays per launch"
+    if tj.get("source_hash") == source_hash():
+        return per_ray, what + ", captured on source hash " + tj["source_hash"]
+    sig = mem_signature()
+    if tj.get("layout_hash") == layout_hash() and sig is not None and tj.get("mem_signature") == sig:
+        return per_ray, (what + ", captured on source hash %s; the sources now hash to %s, but unit layout and builders are unchanged "
+                         "(layout hash %s) and the shipped trace_kernel<false,false> issues the same memory instructions in the same "
+                         "order as the captured build (signature %s)" % (tj.get("source_hash"), source_hash(), layout_hash(), sig))
+    return None, ("stale: profiles/traffic.json (%.0f B/ray) was captured on source hash %s / layout %s / memory signature %s; now %s / %s / %s"
+                  % (per_ray, tj.get("source_hash"), tj.get("layout_hash"), tj.get("mem_signature"), source_hash(), layout_hash(), sig))
 
 
 if __name__ == "__main__":

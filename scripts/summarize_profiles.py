@@ -85,6 +85,10 @@ if t:
     json.dump({"tag": tag, "trace_kernel_dram_bytes_per_launch": traffic, "rays_per_launch": 16777216,
                "dram_bytes_per_ray": traffic / 16777216, "source_hash": bench.source_hash(),
                "source_hash_of": "sha256 of csrc/{traverse.cuh,accel.cu,bvh.h,triaccel.h,bvh_build.cpp} at capture time (bench.py source_hash())",
+               "layout_hash": bench.layout_hash(),
+               "layout_hash_of": "sha256 of csrc/{bvh.h,bvh_dev.h,triaccel.h,bvh_build.cpp,bvh_build_gpu.cu}: unit layout and builders (bench.py layout_hash())",
+               "mem_signature": bench.mem_signature(),
+               "mem_signature_of": "sha256 of the ordered memory instructions (opcode + modifiers) in the SASS of trace_kernel<false,false> (bench.py mem_signature())",
                "note": "ncu --set full capture of lmb200::trace_kernel<false,false> at 16 Mi rays / 4 M triangles; bench.py scales it per ray"},
               open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print("profiles written for", tag)

@@ -71,3 +71,27 @@ def test_lmb200_arm_json_contract_small():
     c4 = d["config4"]
     assert c4["value"] > 0 and c4["triangles"] > 9_500_000 and c4["film_bytes"] == 3840 * 2160 * 16 and c4["finite"] is True
     assert d["pt_msamples_s"] == pt["value"] and d["config4_msamples_s"] == c4["value"]
+
+
+def test_kept_dram_traffic_rule():
+    """roofline.traffic comes from a kept ncu capture: it is reported only while the capture still describes the shipped
+    kernel (same sources, or same unit layout + builders and the same memory instructions in the kernel's machine code)."""
+    import shutil
+    sys.path.insert(0, ROOT)
+    import bench
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    for k in ("dram_bytes_per_ray", "source_hash", "layout_hash", "mem_signature"):
+        assert k in tj, k
+    per_ray, note = bench.kept_traffic_per_ray()
+    lib = os.path.join(ROOT, "lightmetrica-v2_b200", "lib", "liblmb200.so")
+    have_tool = os.path.exists(lib) and (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump"))
+    fresh = tj["source_hash"] == bench.source_hash()
+    same_kernel = have_tool and tj["layout_hash"] == bench.layout_hash() and tj["mem_signature"] == bench.mem_signature()
+    if fresh or same_kernel:
+        assert per_ray == tj["dram_bytes_per_ray"] and tj["source_hash"] in note
+    else:
+        assert per_ray is None and note.startswith("stale")
+    if have_tool:
+        sig = bench.mem_signature()
+        assert sig is not None and len(sig) == 16 and sig == bench.mem_signature()      # deterministic
+    assert bench.mem_signature("/nonexistent/lib.so") is None
