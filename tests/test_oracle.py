@@ -150,3 +150,87 @@ def test_nanort_speed_baseline_agrees_with_triaccel_accels_almost_everywhere():
     assert agree > 0.998, agree
     both = (n["face"] >= 0) & (n["face"] == q["face"])
     assert np.allclose(n["t"][both], q["tuv"][both, 0], rtol=1e-3, atol=1e-4)
+
+
+def _family(name):
+    """Scene and ray families for the live pinning below: (verts, rays)."""
+    rng = np.random.default_rng(2024)
+    if name == "mesh":                      # closed tessellated surfaces over a ground plane (the configs[2] geometry)
+        verts = scenes.mesh_scene(6000, seed=5, half=20.0, n_objects=12)[0]
+        lo, hi = scenes.bounds(verts)
+        return verts, scenes.random_rays(20000, lo, hi, seed=11)
+    if name == "far_anisotropic":           # far from the origin, one axis 50x longer than the others
+        verts = scenes.soup(4000, seed=8, extent=4.0, edge=0.25).reshape(-1, 3, 3).copy()
+        verts[..., 0] = verts[..., 0] * 50.0 + 900.0
+        verts[..., 1] -= 700.0
+        verts = np.ascontiguousarray(verts.reshape(-1, 9), np.float32)
+        lo, hi = scenes.bounds(verts)
+        return verts, scenes.random_rays(20000, lo, hi, seed=12)
+    if name == "axis_aligned_rays":         # zero direction components and negative zeros, origins on a lattice
+        verts = scenes.soup(4000, seed=9, extent=5.0, edge=0.4)
+        n = 12000
+        o = (rng.integers(0, 21, (n, 3)) * 0.25).astype(np.float32)
+        d = np.zeros((n, 3), np.float32)
+        ax = rng.integers(0, 3, n)
+        d[np.arange(n), ax] = rng.choice(np.array([1.0, -1.0], np.float32), n)
+        d[rng.random((n, 3)) < 0.2] *= np.float32(-1.0)      # some -0.0 components
+        rays = np.concatenate([o, np.zeros((n, 1), np.float32), d, np.full((n, 1), FLT_MAX, np.float32)], axis=1).astype(np.float32)
+        return verts, rays
+    if name == "bounded_ranges":            # tmin > 0 and finite tmax: hits outside [tmin, tmax] must be ignored (triaccel.h:137)
+        verts = scenes.soup(4000, seed=10, extent=5.0, edge=0.4)
+        lo, hi = scenes.bounds(verts)
+        rays = scenes.random_rays(20000, lo, hi, seed=13)
+        rays[:, 3] = rng.uniform(0.0, 2.0, len(rays)).astype(np.float32)
+        rays[:, 7] = rays[:, 3] + rng.uniform(0.0, 3.0, len(rays)).astype(np.float32)
+        return verts, rays
+    if name == "duplicates_and_degenerates":
+        base = scenes.soup(1500, seed=14, extent=3.0, edge=0.5)
+        deg = base[:50].copy()
+        deg[:, 6:9] = deg[:, 3:6]           # two equal vertices: zero-area triangles (k = 3, never hit)
+        verts = np.ascontiguousarray(np.concatenate([base, base[:300], deg, base[100:200]]), np.float32)
+        lo, hi = scenes.bounds(base)
+        return verts, scenes.random_rays(20000, lo, hi, seed=15)
+    if name == "origins_on_surfaces":       # secondary-ray shape: origins on triangles, range starting at the reference's 1e-4
+        verts = scenes.soup(4000, seed=16, extent=4.0, edge=0.5)
+        n = 16000
+        t = rng.integers(0, len(verts), n)
+        b = rng.random((n, 2)).astype(np.float32)
+        flip = b.sum(1) > 1
+        b[flip] = 1 - b[flip]
+        V = verts.reshape(-1, 3, 3)[t]
+        o = (V[:, 0] * (1 - b[:, :1] - b[:, 1:]) + V[:, 1] * b[:, :1] + V[:, 2] * b[:, 1:]).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        rays = np.concatenate([o, np.full((n, 1), 1e-4, np.float32), d.astype(np.float32), np.full((n, 1), FLT_MAX, np.float32)], axis=1).astype(np.float32)
+        return verts, rays
+    raise KeyError(name)
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("family", ["mesh", "far_anisotropic", "axis_aligned_rays", "bounded_ranges", "duplicates_and_degenerates", "origins_on_surfaces"])
+def test_port_vs_reference_live_families(family):
+    """The port is the checker of every GPU parity test, so it is pinned against the compiled reference (accel::qbvh through
+    the real Accel3::Intersect, accel_qbvh.cpp:398-497) on the geometry and ray shapes those tests use: face index and
+    t, u, v bit for bit, any-hit consistent with closest-hit."""
+    verts, rays = _family(family)
+    P = ob.PortScene(verts)
+    tuv, tri = P.closest(rays)
+    r = ob.RefSoup(verts, "qbvh").intersect(rays, threads=2)
+    assert np.array_equal(tuv.view(np.uint32), r["tuv"].view(np.uint32))
+    if family == "duplicates_and_degenerates":
+        # Exact copies of a triangle give exactly equal t: the reference keeps whichever copy it tests LAST (triaccel.h:137
+        # rejects only t > maxT), so the winner depends on the accel's traversal order (SURVEY.md App. B). Hit or miss and
+        # t, u, v are the same bits everywhere; the face differs only between exact copies, and the port's rule - the
+        # larger index - is what the reference's own linear scan (accel::naive) answers.
+        diff = tri != r["face"]
+        assert 0 < diff.sum() and np.array_equal(tri >= 0, r["face"] >= 0)
+        assert np.array_equal(verts[tri[diff]], verts[r["face"][diff]]) and (tri[diff] > r["face"][diff]).all()
+        naive = ob.RefSoup(verts, "naive").intersect(rays[:4000], threads=2)
+        assert np.array_equal(tri[:4000], naive["face"]) and np.array_equal(tuv[:4000].view(np.uint32), naive["tuv"].view(np.uint32))
+    else:
+        assert np.array_equal(tri, r["face"])
+    assert 0.02 < (tri >= 0).mean() < 1.0, "the family must produce both hits and misses"
+    assert np.array_equal(P.any(rays).astype(bool), tri >= 0)
+    # the brute-force scan (accel::naive's loop, accel_naive.cpp:92-124) agrees with the tree on a subset
+    tuv_n, tri_n = P.closest(rays[:1500], use_bvh=False)
+    assert np.array_equal(tri_n, tri[:1500]) and np.array_equal(tuv_n.view(np.uint32), tuv[:1500].view(np.uint32))
