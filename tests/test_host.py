@@ -217,3 +217,22 @@ def test_error_paths_without_a_device():
     keep["ls"][0].primitive = 99
     assert L.lmb200_scene_create(0, C.byref(d)) is None
     assert L.lmb200_last_error() != b""
+
+
+@pytest.mark.parametrize("family", ["mesh", "far_anisotropic", "axis_aligned_rays", "bounded_ranges", "duplicates_and_degenerates", "origins_on_surfaces"])
+def test_wide_tree_on_the_pinned_families(family):
+    """The 64-byte-unit tree (host builder) walked on the CPU in the device's format, on the scene / ray families the port is
+    pinned on against the compiled reference (tests/test_oracle.py::test_port_vs_reference_live_families): the quantised
+    child boxes never cull a hit, ranges and the tie rule hold, every hit bit for bit."""
+    from test_oracle import _family
+    verts, rays = _family(family)
+    A = capi.Accel(host_only=True)
+    st = A.build(verts)
+    units, num_nodes, num_tris, grid = A.host_layout()
+    P = ob.PortScene(verts)
+    check_structure(units, num_nodes, num_tris, grid, verts, P.records())
+    assert st["num_valid_triangles"] == num_tris <= len(verts)
+    tuv_w, tri_w = ob.wide_closest(units, grid, rays)
+    tuv_p, tri_p = P.closest(rays)
+    assert np.array_equal(tri_w, tri_p)
+    assert np.array_equal(tuv_w.view(np.uint32), tuv_p.view(np.uint32))
