@@ -133,8 +133,10 @@ static void tri_geom(const orc_pt_scene* S, uint32_t tri, float b0, float b1, v3
 static v3 tex_eval(const orc_texture* T, float u, float v)
 {
     int x = (int)((u - floorf(u)) * (float)T->width), y = (int)((v - floorf(v)) * (float)T->height);
-    if (x < 0) x = 0; if (x > T->width - 1) x = T->width - 1;
-    if (y < 0) y = 0; if (y > T->height - 1) y = T->height - 1;
+    if (x < 0) x = 0;
+    if (x > T->width - 1) x = T->width - 1;
+    if (y < 0) y = 0;
+    if (y > T->height - 1) y = T->height - 1;
     return ld3(T->rgb + 3 * ((size_t)T->width * y + x));
 }
 /* R of bsdf::diffuse / bsdf::cook_torrance: constant or TexR at geom.uv (bsdf_diffuse.cpp:102, bsdf_cooktorrance.cpp:118) */
@@ -474,8 +476,10 @@ static void splat(const orc_pt_scene* S, float* film, float rx, float ry, v3 c) 
     const int W = S->d.camera.width, H = S->d.camera.height;
     int px = (int)(rx * (float)W), py = (int)(ry * (float)H);
     float* f;
-    if (px < 0) px = 0; if (px > W - 1) px = W - 1;
-    if (py < 0) py = 0; if (py > H - 1) py = H - 1;
+    if (px < 0) px = 0;
+    if (px > W - 1) px = W - 1;
+    if (py < 0) py = 0;
+    if (py > H - 1) py = H - 1;
     f = film + 4 * ((size_t)py * W + px);
     f[0] += c.x; f[1] += c.y; f[2] += c.z;
 }
@@ -560,7 +564,8 @@ static void sample_path(const orc_pt_scene* S, int mode, int max_verts, int min_
             geom_t gL;
             v3 ppL, fsE, fsL, C, d;
             float pdfL, pdfPL, G, d2, dl;
-            if (li < 0) li = 0; if (li > nL - 1) li = nL - 1;                       /* scene3.cpp:508-513 */
+            if (li < 0) li = 0;                                                      /* scene3.cpp:508-513 */
+            if (li > nL - 1) li = nL - 1;
             pdfL = 1.0f / (float)nL;                                                 /* scene3.cpp:526-530 */
             if (!light_sample(S, li, geom.p, ua[1], ua[2], &gL, &pdfPL)) goto nee_done;
             ppL = vnorm(vsub(gL.p, geom.p));
