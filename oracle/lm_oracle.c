@@ -3,7 +3,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may call this; it is never
  * shipped and never on the product path.
  *
- * Parity status: PINNED. tests/test_oracle_ref.py checks every function below bit-for-bit against
+ * Parity status: PINNED. tests/test_oracle.py checks every function below bit-for-bit against
  * the reference itself compiled from /root/reference (oracle/_ref, see oracle/ref/build_ref.sh)
  * and against the reference's own known-answer tests Accel3Test.Simple/Simple2
  * (src/lightmetrica-test/test_accel3.cpp:272-345); the resulting vectors are committed under
