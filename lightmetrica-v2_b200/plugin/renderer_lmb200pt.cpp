@@ -13,6 +13,7 @@
 // (renderer_pt.cpp:236-241). Scenes using assets outside the supported set (textured BSDFs, light::env
 // outside mode ptdirect, unknown plugins) are rejected with an error, never mis-rendered.
 #include <lightmetrica/lightmetrica.h>
+#include <chrono>
 #include <vector>
 #include <map>
 #include <cstring>
@@ -89,7 +90,9 @@ public:
         std::vector<float> verts, normals, uvs;
         std::vector<uint32_t> primOfTri, faceOfTri;
         std::vector<lmb200_primitive> prims;
+        const auto tFlatten0 = std::chrono::steady_clock::now();
         lmb200plugin::FlattenTriangles(scene, verts, &normals, primOfTri, faceOfTri, &prims, &uvs);
+        const double flattenSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tFlatten0).count();
         curScene_ = scene;
         textures_.clear(); textureData_.clear(); textureIndex_.clear();
         bool anyNormals = false;
@@ -245,7 +248,7 @@ public:
         }
         d.num_tris = verts.size() / 9;
         d.verts = verts.data();
-        d.normals = anyNormals ? normals.data() : nullptr;
+        d.normals = (anyNormals && !normals.empty()) ? normals.data() : nullptr;      // FlattenTriangles leaves it empty when no mesh has normals
         d.tri_prim = primOfTri.data();
         d.num_prims = (uint32_t)prims.size();
         d.prims = prims.data();
@@ -256,8 +259,11 @@ public:
         for (size_t t = 0; t < textures_.size(); t++) textures_[t].rgb = textureData_[t].data();
         d.num_textures = (uint32_t)textures_.size();
         d.textures = textures_.empty() ? nullptr : textures_.data();
-        d.uvs = textures_.empty() ? nullptr : uvs.data();
+        d.uvs = (textures_.empty() || uvs.empty()) ? nullptr : uvs.data();            // no texture coordinates anywhere: (0, 0), as the reference (intersectionutils.h:107-115)
 
+        LM_LOG_INFO("renderer::lmb200pt: " + std::to_string(d.num_tris) + " triangles of " + std::to_string(d.num_prims) + " primitives flattened in " +
+                    std::to_string(flattenSeconds) + " s, scene read in " +
+                    std::to_string(std::chrono::duration<double>(std::chrono::steady_clock::now() - tFlatten0).count()) + " s");
         if (const char* dump = std::getenv("LMB200_DUMP_SCENE"))
         {
             // debugging aid: the flattened scene exactly as handed to lmb200_scene_create
@@ -282,6 +288,7 @@ public:
                     fwrite(d.textures[t].rgb, sizeof(float), 3 * (size_t)wh[0] * wh[1], f);
                 }
                 if (d.uvs) fwrite(d.uvs, sizeof(float), 6 * d.num_tris, f);
+                if (d.normals) fwrite(d.normals, sizeof(float), 9 * d.num_tris, f);
                 fclose(f);
             }
         }

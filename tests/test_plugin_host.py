@@ -57,7 +57,9 @@ def _read_dump(path):
             tw, th = (int(x) for x in np.frombuffer(f.read(8), np.int32))
             textures.append(np.frombuffer(f.read(12 * tw * th), np.float32).reshape(th, tw, 3))
         uvs = np.frombuffer(f.read(24 * nt), np.float32).reshape(-1, 6) if has_uv else None
-    return dict(nt=nt, npr=npr, nb=nb, nl=nl, has_n=has_n, cam=cam, sphere=sphere, verts=verts, tri_prim=tri_prim,
+        normals = np.frombuffer(f.read(36 * nt), np.float32).reshape(-1, 9) if has_n else None
+        assert f.read(1) == b""
+    return dict(normals=normals, nt=nt, npr=npr, nb=nb, nl=nl, has_n=has_n, cam=cam, sphere=sphere, verts=verts, tri_prim=tri_prim,
                 prims=prims, bsdfs=bsdfs, lights=lights, textures=textures, uvs=uvs)
 
 
@@ -77,6 +79,7 @@ def test_renderer_plugin_scene_extraction(tmp_path, monkeypatch):
     nt, npr, nl, has_n, cam, verts, tri_prim, prims, bsdfs, lights = (D[k] for k in ("nt", "npr", "nl", "has_n", "cam", "verts", "tri_prim", "prims", "bsdfs", "lights"))
     d, keep = sc.flatten()
     assert (nt, npr, nl, has_n) == (d.num_tris, d.num_prims, d.num_lights, 0)
+    assert D["normals"] is None and D["uvs"] is None      # no mesh has any: the arrays are not even made (flatten.h)
     assert np.array_equal(verts, keep["verts"]) and np.array_equal(tri_prim, keep["tri_prim"])
     for i in range(npr):
         a, b = prims[i], keep["prims"][i]
@@ -136,6 +139,7 @@ def test_renderer_plugin_bakes_textures(tmp_path, monkeypatch):
     d, keep = sc.flatten()
     assert len(D["textures"]) == 2 and D["uvs"] is not None
     assert np.array_equal(D["uvs"], keep["uvs"])
+    assert D["has_n"] == 0 and D["normals"] is None      # no vertex normals in this scene
     got_tex = {D["bsdfs"][D["prims"][i].bsdf].texR for i in range(D["npr"])}
     assert got_tex == {0, 1, 2}
     for i in range(D["npr"]):
@@ -143,3 +147,31 @@ def test_renderer_plugin_bakes_textures(tmp_path, monkeypatch):
         assert (a.texR > 0) == (b.texR > 0)
         if a.texR > 0:
             assert np.array_equal(D["textures"][a.texR - 1], keep["baked"][b.texR - 1])
+
+
+def test_renderer_plugin_flattens_vertex_normals_of_some_meshes(tmp_path, monkeypatch):
+    """Meshes with and without vertex normals in one scene (intersectionutils.h:88-90 falls back to the geometric normal for
+    the latter): the flattened normal array carries the given normals for the former and zeros for the latter, triangle for
+    triangle in the reference accels' order."""
+    import numpy as np
+    from lmb200py import scenes
+    dump = str(tmp_path / "scene.bin")
+    monkeypatch.setenv("LMB200_DUMP_SCENE", dump)
+    load_plugins()
+    sc = scenedesc.cornell_box(16, 16)
+    c = np.array([0.4, 0.9, 0.3], np.float32)
+    ball = scenes.sphere(c, 0.25, 10, 6)
+    n = ball.reshape(-1, 3) - c
+    n = (n / np.linalg.norm(n, axis=1, keepdims=True)).astype(np.float32)
+    sc.add_mesh_tris(ball, "red", normals=n)
+    sc.add_quad((-0.2, 0.01, 0.5), (-0.2, 0.01, 0.9), (0.2, 0.01, 0.9), (0.2, 0.01, 0.5), "green")      # a mesh without normals AFTER it
+    R = ob.RefScene(sc, accel="qbvh")
+    R.render("lmb200pt", 10, extra={"mode": "ptdirect"}, in_tree=True)
+    D = _read_dump(dump)
+    d, keep = sc.flatten()
+    assert D["has_n"] == 1 and D["nt"] == d.num_tris
+    assert np.array_equal(D["verts"], keep["verts"]) and np.array_equal(D["tri_prim"], keep["tri_prim"])
+    assert np.array_equal(D["normals"], keep["norms"])
+    with_n = np.array([D["prims"][int(p)].has_normals for p in D["tri_prim"]], bool)
+    assert with_n.sum() == len(ball) and not with_n[-2:].any() and not with_n[:36].any()
+    assert (D["normals"][~with_n] == 0).all() and np.allclose(np.linalg.norm(D["normals"][with_n].reshape(-1, 3), axis=1), 1, atol=1e-6)
