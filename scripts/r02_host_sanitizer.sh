@@ -48,3 +48,14 @@ for name, sc in (("cornell", scenedesc.cornell_box(16, 16, glossy_block=True)), 
     print("ok", name, os.path.getsize(os.environ["LMB200_DUMP_SCENE"]), "bytes dumped")
 PY
 fi
+# ---- ThreadSanitizer over the multi-threaded host builder (record preparation and the subtree work queue of bvh_build.cpp) ----
+mkdir -p "$OUT/tsan"
+TS="-fsanitize=thread -fno-omit-frame-pointer"
+NVT="-O1 -g -std=c++17 -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ --fmad=false -I$ROOT/include -Xcompiler -fPIC,-O1,-g,-ffp-contract=off,${TS// /,}"
+for f in accel render bvh_build_gpu service; do LD_PRELOAD= /usr/local/cuda/bin/nvcc $NVT -c "$SRC/$f.cu" -o "$OUT/tsan/$f.o" 2>/dev/null & done
+LD_PRELOAD= g++ -O1 -g -std=c++17 -fPIC -ffp-contract=off $TS -pthread -I"$ROOT/include" -c "$SRC/bvh_build.cpp" -o "$OUT/tsan/bvh_build.o" &
+wait
+LD_PRELOAD= /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -ccbin /usr/bin/g++ -o "$OUT/tsan/liblmb200.so" "$OUT"/tsan/*.o -Xcompiler -fsanitize=thread -lpthread -ldl
+LD_PRELOAD="$(g++ -print-file-name=libtsan.so)" TSAN_OPTIONS="report_signal_unsafe=0 halt_on_error=0" LMB200_LIB="$OUT/tsan/liblmb200.so" \
+  python -m pytest tests/test_host.py -q -s -k "builder or wide_tree" 2>&1 | tee "$OUT/tsan.log" | grep -iE "WARNING: ThreadSanitizer|passed|failed" | sort | uniq -c
+
