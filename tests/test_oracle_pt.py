@@ -192,3 +192,47 @@ def test_port_matches_the_reference_on_the_config2_scene():
     bm = np.minimum(img, 2.0).reshape(45, 6, 80, 6, 3).mean(axis=(1, 3))
     assert float(np.sqrt(np.mean((bm - ra) ** 2)) / np.mean(ra)) < 1.25 * floor
     assert np.allclose(bm.mean(axis=(0, 1)), 0.5 * (ra + rb).mean(axis=(0, 1)), rtol=0.02)
+
+
+def test_coherent_sample_groups_are_stratified_over_the_tiles():
+    """lmb200_render_params::primary_tile in the port (the GPU renderer is checked against it sample for sample,
+    tests/test_gpu_render.py::test_coherent_camera_sample_groups): groups of 32 samples share a tile, consecutive groups visit
+    ALL tiles once per round in a keyed pseudo-random order. Counted with a scene in which every camera ray hits an emitter of
+    radiance 1 (pt, two vertices), so the film is the per-pixel sample count: complete rounds put exactly the same number of
+    samples into every tile (the tile order is a bijection), a partial round at most one group more, any split of the sample
+    range adds up to the same film, and independent positions (primary_tile < 0) do none of this."""
+    W = H = 32
+    s = scenedesc.Scene()
+    s.add_bsdf("black", "diffuse", (0, 0, 0))
+    s.add_light("wall", (1.0, 1.0, 1.0))
+    s.add_quad((-10, -10, 0), (10, -10, 0), (10, 10, 0), (-10, 10, 0), "black", "wall")      # fills the view, faces the camera
+    s.set_camera((0, 0, 3), (0, 0, 0), (0, 1, 0), 40.0, W, H)
+    P = ob.PortPT(s)
+
+    def counts(N, tp, seed=5, **kw):
+        img, _ = P.render(0, N, seed=seed, max_verts=2, primary_tile=tp, **kw)
+        c = img[..., 0] * (N / (W * H))
+        assert np.allclose(c, np.round(c), atol=1e-3)
+        return np.round(c)
+
+    for tp in (4, 8):
+        tiles = (W // tp) * (H // tp)
+        rounds = 4
+        N = rounds * 32 * tiles
+        c = counts(N, tp)
+        per_tile = c.reshape(H // tp, tp, W // tp, tp).sum(axis=(1, 3))
+        assert c.sum() == N and (per_tile == rounds * 32).all()
+        # a partial round: every tile has its complete rounds, some one group more
+        N2 = N + 32 * (tiles // 3) + 7
+        c2 = counts(N2, tp)
+        pt2 = c2.reshape(H // tp, tp, W // tp, tp).sum(axis=(1, 3))
+        assert c2.sum() == N2 and pt2.min() >= rounds * 32 and pt2.max() <= (rounds + 1) * 32
+        # sharding the sample range (what the GPUs of one box do) gives the same counts
+        parts = sum(P.render(0, N, seed=5, max_verts=2, primary_tile=tp, begin=N * k // 3, end=N * (k + 1) // 3)[0][..., 0] for k in range(3))
+        assert np.allclose(parts * (N / (W * H)), c, atol=1e-3)
+        # another seed: another order and other positions, the same stratification
+        c3 = counts(N, tp, seed=6)
+        assert (c3 != c).any() and (c3.reshape(H // tp, tp, W // tp, tp).sum(axis=(1, 3)) == rounds * 32).all()
+    free = counts(4 * 32 * 64, -1)
+    ft = free.reshape(8, 4, 8, 4).sum(axis=(1, 3))
+    assert free.sum() == 4 * 32 * 64 and ft.min() < 128 < ft.max()
